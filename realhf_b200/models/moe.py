@@ -1,0 +1,129 @@
+"""Mixture-of-experts MLP: router, token permutation, grouped expert GEMMs, expert parallelism.
+
+Parity: `realhf/impl/model/modules/moe/{router,experts,token_dispatcher,layer}.py` and `utils/moe.py`
+(top-k softmax routing, aux load-balancing loss, z-loss, capacity-factor token dropping, sinkhorn).
+Beyond the reference: real **expert parallelism** — with `ep_group` set, experts are partitioned across
+ranks and tokens travel by all-to-all (`dispatch -> grouped GEMM -> combine`); the reference's
+"AlltoAll" dispatcher never leaves the rank (token_dispatcher.py:17-27).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from realhf_b200.ops import functional as OF
+from realhf_b200.parallel import tp as TP
+
+MOE_STATS: Dict[str, List[torch.Tensor]] = {"aux_loss": [], "z_loss": []}
+
+
+def pop_moe_losses() -> Dict[str, torch.Tensor]:
+    out = {k: (torch.stack(v).sum() if v else None) for k, v in MOE_STATS.items()}
+    for v in MOE_STATS.values():
+        v.clear()
+    return out
+
+
+def sinkhorn(cost: torch.Tensor, tol: float = 1e-4, max_iter: int = 100) -> torch.Tensor:
+    cost = torch.exp(cost.float())
+    d0 = torch.ones(cost.size(0), device=cost.device)
+    d1 = torch.ones(cost.size(1), device=cost.device)
+    eps, err, it = 1e-8, 1e9, 0
+    while err > tol and it < max_iter:
+        d0 = (1.0 / d0.size(0)) / (torch.sum(d1.unsqueeze(0) * cost, 1) + eps)
+        d1_new = (1.0 / d1.size(0)) / (torch.sum(d0.unsqueeze(1) * cost, 0) + eps)
+        err = torch.mean(torch.abs(d1 - d1_new)).item()
+        d1, it = d1_new, it + 1
+    return d1 * cost * d0.unsqueeze(1)
+
+
+def route(h: torch.Tensor, w_router: torch.Tensor, mcfg, training: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """h [T,H] -> (probs [T,k] fp32 normalised over the chosen experts, expert ids [T,k])."""
+    if training and mcfg.input_jitter_eps > 0:
+        h = h * torch.empty_like(h).uniform_(1 - mcfg.input_jitter_eps, 1 + mcfg.input_jitter_eps)
+    logits = F.linear(h.float(), w_router.float())
+    if training and mcfg.z_loss_coeff > 0:
+        MOE_STATS["z_loss"].append(torch.logsumexp(logits, -1).square().mean() * mcfg.z_loss_coeff)
+    if mcfg.routing_type == "sinkhorn" and training:
+        with torch.no_grad():
+            _, idx = torch.topk(sinkhorn(logits), mcfg.top_k, dim=-1)
+        probs = torch.sigmoid(logits).gather(-1, idx) if mcfg.top_k == 1 else torch.softmax(logits, -1).gather(-1, idx)
+        return probs, idx
+    full = torch.softmax(logits, dim=-1)
+    probs, idx = torch.topk(full, mcfg.top_k, dim=-1)
+    probs = probs / probs.sum(-1, keepdim=True)
+    if training and mcfg.routing_type == "aux_loss" and mcfg.aux_loss_coeff > 0:
+        E = logits.shape[-1]
+        frac_tokens = F.one_hot(idx, E).float().sum(1).mean(0)     # share of assignments per expert
+        frac_probs = full.mean(0)
+        MOE_STATS["aux_loss"].append((frac_tokens * frac_probs).sum() * E * mcfg.aux_loss_coeff / mcfg.top_k)
+    return probs, idx
+
+
+def _apply_capacity(probs, idx, n_experts: int, mcfg):
+    """Zero the routing weight of assignments beyond each expert's capacity."""
+    if mcfg.capacity_factor is None:
+        return probs
+    T, k = idx.shape
+    cap = int(mcfg.capacity_factor * T * k / n_experts + 0.999)
+    flat_e = idx.reshape(-1)
+    if mcfg.token_drop_policy == "position":
+        order = torch.arange(T * k, device=idx.device)
+    else:
+        order = torch.argsort(probs.reshape(-1), descending=True, stable=True)
+    e_sorted = flat_e[order]
+    onehot = F.one_hot(e_sorted, n_experts)
+    rank_in_e = (onehot.cumsum(0) * onehot).sum(-1) - 1
+    keep_sorted = rank_in_e < cap
+    keep = torch.empty_like(keep_sorted)
+    keep[order] = keep_sorted
+    return probs * keep.view(T, k).to(probs.dtype)
+
+
+def grouped_mlp(x_sorted: torch.Tensor, counts: List[int], w_gate_up: torch.Tensor, w_down: torch.Tensor, act: str):
+    """Tokens sorted by expert; expert e owns rows [sum(counts[:e]), +counts[e]).  w_gate_up [E,2F,H], w_down [E,H,F]."""
+    outs, off = [], 0
+    for e, n in enumerate(counts):
+        if n == 0:
+            continue
+        xe = x_sorted[off: off + n]
+        outs.append(OF.linear(OF.gated_act(OF.linear(xe, w_gate_up[e]), act), w_down[e]))
+        off += n
+    if not outs:
+        return x_sorted.new_zeros(0, w_down.shape[1])
+    return torch.cat(outs, 0)
+
+
+def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
+    """MoE MLP of block i on normalised hidden states h [T,H] (already gathered if sequence-parallel)."""
+    c, ctx = model.config, model.ctx
+    mcfg = c.moe
+    if model.sequence_parallel:
+        h = TP.gather_from_sp(h, ctx)
+    else:
+        h = TP.copy_to_tp(h, ctx)
+    T, H = h.shape
+    probs, idx = route(h, model.p[f"{i}.mlp.router.weight"], mcfg, model.training)
+    E, k = mcfg.num_experts, mcfg.top_k
+    probs = _apply_capacity(probs, idx, E, mcfg)
+    w_gu, w_dn = model.p[f"{i}.mlp.experts.gate_up.weight"], model.p[f"{i}.mlp.experts.down.weight"]
+    flat_e = idx.reshape(-1)
+    order = torch.argsort(flat_e, stable=True)
+    tok = torch.arange(T, device=h.device).repeat_interleave(k)[order]
+    x_sorted = h.index_select(0, tok)
+    ep_group = getattr(ctx, "ep_group", None)
+    if ep_group is None:
+        counts = torch.bincount(flat_e, minlength=E).tolist()
+        y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)
+    else:
+        from realhf_b200.parallel import ep
+        y_sorted = ep.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ep_group)
+    w = probs.reshape(-1)[order].to(y_sorted.dtype).unsqueeze(-1)
+    out = torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w)
+    if ctx.tp_size > 1:  # experts are F-sharded over TP: partial sums
+        out = TP.reduce_scatter_to_sp(out, ctx) if model.sequence_parallel else TP.reduce_from_tp(out, ctx)
+    return out

@@ -1,0 +1,439 @@
+"""ReaLModel: a packed variable-length decoder-only transformer whose parameters live in ONE flat buffer.
+
+Feature matrix of the reference model (`realhf/impl/model/nn/real_llm_api.py`, `real_llm_base.py`,
+`modules/{attn,mlp,rotary,embedding}.py`): MHA/GQA, RoPE (+linear/dynamic scaling) or learned absolute
+positions, LayerNorm / RMSNorm / Gemma-RMSNorm, GELU MLP / gated (SwiGLU, GeGLU) MLP / MoE, tied
+embeddings, critic (scalar) head, per-block activation checkpointing, tensor + sequence parallelism and
+pipeline stages (a stage holds a contiguous range of layer indices: 0 = embedding, 1..L = blocks,
+L+1 = head).
+
+Design: blocks are *functional* — they read parameter views out of `self.flat_param`, so parameter
+reallocation, ZeRO sharding, host offload and checkpoint I/O all act on one contiguous tensor per shard.
+All projections are fused (one QKV GEMM, one gate|up GEMM); RoPE is applied in place on the QKV output,
+the gated activation reads the fused gate|up output once, and inference fuses residual-add into RMSNorm.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+from realhf_b200.api.model import ReaLModelConfig
+from realhf_b200.base.topology import ParallelContext
+from realhf_b200.models import sharding
+from realhf_b200.models.sharding import ParamSpec
+from realhf_b200.ops import attention as attn_ops
+from realhf_b200.ops import functional as OF
+from realhf_b200.parallel import tp as TP
+
+
+def _numel(shape) -> int:
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+_ALIGN = 64  # every parameter starts on a 64-element boundary (128 B for bf16): vector kernels + TMA
+
+
+@dataclasses.dataclass
+class ParamSlot:
+    spec: ParamSpec
+    shape: Tuple[int, ...]  # local (TP-sharded) shape
+    offset: int             # element offset in the flat buffer
+    numel: int
+
+
+def build_layout(cfg: ReaLModelConfig, layers: Sequence[int], tp_size: int) -> Tuple[Dict[str, ParamSlot], int]:
+    """Flat-buffer layout of one shard: name -> slot, and the padded total element count."""
+    slots: Dict[str, ParamSlot] = {}
+    off = 0
+    for spec in sharding.model_param_specs(cfg, layers):
+        shp = sharding.shard_shape(spec, cfg, tp_size)
+        n = _numel(shp)
+        slots[spec.name] = ParamSlot(spec, shp, off, n)
+        off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+    return slots, off
+
+
+@dataclasses.dataclass
+class ModelOutput:
+    """What a forward returns to a loss / post-processing function.
+
+    `hidden` is the final-norm output [T, H].  Log-probs should be taken through `logprobs()` (fused LM-head +
+    online softmax: the [T, V] logits are never materialised); `logits` builds them on demand for user code
+    that wants them (and for critics, where it is the [T] value head output)."""
+
+    hidden: torch.Tensor
+    head_weight: Optional[torch.Tensor]
+    ctx: Optional[ParallelContext]
+    is_critic: bool = False
+    _logits: Optional[torch.Tensor] = None
+
+    @property
+    def logits(self) -> torch.Tensor:
+        if self._logits is None:
+            if self.is_critic:
+                self._logits = F.linear(self.hidden, self.head_weight).squeeze(-1)
+            else:
+                lg = OF.linear(self.hidden, self.head_weight)
+                self._logits = TP.gather_last_dim(lg, self.ctx) if (self.ctx and self.ctx.tp_size > 1) else lg
+        return self._logits
+
+    @property
+    def values(self) -> torch.Tensor:
+        assert self.is_critic
+        return self.logits.float()
+
+    def logprobs(self, labels: torch.Tensor, mask_bits: Optional[torch.Tensor] = None, temperature: float = 1.0,
+                 rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 log p(labels[i] | hidden[rows[i]]) (rows defaults to all tokens)."""
+        h = self.hidden if rows is None else self.hidden.index_select(0, rows)
+        if self.ctx is not None and self.ctx.tp_size > 1:
+            local = OF.linear(h, self.head_weight)
+            assert mask_bits is None, "logits mask with vocab-parallel head is not supported yet"
+            return TP.vocab_parallel_logprobs(local, labels, self.ctx, temperature)
+        return OF.lm_head_logprobs(h, self.head_weight, labels, mask_bits, temperature)
+
+
+class ReaLModel(nn.Module):
+    def __init__(self, config: ReaLModelConfig, ctx: Optional[ParallelContext] = None, dtype=torch.bfloat16,
+                 device="cpu", layer_range: Optional[Tuple[int, int]] = None):
+        super().__init__()
+        self.config = config
+        self.ctx = ctx if ctx is not None else ParallelContext.single()
+        self.dtype = dtype
+        self.device = torch.device(device)
+        if layer_range is None:
+            layer_range = sharding.partition_pipeline_layers(config, self.ctx.pp_size)[self.ctx.pp_rank]
+        self.layer_range = layer_range
+        self.layers = list(range(*layer_range))
+        self.slots, self.flat_numel = build_layout(config, self.layers, self.ctx.tp_size)
+        self.flat_param: Optional[nn.Parameter] = None
+        self.flat_grad: Optional[torch.Tensor] = None
+        self.p: Dict[str, torch.Tensor] = {}
+        self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        self._rope_len = 0
+        self.gradient_checkpointing = bool(self.ctx.gradient_checkpointing)
+        self.sequence_parallel = bool(self.ctx.sequence_parallel) and self.ctx.tp_size > 1
+        self._offloaded: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ construction
+    @property
+    def is_first_stage(self) -> bool:
+        return self.layer_range[0] == 0
+
+    @property
+    def is_last_stage(self) -> bool:
+        return self.layer_range[1] == self.config.n_layers + 2
+
+    @property
+    def instantiated(self) -> bool:
+        return self.flat_param is not None
+
+    def instantiate(self, init: str = "random", std: float = 0.02, seed: Optional[int] = None) -> "ReaLModel":
+        """Allocate the flat buffer and carve parameter views.  init: random | empty."""
+        flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self.device)
+        self.attach_flat(flat)
+        if init == "random":
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(seed if seed is not None else 1)
+            with torch.no_grad():
+                flat.zero_()
+                for name, slot in self.slots.items():
+                    if slot.spec.init == "ones":
+                        self.p[name].fill_(1.0)
+                    elif slot.spec.init == "normal":
+                        # draw the FULL tensor then shard it, so every TP layout sees the same weights
+                        full = torch.empty(slot.spec.shape, dtype=torch.float32).normal_(0.0, std, generator=gen)
+                        sh = sharding.shard_tensor(slot.spec, self.config, full, self.ctx.tp_rank, self.ctx.tp_size)
+                        self.p[name].copy_(sh.to(self.dtype))
+        return self
+
+    def init_random_fast(self, std: float = 0.02, seed: int = 1):
+        """Device-side random init for benchmarks (no full-tensor host materialisation)."""
+        flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self.device)
+        self.attach_flat(flat)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed + 1000 * self.ctx.tp_rank + 77 * self.ctx.pp_rank)
+        with torch.no_grad():
+            flat.normal_(0.0, std, generator=g)
+            for name, slot in self.slots.items():
+                if slot.spec.init == "ones":
+                    self.p[name].fill_(1.0)
+                elif slot.spec.init == "zeros":
+                    self.p[name].zero_()
+        return self
+
+    def attach_flat(self, flat: torch.Tensor):
+        """(Re)point every parameter view at `flat` (used by instantiate, realloc and offload reload)."""
+        assert flat.numel() == self.flat_numel, (flat.numel(), self.flat_numel)
+        if self.flat_param is None:
+            self.flat_param = nn.Parameter(flat, requires_grad=False)
+        else:
+            self.flat_param.data = flat
+        for name, slot in self.slots.items():
+            view = flat[slot.offset: slot.offset + slot.numel].view(slot.shape)
+            if name in self.p:
+                self.p[name].data = view
+            else:
+                self.p[name] = nn.Parameter(view, requires_grad=True)
+        self.device = flat.device
+
+    def release_params(self):
+        """Drop the flat buffer (reverse direction of a realloc / after offload)."""
+        if self.flat_param is None:
+            return
+        empty = torch.empty(0, dtype=self.dtype, device=self.device)
+        self.flat_param.data = empty
+        for v in self.p.values():
+            v.data = empty
+        self.flat_param = None
+        self.p = {}
+
+    def parameters(self, recurse: bool = True):
+        return iter(self.p.values())
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        return iter(self.p.items())
+
+    def attach_grad_buffer(self, flat_grad: torch.Tensor):
+        """Point every `.grad` into one flat gradient buffer (same layout as the params)."""
+        assert flat_grad.numel() == self.flat_numel
+        self.flat_grad = flat_grad
+        for name, slot in self.slots.items():
+            g = flat_grad[slot.offset: slot.offset + slot.numel].view(slot.shape)
+            if flat_grad.dtype == self.p[name].dtype:
+                self.p[name].grad = g
+            else:
+                self.p[name].main_grad = g  # fp32 bucket: GEMM wgrad accumulates into it directly
+
+    def state_dict(self, *a, **k) -> Dict[str, torch.Tensor]:
+        return {n: t.data for n, t in self.p.items()}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        missing = [k for k in self.p if k not in sd]
+        unexpected = [k for k in sd if k not in self.p]
+        if strict and (missing or unexpected):
+            raise KeyError(f"load_state_dict: missing={missing} unexpected={unexpected}")
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in self.p:
+                    self.p[k].copy_(v.to(self.dtype))
+        return missing, unexpected
+
+    # ------------------------------------------------------------------ host offload (non-trainable roles)
+    def offload(self):
+        """Async D2H of the whole shard into one pinned buffer (reference: real_llm_api.py:274-306)."""
+        if self.flat_param is None or not self.flat_param.is_cuda:
+            return
+        if self._offloaded is None:
+            self._offloaded = torch.empty(self.flat_numel, dtype=self.dtype, device="cpu", pin_memory=True)
+        self._offloaded.copy_(self.flat_param.data, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        dev = self.flat_param.device
+        self.release_params()
+        self._offload_dev = dev
+
+    def reload(self):
+        if self._offloaded is None or self.flat_param is not None:
+            return
+        flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self._offload_dev)
+        flat.copy_(self._offloaded, non_blocking=True)
+        self.attach_flat(flat)
+        for p in self.p.values():
+            p.requires_grad_(False)
+
+    # ------------------------------------------------------------------ helpers
+    def _w(self, name: str) -> Optional[torch.Tensor]:
+        return self.p.get(name)
+
+    def rope_tables(self, need_len: int):
+        c = self.config
+        if self._rope is None or self._rope_len < need_len or self._rope[0].device != self.device:
+            n = max(need_len, c.n_positions or 0, 2048)
+            n = 1 << (n - 1).bit_length()
+            self._rope = OF.rope_tables(n, c.head_dim, c.rotary_base, self.device, c.rotary_scaling, c.rotary_scaling_type)
+            self._rope_len = n
+        return self._rope
+
+    def _norm(self, x, prefix: str):
+        c = self.config
+        w = self.p[f"{prefix}.weight"]
+        if c.layer_norm_type is None:
+            return F.layer_norm(x, (c.hidden_dim,), w, self.p[f"{prefix}.bias"], c.layer_norm_epsilon)
+        return OF.rmsnorm(x, w, c.layer_norm_epsilon, 1.0 if c.layer_norm_type == "gemma" else 0.0)
+
+    def _local_heads(self) -> Tuple[int, int]:
+        c, t = self.config, self.ctx.tp_size
+        return c.n_q_heads // t, max(1, c.n_kv_heads // t)
+
+    def _attn_scale(self, layer_idx: int) -> float:
+        c = self.config
+        s = 1.0 / math.sqrt(c.head_dim) if c.scale_attn_weights else 1.0
+        if c.scale_attn_by_inverse_layer_idx:
+            s /= float(layer_idx)
+        return s
+
+    # ------------------------------------------------------------------ layers
+    def _embed(self, input_ids, position_ids):
+        c = self.config
+        x = TP.vocab_parallel_embedding(input_ids, self.p["0.wte.weight"], self.ctx, sp=self.sequence_parallel)
+        if not c.apply_rotary:
+            pe = F.embedding(position_ids.long() + c.abs_position_embedding_offset, self.p["0.wpe.weight"])
+            if self.sequence_parallel:
+                pe = TP._split_first_dim(pe, self.ctx)
+            x = x + pe
+        if c.normalize_embed:
+            x = x * torch.tensor(c.hidden_dim ** 0.5, dtype=x.dtype, device=x.device)
+        if self.training and c.embd_pdrop > 0:
+            x = F.dropout(x, c.embd_pdrop)
+        return x
+
+    def _attention_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink: Optional[list]):
+        c = self.config
+        nq, nkv = self._local_heads()
+        hd = c.head_dim
+        h = self._norm(x, f"{i}.attn.ln")
+        qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, self.sequence_parallel)
+        if c.apply_rotary:
+            cos, sin = self.rope_tables(max_seqlen)
+            qkv = OF.apply_rope(qkv, cos, sin, position_ids, nq + nkv, hd, hd, c.rotary_interleaved)
+        T = qkv.shape[0]
+        q = qkv[:, : nq * hd].view(T, nq, hd)
+        k = qkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd)
+        v = qkv[:, (nq + nkv) * hd:].view(T, nkv, hd)
+        if kv_sink is not None:
+            kv_sink.append((k, v))
+        o = attn_ops.varlen_attention(q, k, v, cu_seqlens, max_seqlen, self._attn_scale(i), True,
+                                      c.attn_pdrop if self.training else 0.0)
+        o = TP.row_linear(o.reshape(T, nq * hd), self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx,
+                          self.sequence_parallel)
+        if self.training and c.resid_pdrop > 0:
+            o = F.dropout(o, c.resid_pdrop)
+        return o
+
+    def _mlp(self, i: int, x):
+        c = self.config
+        h = self._norm(x, f"{i}.mlp.ln")
+        sp = self.sequence_parallel
+        if c.mlp_type == "llama":
+            gu = TP.col_linear(h, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, sp)
+            a = OF.gated_act(gu, c.activation_function)
+            o = TP.row_linear(a, self.p[f"{i}.mlp.down.weight"], None, self.ctx, sp)
+        elif c.mlp_type == "moe":
+            from realhf_b200.models import moe
+            o = moe.moe_forward(self, i, h)
+        else:
+            a = TP.col_linear(h, self.p[f"{i}.mlp.fc.weight"], self._w(f"{i}.mlp.fc.bias"), self.ctx, sp)
+            a = _ACT[c.activation_function](a)
+            o = TP.row_linear(a, self.p[f"{i}.mlp.proj.weight"], self._w(f"{i}.mlp.proj.bias"), self.ctx, sp)
+        if self.training and c.resid_pdrop > 0:
+            o = F.dropout(o, c.resid_pdrop)
+        return o
+
+    def _block_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink=None):
+        x = x + self._attention_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
+        x = x + self._mlp(i, x)
+        if i == self.config.n_layers:
+            x = self._norm(x, f"{i}.ln_f")
+        return x
+
+    def head_weight(self) -> Optional[torch.Tensor]:
+        c = self.config
+        L1 = c.n_layers + 1
+        if f"{L1}.head.weight" in self.p:
+            return self.p[f"{L1}.head.weight"]
+        if c.tied_embedding:
+            return self.p.get("0.wte.weight", getattr(self, "_tied_head", None))
+        return None
+
+    # ------------------------------------------------------------------ forward (packed)
+    def forward(self, input_ids: Optional[torch.Tensor] = None, cu_seqlens: Optional[torch.Tensor] = None,
+                max_seqlen: Optional[int] = None, hidden: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, kv_sink: Optional[list] = None) -> ModelOutput:
+        """Packed forward over this stage's layers.
+
+        First stage: `input_ids` [T]; later stages: `hidden` [T(/tp), H].  cu_seqlens: int32 [B+1].
+        With sequence parallelism the caller (engine) has padded T to a multiple of tp.
+        Returns a ModelOutput on the last stage, else the hidden-state tensor for the next stage.
+        """
+        c = self.config
+        cu_seqlens = cu_seqlens.int()
+        if max_seqlen is None:
+            max_seqlen = int((cu_seqlens[1:] - cu_seqlens[:-1]).max())
+        T = int(input_ids.shape[0]) if input_ids is not None else None
+        if position_ids is None:
+            position_ids = packed_position_ids(cu_seqlens, T if T is not None else int(cu_seqlens[-1]))
+        x = hidden
+        for i in self.layers:
+            if i == 0:
+                x = self._embed(input_ids, position_ids)
+            elif i <= c.n_layers:
+                if self.gradient_checkpointing and self.training and torch.is_grad_enabled() and kv_sink is None:
+                    x = checkpoint(self._block_packed, i, x, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
+                else:
+                    x = self._block_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
+        if not self.is_last_stage:
+            return x
+        if self.sequence_parallel:
+            x = TP.gather_from_sp(x, self.ctx, reduce_scatter_bwd=False)
+        return ModelOutput(hidden=x, head_weight=self.head_weight(), ctx=self.ctx, is_critic=c.is_critic)
+
+    # ------------------------------------------------------------------ decode step (one token per sequence)
+    @torch.no_grad()
+    def decode_step(self, input_ids: Optional[torch.Tensor], k_caches: List[torch.Tensor], v_caches: List[torch.Tensor],
+                    cache_lens: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """input_ids [B] -> final hidden [B, H] (last stage: after ln_f).  Appends K/V at `cache_lens` in place.
+        Caches: one [B, S, nkv_local, hd] tensor per local block.  Capturable in a CUDA graph (no host sync)."""
+        c = self.config
+        nq, nkv = self._local_heads()
+        hd = c.head_dim
+        x = hidden
+        cos = sin = None
+        if c.apply_rotary:
+            cos, sin = self.rope_tables(k_caches[0].shape[1] if k_caches else 2048)
+        li = 0
+        for i in self.layers:
+            if i == 0:
+                x = self._embed(input_ids, cache_lens)
+            elif i <= c.n_layers:
+                h = self._norm(x, f"{i}.attn.ln")
+                qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
+                o = attn_ops.decode_attention(qkv, k_caches[li], v_caches[li], cache_lens, nq, nkv, hd, self._attn_scale(i),
+                                              cos, sin, hd, c.rotary_interleaved)
+                li += 1
+                o = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
+                x = x + o
+                x = x + self._mlp(i, x)
+                if i == c.n_layers:
+                    x = self._norm(x, f"{i}.ln_f")
+        return x
+
+    def n_local_blocks(self) -> int:
+        return sum(1 for i in self.layers if 1 <= i <= self.config.n_layers)
+
+
+def packed_position_ids(cu_seqlens: torch.Tensor, total: int) -> torch.Tensor:
+    """int32 [T]: position of every packed token inside its sequence, computed without a host sync."""
+    dev = cu_seqlens.device
+    idx = torch.arange(total, device=dev, dtype=torch.int32)
+    seq = torch.searchsorted(cu_seqlens[1:].contiguous(), idx, right=True)
+    seq = seq.clamp_(max=cu_seqlens.numel() - 2)
+    return (idx - cu_seqlens[seq.long()]).int()
+
+
+_ACT = {
+    "gelu": F.gelu,
+    "gelu_new": lambda x: F.gelu(x, approximate="tanh"),
+    "gelu_pytorch_tanh": lambda x: F.gelu(x, approximate="tanh"),
+    "relu": F.relu,
+    "silu": F.silu,
+}

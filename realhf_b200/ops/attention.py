@@ -1,0 +1,99 @@
+"""Attention entry points: packed varlen causal attention (train / inference / prefill) and
+single-token decode attention over a dense KV cache.
+
+CUDA tensors: decode runs the split-KV sm_100a kernel in `csrc/attn_decode.cu` (with fused RoPE and
+in-place KV append); varlen forward/backward currently calls the flash-attn library kernel (a library
+call on this path, recorded as such in DESIGN.md) until the tcgen05 varlen kernel lands.
+CPU tensors: plain PyTorch reference (also the numerics oracle for the tests).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from realhf_b200.ops import lib, use_native
+
+
+def varlen_attention_ref(q, k, v, cu_seqlens, scale: float, causal: bool = True, sliding_window: Optional[int] = None):
+    """q [T,nq,hd], k/v [T,nkv,hd] packed; fp32 math; returns [T,nq,hd] in q.dtype."""
+    T, nq, hd = q.shape
+    nkv = k.shape[1]
+    rep = nq // nkv
+    out = torch.empty_like(q)
+    cu = cu_seqlens.tolist()
+    for i in range(len(cu) - 1):
+        s, e = cu[i], cu[i + 1]
+        if e == s:
+            continue
+        qi = q[s:e].float().transpose(0, 1)                          # [nq, L, hd]
+        ki = k[s:e].float().transpose(0, 1).repeat_interleave(rep, 0)
+        vi = v[s:e].float().transpose(0, 1).repeat_interleave(rep, 0)
+        att = (qi @ ki.transpose(1, 2)) * scale
+        L = e - s
+        if causal:
+            idx = torch.arange(L, device=q.device)
+            mask = idx[None, :] > idx[:, None]
+            if sliding_window:
+                mask |= idx[None, :] <= idx[:, None] - sliding_window
+            att = att.masked_fill(mask, float("-inf"))
+        out[s:e] = (torch.softmax(att, dim=-1) @ vi).transpose(0, 1).to(q.dtype)
+    return out
+
+
+def varlen_attention(q, k, v, cu_seqlens, max_seqlen: int, scale: Optional[float] = None, causal: bool = True,
+                     dropout_p: float = 0.0):
+    """Packed variable-length causal attention with GQA.  q [T,nq,hd]; k,v [T,nkv,hd]."""
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if use_native(q) and q.dtype in (torch.bfloat16, torch.float16):
+        from flash_attn import flash_attn_varlen_func
+        cu = cu_seqlens.int()
+        return flash_attn_varlen_func(q, k, v, cu, cu, max_seqlen, max_seqlen, dropout_p=dropout_p,
+                                      softmax_scale=scale, causal=causal)
+    return varlen_attention_ref(q, k, v, cu_seqlens, scale, causal)
+
+
+def decode_attention_ref(q, k_cache, v_cache, cache_lens, scale: float):
+    """q [B,nq,hd]; caches [B,S,nkv,hd]; cache_lens [B] = number of valid positions (incl. the new token)."""
+    B, nq, hd = q.shape
+    nkv = k_cache.shape[2]
+    rep = nq // nkv
+    S = k_cache.shape[1]
+    kk = k_cache.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)   # [B,nq,S,hd]
+    vv = v_cache.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)
+    att = torch.einsum("bhd,bhsd->bhs", q.float(), kk) * scale
+    mask = torch.arange(S, device=q.device)[None, :] >= cache_lens[:, None].to(q.device)
+    att = att.masked_fill(mask[:, None, :], float("-inf"))
+    return torch.einsum("bhs,bhsd->bhd", torch.softmax(att, -1), vv).to(q.dtype)
+
+
+def decode_attention(qkv, k_cache, v_cache, cache_lens, n_q: int, n_kv: int, hd: int, scale: Optional[float] = None,
+                     cos=None, sin=None, rot_dim: Optional[int] = None, interleaved: bool = False):
+    """One decode step for B sequences.
+
+    qkv: [B, (n_q+2*n_kv)*hd] fused projection of the new token.  `cache_lens[b]` is the number of tokens
+    already in the cache (= position of the new token).  The op applies RoPE to q and k (if cos/sin given),
+    writes the new k,v at position cache_lens[b] of the caches *in place*, and returns attention over
+    positions [0, cache_lens[b]] as [B, n_q*hd].  Does not advance cache_lens.
+    """
+    scale = scale if scale is not None else 1.0 / math.sqrt(hd)
+    B = qkv.shape[0]
+    if use_native(qkv) and qkv.dtype in (torch.bfloat16, torch.float16) and hd in (64, 128) \
+            and k_cache.dtype == qkv.dtype:
+        return lib().decode_attention(qkv, k_cache, v_cache, cache_lens.int(), n_q, n_kv, hd, scale, cos, sin,
+                                      rot_dim or hd, interleaved)
+    # reference path
+    from realhf_b200.ops.functional import rope_ref
+    x = qkv
+    if cos is not None:
+        x = rope_ref(qkv, cos, sin, cache_lens, n_q + n_kv, hd, rot_dim or hd, interleaved)
+    q = x[:, : n_q * hd].reshape(B, n_q, hd)
+    k = x[:, n_q * hd:(n_q + n_kv) * hd].reshape(B, n_kv, hd)
+    v = x[:, (n_q + n_kv) * hd:].reshape(B, n_kv, hd)
+    idx = torch.arange(B, device=qkv.device)
+    pos = cache_lens.long()
+    k_cache[idx, pos] = k.to(k_cache.dtype)
+    v_cache[idx, pos] = v.to(v_cache.dtype)
+    return decode_attention_ref(q, k_cache, v_cache, cache_lens + 1, scale).reshape(B, n_q * hd)

@@ -1,2 +1,56 @@
+// torch bindings for attention kernels.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
-void register_attn_ops(torch::Library& m) {}
+#include <torch/types.h>
+
+using at::Tensor;
+
+extern "C" int rb_decode_attention(const void* qkv, void* k_cache, void* v_cache, const int* cache_lens, void* out,
+                                   float* part_acc, float* part_ml, const float* cos, const float* sin, int64_t qkv_stride,
+                                   int64_t kb, int64_t ks, int64_t kh, int64_t vb, int64_t vs, int64_t vh, int B, int nq,
+                                   int nkv, int hd, int S_max, int splits, int rot_dim, int interleaved, float scale, int dt,
+                                   cudaStream_t s);
+
+// qkv [B, (nq+2nkv)*hd]; caches logical [B, S, nkv, hd] (any b/s/h strides, unit hd stride); cache_lens int32 [B].
+Tensor decode_attention(const Tensor& qkv, Tensor k_cache, Tensor v_cache, const Tensor& cache_lens, int64_t nq, int64_t nkv,
+                        int64_t hd, double scale, const c10::optional<Tensor>& cos, const c10::optional<Tensor>& sin,
+                        int64_t rot_dim, bool interleaved) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 2 && qkv.stride(1) == 1);
+  TORCH_CHECK(k_cache.dim() == 4 && v_cache.dim() == 4 && k_cache.stride(3) == 1 && v_cache.stride(3) == 1);
+  TORCH_CHECK(k_cache.scalar_type() == qkv.scalar_type() && v_cache.scalar_type() == qkv.scalar_type());
+  TORCH_CHECK(cache_lens.scalar_type() == at::kInt && cache_lens.is_contiguous());
+  TORCH_CHECK(qkv.size(1) == (nq + 2 * nkv) * hd && nq % nkv == 0);
+  const int B = qkv.size(0);
+  const int S = k_cache.size(1);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  auto out = at::empty({B, nq * hd}, qkv.options());
+  int splits = 1;
+  const int64_t ctas = (int64_t)B * nkv;
+  if (ctas < 2 * 148 && S >= 512) {
+    splits = (int)std::min<int64_t>(16, (2 * 148 + ctas - 1) / ctas);
+  }
+  Tensor pa, pm;
+  if (splits > 1) {
+    pa = at::empty({B, nq, splits, hd}, qkv.options().dtype(at::kFloat));
+    pm = at::empty({B, nq, splits, 2}, qkv.options().dtype(at::kFloat));
+  }
+  const float *cp = nullptr, *sp = nullptr;
+  if (cos.has_value()) {
+    TORCH_CHECK(sin.has_value() && cos->scalar_type() == at::kFloat && cos->is_contiguous() && sin->is_contiguous());
+    cp = cos->data_ptr<float>();
+    sp = sin->data_ptr<float>();
+  }
+  const int dt = qkv.scalar_type() == at::kBFloat16 ? 1 : (qkv.scalar_type() == at::kHalf ? 2 : -1);
+  int rc = rb_decode_attention(qkv.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), cache_lens.data_ptr<int>(), out.data_ptr(),
+                               splits > 1 ? pa.data_ptr<float>() : nullptr, splits > 1 ? pm.data_ptr<float>() : nullptr, cp, sp,
+                               qkv.stride(0), k_cache.stride(0), k_cache.stride(1), k_cache.stride(2), v_cache.stride(0),
+                               v_cache.stride(1), v_cache.stride(2), B, (int)nq, (int)nkv, (int)hd, S, splits, (int)rot_dim,
+                               interleaved, (float)scale, dt, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "decode_attention: unsupported configuration (", rc, ")");
+  return out;
+}
+
+void register_attn_ops(torch::Library& m) {
+  m.def("decode_attention(Tensor qkv, Tensor(a!) k_cache, Tensor(b!) v_cache, Tensor cache_lens, int nq, int nkv, int hd, float scale, Tensor? cos, Tensor? sin, int rot_dim, bool interleaved) -> Tensor", &decode_attention);
+}

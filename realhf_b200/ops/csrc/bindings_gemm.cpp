@@ -1,2 +1,56 @@
+// torch bindings for the tcgen05 GEMM family.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
-void register_gemm_ops(torch::Library& m) {}
+#include <torch/types.h>
+
+using at::Tensor;
+
+extern "C" int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda,
+                               int64_t ldb, int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn,
+                               int num_sms, cudaStream_t s);
+
+static int dtc(at::ScalarType t) {
+  switch (t) {
+    case at::kFloat: return 0;
+    case at::kBFloat16: return 1;
+    case at::kHalf: return 2;
+    default: TORCH_CHECK(false, "gemm: unsupported dtype ", t);
+  }
+}
+
+// a: a_mn ? [K, M] : [M, K];  b: b_mn ? [K, N] : [N, K].  Inner stride must be 1, row pitch a multiple of 8.
+// out: optional destination [M, N] (any supported dtype); with accumulate=True computes out += a x b.
+Tensor gemm(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, const c10::optional<Tensor>& bias, bool a_mn,
+            bool b_mn, bool accumulate, c10::optional<at::ScalarType> out_dtype, int64_t bn, int64_t num_sms) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2, "gemm: 2-D CUDA tensors expected");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1, "gemm: inner stride must be 1");
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), "gemm: operand dtypes differ");
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(K == Kb, "gemm: reduction dims differ: ", K, " vs ", Kb);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor c;
+  if (out.has_value()) {
+    c = *out;
+    TORCH_CHECK(c.dim() == 2 && c.size(0) == M && c.size(1) == N && c.stride(1) == 1, "gemm: bad out shape");
+  } else {
+    TORCH_CHECK(!accumulate, "gemm: accumulate needs `out`");
+    c = at::empty({M, N}, a.options().dtype(out_dtype.value_or(a.scalar_type())));
+  }
+  const void* bp = nullptr;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->scalar_type() == c.scalar_type() && bias->numel() == N && bias->is_contiguous());
+    bp = bias->data_ptr();
+  }
+  if (M == 0 || N == 0) return c;
+  int rc = rb_gemm_tcgen05(a.data_ptr(), b.data_ptr(), c.data_ptr(), bp, (int)M, (int)N, (int)K, a.stride(0), b.stride(0),
+                           c.stride(0), a_mn, b_mn, dtc(a.scalar_type()), dtc(c.scalar_type()), accumulate, (int)bn, (int)num_sms,
+                           at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gemm_tcgen05 failed with code ", rc);
+  return c;
+}
+
+void register_gemm_ops(torch::Library& m) {
+  m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms) -> Tensor", &gemm);
+}

@@ -1,0 +1,358 @@
+// Persistent warp-specialised GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma -> TMEM -> epilogue.
+//
+//   D[M,N] (+)= A x B (+ bias)      bf16/fp16 operands, fp32 accumulation in tensor memory.
+//
+// Both operands may be K-major or MN-major, which covers the three GEMMs of a linear layer without
+// any transposed copy (reference: cuBLAS via torch.matmul, parallelism/model_parallel/modules.py:302,382,532):
+//   forward  y  = x  @ W^T : A = x  [M,K]  K-major,   B = W [N,K]            K-major
+//   dgrad    dx = dy @ W   : A = dy [M,N'] K-major,   B = W [N',K'] as [K,N] MN-major
+//   wgrad    dW = dy^T @ x : A = dy [T,N'] as [K,M]   MN-major, B = x [T,K'] as [K,N] MN-major (fp32 accumulate-into)
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected lane issues tcgen05.mma) + TMEM
+// allocator, warps 2-5 epilogue (each owns the TMEM lane quadrant warp_id%4).  Three pipelines:
+// smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue), and a static
+// persistent tile loop (one CTA per SM).  The epilogue converts and stores straight from TMEM
+// registers with 16-byte stores, with optional bias and accumulate-into-C.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kThreads = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Params {
+  void* C;
+  const void* bias;
+  int64_t ldc;
+  int M, N, K;
+  int accumulate;  // C += result
+};
+
+template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok);
+
+template <> RB_DEVICE void store_chunk<float>(float* dst, const float* v, int n_valid, bool vec_ok) {
+  if (n_valid == 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    for (int i = 0; i < n_valid; ++i) dst[i] = v[i];
+  }
+}
+template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok) {
+  if (n_valid == 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rb::Pack<T, 8> p;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p.v[k] = rb::from_f<T>(v[8 * i + k]);
+      reinterpret_cast<rb::Pack<T, 8>*>(dst)[i] = p;
+    }
+  } else {
+    for (int i = 0; i < n_valid; ++i) dst[i] = rb::from_f<T>(v[i]);
+  }
+}
+
+// L2-friendly rasterisation: tiles are walked in bands of kGroupM m-tiles, m fastest inside a band, so the
+// ~148 tiles in flight cover a roughly square region of C and every A / B panel is fetched from HBM once.
+constexpr int kGroupM = 16;
+RB_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int bn, int& m0, int& n0) {
+  const int per_group = kGroupM * tiles_n;
+  const int group = tile / per_group, within = tile - group * per_group;
+  const int gm0 = group * kGroupM;
+  const int gsize = min(kGroupM, tiles_m - gm0);
+  m0 = (gm0 + within % gsize) * BM;
+  n0 = (within / gsize) * bn;
+}
+
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                   const __grid_constant__ CUtensorMap tma_b, Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = RB_CEIL_DIV(p.M, BM), tiles_n = RB_CEIL_DIV(p.N, BN);
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = RB_CEIL_DIV(p.K, BK);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tma_a);
+    ptx::prefetch_tensormap(&tma_b);
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tmem_empty[i]), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr), C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0;
+        tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+          ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * C::kABytes);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * C::kBBytes);
+          const int k0 = kb * BK;
+          if constexpr (kAMN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * (BK * 128), &tma_a, fb, m0 + 64 * j, k0);
+          } else {
+            ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);
+          }
+          if constexpr (kBMN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n0 + 64 * j, k0);
+          } else {
+            ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kFmt, BM, BN, kAMN ? 1 : 0, kBMN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty[as]), aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * C::kABytes);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = kAMN ? ptx::make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = kBMN ? ptx::make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            ptx::tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // smem slot reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(ptx::smem_u32(&tmem_full[as]));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (4 warps, TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    OutT* Cp = reinterpret_cast<OutT*>(p.C);
+    const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
+    const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, n0;
+        tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full[as]), aphase);
+      ptx::tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tc_ld_32x32(taddr + c * 32, r);
+        ptx::tc_wait_ld();
+        const int col = n0 + c * 32;
+        const int n_valid = min(32, p.N - col);
+        if (row < p.M && n_valid > 0) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(bias[col + i]);
+          }
+          OutT* dst = Cp + (int64_t)row * p.ldc + col;
+          if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(dst[i]);
+          }
+          store_chunk<OutT>(dst, v, n_valid, vec_ok);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty[as]));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] (cols contiguous, row pitch `ld` elements), 2-byte elements, 128B swizzle.
+int g_last_tmap_err = 0;
+bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+               uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_tmap_err = (int)r;
+    fprintf(stderr, "[rb_gemm] cuTensorMapEncodeTiled failed: %d ptr=%p rows=%llu cols=%llu ld=%llu box=(%u,%u)\n", (int)r, ptr,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+  }
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int num_sms, cudaStream_t s) {
+  auto kern = gemm_tcgen05_kernel<BN, kAMN, kBMN, OutT, kFmt>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes) != cudaSuccess) return -2;
+    configured = true;
+  }
+  const int tiles = RB_CEIL_DIV(p.M, BM) * RB_CEIL_DIV(p.N, BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+template <int BN, typename OutT, int kFmt>
+int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int sms, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false, OutT, kFmt>(ta, tb, p, sms, s);
+  if constexpr (BN >= 64) {
+    if (!a_mn && b_mn) return launch<BN, false, true, OutT, kFmt>(ta, tb, p, sms, s);
+    if (a_mn && b_mn) return launch<BN, true, true, OutT, kFmt>(ta, tb, p, sms, s);
+    if (a_mn && !b_mn) return launch<BN, true, false, OutT, kFmt>(ta, tb, p, sms, s);
+  } else {
+    if (a_mn && !b_mn) return launch<BN, true, false, OutT, kFmt>(ta, tb, p, sms, s);
+  }
+  return -4;
+}
+
+template <typename OutT, int kFmt>
+int dispatch_bn(int bn, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int sms, cudaStream_t s) {
+  switch (bn) {
+    case 256: return dispatch_major<256, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
+    case 128: return dispatch_major<128, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
+    case 64: return dispatch_major<64, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
+    case 32: return dispatch_major<32, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
+    default: return -5;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// in_dt: 1 bf16, 2 fp16.  out_dt: 0 fp32, 1 bf16, 2 fp16.
+// A: a_mn ? [K, M] : [M, K] with row pitch lda;  B: b_mn ? [K, N] : [N, K] with row pitch ldb.
+// bn = 0 picks the tile width from the problem size.
+int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (in_dt != 1 && in_dt != 2) return -10;
+  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
+  if (num_sms <= 0) num_sms = rb::kNumSMs;
+  if (bn == 0) {
+    const int tm = RB_CEIL_DIV(M, BM);
+    const int cands[4] = {256, 128, 64, 32};
+    bn = b_mn ? 64 : 32;
+    for (int i = 0; i < 4; ++i) {
+      if (b_mn && cands[i] < 64) continue;
+      if ((int64_t)tm * RB_CEIL_DIV(N, cands[i]) >= num_sms || cands[i] <= (b_mn ? 64 : 32)) { bn = cands[i]; break; }
+    }
+    while (bn > N && bn > (b_mn ? 64 : 32)) bn >>= 1;
+  }
+  if (b_mn && bn < 64) return -12;
+  CUtensorMap ta, tb;
+  const int bf = in_dt == 1;
+  bool ok = a_mn ? make_tmap(&ta, A, bf, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK)
+                 : make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM);
+  ok = ok && (b_mn ? make_tmap(&tb, B, bf, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK)
+                   : make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn));
+  if (!ok) return -13;
+  Params p{C, bias, ldc, M, N, K, accumulate};
+#define RB_GO(OutT, FMT) return dispatch_bn<OutT, FMT>(bn, a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s)
+  if (in_dt == 1) {
+    if (out_dt == 1) RB_GO(__nv_bfloat16, 1);
+    if (out_dt == 0) RB_GO(float, 1);
+  } else {
+    if (out_dt == 2) RB_GO(__half, 0);
+    if (out_dt == 0) RB_GO(float, 0);
+  }
+#undef RB_GO
+  return -14;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+"""tcgen05 GEMM numerics vs fp32 PyTorch for every operand-major combination used by a linear layer."""
+import pytest
+import torch
+
+from realhf_b200.ops import gemm as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    return A @ B
+
+
+@pytest.mark.parametrize("bn", [0, 256, 128, 64, 32])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 256), (1000, 1032, 520), (4096, 4096, 4096), (77, 40, 72)])
+def test_gemm_kmajor(shape, bn):
+    M, N, K = shape
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=DEV, dtype=torch.bfloat16)
+    c = G.gemm(a, b, bn=bn)
+    ref = _ref(a, b, False, False)
+    torch.testing.assert_close(c.float(), ref, atol=K ** 0.5 * 0.05, rtol=2e-2)
+
+
+@pytest.mark.parametrize("majors", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (512, 384, 256), (1000, 1032, 520), (4096, 11008, 2048)])
+def test_gemm_mn_major(shape, majors):
+    M, N, K = shape
+    a_mn, b_mn = majors
+    torch.manual_seed(1)
+    a = torch.randn((K, M) if a_mn else (M, K), device=DEV, dtype=torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), device=DEV, dtype=torch.bfloat16)
+    c = G.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    ref = _ref(a, b, a_mn, b_mn)
+    torch.testing.assert_close(c.float(), ref, atol=K ** 0.5 * 0.05, rtol=2e-2)
+
+
+def test_gemm_bias_fp32_out_accumulate_fp16():
+    torch.manual_seed(2)
+    M, N, K = 300, 520, 264
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=DEV, dtype=torch.bfloat16)
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    c = G.gemm(a, b, bias=bias)
+    torch.testing.assert_close(c.float(), _ref(a, b, False, False) + bias.float(), atol=1.0, rtol=2e-2)
+    acc = torch.randn(M, N, device=DEV, dtype=torch.float32)
+    acc0 = acc.clone()
+    G.gemm(a, b, out=acc, accumulate=True)
+    torch.testing.assert_close(acc, acc0 + _ref(a, b, False, False), atol=1e-2, rtol=1e-3)
+    ah, bh = a.half(), b.half()
+    ch = G.gemm(ah, bh)
+    torch.testing.assert_close(ch.float(), _ref(ah, bh, False, False), atol=0.5, rtol=1e-2)
+
+
+def test_linear_autograd_matches_torch():
+    torch.manual_seed(3)
+    T, K, N = 777, 512, 1024
+    x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    y = G.linear(x, w, bias)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, bias))
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(dy.float())
+    torch.testing.assert_close(y.float(), yr, atol=0.1, rtol=2e-2)
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.1, rtol=2e-2)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.5, rtol=2e-2)
+    torch.testing.assert_close(bias.grad.float(), br.grad, atol=0.5, rtol=2e-2)
+
+
+def test_gemm_strided_operand():
+    torch.manual_seed(4)
+    big = torch.randn(640, 3 * 512, device=DEV, dtype=torch.bfloat16)
+    a = big[:, 512:1024]  # row pitch 1536, offset 1024 bytes
+    b = torch.randn(256, 512, device=DEV, dtype=torch.bfloat16)
+    c = G.gemm(a, b)
+    torch.testing.assert_close(c.float(), a.float() @ b.float().t(), atol=1.5, rtol=2e-2)
