@@ -49,10 +49,12 @@ _VALIDATE = True
 # key -> per-item sequence length rule used by `from_default` (L = length of the main sequence)
 _LEN_ONE = {"seq_no_eos_mask", "greedy_seq_no_eos_mask", "loss_mask", "rewards", "greedy_rewards", "scores",
             "group_factor", "pos_input_lens"}
-_LEN_FULL = {"input_ids", "packed_seq", "seq", "packed_logits_mask", "logits_mask", "prompt_mask",
+_LEN_FULL = {"input_ids", "packed_seq", "seq", "prompt_mask",
              "greedy_prompt_mask", "packed_input_ids", "greedy_packed_input_ids", "values", "packed_prompts"}
 _LEN_MINUS1 = {"packed_logprobs", "logprobs", "packed_ref_logprobs", "ref_logprobs", "old_logp", "ref_logp",
-               "advantages", "ppo_loss_mask", "kl_rewards", "returns"}
+               "advantages", "ppo_loss_mask", "kl_rewards", "returns",
+               # bit-packed [L-1, V/8] here (aligned with the log-probs); the reference ships a bool [L, V]
+               "packed_logits_mask", "logits_mask"}
 
 
 class SequenceSample:

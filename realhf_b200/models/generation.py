@@ -1,0 +1,231 @@
+"""Autoregressive generation: packed prefill -> dense KV cache -> CUDA-graph decode loop -> sampling.
+
+Parity: `realhf/impl/model/nn/real_llm_generate.py` (genstep :26-141, generate :252-368,
+concat_prompt_to_generation_output :451-530) and `utils/logits_warper.py`.  Differences by design:
+  * termination is checked on the device and read back only every `sync_every` steps (and never before
+    `min_new_tokens`), instead of one host sync per token (reference :123-129);
+  * the "filtered by top-k/top-p" logits mask is produced bit-packed ([T, V/8] uint8), 8x smaller than the
+    reference's bool [T, V];
+  * the KV cache is laid out [B, n_kv, S, hd] so every (sequence, head) stream is contiguous for the
+    split-KV decode kernel, which also applies RoPE and appends K/V in place.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Tuple
+
+import torch
+
+from realhf_b200.api.model import GenerationHyperparameters
+from realhf_b200.models.real_model import ReaLModel
+from realhf_b200.ops import functional as OF
+from realhf_b200.parallel import tp as TP
+
+
+@dataclasses.dataclass
+class GenerationOutput:
+    tokens: torch.Tensor        # [B, n_gen] generated ids (pad after EOS)
+    logprobs: torch.Tensor      # [B, n_gen] fp32 log-prob of each generated token under the sampling distribution
+    mask_bits: Optional[torch.Tensor]  # [B, n_gen, ceil(V/8)] uint8, bit set = token was filtered out; None if disabled
+    gen_lens: torch.Tensor      # [B] number of generated tokens including EOS
+    no_eos: torch.Tensor        # [B] bool: hit max_new_tokens without EOS
+
+
+def _filter_logits(logits: torch.Tensor, g: GenerationHyperparameters) -> torch.Tensor:
+    """top-k then top-p on fp32 logits [B, V]; filtered entries -> -inf."""
+    V = logits.shape[-1]
+    neg = torch.finfo(logits.dtype).min
+    if g.top_k < V:
+        kth = torch.topk(logits, g.top_k, dim=-1).values[..., -1:]
+        logits = logits.masked_fill(logits < kth, neg)
+    if g.top_p < 1.0:
+        sl, si = torch.sort(logits, descending=True, dim=-1)
+        cp = torch.softmax(sl, dim=-1).cumsum(-1)
+        remove = cp - torch.softmax(sl, dim=-1) >= g.top_p  # keep the first token that crosses top_p
+        remove[..., 0] = False
+        sl = sl.masked_fill(remove, neg)
+        logits = torch.empty_like(logits).scatter_(-1, si, sl)
+    return logits
+
+
+def genstep(logits: torch.Tensor, g: GenerationHyperparameters, step: int, eos_id: Optional[int], pad_id: int,
+            unfinished: torch.Tensor, generator: Optional[torch.Generator] = None, want_mask: bool = True):
+    """One sampling step on full-vocab logits [B, V].  Returns (next_tokens, logprob, mask_bits | None, unfinished)."""
+    x = logits.float()
+    if eos_id is not None and step < g.min_new_tokens:
+        x[:, eos_id] = torch.finfo(x.dtype).min
+    if not g.greedy:
+        x = x / g.temperature
+        x = _filter_logits(x, g)
+    lp_all = torch.log_softmax(x, dim=-1)
+    if g.greedy:
+        nxt = x.argmax(dim=-1)
+    else:
+        nxt = torch.multinomial(lp_all.exp(), 1, generator=generator).squeeze(-1)
+    lp = lp_all.gather(-1, nxt.unsqueeze(-1)).squeeze(-1)
+    mask_bits = None
+    if want_mask and not g.force_no_logits_mask and not g.greedy:
+        mask_bits = OF.pack_mask_bits(x == torch.finfo(x.dtype).min)
+    nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_id))
+    lp = torch.where(unfinished, lp, torch.zeros_like(lp))
+    if eos_id is not None:
+        unfinished = unfinished & (nxt != eos_id)
+    return nxt, lp, mask_bits, unfinished
+
+
+class DecodeState:
+    """Static buffers of one decode session (fixed addresses => CUDA-graph replayable)."""
+
+    def __init__(self, model: ReaLModel, B: int, S: int):
+        c = model.config
+        nq, nkv = model._local_heads()
+        dev, dt = model.device, model.dtype
+        nb = model.n_local_blocks()
+        # [B, nkv, S, hd] storage viewed as logical [B, S, nkv, hd]
+        self.k = [torch.zeros(B, nkv, S, c.head_dim, dtype=dt, device=dev).permute(0, 2, 1, 3) for _ in range(nb)]
+        self.v = [torch.zeros(B, nkv, S, c.head_dim, dtype=dt, device=dev).permute(0, 2, 1, 3) for _ in range(nb)]
+        self.cache_lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.input_ids = torch.zeros(B, dtype=torch.long, device=dev)
+        self.hidden_in = torch.zeros(B, c.hidden_dim, dtype=dt, device=dev) if not model.is_first_stage else None
+        self.out: Optional[torch.Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.B, self.S = B, S
+
+    def fill_from_prefill(self, kv: List[Tuple[torch.Tensor, torch.Tensor]], cu_seqlens: torch.Tensor, lens: torch.Tensor):
+        """Scatter the packed prefill K/V of every block into the dense caches."""
+        dev = cu_seqlens.device
+        T = int(kv[0][0].shape[0])
+        tok = torch.arange(T, device=dev)
+        seq = torch.searchsorted(cu_seqlens[1:].long().contiguous(), tok, right=True)
+        pos = tok - cu_seqlens.long()[seq]
+        for li, (k, v) in enumerate(kv):
+            self.k[li][seq, pos] = k
+            self.v[li][seq, pos] = v
+        self.cache_lens.copy_(lens.int())
+
+
+def _final_logits(model: ReaLModel, hidden: torch.Tensor) -> torch.Tensor:
+    """[B, H] -> full-vocab fp32-able logits on every TP rank."""
+    lg = OF.linear(hidden, model.head_weight())
+    if model.ctx.tp_size > 1:
+        lg = TP._gather_last_dim(lg, model.ctx)
+    return lg
+
+
+@torch.no_grad()
+def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor, g: GenerationHyperparameters,
+             eos_id: Optional[int], pad_id: int, generator: Optional[torch.Generator] = None,
+             state: Optional[DecodeState] = None, sync_every: int = 16) -> Tuple[GenerationOutput, DecodeState]:
+    """Generate for a packed batch of prompts on a single pipeline stage (pp == 1)."""
+    assert model.is_first_stage and model.is_last_stage, "pipelined generation goes through engine.pipe_runner"
+    dev = model.device
+    cu = cu_seqlens.int()
+    B = cu.numel() - 1
+    lens = (cu[1:] - cu[:-1])
+    max_prompt = int(lens.max())
+    S = max_prompt + g.max_new_tokens
+    was_training = model.training
+    model.eval()
+    # ---- prefill
+    kv: List[Tuple[torch.Tensor, torch.Tensor]] = []
+    out = model(input_ids=input_ids, cu_seqlens=cu, max_seqlen=max_prompt, kv_sink=kv)
+    last = (cu[1:] - 1).long()
+    logits = _final_logits(model, out.hidden.index_select(0, last))
+    if state is None or state.B != B or state.S < S:
+        state = DecodeState(model, B, S)
+    state.fill_from_prefill(kv, cu, lens)
+    del kv, out
+    unfinished = torch.ones(B, dtype=torch.bool, device=dev)
+    toks, lps, masks = [], [], []
+    nxt, lp, mb, unfinished = genstep(logits, g, 0, eos_id, pad_id, unfinished, generator)
+    toks.append(nxt); lps.append(lp); masks.append(mb)
+    # ---- decode loop
+    use_graph = g.use_cuda_graph and dev.type == "cuda"
+
+    def one_step():
+        h = model.decode_step(state.input_ids, state.k, state.v, state.cache_lens)
+        return _final_logits(model, h)
+
+    if use_graph and state.graph is None:
+        state.input_ids.copy_(nxt)
+        lens_backup = state.cache_lens.clone()
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            one_step()  # warm-up outside capture (allocations, lazy inits)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        state.cache_lens.copy_(lens_backup)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            state.out = one_step()
+        state.graph = graph
+    step = 1
+    while step < g.max_new_tokens:
+        state.input_ids.copy_(nxt)
+        if use_graph:
+            state.graph.replay()
+            logits = state.out
+        else:
+            logits = one_step()
+        state.cache_lens += 1
+        nxt, lp, mb, unfinished = genstep(logits, g, step, eos_id, pad_id, unfinished, generator)
+        toks.append(nxt); lps.append(lp); masks.append(mb)
+        step += 1
+        if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(unfinished.any()):
+            break
+    tokens = torch.stack(toks, 1)
+    logprobs = torch.stack(lps, 1)
+    mask_bits = torch.stack(masks, 1) if masks[0] is not None else None
+    n_gen = tokens.shape[1]
+    if eos_id is not None:
+        is_eos = tokens == eos_id
+        first = torch.where(is_eos.any(1), is_eos.float().argmax(1) + 1, torch.full((B,), n_gen, device=dev))
+        no_eos = ~is_eos.any(1)
+    else:
+        first = torch.full((B,), n_gen, device=dev)
+        no_eos = torch.ones(B, dtype=torch.bool, device=dev)
+    if g.force_cudagraph_recapture and state.graph is not None:
+        state.graph = None
+        state.out = None
+    model.train(was_training)
+    return GenerationOutput(tokens, logprobs, mask_bits, first.long(), no_eos), state
+
+
+def concat_prompt_to_generation_output(prompt_ids: torch.Tensor, prompt_cu: torch.Tensor, out: GenerationOutput):
+    """Build packed `seq = prompt + generation` per sample without Python loops over samples.
+
+    Returns (packed_seq [sum L], seq_lens [B], packed_logprobs [sum (L-1)], packed_mask_bits [sum L, V/8] | None,
+    prompt_mask [sum L] bool).  Log-probs / masks are aligned the reference way: entry t of a sequence belongs to the
+    prediction of token t+1, zero over the prompt part (real_llm_generate.py:451-530)."""
+    dev = prompt_ids.device
+    B = out.tokens.shape[0]
+    plens = (prompt_cu[1:] - prompt_cu[:-1]).long()
+    glens = out.gen_lens.long()
+    slens = plens + glens
+    cu = torch.zeros(B + 1, dtype=torch.long, device=dev)
+    cu[1:] = slens.cumsum(0)
+    total = int(cu[-1])
+    tok = torch.arange(total, device=dev)
+    seq = torch.searchsorted(cu[1:].contiguous(), tok, right=True)
+    pos = tok - cu[seq]
+    in_prompt = pos < plens[seq]
+    packed = torch.empty(total, dtype=prompt_ids.dtype, device=dev)
+    packed[in_prompt] = prompt_ids[(prompt_cu.long()[seq] + pos)[in_prompt]]
+    gpos = (pos - plens[seq]).clamp(min=0)
+    packed[~in_prompt] = out.tokens[seq[~in_prompt], gpos[~in_prompt]]
+    # logprobs: length L-1 per sequence; position t (0-based) predicts token t+1
+    cu1 = cu - torch.arange(B + 1, device=dev)
+    total1 = int(cu1[-1])
+    tok1 = torch.arange(total1, device=dev)
+    seq1 = torch.searchsorted(cu1[1:].contiguous(), tok1, right=True)
+    pos1 = tok1 - cu1[seq1]
+    is_gen1 = pos1 >= plens[seq1] - 1
+    gp1 = (pos1 - (plens[seq1] - 1)).clamp(min=0)
+    lp = torch.zeros(total1, dtype=torch.float32, device=dev)
+    lp[is_gen1] = out.logprobs[seq1[is_gen1], gp1[is_gen1]]
+    mask_bits = None
+    if out.mask_bits is not None:
+        mask_bits = torch.zeros(total1, out.mask_bits.shape[-1], dtype=torch.uint8, device=dev)
+        mask_bits[is_gen1] = out.mask_bits[seq1[is_gen1], gp1[is_gen1]]
+    return packed, slens, lp, mask_bits, in_prompt

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(DecodeParams p) {
     for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
   }
 
+  // row groups run different trip counts near the range end: shuffles must name only the group's own lanes
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (rsel * LPR));
   auto consume = [&](const float* kf, const float* vf) {
 #pragma unroll
     for (int r = 0; r < REP; ++r) {
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(DecodeParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) s = fmaf(q[r][i], kf[i], s);
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, LPR);
       const float mn = fmaxf(m[r], s);
       const float corr = __expf(m[r] - mn), pr = __expf(s - mn);
       l[r] = l[r] * corr + pr;
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(DecodeParams p) {
   // the new token itself: exactly one row-group of the last split takes it
   if (split == p.splits - 1 && warp == 0 && rsel == 0) consume(kn, vn);
 
+  __syncwarp();
   // ---- merge the RPW row-groups of each warp, then the warps
   __shared__ float sm_acc[kWarps][REP][HD];
   __shared__ float sm_m[kWarps][REP], sm_l[kWarps][REP];
