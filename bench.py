@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Headline benchmark: PPO iteration throughput (tokens/s, generation + inference + training) for
+LLaMA-7B actor + 7B critic + 7B reference + 7B reward model, synthetic prompts, random-init weights, bf16.
+
+    python bench.py --gpus 1 --steps 2 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 2 --warmup 3
+
+Config = the reference's quickstart PPO script (`examples/scripts/local/ppo.sh`): 128 prompts x 128 tokens,
+512 new tokens (min = max), top_p 0.9, top_k 1000, 4 PPO minibatches, CUDA-graph generation.  One step = one full
+traversal of the 6-MFC PPO dataflow graph (actor_gen -> rew_inf, ref_inf, critic_inf -> actor_train, critic_train).
+Total work is fixed as N grows (strong scaling): tokens per step = 128 x 640.
+
+Allocation on B200: every MFC is data-parallel over all N GPUs (four 7B models are 54 GB in bf16; 180 GB HBM
+holds them all), trainable models use the ZeRO-1 sharded flat AdamW.  Timing: CUDA events on the launching stream
+bracketed by barrier + synchronize, MAX over ranks.  Inputs (> L2: weights alone are 54 GB) are copied from pinned
+host memory every step and the step's statistics are read back to the host inside the e2e region.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PPO tokens/sec (gen+train, device-timed max-over-ranks) LLaMA-7B x4"
+BASELINE_TOKENS_PER_S = 128 * 640 / (574.312 / 39)  # reference quickstart log: 39 steps in 574.312 s on 8 GPUs
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of this rank's GPU with nvidia-smi during the timed region."""
+
+    def __init__(self, index: int, period: float = 0.5):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_ev = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_ev.wait(self.period)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args):
+    """The unmodified reference cannot run in this image: see DESIGN.md ("Reference arm")."""
+    why = ("reference installs into baseline/_ref only with --no-deps --ignore-requires-python (needs python<3.12) and its "
+           "PPO path imports megatron-core 0.6, deepspeed 0.14, hydra-core and colorlog, none of which exist in this offline image")
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers (result is then NOT the headline config)")
+    ap.add_argument("--prompts", type=int, default=128)
+    ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--new-tokens", type=int, default=512)
+    ap.add_argument("--gemm", default=os.environ.get("REAL_GEMM", "tcgen05"), choices=["tcgen05", "cublas"])
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from realhf_b200.api.config import ModelInterfaceAbstraction, ModelInterfaceType, ModelName
+    from realhf_b200.api.data import SequenceSample
+    from realhf_b200.api.dfg import MFCDef
+    from realhf_b200.api.model import FinetuneSpec, Model, ReaLModelConfig
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import InferenceBackend, TrainBackend
+    from realhf_b200.interfaces import basic, ppo
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.ops import functional as OF
+    from realhf_b200.ops import launches
+    from realhf_b200.system.spmd import SPMDExecutor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        ctx = ParallelContext.build(ProcessTopology(1, world, 1), list(range(world)), rank, backend="nccl",
+                                    gradient_checkpointing=True)
+    else:
+        ctx = ParallelContext.single()
+        ctx.gradient_checkpointing = True
+    if args.gemm == "tcgen05":
+        from realhf_b200.ops import gemm as G
+        OF.set_gemm_impl(G.linear)
+
+    def llama7b(is_critic):
+        return ReaLModelConfig(n_layers=args.layers, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008,
+                               vocab_size=32000, n_positions=4096, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0,
+                               layer_norm_epsilon=1e-5, activation_function="silu", scale_attn_by_inverse_layer_idx=False,
+                               use_attention_bias=False, use_attn_proj_bias=False, use_mlp_bias=False, layer_norm_type="rms",
+                               mlp_type="llama", apply_rotary=True, is_critic=is_critic)
+
+    tok = types.SimpleNamespace(eos_token_id=2, pad_token_id=0)
+    spec = FinetuneSpec(total_train_epochs=1, total_train_steps=1000, steps_per_epoch=1000)
+    lean = dict(lr=1e-5, weight_decay=0.05, state_dtype="bf16", use_master_weights=False, grad_dtype="bf16",
+                share_grad_buffer=True, warmup_steps_proportion=0.0, lr_scheduler_type="constant")
+    models = {}
+    for role, critic, train in (("actor", False, True), ("critic", True, True), ("ref", False, False), ("reward", True, False)):
+        m = ReaLModel(llama7b(critic), ctx, dtype=torch.bfloat16, device=dev).init_random_fast(seed=11 + len(models))
+        model = Model(ModelName(role, 0), m, tok, dev)
+        be = TrainBackend(optimizer=dict(lean)) if train else InferenceBackend()
+        models[role] = be.initialize(model, spec)
+    torch.cuda.synchronize()
+
+    per_rank = args.prompts // world
+    assert per_rank * world == args.prompts
+    gen_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
+    inf_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
+    gcfg = dict(max_new_tokens=args.new_tokens, min_new_tokens=args.new_tokens, greedy=False, top_p=0.9, top_k=1000,
+                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=False)
+    ppo_kw = dict(n_minibatches=4, kl_ctl=0.1, discount=1.0, gae_lambda=1.0, eps_clip=0.2, value_eps_clip=0.2,
+                  max_reward_clip=20.0, adaptive_kl_ctl=False, value_norm=True)
+    A = lambda t, **a: ModelInterfaceAbstraction(t, a)
+    T = ModelInterfaceType
+    n = args.prompts
+    rpcs = [
+        MFCDef("actor_gen", n, T.GENERATE, A("ppo_actor"), "actor", input_keys=("packed_prompts",),
+               output_keys=("seq_no_eos_mask", "packed_input_ids", "packed_logprobs", "prompt_mask", "packed_logits_mask"), n_mbs=gen_mbs),
+        MFCDef("rew_inf", n, T.INFERENCE, A("paired_rw"), "reward", input_keys=("packed_input_ids",), output_keys=("rewards",), n_mbs=inf_mbs),
+        MFCDef("ref_inf", n, T.INFERENCE, A("ppo_actor"), "ref", input_keys=("packed_input_ids", "packed_logits_mask"),
+               output_keys=("packed_ref_logprobs",), n_mbs=inf_mbs),
+        MFCDef("critic_inf", n, T.INFERENCE, A("ppo_critic"), "critic", input_keys=("packed_input_ids", "seq_no_eos_mask"),
+               output_keys=("values",), n_mbs=inf_mbs),
+        MFCDef("actor_train", n, T.TRAIN_STEP, A("ppo_actor"), "actor",
+               input_keys=("packed_input_ids", "packed_logprobs", "packed_ref_logprobs", "rewards", "values", "prompt_mask",
+                           "seq_no_eos_mask", "packed_logits_mask"), n_mbs=1, log_return_value=True),
+        MFCDef("critic_train", n, T.TRAIN_STEP, A("ppo_critic"), "critic",
+               input_keys=("packed_input_ids", "packed_logprobs", "packed_ref_logprobs", "rewards", "values", "prompt_mask",
+                           "seq_no_eos_mask"), n_mbs=1, log_return_value=True),
+    ]
+    actor_itf = ppo.PPOActorInterface(generation_config=gcfg, **ppo_kw)
+    critic_itf = ppo.PPOCriticInterface(**{k: v for k, v in ppo_kw.items() if k not in ("eps_clip",)})
+    rw_itf = basic.PairedRewardInterface()
+    interfaces = {"actor_gen": actor_itf, "ref_inf": actor_itf, "actor_train": actor_itf, "critic_inf": critic_itf,
+                  "critic_train": critic_itf, "rew_inf": rw_itf}
+    ex = SPMDExecutor(rpcs, models, interfaces, dev)
+
+    # synthetic prompts of the dataset's padded shape, in pinned host memory
+    gcpu = torch.Generator().manual_seed(1234 + rank)
+    host_prompts = torch.randint(3, 32000, (args.warmup + args.steps, per_rank * args.prompt_len), generator=gcpu).pin_memory()
+    h2d_bytes = per_rank * args.prompt_len * host_prompts.element_size()
+    result_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+
+    def one_step(i):
+        ids = host_prompts[i].to(dev, non_blocking=True)
+        batch = SequenceSample.from_default(seqlens=[args.prompt_len] * per_rank,
+                                            ids=[f"s{i}r{rank}p{j}" for j in range(per_rank)], data=dict(packed_prompts=ids))
+        rec = ex.run_step(batch)
+        st_a, st_c = rec["actor_train"].result, rec["critic_train"].result
+        res = torch.tensor([st_a["actor_loss"], st_a["task_reward"], st_a["importance_weight"], st_c["value_loss"],
+                            float(st_a["n_tokens"]), float(st_a["grad_norm"]), float(st_c["grad_norm"]), 0.0])
+        result_host.copy_(res)
+        return rec, st_a, st_c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        rec, st_a, st_c = one_step(i)
+        if args.verbose and rank == 0:
+            print(f"[warmup {i}] " + " ".join(f"{k}={v.device_ms:.0f}ms" for k, v in rec.items()), file=sys.stderr, flush=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    mfc_ms = {}
+    n_tokens_total = 0.0
+    for i in range(args.steps):
+        rec, st_a, st_c = one_step(args.warmup + i)
+        for k, v in rec.items():
+            mfc_ms[k] = mfc_ms.get(k, 0.0) + v.device_ms / args.steps
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop()
+    n_launch = launches.total
+    pool = ex.last_pool
+    tokens_this_rank = float(sum(pool.flat_seqlens("packed_input_ids")))
+    t = torch.tensor([dev_s, wall, tokens_this_rank, float(n_launch)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dev_s, wall = float(tmax[0]), float(tmax[1])
+    tokens_per_step = float(t[2]) if world > 1 else tokens_this_rank
+    value = tokens_per_step * args.steps / dev_s
+    e2e = tokens_per_step * args.steps / wall
+    headline = args.layers == 32 and args.prompts == 128 and args.prompt_len == 128 and args.new_tokens == 512
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dev_s * 1e3 / args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3) if headline else None, "dtype": "bf16",
+            "data": "synthetic prompts (uniform random token ids), random-init weights",
+            "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline else f" [DEBUG layers={args.layers}]"),
+                       "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens,
+                       "prompt_len": args.prompt_len, "new_tokens": args.new_tokens, "ppo_minibatches": 4,
+                       "parallelism": f"dp{world} (all 6 MFCs), ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
+                       "optimizer": "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads",
+                       "gemm": args.gemm, "attention": "flash-attn lib (varlen) + own split-KV decode kernel",
+                       "l2": "working set >> L2 (54 GB weights per GPU); fresh inputs every step",
+                       "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": result_host.numel() * 4 * world},
+            "gpu_launches": int(float(t[3]) if world > 1 else n_launch),
+            "impl": "ours",
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

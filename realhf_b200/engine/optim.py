@@ -50,6 +50,7 @@ class OptimizerConfig:
     state_dtype: str = "fp32"      # fp32 | bf16 (bf16 moments, stochastic rounding, no master copy)
     use_master_weights: bool = True
     grad_dtype: str = "bf16"       # dtype of the flat gradient buffer: bf16 | fp32
+    share_grad_buffer: bool = False  # trainable models on one GPU that never train concurrently share one grad buffer
 
 
 class LRScheduler:
@@ -90,6 +91,20 @@ class LRScheduler:
 
 _DT = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
+_GRAD_POOL: Dict[Tuple, torch.Tensor] = {}
+
+
+def _grad_pool_get(numel: int, dtype, device) -> torch.Tensor:
+    """One gradient buffer per (dtype, device), grown to the largest request; every train_batch zeroes it first and
+    consumes it in its own optimizer step, so sequentially-trained models (PPO actor / critic) can alias it."""
+    key = (dtype, str(device))
+    buf = _GRAD_POOL.get(key)
+    if buf is None or buf.numel() < numel:
+        assert buf is None, "grad pool must be sized by its largest user first (create the largest model's optimizer first)"
+        buf = torch.zeros(numel, dtype=dtype, device=device)
+        _GRAD_POOL[key] = buf
+    return buf[:numel]
+
 
 class FlatAdamW:
     """AdamW over a ReaLModel's flat parameter buffer, sharded across the data-parallel group."""
@@ -107,7 +122,8 @@ class FlatAdamW:
         self.lo = self.ctx.dp_rank * self.shard_n
         self.hi = min(n, self.lo + self.shard_n)
         self.grad_dtype = _DT[cfg.grad_dtype]
-        self.flat_grad = torch.zeros(self.padded, dtype=self.grad_dtype, device=dev)
+        self.flat_grad = _grad_pool_get(self.padded, self.grad_dtype, dev) if cfg.share_grad_buffer else \
+            torch.zeros(self.padded, dtype=self.grad_dtype, device=dev)
         model.attach_grad_buffer(self.flat_grad[:n])
         self.state_dtype = _DT[cfg.state_dtype]
         pdt = model.dtype

@@ -20,6 +20,7 @@ import torch
 from realhf_b200.api.model import GenerationHyperparameters
 from realhf_b200.models.real_model import ReaLModel
 from realhf_b200.ops import functional as OF
+from realhf_b200.ops import launches
 from realhf_b200.parallel import tp as TP
 
 
@@ -90,6 +91,7 @@ class DecodeState:
         self.hidden_in = torch.zeros(B, c.hidden_dim, dtype=dt, device=dev) if not model.is_first_stage else None
         self.out: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_launches = 0
         self.B, self.S = B, S
 
     def fill_from_prefill(self, kv: List[Tuple[torch.Tensor, torch.Tensor]], cu_seqlens: torch.Tensor, lens: torch.Tensor):
@@ -157,14 +159,17 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         torch.cuda.current_stream(dev).wait_stream(s)
         state.cache_lens.copy_(lens_backup)
         graph = torch.cuda.CUDAGraph()
+        launches.begin_capture()
         with torch.cuda.graph(graph):
             state.out = one_step()
+        state.graph_launches = launches.end_capture()
         state.graph = graph
     step = 1
     while step < g.max_new_tokens:
         state.input_ids.copy_(nxt)
         if use_graph:
             state.graph.replay()
+            launches.count_replay(state.graph_launches)
             logits = state.out
         else:
             logits = one_step()

@@ -213,7 +213,14 @@ class ReaLModel(nn.Module):
             if flat_grad.dtype == self.p[name].dtype:
                 self.p[name].grad = g
             else:
-                self.p[name].main_grad = g  # fp32 bucket: GEMM wgrad accumulates into it directly
+                p = self.p[name]
+                p.main_grad = g  # fp32 bucket: the GEMM wgrad kernel accumulates into it directly
+                if not getattr(p, "_main_grad_hooked", False):
+                    def _fold(param):  # params whose grad comes from autograd (norms, embeddings, biases)
+                        param.main_grad.add_(param.grad.view_as(param.main_grad))
+                        param.grad = None
+                    p.register_post_accumulate_grad_hook(_fold)
+                    p._main_grad_hooked = True
 
     def state_dict(self, *a, **k) -> Dict[str, torch.Tensor]:
         return {n: t.data for n, t in self.p.items()}

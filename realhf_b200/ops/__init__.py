@@ -19,6 +19,63 @@ _lib = None
 _host = None
 
 
+# kernels launched per op call (for the `gpu_launches` accounting of bench.py)
+_KERNELS_PER_OP = {"rmsnorm_bwd": 2, "adamw_step": 1, "decode_attention": 1}
+
+
+class _LaunchCounter:
+    """Counts launches of OUR kernels.  Launches recorded while a CUDA graph is being captured are attributed
+    to that graph (`begin_capture` / `end_capture`) and re-counted on every replay (`count_replay`)."""
+
+    def __init__(self):
+        self.total = 0
+        self.by_op = {}
+        self._capturing = None
+
+    def add(self, op: str, n: int = 1):
+        self.total += n
+        self.by_op[op] = self.by_op.get(op, 0) + n
+        if self._capturing is not None:
+            self._capturing[0] += n
+
+    def begin_capture(self):
+        self._capturing = [0]
+
+    def end_capture(self) -> int:
+        n, self._capturing = self._capturing[0], None
+        self.total -= n  # a capture does not execute the kernels
+        return n
+
+    def count_replay(self, n: int):
+        self.total += n
+        self.by_op["<graph replay>"] = self.by_op.get("<graph replay>", 0) + n
+
+    def reset(self):
+        self.total, self.by_op = 0, {}
+
+
+launches = _LaunchCounter()
+
+
+class _CountingLib:
+    def __init__(self, ns):
+        self._ns = ns
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            op = getattr(self._ns, name)
+            k = _KERNELS_PER_OP.get(name, 1)
+
+            def fn(*a, _op=op, _k=k, _name=name, **kw):
+                launches.add(_name, _k)
+                return _op(*a, **kw)
+
+            self._cache[name] = fn
+        return fn
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -27,7 +84,7 @@ def lib():
                 f"{_LIB_PATH} is missing. Build it with `python -m realhf_b200.ops.build` "
                 "(or `python -c 'import __graft_entry__ as g; g.build()'`).")
         torch.ops.load_library(str(_LIB_PATH))
-        _lib = torch.ops.realhf_b200
+        _lib = _CountingLib(torch.ops.realhf_b200)
     return _lib
 
 

@@ -258,6 +258,10 @@ bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint
                uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
+  // The driver entry point needs a current context in *this* thread; autograd's backward threads only ever
+  // called cudaSetDevice, which does not bind the primary context for driver-API calls until a runtime call does.
+  static thread_local bool ctx_ready = false;
+  if (!ctx_ready) { cudaFree(nullptr); ctx_ready = true; }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
