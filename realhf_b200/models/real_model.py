@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import zlib
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -151,7 +152,9 @@ class ReaLModel(nn.Module):
                     if slot.spec.init == "ones":
                         self.p[name].fill_(1.0)
                     elif slot.spec.init == "normal":
-                        # draw the FULL tensor then shard it, so every TP layout sees the same weights
+                        # draw the FULL tensor from a per-parameter stream, then shard it: every (pp, tp) layout
+                        # of the same seed holds the same weights
+                        gen.manual_seed(((seed if seed is not None else 1) * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
                         full = torch.empty(slot.spec.shape, dtype=torch.float32).normal_(0.0, std, generator=gen)
                         sh = sharding.shard_tensor(slot.spec, self.config, full, self.ctx.tp_rank, self.ctx.tp_size)
                         self.p[name].copy_(sh.to(self.dtype))
@@ -384,7 +387,7 @@ class ReaLModel(nn.Module):
             if i == 0:
                 x = self._embed(input_ids, position_ids)
             elif i <= c.n_layers:
-                if self.gradient_checkpointing and self.training and torch.is_grad_enabled() and kv_sink is None:
+                if self.gradient_checkpointing and torch.is_grad_enabled() and kv_sink is None:
                     x = checkpoint(self._block_packed, i, x, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
                 else:
                     x = self._block_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)

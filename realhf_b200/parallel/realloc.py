@@ -1,0 +1,219 @@
+"""Parameter reallocation: re-shard a role's weights between two (mesh, dp, tp, pp) layouts.
+
+Parity: `realhf/impl/model/comm/param_realloc.py` (plan derivation :312-522, sender selection :82-138) and
+`nn/real_llm_api.py:610-785` (execution, EMA patch).  The plan is pure index math over the sharding table
+(`models/sharding.py`): for every destination shard and parameter, the element intervals it needs are
+intersected with the intervals each source TP rank holds, giving (source offset, destination offset, length)
+segments in the two flat buffers.
+
+Execution differs by design.  The reference packs with `slice_intervals`, broadcasts over a dedicated NCCL
+group per sender and unpacks with `set_intervals`.  Here a transfer is ONE launch of the segment-copy kernel
+(`ops/csrc/segcopy.cu`) whose destination pointer is the peer GPU's flat buffer mapped through CUDA IPC
+(`parallel/symm_mem.py`): the kernel writes the destination layout directly over NVLink — no pack buffer, no
+unpack kernel, no per-pair communicator.  Without peer access (CPU/gloo, different nodes) it falls back to
+pack -> batched isend/irecv -> unpack.  On NVSwitch every GPU reaches every peer at full bandwidth, so senders
+are chosen only to spread load over source DP replicas (the reference's one-sender-per-node rule disappears).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from realhf_b200.api.model import ReaLModelConfig
+from realhf_b200.base.topology import ProcessTopology
+from realhf_b200.models import sharding
+from realhf_b200.models.real_model import build_layout
+from realhf_b200.ops.functional import SegmentPlan
+
+
+@dataclasses.dataclass
+class Transfer:
+    src_worker: int
+    dst_worker: int
+    src_off: List[int]   # element offsets in the source flat buffer
+    dst_off: List[int]   # element offsets in the destination flat buffer
+    lens: List[int]      # elements
+
+    @property
+    def numel(self) -> int:
+        return sum(self.lens)
+
+
+@dataclasses.dataclass
+class ReallocPlan:
+    transfers: List[Transfer]
+    dst_numel: Dict[int, int]  # dst worker -> flat numel of its destination shard
+
+
+def _intersect(a: List[Tuple[int, int]], b: List[Tuple[int, int]]):
+    """Sorted-by-start interval lists in the same coordinate system -> [(a_local_off, b_local_off, length)],
+    where local offsets are positions inside the concatenation of each list's intervals (i.e. inside the shards)."""
+    # shard order == list order; both lists are increasing in full-tensor coordinates by construction
+    out = []
+    i = j = 0
+    a_base = b_base = 0
+    while i < len(a) and j < len(b):
+        a0, a1 = a[i]
+        b0, b1 = b[j]
+        lo, hi = max(a0, b0), min(a1, b1)
+        if hi > lo:
+            out.append((a_base + lo - a0, b_base + lo - b0, hi - lo))
+        if a1 <= b1:
+            a_base += a1 - a0
+            i += 1
+        else:
+            b_base += b1 - b0
+            j += 1
+    return out
+
+
+def _sorted_with_local(iv: List[Tuple[int, int]]):
+    """Intervals may come in shard order that is not monotone (section splits are, row splits are): return them sorted
+    by start together with each interval's local offset inside the shard."""
+    loc, off = [], 0
+    for a, b in iv:
+        loc.append((a, b, off))
+        off += b - a
+    loc.sort()
+    return loc
+
+
+def _intersect_general(src_iv, dst_iv):
+    s, d = _sorted_with_local(src_iv), _sorted_with_local(dst_iv)
+    out = []
+    i = j = 0
+    while i < len(s) and j < len(d):
+        a0, a1, ao = s[i]
+        b0, b1, bo = d[j]
+        lo, hi = max(a0, b0), min(a1, b1)
+        if hi > lo:
+            out.append((ao + lo - a0, bo + lo - b0, hi - lo))
+        if a1 <= b1:
+            i += 1
+        else:
+            j += 1
+    return out
+
+
+def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Sequence[int], dst_topo: ProcessTopology,
+                dst_workers: Sequence[int]) -> ReallocPlan:
+    """`*_workers[r]` = worker (GPU) index of layout-local rank r.  Critic / actor pairs must share the architecture."""
+    s_pp, s_dp, s_tp = src_topo.dims
+    d_pp, d_dp, d_tp = dst_topo.dims
+    src_stage = sharding.partition_pipeline_layers(cfg, s_pp)
+    dst_stage = sharding.partition_pipeline_layers(cfg, d_pp)
+    layer_to_src_pp = {l: p for p, (a, b) in src_stage.items() for l in range(a, b)}
+    src_layouts = {p: build_layout(cfg, range(*src_stage[p]), s_tp)[0] for p in range(s_pp)}
+    merged: Dict[Tuple[int, int], Transfer] = {}
+    dst_numel: Dict[int, int] = {}
+    for dpp in range(d_pp):
+        d_slots, d_total = build_layout(cfg, range(*dst_stage[dpp]), d_tp)
+        for ddp in range(d_dp):
+            for dtp in range(d_tp):
+                dw = dst_workers[dst_topo.get_rank(pipe=dpp, data=ddp, model=dtp)]
+                dst_numel[dw] = d_total
+                for name, dslot in d_slots.items():
+                    spec = dslot.spec
+                    li = int(name.split(".", 1)[0])
+                    spp = layer_to_src_pp[li]
+                    sslot = src_layouts[spp][name]
+                    d_iv = sharding.shard_intervals(spec, cfg, dtp, d_tp)
+                    # source TP ranks that hold any of it
+                    for stp in range(s_tp):
+                        s_iv = sharding.shard_intervals(spec, cfg, stp, s_tp)
+                        if s_tp == d_tp and stp == dtp:
+                            segs = [(0, 0, dslot.numel)]
+                        elif spec.split_dim is None:
+                            if stp != dtp % s_tp:
+                                continue  # replicated tensor: one source copy is enough
+                            segs = [(0, 0, dslot.numel)]
+                        else:
+                            segs = _intersect_general(s_iv, d_iv)
+                        if not segs:
+                            continue
+                        # pick the source DP replica: same GPU if possible, else spread by destination dp rank
+                        cands = [src_workers[src_topo.get_rank(pipe=spp, data=k, model=stp)] for k in range(s_dp)]
+                        sw = dw if dw in cands else cands[(ddp * d_tp + dtp) % s_dp]
+                        t = merged.setdefault((sw, dw), Transfer(sw, dw, [], [], []))
+                        for so, do, ln in segs:
+                            t.src_off.append(sslot.offset + so)
+                            t.dst_off.append(dslot.offset + do)
+                            t.lens.append(ln)
+                        if s_tp == d_tp and stp == dtp:
+                            break
+    for t in merged.values():
+        _coalesce(t)
+    return ReallocPlan(sorted(merged.values(), key=lambda t: (t.src_worker, t.dst_worker)), dst_numel)
+
+
+def _coalesce(t: Transfer):
+    """Merge segments that are adjacent on both sides (whole parameters, consecutive rows of equal pitch...)."""
+    so, do, ln = [], [], []
+    for a, b, n in zip(t.src_off, t.dst_off, t.lens):
+        if so and so[-1] + ln[-1] == a and do[-1] + ln[-1] == b:
+            ln[-1] += n
+        else:
+            so.append(a); do.append(b); ln.append(n)
+    t.src_off, t.dst_off, t.lens = so, do, ln
+
+
+class ReallocExecutor:
+    """Runs a plan for the process of `my_worker`.  `src_flat` / `dst_flat` are this worker's flat buffers (or None)."""
+
+    def __init__(self, plan: ReallocPlan, my_worker: int, elem_size: int, device, worker_to_rank=None):
+        self.plan, self.me, self.es, self.device = plan, my_worker, elem_size, torch.device(device)
+        self.w2r = worker_to_rank or (lambda w: w)
+        self.local = [t for t in plan.transfers if t.src_worker == my_worker and t.dst_worker == my_worker]
+        self.sends = [t for t in plan.transfers if t.src_worker == my_worker and t.dst_worker != my_worker]
+        self.recvs = [t for t in plan.transfers if t.dst_worker == my_worker and t.src_worker != my_worker]
+        es = elem_size
+        mk = lambda so, do, ln: SegmentPlan([x * es for x in so], [x * es for x in do], [x * es for x in ln], self.device)
+        self.local_plans = [mk(t.src_off, t.dst_off, t.lens) for t in self.local]
+        # direct peer-store plans (source offsets -> destination offsets in the PEER's flat buffer)
+        self.direct_plans = [mk(t.src_off, t.dst_off, t.lens) for t in self.sends]
+        # pack / unpack plans for the NCCL / gloo fallback
+        self.pack_plans = [mk(t.src_off, _prefix(t.lens), t.lens) for t in self.sends]
+        self.unpack_plans = [mk(_prefix(t.lens), t.dst_off, t.lens) for t in self.recvs]
+
+    def dst_numel(self) -> Optional[int]:
+        return self.plan.dst_numel.get(self.me)
+
+    def run(self, src_flat: Optional[torch.Tensor], dst_flat: Optional[torch.Tensor], eta: float = 1.0,
+            peer_dst_ptrs: Optional[Dict[int, int]] = None, group=None):
+        """peer_dst_ptrs: dst worker -> device address of its destination flat buffer mapped into this process.
+        When given for every send, transfers are direct peer stores; else pack + isend/irecv + unpack."""
+        for pl in self.local_plans:
+            pl.run(src_flat, dst_flat, eta=eta)
+        direct = peer_dst_ptrs is not None and all(t.dst_worker in peer_dst_ptrs for t in self.sends)
+        if direct:
+            for t, pl in zip(self.sends, self.direct_plans):
+                pl.run(src_flat, None, dst_ptr=peer_dst_ptrs[t.dst_worker], eta=eta)
+            return
+        ops, staged = [], []
+        for t, pl in zip(self.sends, self.pack_plans):
+            buf = torch.empty(t.numel, dtype=src_flat.dtype, device=src_flat.device)
+            pl.run(src_flat, buf)
+            ops.append(dist.P2POp(dist.isend, buf, self.w2r(t.dst_worker), group))
+            staged.append(buf)
+        rbufs = []
+        for t in self.recvs:
+            buf = torch.empty(t.numel, dtype=dst_flat.dtype, device=dst_flat.device)
+            ops.append(dist.P2POp(dist.irecv, buf, self.w2r(t.src_worker), group))
+            rbufs.append(buf)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for buf, pl in zip(rbufs, self.unpack_plans):
+            pl.run(buf, dst_flat, eta=eta)
+
+
+def _prefix(lens: List[int]) -> List[int]:
+    out, acc = [], 0
+    for n in lens:
+        out.append(acc)
+        acc += n
+    return out
