@@ -146,10 +146,10 @@ def main():
 
     per_rank = args.prompts // world
     assert per_rank * world == args.prompts
-    gen_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
+    gen_mbs = 1  # one decode pass over all local sequences: weights are streamed once per token (KV cache 43 GB at N=1)
     inf_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
     gcfg = dict(max_new_tokens=args.new_tokens, min_new_tokens=args.new_tokens, greedy=False, top_p=0.9, top_k=1000,
-                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=False)
+                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=True)  # recapture: KV cache is freed before training
     ppo_kw = dict(n_minibatches=4, kl_ctl=0.1, discount=1.0, gae_lambda=1.0, eps_clip=0.2, value_eps_clip=0.2,
                   max_reward_clip=20.0, adaptive_kl_ctl=False, value_norm=True)
     A = lambda t, **a: ModelInterfaceAbstraction(t, a)

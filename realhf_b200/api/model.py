@@ -159,6 +159,8 @@ class Model:
     version: ModelVersion = dataclasses.field(default_factory=ModelVersion)
     ft_spec: Optional[FinetuneSpec] = None
     backend_name: Optional[str] = None
+    module_config: Optional[ReaLModelConfig] = None
+    hf_family: Optional[str] = None
 
     def __post_init__(self):
         try:
@@ -247,8 +249,6 @@ class NullInterface(ModelInterface):
         return SequenceSample.from_default(seqlens=[1] * data.bs, ids=data.ids, data={"rewards": scores})
 
     def train_step(self, model, data, n_mbs=None):
-        from realhf_b200.base import constants
-        n = sum(constants.flat2d_seqlens(data)) if False else 0
         model.inc_version()
         return {}
 

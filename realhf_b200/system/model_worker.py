@@ -1,0 +1,313 @@
+"""Model worker: one process per GPU; holds model shards, datasets and the on-device data store.
+
+Parity: `realhf/system/model_worker.py` (lazy setup :185-399, request handling :505-661, data transfer :781-814,
+param realloc :422-463, offload :464-475, save / evaluate, recover).  Tensors never leave the worker: replies to
+the master carry metadata only.  Runs with `nccl` on GPUs and with `gloo` on CPUs (the plumbing configuration).
+"""
+
+from __future__ import annotations
+
+import os
+import time
+import traceback
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from realhf_b200.api import data as data_api
+from realhf_b200.api import model as model_api
+from realhf_b200.api import system as system_api
+from realhf_b200.api.config import ModelName, ModelShardID
+from realhf_b200.api.data import SequenceSample
+from realhf_b200.api.dfg import OffloadHook, ParamReallocHook
+from realhf_b200.base import constants, logging, name_resolve, seeding
+from realhf_b200.base.topology import ParallelContext
+from realhf_b200.parallel import realloc
+from realhf_b200.system.stream import Payload, WorkerStream
+
+logger = logging.getLogger("model_worker")
+
+
+def _pg_key(exp, trial):
+    return f"{exp}/{trial}/global_pg_addr"
+
+
+class ModelWorker:
+    def __init__(self, cfg: system_api.ModelWorker):
+        self.cfg = cfg
+        info = cfg.worker_info
+        self.exp, self.trial, self.index, self.count = info.experiment_name, info.trial_name, info.worker_index, info.worker_count
+        self.models: Dict[ModelName, model_api.Model] = {}
+        self.ctxs: Dict[ModelName, ParallelContext] = {}
+        self.backends: Dict[ModelName, model_api.ModelBackend] = {}
+        self.interfaces: Dict[str, model_api.ModelInterface] = {}
+        self.shard_ids: Dict[ModelName, ModelShardID] = {}
+        self.data_storage: Dict[Any, SequenceSample] = {}
+        self.dataloader = None
+        self.data_iter = None
+        self.epoch = 0
+        self._realloc_cache: Dict[Tuple[ModelName, ModelName], realloc.ReallocExecutor] = {}
+        self._exiting = False
+
+    # ------------------------------------------------------------------ setup
+    def setup(self):
+        cfg = self.cfg
+        seeding.set_random_seed(cfg.seed + self.index)
+        if cfg.device == "cuda":
+            torch.cuda.set_device(int(os.environ.get("REAL_LOCAL_GPU", self.index % max(torch.cuda.device_count(), 1))))
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device("cpu")
+        self.stream = WorkerStream(self.exp, self.trial, self.index)
+        # global process group over all model workers
+        if self.index == 0:
+            from realhf_b200.system.stream import free_port
+            name_resolve.add(_pg_key(self.exp, self.trial), f"tcp://127.0.0.1:{free_port()}", replace=True)
+        addr = name_resolve.wait(_pg_key(self.exp, self.trial), timeout=300)
+        kw = dict(device_id=self.device) if cfg.device == "cuda" else {}
+        dist.init_process_group(cfg.backend, init_method=addr, rank=self.index, world_size=self.count, **kw)
+        # every worker builds the groups of EVERY model in the same order (new_group is collective)
+        worker_of: Dict[ModelName, List[int]] = {}
+        for sid, wi in cfg.msid2mwid.items():
+            worker_of.setdefault(sid.model_name, [None] * cfg.model_topos[sid.model_name].world_size())
+            worker_of[sid.model_name][sid.parallelism_rank if sid.topo is not None else
+                                      cfg.model_topos[sid.model_name].get_rank(pipe=sid.pp_rank, data=sid.dp_rank, model=sid.tp_rank)] = wi
+        self.worker_of = worker_of
+        for name in sorted(cfg.model_topos, key=str):
+            topo = cfg.model_topos[name]
+            ctx = ParallelContext.build(topo, worker_of[name], self.index, backend=cfg.backend,
+                                        sequence_parallel=getattr(topo, "sequence_parallel", False),
+                                        gradient_checkpointing=getattr(topo, "gradient_checkpointing", False))
+            if ctx.is_member:
+                self.ctxs[name] = ctx
+        # models / backends / interfaces
+        for shard in cfg.shards:
+            name = shard.id.model_name
+            self.shard_ids[name] = shard.id
+            with constants.model_scope(name, self.ctxs[name], instantiate=shard.should_instantiate):
+                model = model_api.make_model(shard.model, name=name, device=self.device)
+            self.models[name] = model
+            self.backends[name] = model_api.make_backend(shard.backend)
+            self._eval_dataset_cfg = shard.eval_dataset
+        for rpc in cfg.model_rpcs:
+            if rpc.model_name in self.models:
+                self.interfaces[rpc.name] = model_api.make_interface(rpc.interface_impl)
+        # dataset (only on data-owner workers)
+        if cfg.datasets:
+            src = next(r for r in cfg.model_rpcs if r.is_src)
+            ctx = self.ctxs[src.model_name]
+            ds = [data_api.make_dataset(d, cfg.seed, ctx.dp_rank, ctx.dp_size, cfg.tokenizer_name_or_path, self.exp, self.trial)
+                  for d in cfg.datasets]
+            dataset = ds[0] if len(ds) == 1 else torch.utils.data.ConcatDataset(ds)
+            self.dataset = dataset
+            self.dataset_size = len(dataset)
+            g = torch.Generator()
+            g.manual_seed(cfg.seed)
+            self.dataloader = torch.utils.data.DataLoader(dataset, batch_size=max(1, src.n_seqs // ctx.dp_size), shuffle=True,
+                                                          collate_fn=SequenceSample.gather, generator=g)
+            self.data_iter = iter(self.dataloader)
+        logger.info(f"model worker {self.index} ready: models {[str(n) for n in self.models]}")
+
+    # ------------------------------------------------------------------ hooks
+    def _data_transfer(self, plan: List[dict]):
+        """plan entries: {key, ids, lens(list per id of list[int]), dtype, trailing, src, dsts} executed identically (same
+        order) by every involved worker through one batch of isend/irecv."""
+        ops, recvs, keep = [], [], []
+        for e in plan:
+            src, dsts = e["src"], e["dsts"]
+            if self.index == src:
+                items = [self.data_storage[i] for i in e["ids"]]
+                t = torch.cat([it.data[e["key"]] for it in items], 0) if len(items) > 1 else items[0].data[e["key"]]
+                t = t.contiguous()
+                keep.append(t)
+                for d in dsts:
+                    if d != src:
+                        ops.append(dist.P2POp(dist.isend, t, d))
+            elif self.index in dsts:
+                total = sum(sum(l) for l in e["lens"])
+                buf = torch.empty((total, *e["trailing"]), dtype=e["dtype"], device=self.device)
+                ops.append(dist.P2POp(dist.irecv, buf, src))
+                recvs.append((e, buf))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for e, buf in recvs:
+            off = 0
+            for i, lens in zip(e["ids"], e["lens"]):
+                n = sum(lens)
+                piece = buf[off: off + n]
+                off += n
+                with SequenceSample.disable_validation():
+                    s = SequenceSample(keys=[e["key"]], ids=[i], seqlens={e["key"]: [lens]}, trailing_shapes={e["key"]: e["trailing"]},
+                                       dtypes={e["key"]: e["dtype"]}, data={e["key"]: piece})
+                if i in self.data_storage:
+                    self.data_storage[i].update_(s)
+                else:
+                    self.data_storage[i] = s
+
+    def _param_realloc(self, spec: dict):
+        """spec: {src: ModelName, dst: ModelName, eta}.  Both replicas' workers call this."""
+        src_name, dst_name, eta = spec["src"], spec["dst"], spec.get("eta", 1.0)
+        key = (src_name, dst_name)
+        src_model, dst_model = self.models.get(src_name), self.models.get(dst_name)
+        mcfg = (src_model or dst_model).module_config
+        if key not in self._realloc_cache:
+            plan = realloc.derive_plan(mcfg, self.cfg.model_topos[src_name], self.worker_of[src_name],
+                                       self.cfg.model_topos[dst_name], self.worker_of[dst_name])
+            es = torch.tensor([], dtype=(src_model or dst_model).dtype).element_size()
+            self._realloc_cache[key] = realloc.ReallocExecutor(plan, self.index, es, self.device)
+        ex = self._realloc_cache[key]
+        src_flat = _real(src_model).flat_param.data if src_model is not None and _real(src_model).instantiated else None
+        dst_flat = None
+        if dst_model is not None:
+            m = _real(dst_model)
+            if not m.instantiated:
+                m.attach_flat(torch.zeros(m.flat_numel, dtype=m.dtype, device=self.device))
+                for p in m.parameters():
+                    p.requires_grad_(False)
+            dst_flat = m.flat_param.data
+        ex.run(src_flat, dst_flat, eta=eta)
+        # a non-trainable source replica is dropped after handing its weights back
+        if spec.get("release_src") and src_model is not None:
+            _real(src_model).release_params()
+
+    # ------------------------------------------------------------------ request handling
+    def _handle(self, req: Payload) -> Any:
+        for h, d in zip(req.pre_hooks, req.pre_hook_data):
+            self._run_hook(h, d)
+        res = self._handle_core(req)
+        for h, d in zip(req.post_hooks, req.post_hook_data):
+            self._run_hook(h, d)
+        return res
+
+    def _run_hook(self, h: str, d: Any):
+        if h == "data_transfer":
+            self._data_transfer(d)
+        elif h == "param_realloc":
+            self._param_realloc(d)
+        elif h == "offload":
+            m = self.models.get(d["model"])
+            if m is not None:
+                _real(m).offload()
+        else:
+            raise NotImplementedError(h)
+
+    def _handle_core(self, req: Payload) -> Any:
+        h = req.handle_name
+        if h == "empty":
+            return None
+        if h == "spec":
+            return dict(dataset_size=self.dataset_size, steps_per_epoch=len(self.dataloader))
+        if h == "fetch":
+            try:
+                batch = next(self.data_iter)
+                final = False
+            except StopIteration:
+                self.epoch += 1
+                self.data_iter = iter(self.dataloader)
+                batch = next(self.data_iter)
+                final = False
+            ignore = set(req.data.get("ignore_ids", [])) if isinstance(req.data, dict) else set()
+            items = [x for x in batch.unpack() if x.ids[0] not in ignore]
+            for it in items:
+                self.data_storage[it.ids[0]] = it.to_device(self.device)
+            meta = SequenceSample.gather(items).meta() if items else None
+            return data_api.DataBatchMeta(dp_rank=self.ctxs[next(r for r in self.cfg.model_rpcs if r.is_src).model_name].dp_rank,
+                                          meta_sample=meta, epoch=self.epoch, is_final_batch=final)
+        if h == "clear_data_cache":
+            for i in req.data:
+                self.data_storage.pop(i, None)
+            if self.device.type == "cuda" and self.cfg.cuda_cache_cleanliness:
+                torch.cuda.empty_cache()
+            return None
+        name = req.model_name
+        model = self.models[name]
+        if h == "model_config":
+            return model.module_config
+        if h == "initialize":
+            m = _real(model)
+            if not m.instantiated:  # replica that only ever receives weights by realloc
+                m.attach_flat(torch.zeros(m.flat_numel, dtype=m.dtype, device=self.device))
+            self.models[name] = self.backends[name].initialize(model, req.data)
+            return None
+        if h == "save":
+            rpc = next(r for r in self.cfg.model_rpcs if r.model_name == name)
+            self.interfaces[rpc.name].save(model, req.data)
+            self.backends[name].save(model, os.path.join(req.data, "optim"))
+            return None
+        if h == "evaluate":
+            rpc = next(r for r in self.cfg.model_rpcs if r.model_name == name)
+            if self._eval_dataset_cfg is None:
+                return {}
+            ctx = self.ctxs[name]
+            ds = data_api.make_dataset(self._eval_dataset_cfg, self.cfg.seed, ctx.dp_rank, ctx.dp_size, self.cfg.tokenizer_name_or_path)
+            dl = data_api.make_dataloader("packed_eval", ds)
+            return self.interfaces[rpc.name].evaluate(model, dl)
+        if h in ("generate", "inference", "train_step"):
+            rpc = next(r for r in self.cfg.model_rpcs if r.name == req.data["rpc_name"])
+            ids = req.data["ids"]
+            inp = SequenceSample.gather([self.data_storage[i] for i in ids], keys=rpc.input_keys)
+            if rpc.input_key_remap:
+                inp.remap_keys_(rpc.input_key_remap)
+            t0 = time.perf_counter()
+            res = getattr(self.interfaces[rpc.name], h)(model, inp, n_mbs=rpc.n_mbs)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ctx = self.ctxs[name]
+            if isinstance(res, SequenceSample):
+                if rpc.output_key_remap:
+                    res.remap_keys_(rpc.output_key_remap)
+                if ctx.is_dp_head:
+                    for it in res.unpack():
+                        if it.ids[0] in self.data_storage:
+                            self.data_storage[it.ids[0]].update_(it)
+                        else:
+                            self.data_storage[it.ids[0]] = it
+                return dict(meta=res.meta() if ctx.is_dp_head else None, secs=dt)
+            return dict(stats=res if ctx.is_dp_head else None, secs=dt)
+        raise NotImplementedError(f"unknown request `{h}`")
+
+    # ------------------------------------------------------------------ main loop
+    def run(self):
+        self.setup()
+        while not self._exiting:
+            req = self.stream.poll(timeout_ms=50)
+            if req is None:
+                continue
+            if req.handle_name == "exit":
+                self.stream.reply(req, None)
+                break
+            try:
+                res = self._handle(req)
+                self.stream.reply(req, res)
+            except Exception as e:  # report and die: the controller / scheduler handles recovery
+                err = f"{type(e).__name__}: {e}\n{traceback.format_exc()}"
+                logger.error(err)
+                self.stream.reply(req, None, error=err)
+                break
+        self.exit()
+
+    def exit(self):
+        if os.environ.get("REAL_SAVE_RECOVER_STATES", "0") == "1":
+            self.save_recover_states()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        self.stream.close()
+
+    def save_recover_states(self):
+        root = os.path.join(constants.RECOVER_ROOT, self.exp, self.trial, "ckpt")
+        for name, model in self.models.items():
+            if _real(model).instantiated:
+                rpc = next((r for r in self.cfg.model_rpcs if r.model_name == name), None)
+                if rpc is not None:
+                    self.interfaces[rpc.name].save(model, os.path.join(root, name.role))
+                    self.backends[name].save(model, os.path.join(root, name.role, "optim"))
+
+
+def _real(model: model_api.Model):
+    m = model.module
+    return getattr(m, "module", m)
