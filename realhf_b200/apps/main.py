@@ -1,0 +1,92 @@
+"""Launcher (parity: `realhf/apps/main.py` main_start :74-230 and `system/controller.py`): resolve the experiment into
+system configs, start the workers through a scheduler client, watch them, and re-enter on failure when
+`recover_mode` asks for it."""
+
+from __future__ import annotations
+
+import os
+import pickle
+import signal
+import time
+from typing import Optional
+
+from realhf_b200.api.system import Experiment
+from realhf_b200.apps.remote import config_path, status_key
+from realhf_b200.base import constants, logging, name_resolve
+from realhf_b200.scheduler import client as sched_client
+
+logger = logging.getLogger("main", "system")
+
+
+class Controller:
+    """Polls worker status keys; raises on ERROR (reference: Controller.start polling loop, controller.py:275-318)."""
+
+    def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int):
+        self.exp, self.trial, self.sched, self.n = exp, trial, sched, n_model_workers
+
+    def statuses(self):
+        out = {}
+        for wt, cnt in (("master_worker", 1), ("model_worker", self.n)):
+            for i in range(cnt):
+                try:
+                    out[f"{wt}/{i}"] = name_resolve.get(status_key(self.exp, self.trial, wt, i))
+                except name_resolve.NameEntryNotFoundError:
+                    out[f"{wt}/{i}"] = "UNKNOWN"
+        return out
+
+    def wait(self, timeout: Optional[float] = None, poll: float = 0.5):
+        t0 = time.monotonic()
+        while True:
+            infos = self.sched.find_all()
+            master = next((i for i in infos if i.name.startswith("master_worker")), None)
+            failed = [i for i in infos if i.state == sched_client.JobState.FAILED]
+            if failed:
+                raise sched_client.JobException(self.sched.run_name, failed[0].name, "localhost", failed[0].state)
+            if master is not None and master.state == sched_client.JobState.COMPLETED:
+                return
+            if timeout is not None and time.monotonic() - t0 > timeout:
+                raise TimeoutError(f"experiment did not finish in {timeout}s; statuses: {self.statuses()}")
+            time.sleep(poll)
+
+
+def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[float] = None, env_vars=None):
+    exp, trial = exp_cfg.experiment_name, exp_cfg.trial_name
+    mode = getattr(exp_cfg, "mode", "local")
+    recover_mode = getattr(exp_cfg, "recover_mode", "disabled")
+    if mode == "local" and recover_mode == "auto":
+        logger.warning("recover_mode=auto in local mode restarts all local processes on failure")
+    os.environ["REAL_MODE"] = mode.upper()
+    os.environ["REAL_RECOVER_RUN"] = "1" if (recover_mode == "resume" or recover_count > 0) else "0"
+    os.environ["REAL_SAVE_RECOVER_STATES"] = "1" if recover_mode in ("auto", "save") else "0"
+    name_resolve.clear_subtree(f"{exp}/{trial}")
+    sys_cfg = exp_cfg.initial_setup()
+    sched_cfg = exp_cfg.scheduling_setup()
+    with open(config_path(exp, trial), "wb") as f:
+        pickle.dump(sys_cfg, f)
+    sched = sched_client.make(mode, exp, trial)
+    env = {k: os.environ[k] for k in constants.FORWARDED_ENV if k in os.environ}
+    env.update(env_vars or {})
+    debug = getattr(exp_cfg, "debug", True)
+    sched.submit_array("master_worker", sched_client.remote_worker_cmd(exp, trial, debug, "master_worker"), count=1, env_vars=env)
+    mw = sched_cfg.model_worker
+    sched.submit_array("model_worker", sched_client.remote_worker_cmd(exp, trial, debug, "model_worker"), count=mw.count,
+                       gpu=mw.scheduling.gpu, env_vars=env)
+    ctl = Controller(exp, trial, sched, mw.count)
+    try:
+        ctl.wait(timeout=timeout)
+        sched.wait(timeout=60)
+    except (KeyboardInterrupt, sched_client.JobException, TimeoutError) as e:
+        # give workers the chance to dump recover states (they listen for SIGINT), then stop everything
+        sched.stop_all(signal.SIGINT if recover_mode in ("auto", "save") else signal.SIGTERM)
+        if isinstance(sched, sched_client.LocalSchedulerClient):
+            for info_name in ("master_worker/0", "model_worker/0"):
+                tail = sched.log_tail(info_name)
+                if tail:
+                    logger.error(f"---- tail of {info_name} ----\n{tail}")
+        if recover_mode == "auto" and recover_count < getattr(exp_cfg, "recover_retries", 1) and not isinstance(e, KeyboardInterrupt):
+            logger.warning(f"run failed ({e}); recovering (attempt {recover_count + 1})")
+            return main_start(exp_cfg, recover_count + 1, timeout, env_vars)
+        raise
+    finally:
+        sched.stop_all()
+    return sys_cfg

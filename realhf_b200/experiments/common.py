@@ -161,6 +161,8 @@ class CommonExperimentConfig(Experiment):
             cfgd = self.allocations.get(a.rpc.name) if self._has_allocations() else None
             if cfgd is not None and cfgd.n_mbs is not None and a.rpc.n_mbs is None:
                 a.rpc.n_mbs = cfgd.n_mbs
+        from realhf_b200.api.dfg import build_graph
+        build_graph([a.rpc for a in rpc_allocs])
         resolve_replica_ids(rpc_allocs)
         resolve_rpc_hooks(rpc_allocs, self.models)
         self._check(rpc_allocs)

@@ -99,8 +99,7 @@ class ModelOutput:
         h = self.hidden if rows is None else self.hidden.index_select(0, rows)
         if self.ctx is not None and self.ctx.tp_size > 1:
             local = OF.linear(h, self.head_weight)
-            assert mask_bits is None, "logits mask with vocab-parallel head is not supported yet"
-            return TP.vocab_parallel_logprobs(local, labels, self.ctx, temperature)
+            return TP.vocab_parallel_logprobs(local, labels, self.ctx, temperature, mask_bits)
         return OF.lm_head_logprobs(h, self.head_weight, labels, mask_bits, temperature)
 
 

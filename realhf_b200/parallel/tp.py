@@ -244,10 +244,14 @@ class _VocabParallelLogProb(torch.autograd.Function):
     (the reference issues three: max, sum-exp, target logit; modules.py:1056,1091,1101)."""
 
     @staticmethod
-    def forward(ctx, logits, labels, pctx, inv_temp):
+    def forward(ctx, logits, labels, pctx, inv_temp, mask_bits=None):
         V = logits.shape[-1]
         lo = pctx.tp_rank * V
         x = logits.float() * inv_temp
+        if mask_bits is not None:  # bit-packed over the FULL vocabulary: take this rank's byte range
+            assert lo % 8 == 0 and V % 8 == 0, "vocab shard must be byte aligned for the packed logits mask"
+            local = OF.unpack_mask_bits(mask_bits[:, lo // 8:(lo + V) // 8], V)
+            x = x.masked_fill(local, float("-inf"))
         m = x.max(dim=-1).values
         gm = m.clone()
         dist.all_reduce(gm, op=dist.ReduceOp.MAX, group=pctx.tp_group)
@@ -268,11 +272,11 @@ class _VocabParallelLogProb(torch.autograd.Function):
         grad = -p
         grad.scatter_add_(-1, loc.unsqueeze(-1), own.float().unsqueeze(-1))
         grad = grad * (g * ctx.inv_temp).unsqueeze(-1)
-        return grad, None, None, None
+        return grad, None, None, None, None
 
 
-def vocab_parallel_logprobs(logits, labels, ctx: Optional[ParallelContext], temperature: float = 1.0):
+def vocab_parallel_logprobs(logits, labels, ctx: Optional[ParallelContext], temperature: float = 1.0, mask_bits=None):
     if _tp(ctx) == 1:
-        return OF.logprob_from_logits_ref(logits, labels, None, 1.0 / temperature)[0] if logits.requires_grad \
-            else OF.logprob_from_logits(logits, labels, None, 1.0 / temperature)[0]
-    return _VocabParallelLogProb.apply(logits, labels, ctx, 1.0 / temperature)
+        return OF.logprob_from_logits_ref(logits, labels, mask_bits, 1.0 / temperature)[0] if logits.requires_grad \
+            else OF.logprob_from_logits(logits, labels, mask_bits, 1.0 / temperature)[0]
+    return _VocabParallelLogProb.apply(logits, labels, ctx, 1.0 / temperature, mask_bits)

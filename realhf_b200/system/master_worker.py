@@ -1,0 +1,296 @@
+"""Master worker: walks the dataflow graph, holds only metadata, dispatches MFCs to model workers.
+
+Parity: `realhf/system/master_worker.py` (lazy init :927-1271, request/reply coroutines :455-680, data loading
+:683-781, save / eval / benchmark control :1307-1400, e2e logging :1407-1488, recover info :1541-1554).
+One asyncio coroutine per MFC; an MFC fires as soon as `n_seqs` samples carry all of its input keys, so independent
+MFCs (rew_inf / ref_inf / critic_inf of PPO) overlap when their meshes are disjoint.
+"""
+
+from __future__ import annotations
+
+import asyncio
+import collections
+import os
+import time
+from typing import Any, Dict, Hashable, List, Optional, Tuple
+
+import numpy as np
+
+from realhf_b200.api import system as system_api
+from realhf_b200.api.config import ModelInterfaceType, ModelName, ModelShardID
+from realhf_b200.api.data import DataBatchMeta, SequenceSample
+from realhf_b200.api.dfg import MFCDef, OffloadHook, ParamReallocHook
+from realhf_b200.api.model import FinetuneSpec
+from realhf_b200.base import constants, logging, monitor, recover, timeutil
+from realhf_b200.system.buffer import AsyncIOSequenceBuffer
+from realhf_b200.system.stream import MasterStream, Payload
+
+logger = logging.getLogger("master_worker", "system")
+
+
+class MasterWorker:
+    def __init__(self, cfg: system_api.MasterWorker):
+        self.cfg = cfg
+        info = cfg.worker_info
+        self.exp, self.trial = info.experiment_name, info.trial_name
+        self.rpcs = cfg.model_rpcs
+        self.topos = cfg.model_topos
+        self.msid2mwid = cfg.msid2mwid
+        self.workers_of: Dict[ModelName, List[int]] = {}
+        for sid, w in self.msid2mwid.items():
+            topo = self.topos[sid.model_name]
+            self.workers_of.setdefault(sid.model_name, [None] * topo.world_size())
+            self.workers_of[sid.model_name][topo.get_rank(pipe=sid.pp_rank, data=sid.dp_rank, model=sid.tp_rank)] = w
+        self.src_rpc = next(r for r in self.rpcs if r.is_src)
+        self.sink_rpcs = [r for r in self.rpcs if r.is_dst]
+        self.data_owner: Dict[Tuple[Hashable, str], int] = {}
+        self._pending: Dict[str, asyncio.Future] = {}
+        self.step = self.epoch = self.epoch_step = 0
+        self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
+        self.stats_log: List[Dict] = []
+        self._consumed_ids_this_epoch: List[Hashable] = []
+
+    # ------------------------------------------------------------------ transport helpers
+    async def _request(self, p: Payload) -> Payload:
+        fut = asyncio.get_running_loop().create_future()
+        self._pending[p.request_id] = fut
+        self.stream.post(p)
+        return await fut
+
+    async def _pump(self):
+        """Routes replies to the futures waiting for them."""
+        while True:
+            r = self.stream.poll(0)
+            if r is None:
+                await asyncio.sleep(0.001)
+                continue
+            fut = self._pending.pop(r.request_id, None)
+            if fut is not None and not fut.done():
+                if r.error:
+                    fut.set_exception(RuntimeError(f"model worker {r.handler} failed in `{r.handle_name}`:\n{r.error}"))
+                else:
+                    fut.set_result(r)
+
+    async def _group_request(self, workers: List[int], handle: str, data=None, model_name=None, **kw) -> List[Payload]:
+        return await asyncio.gather(*[self._request(Payload(handler=w, handle_name=handle, data=data, model_name=model_name, **kw))
+                                      for w in workers])
+
+    # ------------------------------------------------------------------ init
+    async def _lazy_init(self):
+        cfg = self.cfg
+        n = cfg.n_model_workers
+        self.stream = MasterStream(self.exp, self.trial, n)
+        self.stream.wait_workers()
+        self._pump_task = asyncio.create_task(self._pump())
+        # dataset size from the data owners (dp heads of the source MFC)
+        src_workers = self._dp_heads(self.src_rpc.model_name)
+        specs = await self._group_request(src_workers, "spec")
+        self.dataset_size = sum(s.data["dataset_size"] for s in specs)
+        steps_per_epoch = max(1, self.dataset_size // self.src_rpc.n_seqs)
+        total_steps = steps_per_epoch * cfg.exp_ctrl.total_train_epochs
+        self.ft_spec = FinetuneSpec(cfg.exp_ctrl.total_train_epochs, total_steps, steps_per_epoch)
+        # backends: trainable replicas first so that weight-receiving replicas exist when the first realloc happens
+        names = sorted(self.topos, key=lambda nm: (nm.role, nm.replica_id))
+        for nm in names:
+            await self._group_request(self.workers_of[nm], "initialize", data=self.ft_spec, model_name=nm)
+        self.buffer = AsyncIOSequenceBuffer(self.rpcs)
+        ec = cfg.exp_ctrl
+        self.save_ctl = timeutil.EpochStepTimeFreqCtl(ec.save_freq_epochs, ec.save_freq_steps, ec.save_freq_secs)
+        self.eval_ctl = timeutil.EpochStepTimeFreqCtl(ec.eval_freq_epochs, ec.eval_freq_steps, ec.eval_freq_secs)
+        self.recover_info = recover.load_recover_info(self.exp, self.trial) if os.environ.get("REAL_RECOVER_RUN", "0") == "1" else None
+        if self.recover_info is not None:
+            self.step, self.epoch, self.epoch_step = (self.recover_info.recover_start.global_step,
+                                                      self.recover_info.recover_start.epoch, self.recover_info.recover_start.epoch_step)
+        logger.info(f"master ready: dataset {self.dataset_size} samples, {steps_per_epoch} steps/epoch, {total_steps} steps in total")
+
+    def _dp_heads(self, name: ModelName) -> List[int]:
+        topo = self.topos[name]
+        pp, dp, tp = topo.dims
+        return [self.workers_of[name][topo.get_rank(pipe=pp - 1, data=d, model=0)] for d in range(dp)]
+
+    # ------------------------------------------------------------------ data loading
+    async def _load_data(self):
+        src_workers = self._dp_heads(self.src_rpc.model_name)
+        ignore = list(self.recover_info.hash_vals_to_ignore) if (self.recover_info and self.epoch == self.recover_info.recover_start.epoch) else []
+        replies = await self._group_request(src_workers, "fetch", data=dict(ignore_ids=ignore))
+        samples = []
+        for w, r in zip(src_workers, replies):
+            meta: DataBatchMeta = r.data
+            if meta.meta_sample is None:
+                continue
+            for s in meta.meta_sample.unpack():
+                for k in s.keys:
+                    self.data_owner[(s.ids[0], k)] = w
+                samples.append(s)
+        await self.buffer.put_batch(samples)
+
+    # ------------------------------------------------------------------ one MFC
+    def _transfer_plan(self, rpc: MFCDef, part: Dict[int, List[Hashable]], meta: SequenceSample) -> List[dict]:
+        topo = self.topos[rpc.model_name]
+        pp, dp, tp = topo.dims
+        by_id = {i: s for i, s in zip(meta.ids, meta.unpack())}
+        plan = []
+        for d, ids in part.items():
+            dsts = sorted({self.workers_of[rpc.model_name][topo.get_rank(pipe=p, data=d, model=t)] for p in range(pp) for t in range(tp)})
+            for key in rpc.input_keys:
+                groups: Dict[int, List[Hashable]] = collections.defaultdict(list)
+                for i in ids:
+                    groups[self.data_owner[(i, key)]].append(i)
+                for src, gids in groups.items():
+                    need = [w for w in dsts if w != src]
+                    if not need:
+                        continue
+                    plan.append(dict(key=key, ids=gids, lens=[by_id[i].seqlens[key][0] for i in gids], dtype=meta.dtypes[key],
+                                     trailing=tuple(meta.trailing_shapes[key] or ()), src=src, dsts=need))
+        return plan
+
+    async def _run_rpc_once(self, rpc: MFCDef):
+        ids, meta = await self.buffer.get_batch_for_rpc(rpc)
+        topo = self.topos[rpc.model_name]
+        pp, dp, tp = topo.dims
+        # partition over dp ranks: token-balanced contiguous split (or equal counts with balanced_dp)
+        if rpc.balanced_dp:
+            per = len(ids) // dp
+            assert per * dp == len(ids), f"balanced_dp needs n_seqs % dp == 0 ({len(ids)} % {dp})"
+            parts = [(k * per, (k + 1) * per) for k in range(dp)]
+        else:
+            parts = meta.get_split_spec(dp, min_size=max(1, (rpc.n_mbs or 1) * (2 * pp if pp > 1 else 1))).partitions
+        part = {d: ids[a:b] for d, (a, b) in enumerate(parts)}
+        plan = self._transfer_plan(rpc, part, meta)
+        involved = set(self.workers_of[rpc.model_name])
+        for e in plan:
+            involved.add(e["src"])
+        pre_hooks, pre_data, post_hooks, post_data = ["data_transfer"], [plan], [], []
+        for h in rpc._pre_hooks:
+            if isinstance(h, ParamReallocHook):
+                src, dst = (h.source, rpc.model_name) if h.source is not None else (rpc.model_name, h.target)
+                pre_hooks.append("param_realloc")
+                pre_data.append(dict(src=src, dst=dst, eta=h.eta))
+                involved |= set(self.workers_of[src]) | set(self.workers_of[dst])
+        for h in rpc._post_hooks:
+            if isinstance(h, ParamReallocHook):
+                src, dst = (h.source, rpc.model_name) if h.source is not None else (rpc.model_name, h.target)
+                trainable_dst = any(r.model_name == dst and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in self.rpcs)
+                if trainable_dst and h.eta == 1.0:
+                    # the trainable replica never lost its weights: the reverse direction only drops the copy
+                    post_hooks.append("param_realloc")
+                    post_data.append(dict(src=src, dst=dst, eta=1.0, release_src=True, noop=True))
+                else:
+                    post_hooks.append("param_realloc")
+                    post_data.append(dict(src=src, dst=dst, eta=h.eta))
+                involved |= set(self.workers_of[src]) | set(self.workers_of[dst])
+            elif isinstance(h, OffloadHook):
+                post_hooks.append("offload")
+                post_data.append(dict(model=rpc.model_name))
+        # post every request of this MFC back-to-back: workers see MFCs in one global order
+        t0 = time.perf_counter()
+        futs = []
+        member = {}
+        for r in range(topo.world_size()):
+            member[self.workers_of[rpc.model_name][r]] = topo.get_coord(r)
+        for w in sorted(involved):
+            if w in member:
+                c = member[w]
+                p = Payload(handler=w, handle_name=rpc.interface_type.value, model_name=rpc.model_name,
+                            data=dict(rpc_name=rpc.name, ids=part[c.data]), pre_hooks=pre_hooks, pre_hook_data=pre_data,
+                            post_hooks=post_hooks, post_hook_data=post_data)
+            else:
+                p = Payload(handler=w, handle_name="empty", model_name=rpc.model_name, pre_hooks=pre_hooks, pre_hook_data=pre_data,
+                            post_hooks=[h for h in post_hooks if h == "param_realloc"],
+                            post_hook_data=[d for h, d in zip(post_hooks, post_data) if h == "param_realloc"])
+            futs.append(self._request(p))
+        replies = await asyncio.gather(*futs)
+        self.rpc_secs[rpc.name] += time.perf_counter() - t0
+        heads = set(self._dp_heads(rpc.model_name))
+        stats = []
+        for r in replies:
+            if r.handler not in heads or not isinstance(r.data, dict):
+                continue
+            if r.data.get("meta") is not None:
+                m: SequenceSample = r.data["meta"]
+                items = m.unpack()
+                for it in items:
+                    for k in it.keys:
+                        self.data_owner[(it.ids[0], k)] = r.handler
+                await self.buffer.amend_batch([it.ids[0] for it in items], items)
+            if r.data.get("stats") is not None:
+                stats.append(r.data["stats"])
+        if stats and rpc.log_return_value:
+            merged = {k: float(np.mean([s[k] for s in stats if k in s])) for k in stats[0] if isinstance(stats[0][k], (int, float))}
+            logger.info(f"[{rpc.name}] step {self.step}: " + ", ".join(f"{k}={v:.4g}" for k, v in merged.items()))
+            self.stats_log.append({"rpc": rpc.name, "step": self.step, **merged})
+        if rpc.is_src:
+            self._consumed_ids_this_epoch += ids
+        return ids
+
+    # ------------------------------------------------------------------ main loop
+    async def _run_step(self):
+        t0 = time.perf_counter()
+        if self.buffer.n_ready_for(self.src_rpc) < self.src_rpc.n_seqs:
+            await self._load_data()
+        results = await asyncio.gather(*[self._run_rpc_once(r) for r in self.rpcs])
+        done = self.buffer.pop_fully_consumed()
+        if done:
+            for k in [k for k in self.data_owner if k[0] in set(done)]:
+                del self.data_owner[k]
+            await self._group_request(list(range(self.cfg.n_model_workers)), "clear_data_cache", data=done)
+        self.step += 1
+        self.epoch_step += 1
+        if self.epoch_step >= self.ft_spec.steps_per_epoch:
+            self.epoch += 1
+            self.epoch_step = 0
+            self._consumed_ids_this_epoch = []
+        dt = time.perf_counter() - t0
+        logger.info(f"step {self.step} (epoch {self.epoch}, {self.epoch_step}/{self.ft_spec.steps_per_epoch}) e2e {dt:.3f}s; "
+                    + ", ".join(f"{k} {v:.2f}s" for k, v in self.rpc_secs.items()))
+        self.rpc_secs.clear()
+        return dt
+
+    async def _save(self):
+        for nm in sorted(self.topos, key=str):
+            if any(r.model_name == nm and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in self.rpcs):
+                d = os.path.join(constants.run_dirs(self.exp, self.trial)["save"], nm.role,
+                                 f"epoch{self.epoch}epochstep{self.epoch_step}globalstep{self.step}")
+                await self._group_request(self.workers_of[nm], "save", data=d, model_name=nm)
+                logger.info(f"saved {nm} to {d}")
+
+    async def _eval(self):
+        for nm in sorted(self.topos, key=str):
+            if any(r.model_name == nm and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in self.rpcs):
+                res = await self._group_request(self.workers_of[nm], "evaluate", model_name=nm)
+                logger.info(f"eval {nm}: {[r.data for r in res if r.data][:1]}")
+
+    async def _main(self):
+        await self._lazy_init()
+        ec = self.cfg.exp_ctrl
+        times = []
+        total = self.ft_spec.total_train_steps
+        try:
+            while self.step < total:
+                times.append(await self._run_step())
+                if self.save_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
+                    await self._save()
+                if self.eval_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
+                    await self._eval()
+                if ec.benchmark_steps is not None and self.step >= ec.benchmark_steps:
+                    logger.info(f"benchmark finished: avg #e2e# time {np.mean(times):.3f}s over {len(times)} steps")
+                    break
+        finally:
+            if os.environ.get("REAL_SAVE_RECOVER_STATES", "0") == "1":
+                self._dump_recover()
+            try:
+                await asyncio.wait_for(self._group_request(list(range(self.cfg.n_model_workers)), "exit"), timeout=30)
+            except Exception:
+                pass
+            self._pump_task.cancel()
+            self.stream.close()
+        return times
+
+    def _dump_recover(self):
+        info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),
+                                   last_step_info=recover.StepInfo(self.epoch, max(self.epoch_step - 1, 0), max(self.step - 1, 0)),
+                                   hash_vals_to_ignore=list(self._consumed_ids_this_epoch))
+        recover.dump_recover_info(info, self.exp, self.trial)
+
+    def run(self):
+        return asyncio.run(self._main())

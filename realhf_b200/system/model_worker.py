@@ -151,6 +151,10 @@ class ModelWorker:
         src_name, dst_name, eta = spec["src"], spec["dst"], spec.get("eta", 1.0)
         key = (src_name, dst_name)
         src_model, dst_model = self.models.get(src_name), self.models.get(dst_name)
+        if spec.get("noop"):  # reverse direction of a plain realloc: the destination kept its weights, drop the copy
+            if src_model is not None and spec.get("release_src"):
+                _real(src_model).release_params()
+            return
         mcfg = (src_model or dst_model).module_config
         if key not in self._realloc_cache:
             plan = realloc.derive_plan(mcfg, self.cfg.model_topos[src_name], self.worker_of[src_name],

@@ -1,0 +1,78 @@
+"""Whole runtime on CPU/gloo: launcher -> master worker + 2 model workers (separate OS processes) -> GPT-2 SFT with
+DP=2 on a synthetic dataset (BASELINE.json config #1), then PPO with parameter reallocation between two layouts."""
+import os
+import sys
+import uuid
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fixtures  # noqa: E402
+
+pytestmark = pytest.mark.distributed
+
+
+def _env(tmp_path):
+    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")
+    os.environ["REAL_FILEROOT"] = str(tmp_path / "fileroot")
+    os.environ["REAL_NAME_RESOLVE_ROOT"] = str(tmp_path / "nr")
+    import importlib
+
+    from realhf_b200.base import constants, name_resolve
+    importlib.reload(constants)
+    name_resolve.reconfigure("nfs", record_root=str(tmp_path / "nr"))
+
+
+def test_gpt2_sft_dp2_gloo(tmp_path):
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=64)
+    exp = build_experiment([
+        "sft", f"experiment_name=sft-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1",
+        "n_gpus_per_node=2", "allocation_mode=manual", "allocation.parallel.data_parallel_size=2", "model.type._class=gpt2",
+        f"model.path={ckpt}", f"dataset.train_path={data}", "dataset.train_bs_n_seqs=16", "dataset.max_seqlen=64",
+        "exp_ctrl.total_train_epochs=2", "exp_ctrl.save_freq_steps=4", "model.optimizer.lr=1e-3",
+        "model.optimizer.warmup_steps_proportion=0.0", "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"])
+    main_start(exp, timeout=600)
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "master_worker-0")).read()
+    losses = [float(l.split("loss=")[1].split(",")[0]) for l in log.splitlines() if "[trainDefault]" in l and "loss=" in l]
+    assert len(losses) == 8, log[-3000:]
+    assert losses[-1] < losses[0], losses
+    save_root = os.path.join(os.environ["REAL_FILEROOT"], "checkpoints")
+    found = [os.path.join(d, f) for d, _, fs in os.walk(save_root) for f in fs if f == "config.json"]
+    assert found, "no checkpoint was written"
+    import transformers
+    transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
+
+
+def test_ppo_with_realloc_gloo(tmp_path):
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    actor = str(tmp_path / "actor")
+    critic = str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(actor, "llama")
+    fixtures.make_checkpoint(critic, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    common = ["type._class=llama"]
+    args = ["ppo", f"experiment_name=ppo-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=2",
+            "allocation_mode=manual", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2"]
+    for role, path in (("actor", actor), ("ref", actor), ("critic", critic), ("rew", critic)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    # generation: dp2; actor training: tp2 (a different layout => parameter reallocation around actor_gen)
+    args += ["actor_gen.parallel.data_parallel_size=2", "actor_train.parallel.model_parallel_size=2",
+             "critic_train.parallel.data_parallel_size=2", "critic_inf.parallel.data_parallel_size=2",
+             "ref_inf.parallel.data_parallel_size=2", "rew_inf.parallel.data_parallel_size=2"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=900)
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "master_worker-0")).read()
+    assert log.count("[actor_train]") == 2 and log.count("[critic_train]") == 2, log[-3000:]
+    assert "benchmark finished" in log
