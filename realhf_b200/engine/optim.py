@@ -177,6 +177,12 @@ class FlatAdamW:
             for b in bufs:
                 b.copy_(flat[off: off + b.numel()].to(b.dtype))
                 off += b.numel()
+        tied = self.model.tied_embedding_params()
+        if tied and ctx.embedding_group is not None:  # the two copies of a tied embedding see different gradients
+            for p in tied:
+                g = p.grad if p.grad is not None else getattr(p, "main_grad", None)
+                if g is not None:
+                    dist.all_reduce(g, group=ctx.embedding_group)
         if ctx.dp_size == 1:
             return self.flat_grad[self.lo: self.lo + self.shard_n]
         shard = torch.empty(self.shard_n, dtype=self.grad_dtype, device=self.flat_grad.device)

@@ -129,6 +129,7 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     S = max_prompt + g.max_new_tokens
     was_training = model.training
     model.eval()
+    sp_saved, model.sequence_parallel = model.sequence_parallel, False  # token-sharded activations make no sense for decode
     # ---- prefill
     kv: List[Tuple[torch.Tensor, torch.Tensor]] = []
     out = model(input_ids=input_ids, cu_seqlens=cu, max_seqlen=max_prompt, kv_sink=kv)
@@ -194,6 +195,7 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         state.graph = None
         state.out = None
     model.train(was_training)
+    model.sequence_parallel = sp_saved
     return GenerationOutput(tokens, logprobs, mask_bits, first.long(), no_eos), state
 
 

@@ -98,7 +98,10 @@ def load_from_hf(model: ReaLModel, family_name: str, path: str, init_critic_from
         model.instantiate(init="empty")
     missing = []
     with torch.no_grad():
+        tied_copy = sharding.needs_tied_head_copy(cfg, model.layers)
         for name, slot in model.slots.items():
+            if name not in sd and tied_copy and name.endswith("head.weight") and "0.wte.weight" in sd:
+                sd[name] = sd["0.wte.weight"]
             if name not in sd:
                 missing.append(name)
                 continue
@@ -106,10 +109,6 @@ def load_from_hf(model: ReaLModel, family_name: str, path: str, init_critic_from
             assert tuple(full.shape) == tuple(slot.spec.shape), (name, full.shape, slot.spec.shape)
             sh = sharding.shard_tensor(slot.spec, cfg, full, model.ctx.tp_rank, model.ctx.tp_size)
             model.p[name].copy_(sh.to(model.dtype))
-        if cfg.tied_embedding and model.is_last_stage and not model.is_first_stage and "0.wte.weight" in sd:
-            spec = sharding.layer_param_specs(cfg, 0)[0]
-            model._tied_head = sharding.shard_tensor(spec, cfg, sd["0.wte.weight"], model.ctx.tp_rank, model.ctx.tp_size).to(
-                model.dtype).to(model.device)
     head_name = f"{cfg.n_layers + 1}.head.weight"
     if missing:
         if missing == [head_name] and (init_critic_from_actor or cfg.is_critic):

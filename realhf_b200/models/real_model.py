@@ -84,8 +84,9 @@ class ModelOutput:
             if self.is_critic:
                 self._logits = F.linear(self.hidden, self.head_weight).squeeze(-1)
             else:
-                lg = OF.linear(self.hidden, self.head_weight)
-                self._logits = TP.gather_last_dim(lg, self.ctx) if (self.ctx and self.ctx.tp_size > 1) else lg
+                tp = self.ctx is not None and self.ctx.tp_size > 1
+                lg = OF.linear(TP.copy_to_tp(self.hidden, self.ctx) if tp else self.hidden, self.head_weight)
+                self._logits = TP.gather_last_dim(lg, self.ctx) if tp else lg
         return self._logits
 
     @property
@@ -98,7 +99,7 @@ class ModelOutput:
         """fp32 log p(labels[i] | hidden[rows[i]]) (rows defaults to all tokens)."""
         h = self.hidden if rows is None else self.hidden.index_select(0, rows)
         if self.ctx is not None and self.ctx.tp_size > 1:
-            local = OF.linear(h, self.head_weight)
+            local = OF.linear(TP.copy_to_tp(h, self.ctx), self.head_weight)  # column-parallel head: d(hidden) is summed over TP
             return TP.vocab_parallel_logprobs(local, labels, self.ctx, temperature, mask_bits)
         return OF.lm_head_logprobs(h, self.head_weight, labels, mask_bits, temperature)
 
@@ -153,7 +154,8 @@ class ReaLModel(nn.Module):
                     elif slot.spec.init == "normal":
                         # draw the FULL tensor from a per-parameter stream, then shard it: every (pp, tp) layout
                         # of the same seed holds the same weights
-                        gen.manual_seed(((seed if seed is not None else 1) * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
+                        seed_name = "0.wte.weight" if (name.endswith("head.weight") and self.config.tied_embedding) else name
+                        gen.manual_seed(((seed if seed is not None else 1) * 1000003 + zlib.crc32(seed_name.encode())) % (2 ** 63))
                         full = torch.empty(slot.spec.shape, dtype=torch.float32).normal_(0.0, std, generator=gen)
                         sh = sharding.shard_tensor(slot.spec, self.config, full, self.ctx.tp_rank, self.ctx.tp_size)
                         self.p[name].copy_(sh.to(self.dtype))
@@ -361,8 +363,19 @@ class ReaLModel(nn.Module):
         if f"{L1}.head.weight" in self.p:
             return self.p[f"{L1}.head.weight"]
         if c.tied_embedding:
-            return self.p.get("0.wte.weight", getattr(self, "_tied_head", None))
+            return self.p.get("0.wte.weight")
         return None
+
+    def tied_embedding_params(self) -> List[torch.Tensor]:
+        """Parameters whose gradients must be summed over the embedding group (tied embeddings with pp > 1)."""
+        c = self.config
+        if not c.tied_embedding or self.ctx.pp_size == 1:
+            return []
+        if self.is_first_stage:
+            return [self.p["0.wte.weight"]]
+        if self.is_last_stage:
+            return [self.p[f"{c.n_layers + 1}.head.weight"]]
+        return []
 
     # ------------------------------------------------------------------ forward (packed)
     def forward(self, input_ids: Optional[torch.Tensor] = None, cu_seqlens: Optional[torch.Tensor] = None,

@@ -32,8 +32,10 @@ class ParamSpec:
     sp_grad_sync: bool = False    # replicated param whose grad is partial under sequence parallel (norms)
 
 
-def layer_param_specs(cfg: ReaLModelConfig, layer_idx: int) -> List[ParamSpec]:
-    """Ordered specs of one layer (unsharded)."""
+def layer_param_specs(cfg: ReaLModelConfig, layer_idx: int, tied_head_copy: bool = False) -> List[ParamSpec]:
+    """Ordered specs of one layer (unsharded).  `tied_head_copy`: the stage holds the head but not the embedding of a
+    tied-embedding model (pp > 1), so it keeps its own copy of the matrix; the two copies' gradients are all-reduced over
+    the embedding group before every optimizer step (reference: megatron.py:589-605)."""
     H, F, hd = cfg.hidden_dim, cfg.intermediate_dim, cfg.head_dim
     nq, nkv, L = cfg.n_q_heads, cfg.n_kv_heads, cfg.n_layers
     ln_bias = cfg.layer_norm_type is None
@@ -48,7 +50,7 @@ def layer_param_specs(cfg: ReaLModelConfig, layer_idx: int) -> List[ParamSpec]:
     if layer_idx == L + 1:
         if cfg.is_critic:
             out.append(P("head.weight", (1, H), None))
-        elif not cfg.tied_embedding:
+        elif not cfg.tied_embedding or tied_head_copy:
             out.append(P("head.weight", (cfg.vocab_size, H), 0))
         return out
 
@@ -86,9 +88,15 @@ def layer_param_specs(cfg: ReaLModelConfig, layer_idx: int) -> List[ParamSpec]:
     return out
 
 
+def needs_tied_head_copy(cfg: ReaLModelConfig, layers: Sequence[int]) -> bool:
+    layers = list(layers)
+    return bool(cfg.tied_embedding) and (cfg.n_layers + 1) in layers and 0 not in layers
+
+
 def model_param_specs(cfg: ReaLModelConfig, layers: Optional[Sequence[int]] = None) -> List[ParamSpec]:
-    layers = range(cfg.n_layers + 2) if layers is None else layers
-    return [s for i in layers for s in layer_param_specs(cfg, i)]
+    layers = list(range(cfg.n_layers + 2) if layers is None else layers)
+    tied = needs_tied_head_copy(cfg, layers)
+    return [s for i in layers for s in layer_param_specs(cfg, i, tied_head_copy=tied)]
 
 
 # ------------------------------------------------------------------------------------------- TP shard geometry

@@ -120,7 +120,12 @@ def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Se
                     spec = dslot.spec
                     li = int(name.split(".", 1)[0])
                     spp = layer_to_src_pp[li]
-                    sslot = src_layouts[spp][name]
+                    if name not in src_layouts[spp]:  # destination keeps a copy of the tied embedding as its head
+                        assert cfg.tied_embedding and name.endswith("head.weight"), name
+                        spp = layer_to_src_pp[0]
+                        sslot = src_layouts[spp]["0.wte.weight"]
+                    else:
+                        sslot = src_layouts[spp][name]
                     d_iv = sharding.shard_intervals(spec, cfg, dtp, d_tp)
                     # source TP ranks that hold any of it
                     for stp in range(s_tp):

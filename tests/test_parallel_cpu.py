@@ -1,0 +1,86 @@
+"""TP / SP / PP / DP(ZeRO-1) equivalence on CPU with gloo: a sharded model must reproduce the single-process loss,
+gradients' effect (updated weights) and greedy generation."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.distributed
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _batch(bs=8, seed=0, vocab=128):
+    from realhf_b200.api.data import SequenceSample
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(5, 14, (bs,), generator=g).tolist()
+    ids = torch.randint(2, vocab, (sum(lens),), generator=g)
+    pm = torch.zeros(sum(lens), dtype=torch.bool)
+    off = 0
+    for l in lens:
+        pm[off:off + 2] = True
+        off += l
+    return SequenceSample.from_default(seqlens=lens, ids=list(range(bs)), data=dict(packed_input_ids=ids, prompt_mask=pm))
+
+
+def _worker(rank, world, layout, fam, n_steps, n_mbs=1):
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, GenerationHyperparameters, Model
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.api.data import SequenceSample
+    pp, dp, tp, sp = layout
+    cfg = hf_io.family(fam).make_test_config()
+    cfg.n_layers = 4
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend="gloo", sequence_parallel=sp)
+    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
+                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, "cpu"),
+                                                                                               FinetuneSpec(1, 10, 10))
+    full = _batch(8)
+    mine = full.split(dp)[ctx.dp_rank] if dp > 1 else full
+    itf = basic.SFTInterface()
+    losses = [itf.train_step(model, mine, n_mbs=n_mbs)["loss"] for _ in range(n_steps)]
+    # greedy generation from the updated weights
+    g = GenerationHyperparameters(max_new_tokens=5, min_new_tokens=5, greedy=True)
+    plens = [4, 6, 5, 3][: max(2, 4)]
+    prompts = SequenceSample.from_default(seqlens=plens, ids=list(range(len(plens))),
+                                          data=dict(packed_input_ids=torch.arange(2, 2 + sum(plens)) % cfg.vocab_size))
+    outs = model.module.generate(prompts, tok, g, num_micro_batches=1)
+    gen_tokens = torch.cat([o.tokens for o in outs]).tolist() if outs is not None else None
+    return dict(losses=losses, gen=gen_tokens, coord=tuple(ctx.coord))
+
+
+def _reference(fam, n_steps, n_mbs=1):
+    """Single process with the same micro-batch partition as the sharded run (losses are means per micro-batch)."""
+    from realhf_b200.base.testing import run_distributed
+    return run_distributed(_worker, 1, layout=(1, 1, 1, False), fam=fam, n_steps=n_steps, n_mbs=n_mbs)[0]
+
+
+@pytest.mark.parametrize("layout", [(1, 1, 2, False), (1, 1, 2, True), (2, 1, 1, False), (1, 2, 1, False), (2, 1, 2, True), (2, 2, 1, False)])
+def test_layout_matches_single_process(layout):
+    from realhf_b200.base.testing import run_distributed
+    fam, n_steps = "llama", 3
+    pp, dp, tp, sp = layout
+    ref = _reference(fam, n_steps, n_mbs=dp * (2 * pp if pp > 1 else 1))
+    res = run_distributed(_worker, pp * dp * tp, layout=layout, fam=fam, n_steps=n_steps)
+    for r in res:
+        for a, b in zip(r["losses"], ref["losses"]):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (layout, r["losses"], ref["losses"])
+    gens = [r["gen"] for r in res if r["gen"] is not None]
+    assert gens and all(g == ref["gen"] for g in gens), (gens, ref["gen"])
+
+
+def test_gpt2_tied_embedding_pp2():
+    from realhf_b200.base.testing import run_distributed
+    ref = _reference("gpt2", 2, n_mbs=4)
+    res = run_distributed(_worker, 2, layout=(2, 1, 1, False), fam="gpt2", n_steps=2)
+    for r in res:
+        for a, b in zip(r["losses"], ref["losses"]):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (r["losses"], ref["losses"])
