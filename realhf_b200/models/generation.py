@@ -24,6 +24,13 @@ from realhf_b200.ops import launches
 from realhf_b200.parallel import tp as TP
 
 
+_SAMPLE_SEED = [0x5DEECE66D]
+
+
+def seed_sampling(seed: int):
+    _SAMPLE_SEED[0] = int(seed) % (1 << 62)
+
+
 @dataclasses.dataclass
 class GenerationOutput:
     tokens: torch.Tensor        # [B, n_gen] generated ids (pad after EOS)
@@ -52,7 +59,20 @@ def _filter_logits(logits: torch.Tensor, g: GenerationHyperparameters) -> torch.
 
 def genstep(logits: torch.Tensor, g: GenerationHyperparameters, step: int, eos_id: Optional[int], pad_id: int,
             unfinished: torch.Tensor, generator: Optional[torch.Generator] = None, want_mask: bool = True):
-    """One sampling step on full-vocab logits [B, V].  Returns (next_tokens, logprob, mask_bits | None, unfinished)."""
+    """One sampling step on full-vocab logits [B, V].  Returns (next_tokens, logprob, mask_bits | None, unfinished).
+
+    CUDA tensors take the fused sampling kernel (`csrc/sampling.cu`); `generator` selects the PyTorch reference path
+    (reproducible with torch RNG), which is also what CPU tensors use."""
+    if logits.is_cuda and generator is None and logits.shape[1] * 4 <= 200 * 1024:
+        from realhf_b200.ops import lib
+        need_mask = want_mask and not g.force_no_logits_mask and not g.greedy
+        seed = int(_SAMPLE_SEED[0])
+        _SAMPLE_SEED[0] = (seed * 6364136223846793005 + 1442695040888963407) % (1 << 62)
+        nxt, lp, mb = lib().sample(logits, unfinished, g.top_k, g.top_p, 1.0 / g.temperature, eos_id if eos_id is not None else -1,
+                                   eos_id is not None and step < g.min_new_tokens, g.greedy, pad_id, seed, step, need_mask)
+        if eos_id is not None:
+            unfinished = unfinished & (nxt != eos_id)
+        return nxt, lp, (mb if need_mask else None), unfinished
     x = logits.float()
     if eos_id is not None and step < g.min_new_tokens:
         x[:, eos_id] = torch.finfo(x.dtype).min

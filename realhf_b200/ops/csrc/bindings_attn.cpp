@@ -4,6 +4,8 @@
 #include <torch/library.h>
 #include <torch/types.h>
 
+#include <vector>
+
 using at::Tensor;
 
 extern "C" int rb_decode_attention(const void* qkv, void* k_cache, void* v_cache, const int* cache_lens, void* out,
@@ -51,6 +53,35 @@ Tensor decode_attention(const Tensor& qkv, Tensor k_cache, Tensor v_cache, const
   return out;
 }
 
+extern "C" int rb_sample(const void* logits, int64_t row_stride, int64_t* next_tok, float* logprob, uint8_t* mask_bits,
+                         int64_t mask_stride, const bool* unfinished, int B, int V, int top_k, float top_p, float inv_temp,
+                         int eos_id, int suppress_eos, int greedy, int pad_id, uint64_t seed, uint32_t step, int dt,
+                         cudaStream_t s);
+
+// logits [B, V] -> (next token int64 [B], logprob fp32 [B], mask bits uint8 [B, ceil(V/8)] or empty)
+std::vector<Tensor> sample(const Tensor& logits, const c10::optional<Tensor>& unfinished, int64_t top_k, double top_p, double inv_temp,
+                           int64_t eos_id, bool suppress_eos, bool greedy, int64_t pad_id, int64_t seed, int64_t step, bool want_mask) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  const int B = logits.size(0), V = logits.size(1);
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto tok = at::empty({B}, logits.options().dtype(at::kLong));
+  auto lp = at::empty({B}, logits.options().dtype(at::kFloat));
+  Tensor mask = want_mask ? at::empty({B, (V + 7) / 8}, logits.options().dtype(at::kByte)) : at::empty({0}, logits.options().dtype(at::kByte));
+  const bool* uf = nullptr;
+  if (unfinished.has_value()) {
+    TORCH_CHECK(unfinished->scalar_type() == at::kBool && unfinished->is_contiguous() && unfinished->numel() == B);
+    uf = unfinished->data_ptr<bool>();
+  }
+  const int dt = logits.scalar_type() == at::kFloat ? 0 : (logits.scalar_type() == at::kBFloat16 ? 1 : (logits.scalar_type() == at::kHalf ? 2 : -1));
+  int rc = rb_sample(logits.data_ptr(), logits.stride(0), tok.data_ptr<int64_t>(), lp.data_ptr<float>(),
+                     want_mask ? mask.data_ptr<uint8_t>() : nullptr, want_mask ? mask.stride(0) : 0, uf, B, V, (int)top_k, (float)top_p,
+                     (float)inv_temp, (int)eos_id, suppress_eos, greedy, (int)pad_id, (uint64_t)seed, (uint32_t)step, dt,
+                     at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "sample: unsupported configuration (", rc, ")");
+  return {tok, lp, mask};
+}
+
 void register_attn_ops(torch::Library& m) {
+  m.def("sample(Tensor logits, Tensor? unfinished, int top_k, float top_p, float inv_temp, int eos_id, bool suppress_eos, bool greedy, int pad_id, int seed, int step, bool want_mask) -> Tensor[]", &sample);
   m.def("decode_attention(Tensor qkv, Tensor(a!) k_cache, Tensor(b!) v_cache, Tensor cache_lens, int nq, int nkv, int hd, float scale, Tensor? cos, Tensor? sin, int rot_dim, bool interleaved) -> Tensor", &decode_attention);
 }

@@ -15,6 +15,7 @@
 // registers with 16-byte stores, with optional bias and accumulate-into-C.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -78,9 +79,14 @@ RB_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int bn, int& m0, 
   n0 = (within / gsize) * bn;
 }
 
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+// kMC > 1: thread-block cluster of kMC CTAs working on kMC adjacent n-tiles of the SAME m-tile (small-M / decode
+// shapes).  Every CTA loads 1/kMC of the shared A tile and TMA-multicasts it to the whole cluster, so A is fetched
+// from L2 once per cluster instead of once per CTA; a smem stage is recycled only after all kMC consumers released it
+// (tcgen05.commit multicast onto every CTA's empty barrier).
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                    const __grid_constant__ CUtensorMap tma_b, Params p) {
+  static_assert(kMC == 1 || !kAMN, "A multicast is implemented for K-major A");
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -95,15 +101,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = RB_CEIL_DIV(p.M, BM), tiles_n = RB_CEIL_DIV(p.N, BN);
-  const int num_tiles = tiles_m * tiles_n;
+  // with multicast every CTA of a cluster runs the same number of iterations (padded tiles load zeros, store nothing)
+  const int num_tiles = kMC == 1 ? tiles_m * tiles_n : RB_CEIL_DIV(tiles_m * tiles_n, kMC) * kMC;
   const int num_kb = RB_CEIL_DIV(p.K, BK);
+  const uint32_t cta_rank = kMC == 1 ? 0u : (blockIdx.x % kMC);
+  constexpr uint16_t kMcMask = (uint16_t)((1u << kMC) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
     for (int i = 0; i < C::kStages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), kMC);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&tmem_full[i]), 1);
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kMC > 1) ptx::cluster_sync();  // peers' barriers must be initialised before any remote arrive / multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -138,6 +148,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           if constexpr (kAMN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * (BK * 128), &tma_a, fb, m0 + 64 * j, k0);
+          } else if constexpr (kMC > 1) {
+            constexpr int kRows = BM / kMC;  // my slice of the A tile, delivered to every CTA of the cluster
+            ptx::tma_load_2d_mcast(sa + cta_rank * (kRows * 128), &tma_a, fb, k0, m0 + (int)cta_rank * kRows, kMcMask);
           } else {
             ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);
           }
@@ -176,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
                                         : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
             ptx::tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // smem slot reusable once these MMAs retire
+          if constexpr (kMC > 1) ptx::tc_commit_mcast(ptx::smem_u32(&empty_bar[stage]), kMcMask);
+          else ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // smem slot reusable once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         ptx::tc_commit(ptx::smem_u32(&tmem_full[as]));  // accumulator complete -> epilogue
@@ -230,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kMC > 1) ptx::cluster_sync();  // no CTA may exit while peers still multicast into / arrive on its smem
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
@@ -277,17 +292,35 @@ bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int num_sms, cudaStream_t s) {
-  auto kern = gemm_tcgen05_kernel<BN, kAMN, kBMN, OutT, kFmt>;
+  auto kern = gemm_tcgen05_kernel<BN, kAMN, kBMN, OutT, kFmt, kMC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes) != cudaSuccess) return -2;
     configured = true;
   }
   const int tiles = RB_CEIL_DIV(p.M, BM) * RB_CEIL_DIV(p.N, BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, p);
+  if constexpr (kMC == 1) {
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, p);
+  } else {
+    const int padded = RB_CEIL_DIV(tiles, kMC) * kMC;
+    const int cap = (num_sms / kMC) * kMC;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(padded < cap ? padded : cap);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<BN>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kMC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return -3;
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -305,7 +338,12 @@ int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMa
 }
 
 template <typename OutT, int kFmt>
-int dispatch_bn(int bn, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int sms, cudaStream_t s) {
+int dispatch_bn(int bn, bool a_mn, bool b_mn, int mc, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int sms, cudaStream_t s) {
+  if (mc == 4) {  // small-M K-major shapes only (checked by the caller)
+    if (bn == 32) return launch<32, false, false, OutT, kFmt, 4>(ta, tb, p, sms, s);
+    if (bn == 64) return launch<64, false, false, OutT, kFmt, 4>(ta, tb, p, sms, s);
+    return -6;
+  }
   switch (bn) {
     case 256: return dispatch_major<256, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
     case 128: return dispatch_major<128, OutT, kFmt>(a_mn, b_mn, ta, tb, p, sms, s);
@@ -324,10 +362,14 @@ extern "C" {
 // bn = 0 picks the tile width from the problem size.
 int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
                     int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, cudaStream_t s) {
+  static const int mc_mode = [] { const char* e = getenv("REAL_GEMM_MULTICAST"); return e ? atoi(e) : 1; }();
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (in_dt != 1 && in_dt != 2) return -10;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
   if (num_sms <= 0) num_sms = rb::kNumSMs;
+  if (bn == 0 && M <= BM && !a_mn && !b_mn && mc_mode != 0 && N >= 256) {
+    bn = 32;  // decode shapes: many small tiles balance the 148 SMs; A traffic is shared by TMA multicast
+  }
   if (bn == 0) {
     const int tm = RB_CEIL_DIV(M, BM);
     const int cands[4] = {256, 128, 64, 32};
@@ -339,15 +381,18 @@ int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int
     while (bn > N && bn > (b_mn ? 64 : 32)) bn >>= 1;
   }
   if (b_mn && bn < 64) return -12;
+  // decode-shaped problems (one m-tile, K-major operands): cluster of 4 CTAs shares the A tile by TMA multicast
+  int mc = 1;
+  if (M <= BM && !a_mn && !b_mn && bn <= 64 && RB_CEIL_DIV(N, bn) >= 8 && mc_mode != 0) mc = 4;
   CUtensorMap ta, tb;
   const int bf = in_dt == 1;
   bool ok = a_mn ? make_tmap(&ta, A, bf, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK)
-                 : make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM);
+                 : make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)(BM / mc));
   ok = ok && (b_mn ? make_tmap(&tb, B, bf, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK)
                    : make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn));
   if (!ok) return -13;
   Params p{C, bias, ldc, M, N, K, accumulate};
-#define RB_GO(OutT, FMT) return dispatch_bn<OutT, FMT>(bn, a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s)
+#define RB_GO(OutT, FMT) return dispatch_bn<OutT, FMT>(bn, a_mn != 0, b_mn != 0, mc, ta, tb, p, num_sms, s)
   if (in_dt == 1) {
     if (out_dt == 1) RB_GO(__nv_bfloat16, 1);
     if (out_dt == 0) RB_GO(float, 1);

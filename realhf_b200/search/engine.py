@@ -1,0 +1,161 @@
+"""Allocation search driver: enumerate (device mesh, dp/tp/pp) candidates per MFC, cost them with the B200 model,
+let the native MCMC + simulator (`_C/host_ext`: `multi_mcmc_search`) pick one per MFC.
+
+Parity: `realhf/search_engine/{search,enumerate,estimate,param_realloc}.py` + `csrc/search`.  The reference's Python
+driver is broken against its own DFG API; this one is exercised by `tests/test_search.py`.
+Costs come from an analytic roofline model fed by the measured peaks (`MEASURED_PEAKS.json`) or, when available, from
+the layer profiler's table (`search/layers.py`).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+from realhf_b200.api.config import ModelInterfaceType
+from realhf_b200.api.dfg import MFCDef, build_graph
+from realhf_b200.api.quickstart import DeviceMesh, ModelTrainEvalConfig, ParallelismConfig, RPCAllocation, find_parallel_strategies
+from realhf_b200.ops import host
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+@dataclasses.dataclass
+class HardwareModel:
+    bf16_flops: float = 1.43e15      # sustained dense bf16 (MEASURED_PEAKS.json: bf16_tflops_sustained)
+    hbm_bw: float = 6.58e12          # bytes/s
+    link_bw: float = 7.7e11          # NVLink 5 peer copy, per direction per GPU
+    mem_cap: float = 180e9
+    gemm_eff: float = 0.75           # achieved fraction of peak for training-sized GEMMs
+    launch_us: float = 4.0
+
+    @classmethod
+    def from_measured(cls) -> "HardwareModel":
+        hw = cls()
+        p = os.path.join(_ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(p):
+            try:
+                d = json.load(open(p))
+                hw.bf16_flops = d.get("bf16_tflops_sustained", hw.bf16_flops / 1e12) * 1e12
+                hw.hbm_bw = d.get("hbm_gbs", hw.hbm_bw / 1e9) * 1e9
+            except Exception:
+                pass
+        return hw
+
+
+def model_shape(mcfg: ModelTrainEvalConfig) -> Dict[str, float]:
+    """Approximate LLaMA-family shapes by nominal size in billions (path-less configs), or read config.json."""
+    if mcfg.path and os.path.exists(os.path.join(mcfg.path, "config.json")):
+        c = json.load(open(os.path.join(mcfg.path, "config.json")))
+        h = c.get("hidden_size", c.get("n_embd"))
+        L = c.get("num_hidden_layers", c.get("n_layer"))
+        f = c.get("intermediate_size", 4 * h)
+        v = c.get("vocab_size", 32000)
+        n = L * (4 * h * h + 3 * h * f) + 2 * v * h
+        return dict(h=h, L=L, f=f, v=v, n=n)
+    table = {7: (4096, 32, 11008), 13: (5120, 40, 13824), 34: (8192, 48, 22016), 70: (8192, 80, 28672)}
+    size = mcfg.type.size or 7
+    h, L, f = table.get(size, (4096, max(1, int(32 * size / 7)), 11008))
+    v = 32000
+    return dict(h=h, L=L, f=f, v=v, n=L * (4 * h * h + 3 * h * f) + 2 * v * h)
+
+
+def estimate(rpc: MFCDef, shape: Dict[str, float], par: ParallelismConfig, hw: HardwareModel, seq_len: int, gen_len: int,
+             n_minibatches: int, trainable_role: bool) -> Tuple[float, float, float]:
+    """(time_us, static bytes / GPU, active bytes / GPU) of one MFC under one layout."""
+    dp, tp, pp = par.data_parallel_size, par.model_parallel_size, par.pipeline_parallel_size
+    n, h, L, v = shape["n"], shape["h"], shape["L"], shape["v"]
+    T = rpc.n_seqs * (seq_len + gen_len)
+    per_gpu_tokens = T / dp
+    wbytes = 2 * n / (tp * pp)
+    flops_fwd = 2 * n * per_gpu_tokens / (tp * pp)
+    tp_comm = 0.0
+    if tp > 1:  # 2 collectives per layer fwd (4 with bwd), [tokens, h] bf16 each
+        vol = 2 * per_gpu_tokens * h * (tp - 1) / tp
+        tp_comm = (L / pp) * 2 * vol / hw.link_bw
+    bubble = (pp - 1) / max(1, 2 * pp) if pp > 1 else 0.0
+    if rpc.interface_type == ModelInterfaceType.TRAIN_STEP:
+        t = 4 * flops_fwd / (hw.bf16_flops * hw.gemm_eff) + 3 * tp_comm
+        t *= 1 + bubble
+        opt = n_minibatches * (14 * n / (tp * pp * dp)) / hw.hbm_bw  # fused AdamW over the shard
+        zero_comm = n_minibatches * 2 * (2 * n / (tp * pp)) * (dp - 1) / dp / hw.link_bw if dp > 1 else 0.0
+        t += opt + zero_comm
+        static = wbytes + 12 * n / (tp * pp * dp)
+        active = wbytes + 34 * per_gpu_tokens / n_minibatches * h * (L / pp) / tp / 8
+    elif rpc.interface_type == ModelInterfaceType.GENERATE:
+        bs = rpc.n_seqs / dp
+        prefill = 2 * n * bs * seq_len / (tp * pp) / (hw.bf16_flops * hw.gemm_eff)
+        kv_per_tok = 2 * 2 * h * L / (tp * pp)
+        # one token round: every stage runs its pp micro-batches, re-reading its weight shard for each of them
+        m = pp
+        step = (wbytes * m + bs * (seq_len + gen_len / 2) * kv_per_tok) / hw.hbm_bw + m * (L / pp) * 9 * hw.launch_us * 1e-6 / 8
+        if tp > 1:
+            step += m * (L / pp) * 2 * (8e-6)  # small all-reduce latency per layer
+        if pp > 1:
+            step += pp * 10e-6                 # p2p hops of the token ring
+        t = prefill + gen_len * step
+        static = 0.0 if trainable_role else wbytes
+        active = bs * (seq_len + gen_len) * kv_per_tok + (wbytes if trainable_role else 0.0)
+    else:
+        t = flops_fwd / (hw.bf16_flops * hw.gemm_eff) + tp_comm
+        t *= 1 + bubble
+        static = 0.0 if trainable_role else wbytes
+        active = 6 * per_gpu_tokens * h / tp + (wbytes if trainable_role else 0.0)
+    return t * 1e6, static, active
+
+
+def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int, gen_len: int,
+                  n_ppo_minibatches: int, hw: HardwareModel, max_cands: int = 1000):
+    G = build_graph(rpcs)
+    roles = sorted({r.role for r in rpcs})
+    role_idx = {r: i for i, r in enumerate(roles)}
+    shapes = {r: model_shape(models[r]) for r in roles}
+    trainable = {r.role for r in rpcs if r.interface_type == ModelInterfaceType.TRAIN_STEP}
+    sub = [mesh] + [m for m in mesh.sub_device_meshes() if m != mesh]
+    mesh_ranks = [m.global_ranks() for m in sub]
+    kind = {ModelInterfaceType.GENERATE: 0, ModelInterfaceType.INFERENCE: 1, ModelInterfaceType.TRAIN_STEP: 2}
+    prpcs, table = [], []
+    for r in rpcs:
+        cands = []
+        for mi, m in enumerate(sub):
+            for par in find_parallel_strategies(m):
+                if r.n_seqs < par.data_parallel_size * par.pipeline_parallel_size:
+                    continue
+                if shapes[r.role]["v"] % par.model_parallel_size or shapes[r.role]["L"] < par.pipeline_parallel_size:
+                    continue
+                g = gen_len if r.interface_type == ModelInterfaceType.GENERATE else gen_len
+                t, st, ac = estimate(r, shapes[r.role], par, hw, seq_len, g, n_ppo_minibatches if r.interface_type == ModelInterfaceType.TRAIN_STEP else 1,
+                                     r.role in trainable)
+                cands.append((mi, par.data_parallel_size, par.model_parallel_size, par.pipeline_parallel_size, t, st, ac, par))
+        cands.sort(key=lambda c: c[4])
+        cands = cands[:max_cands]
+        table.append(cands)
+        prpcs.append(dict(name=r.name, role=role_idx[r.role], kind=kind[r.interface_type], cands=[c[:7] for c in cands]))
+    name_idx = {r.name: i for i, r in enumerate(rpcs)}
+    edges = [(name_idx[u], name_idx[v]) for u, v in G.edges()]
+    prob = dict(n_gpus=mesh.n_nodes * mesh.n_gpus_per_node, mem_cap=hw.mem_cap, link_bw=hw.link_bw, n_iters=2,
+                role_bytes=[2 * shapes[r]["n"] for r in roles], meshes=mesh_ranks, edges=edges, rpcs=prpcs)
+    return prob, table, sub
+
+
+def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int = 128,
+                           num_gen_tokens: int = 256, n_ppo_minibatches: int = 4, time_limit_s: float = 5.0,
+                           hw: Optional[HardwareModel] = None, return_details: bool = False):
+    h = host()
+    if h is None:
+        raise RuntimeError("allocation search needs the native host extension: run `python -m realhf_b200.ops.build`")
+    hw = hw or HardwareModel.from_measured()
+    prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw)
+    results = h.multi_mcmc_search(prob, [0.5, 2.0, 8.0, 32.0], time_limit_s, 1, 10)
+    best = results[0]
+    allocs = []
+    for r, ci, cands in zip(rpcs, best["choice"], table):
+        c = cands[ci]
+        par: ParallelismConfig = dataclasses.replace(c[7])
+        par.use_sequence_parallel = (r.interface_type == ModelInterfaceType.TRAIN_STEP and par.model_parallel_size > 1)
+        allocs.append(RPCAllocation(r, sub[c[0]], par))
+    if return_details:
+        return allocs, dict(best=best, results=results, problem=prob)
+    return allocs
