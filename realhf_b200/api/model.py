@@ -53,6 +53,7 @@ class ReaLMoEConfig:
     z_loss_coeff: float = 0.0
     input_jitter_eps: float = 0.0
     use_grouped_gemm: bool = True
+    expert_parallel: bool = False  # partition experts over the TP group (all-to-all dispatch); reference: not available
 
 
 @dataclasses.dataclass

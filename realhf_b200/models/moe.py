@@ -99,31 +99,48 @@ def grouped_mlp(x_sorted: torch.Tensor, counts: List[int], w_gate_up: torch.Tens
 
 
 def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
-    """MoE MLP of block i on normalised hidden states h [T,H] (already gathered if sequence-parallel)."""
+    """MoE MLP of block i on normalised hidden states h ([T, H], or [T/t, H] under sequence parallelism)."""
     c, ctx = model.config, model.ctx
     mcfg = c.moe
-    if model.sequence_parallel:
+    E, k = mcfg.num_experts, mcfg.top_k
+    w_gu, w_dn = model.p[f"{i}.mlp.experts.gate_up.weight"], model.p[f"{i}.mlp.experts.down.weight"]
+    ep = mcfg.expert_parallel and ctx.tp_size > 1
+    sp = model.sequence_parallel
+    if ep and sp:
+        pass  # tokens stay sharded: they travel to the experts' owners by all-to-all
+    elif sp:
         h = TP.gather_from_sp(h, ctx)
     else:
         h = TP.copy_to_tp(h, ctx)
     T, H = h.shape
     probs, idx = route(h, model.p[f"{i}.mlp.router.weight"], mcfg, model.training)
-    E, k = mcfg.num_experts, mcfg.top_k
     probs = _apply_capacity(probs, idx, E, mcfg)
-    w_gu, w_dn = model.p[f"{i}.mlp.experts.gate_up.weight"], model.p[f"{i}.mlp.experts.down.weight"]
     flat_e = idx.reshape(-1)
     order = torch.argsort(flat_e, stable=True)
     tok = torch.arange(T, device=h.device).repeat_interleave(k)[order]
-    x_sorted = h.index_select(0, tok)
-    ep_group = getattr(ctx, "ep_group", None)
-    if ep_group is None:
-        counts = torch.bincount(flat_e, minlength=E).tolist()
+    w_sorted = probs.reshape(-1)[order]
+    if ep and sp:
+        from realhf_b200.parallel import ep as EP
+        x_sorted = h.index_select(0, tok)
+        y_sorted = EP.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ctx.tp_group)
+        return torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
+    if ep:
+        # replicated tokens: keep only the assignments of my experts, all-reduce the partial outputs
+        e_local = E // ctx.tp_size
+        lo = ctx.tp_rank * e_local
+        e_sorted = flat_e[order]
+        mine = (e_sorted >= lo) & (e_sorted < lo + e_local)
+        sel = torch.nonzero(mine).squeeze(-1)
+        x_sorted = h.index_select(0, tok[sel])
+        counts = torch.bincount(e_sorted[sel] - lo, minlength=e_local).tolist()
         y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)
-    else:
-        from realhf_b200.parallel import ep
-        y_sorted = ep.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ep_group)
-    w = probs.reshape(-1)[order].to(y_sorted.dtype).unsqueeze(-1)
-    out = torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w)
+        out = torch.zeros(T, H, dtype=h.dtype, device=h.device).index_add_(
+            0, tok[sel], (y_sorted * w_sorted[sel].to(y_sorted.dtype).unsqueeze(-1)).to(h.dtype))
+        return TP.reduce_from_tp(out, ctx)
+    x_sorted = h.index_select(0, tok)
+    counts = torch.bincount(flat_e, minlength=E).tolist()
+    y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)
+    out = torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
     if ctx.tp_size > 1:  # experts are F-sharded over TP: partial sums
-        out = TP.reduce_scatter_to_sp(out, ctx) if model.sequence_parallel else TP.reduce_from_tp(out, ctx)
+        out = TP.reduce_scatter_to_sp(out, ctx) if sp else TP.reduce_from_tp(out, ctx)
     return out

@@ -74,8 +74,12 @@ def layer_param_specs(cfg: ReaLModelConfig, layer_idx: int, tied_head_copy: bool
     elif cfg.mlp_type == "moe":
         E = cfg.moe.num_experts
         out.append(P("mlp.router.weight", (E, H), None))
-        out.append(P("mlp.experts.gate_up.weight", (E, 2 * F, H), 1, expert_dim=True))
-        out.append(P("mlp.experts.down.weight", (E, H, F), 2, expert_dim=True))
+        if cfg.moe.expert_parallel:  # whole experts per rank: split along the expert dim
+            out.append(P("mlp.experts.gate_up.weight", (E, 2 * F, H), 0))
+            out.append(P("mlp.experts.down.weight", (E, H, F), 0))
+        else:                        # every rank holds all experts, FFN dim sliced (the reference's layout)
+            out.append(P("mlp.experts.gate_up.weight", (E, 2 * F, H), 1, expert_dim=True))
+            out.append(P("mlp.experts.down.weight", (E, H, F), 2, expert_dim=True))
     else:
         out.append(P("mlp.fc.weight", (F, H), 0))
         if cfg.use_mlp_bias:

@@ -145,14 +145,17 @@ __global__ void __launch_bounds__(kThreads) allreduce_2shot_kernel(Peers P, cons
   block_barrier(P, rank, world);
 }
 
-// Sum `world` partial slabs that peers have written into this rank's data region: slab s at byte offset s*slab_bytes.
-// `counter` (in the pad, after the flags) is incremented by producers once per written tile; wait until it reaches
-// `expect` (monotonic across calls: expect = calls * tiles_per_call).
+// Sum `world` partial slabs that peers have written into this rank's data region (slab s at offset s*slab_vec).
+// Producers bump `counter` once per delivered row-tile; the kernel waits until it reaches calls * per_call, where
+// `calls` is a per-block counter kept on the device (so the kernel is replayable inside a CUDA graph).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) reduce_slabs_kernel(const uint8_t* __restrict__ base, int4* __restrict__ out, int64_t nvec,
                                                                 int64_t slab_vec, int world, const uint32_t* __restrict__ counter,
-                                                                uint32_t expect) {
+                                                                uint32_t* __restrict__ calls, uint32_t per_call) {
   if (threadIdx.x == 0) {
+    const uint32_t c = calls[blockIdx.x] + 1;
+    calls[blockIdx.x] = c;
+    const uint32_t expect = c * per_call;
     while ((int32_t)(ld_acquire_sys(counter) - expect) < 0) {}
   }
   __syncthreads();
@@ -178,8 +181,11 @@ Peers make_peers(const int64_t* data_ptrs, const int64_t* pad_ptrs, int world) {
 
 extern "C" {
 
-int rb_symm_pad_words() { return kMaxBlocks + kMaxBlocks * kMaxRanks + 64; }
+// pad words: [0,64) barrier epochs | [64,576) barrier flags | 576,577 RS arrival counters (parity 0/1) |
+//            [640,800) reduce call counters parity 0 | [800,960) parity 1
+int rb_symm_pad_words() { return 1024; }
 int rb_symm_counter_word() { return kMaxBlocks + kMaxBlocks * kMaxRanks; }
+int rb_symm_calls_word(int parity) { return 640 + 160 * parity; }
 
 int rb_symm_barrier(const int64_t* data_ptrs, const int64_t* pad_ptrs, int rank, int world, cudaStream_t s) {
   if (world > kMaxRanks) return -1;
@@ -204,13 +210,13 @@ int rb_symm_allreduce(const int64_t* data_ptrs, const int64_t* pad_ptrs, const v
   return 0;
 }
 
-int rb_reduce_slabs(const void* base, void* out, int64_t nbytes, int64_t slab_bytes, int world, const uint32_t* counter, uint32_t expect,
-                    int dt, cudaStream_t s) {
+int rb_reduce_slabs(const void* base, void* out, int64_t nbytes, int64_t slab_bytes, int world, const uint32_t* counter, uint32_t* calls,
+                    uint32_t per_call, int dt, cudaStream_t s) {
   if ((nbytes & 15) || (slab_bytes & 15)) return -1;
   const int64_t nvec = nbytes / 16;
   int blocks = (int)((nvec + kThreads - 1) / kThreads);
   blocks = blocks < 1 ? 1 : (blocks > rb::kNumSMs ? rb::kNumSMs : blocks);
-#define RB_GO(T) reduce_slabs_kernel<T><<<blocks, kThreads, 0, s>>>((const uint8_t*)base, (int4*)out, nvec, slab_bytes / 16, world, counter, expect)
+#define RB_GO(T) reduce_slabs_kernel<T><<<blocks, kThreads, 0, s>>>((const uint8_t*)base, (int4*)out, nvec, slab_bytes / 16, world, counter, calls, per_call)
   if (dt == 0) RB_GO(float); else if (dt == 1) RB_GO(__nv_bfloat16); else if (dt == 2) RB_GO(__half); else return -2;
 #undef RB_GO
   return 0;

@@ -14,7 +14,11 @@ int rb_symm_pad_words();
 int rb_symm_counter_word();
 int rb_symm_barrier(const int64_t*, const int64_t*, int, int, cudaStream_t);
 int rb_symm_allreduce(const int64_t*, const int64_t*, const void*, void*, int64_t, int, int, int, int, cudaStream_t);
-int rb_reduce_slabs(const void*, void*, int64_t, int64_t, int, const uint32_t*, uint32_t, int, cudaStream_t);
+int rb_reduce_slabs(const void*, void*, int64_t, int64_t, int, const uint32_t*, uint32_t*, uint32_t, int, cudaStream_t);
+int rb_symm_calls_word(int);
+int rb_gemm_fused_tp(int mode, const void* A, const int64_t* peer_a, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
+                     int64_t ldc, int b_mn, const int64_t* peer_base, const int64_t* peer_counter, int rows_per_rank, int my_rank,
+                     int world, int num_sms, cudaStream_t s);
 }
 
 static int dtc(at::ScalarType t) {
@@ -45,13 +49,48 @@ void symm_allreduce(const Tensor& in, Tensor out, std::vector<int64_t> data_ptrs
   TORCH_CHECK(rc == 0, "symm_allreduce failed: ", rc);
 }
 
-// out[nbytes] = sum_s slabs[s] where slab s starts at base_ptr + s*slab_bytes; waits for *counter >= expect first.
-void reduce_slabs(int64_t base_ptr, Tensor out, int64_t slab_bytes, int64_t world, int64_t counter_ptr, int64_t expect) {
-  c10::cuda::CUDAGuard g(out.device());
-  int rc = rb_reduce_slabs(reinterpret_cast<const void*>(base_ptr), out.data_ptr(), out.nbytes(), slab_bytes, (int)world,
-                           reinterpret_cast<const uint32_t*>(counter_ptr), (uint32_t)expect, dtc(out.scalar_type()),
-                           at::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(rc == 0, "reduce_slabs failed: ", rc);
+int64_t symm_calls_word(int64_t parity) { return rb_symm_calls_word((int)parity); }
+
+// GEMM -> reduce-scatter in one op: y[rows_per_rank, N] = sum_ranks (x_rank @ w_rank^T)[my rows].
+//   x [T, Kl], w: b_mn ? [Kl, N] : [N, Kl].  The GEMM epilogue stores every output row into the owning rank's inbox
+//   (peer memory) while later tiles are still on the tensor cores; the tail kernel sums the `world` slabs of my rows.
+Tensor gemm_rs(const Tensor& x, const Tensor& w, bool b_mn, std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_counter,
+               int64_t my_calls_ptr, int64_t rank, int64_t num_sms) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1);
+  const int world = (int)peer_inbox.size();
+  const int64_t T = x.size(0), K = x.size(1), N = b_mn ? w.size(1) : w.size(0);
+  TORCH_CHECK(T % world == 0, "gemm_rs: token count must divide by the TP size");
+  const int rows = (int)(T / world);
+  c10::cuda::CUDAGuard g(x.device());
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  int bn = rb_gemm_fused_tp(1, x.data_ptr(), nullptr, w.data_ptr(), nullptr, (int)T, (int)N, (int)K, x.stride(0), w.stride(0), N, b_mn,
+                            peer_inbox.data(), peer_counter.data(), rows, (int)rank, world, (int)num_sms, stream);
+  TORCH_CHECK(bn == 0, "gemm_rs: fused GEMM launch failed (", bn, ")");
+  auto y = at::empty({rows, N}, x.options());
+  // arrivals per call at this rank: every source delivers each of my rows once per n-tile
+  const int tm = (int)((T + 127) / 128);
+  int bnv = (((int64_t)tm * ((N + 255) / 256) >= (num_sms > 0 ? num_sms : 148)) || N % 256 == 0) ? 256 : 128;
+  if (N < 256) bnv = 128;
+  const uint32_t per_call = (uint32_t)((int64_t)rows * ((N + bnv - 1) / bnv) * world);
+  int rc = rb_reduce_slabs(reinterpret_cast<const void*>(peer_inbox[rank]), y.data_ptr(), y.nbytes(), (int64_t)rows * N * 2, world,
+                           reinterpret_cast<const uint32_t*>(peer_counter[rank]), reinterpret_cast<uint32_t*>(my_calls_ptr), per_call, 1,
+                           stream);
+  TORCH_CHECK(rc == 0, "gemm_rs: reduce launch failed");
+  return y;
+}
+
+// all-gather -> GEMM: y[T, N] = concat_r(x_r) @ w^T where x_r [rows, K] lives at peer_a[r] (symmetric staging buffers).
+Tensor ag_gemm(std::vector<int64_t> peer_a, int64_t rows, int64_t K, const Tensor& w, bool b_mn, int64_t rank, int64_t num_sms) {
+  TORCH_CHECK(w.is_cuda() && w.dim() == 2 && w.scalar_type() == at::kBFloat16 && w.stride(1) == 1);
+  const int world = (int)peer_a.size();
+  const int64_t N = b_mn ? w.size(1) : w.size(0);
+  c10::cuda::CUDAGuard g(w.device());
+  auto y = at::empty({rows * world, N}, w.options());
+  int rc = rb_gemm_fused_tp(2, nullptr, peer_a.data(), w.data_ptr(), y.data_ptr(), (int)(rows * world), (int)N, (int)K, K, w.stride(0), N, b_mn,
+                            nullptr, nullptr, (int)rows, (int)rank, world, (int)num_sms, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "ag_gemm: fused GEMM launch failed (", rc, ")");
+  return y;
 }
 
 // ---- symmetric allocations: raw cudaMalloc so that the IPC handle maps exactly this buffer, opened by each peer in ITS
@@ -90,5 +129,7 @@ void register_comm_ops(torch::Library& m) {
   m.def("symm_counter_word() -> int", &symm_counter_word);
   m.def("symm_barrier(Tensor anchor, int[] data_ptrs, int[] pad_ptrs, int rank) -> ()", &symm_barrier);
   m.def("symm_allreduce(Tensor inp, Tensor(a!) out, int[] data_ptrs, int[] pad_ptrs, int rank, int algo) -> ()", &symm_allreduce);
-  m.def("reduce_slabs(int base_ptr, Tensor(a!) out, int slab_bytes, int world, int counter_ptr, int expect) -> ()", &reduce_slabs);
+  m.def("symm_calls_word(int parity) -> int", &symm_calls_word);
+  m.def("gemm_rs(Tensor x, Tensor w, bool b_mn, int[] peer_inbox, int[] peer_counter, int my_calls_ptr, int rank, int num_sms) -> Tensor", &gemm_rs);
+  m.def("ag_gemm(int[] peer_a, int rows, int K, Tensor w, bool b_mn, int rank, int num_sms) -> Tensor", &ag_gemm);
 }

@@ -43,6 +43,22 @@ struct Params {
   int accumulate;  // C += result
 };
 
+// Fused tensor-parallel modes (kMode): 0 plain; 1 GEMM -> reduce-scatter: the epilogue stores every output row straight
+// into the inbox slab of the rank that owns it (peer memory over NVLink) and bumps that rank's arrival counter;
+// 2 all-gather -> GEMM: A row-blocks are TMA-loaded directly from the owning rank's symmetric buffer.
+constexpr int kMaxTP = 8;
+struct FusedParams {
+  int64_t peer_base[kMaxTP];     // mode 1: byte address of this call's inbox on every rank
+  int64_t peer_counter[kMaxTP];  // mode 1: byte address of the arrival counter on every rank
+  int64_t slab_elems;            // mode 1: rows_per_rank * N
+  int rows_per_rank, my_rank, world;
+};
+struct TmaArray { CUtensorMap m[kMaxTP]; };
+
+RB_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok);
 
 template <> RB_DEVICE void store_chunk<float>(float* dst, const float* v, int n_valid, bool vec_ok) {
@@ -83,10 +99,13 @@ RB_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, int bn, int& m0, 
 // shapes).  Every CTA loads 1/kMC of the shared A tile and TMA-multicasts it to the whole cluster, so A is fetched
 // from L2 once per cluster instead of once per CTA; a smem stage is recycled only after all kMC consumers released it
 // (tcgen05.commit multicast onto every CTA's empty barrier).
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC>
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC, int kMode = 0>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
-                                                                   const __grid_constant__ CUtensorMap tma_b, Params p) {
+                                                                   const __grid_constant__ CUtensorMap tma_b, Params p,
+                                                                   const __grid_constant__ FusedParams fp,
+                                                                   const __grid_constant__ TmaArray tma_a_peers) {
   static_assert(kMC == 1 || !kAMN, "A multicast is implemented for K-major A");
+  static_assert(kMode == 0 || (kMC == 1 && !kAMN), "fused TP modes: K-major A, no cluster");
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,6 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           } else if constexpr (kMC > 1) {
             constexpr int kRows = BM / kMC;  // my slice of the A tile, delivered to every CTA of the cluster
             ptx::tma_load_2d_mcast(sa + cta_rank * (kRows * 128), &tma_a, fb, k0, m0 + (int)cta_rank * kRows, kMcMask);
+          } else if constexpr (kMode == 2) {
+            const int src = m0 / fp.rows_per_rank;  // rows_per_rank % BM == 0 (checked on the host)
+            ptx::tma_load_2d(sa, &tma_a_peers.m[src], fb, k0, m0 - src * fp.rows_per_rank);
           } else {
             ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);
           }
@@ -204,7 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     uint32_t aphase = 0;
     OutT* Cp = reinterpret_cast<OutT*>(p.C);
     const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
-    const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = kMode == 1 ? (p.N % (16 / sizeof(OutT)) == 0)
+                                   : ((p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
         tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
@@ -228,11 +251,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(bias[col + i]);
           }
           OutT* dst = Cp + (int64_t)row * p.ldc + col;
+          if constexpr (kMode == 1) {
+            const int d = row / fp.rows_per_rank;
+            dst = reinterpret_cast<OutT*>(fp.peer_base[d]) + (int64_t)fp.my_rank * fp.slab_elems +
+                  (int64_t)(row - d * fp.rows_per_rank) * p.N + col;
+          }
           if (p.accumulate) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(dst[i]);
           }
           store_chunk<OutT>(dst, v, n_valid, vec_ok);
+        }
+      }
+      if constexpr (kMode == 1) {
+        // publish this tile's rows: one counter bump per destination (warp-aggregated when the 32 rows share a rank)
+        __threadfence_system();
+        const bool valid = row < p.M && n0 < p.N;
+        const int d = valid ? row / fp.rows_per_rank : -1;
+        const int d0 = __shfl_sync(0xffffffffu, d, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, d == d0);
+        if (same == 0xffffffffu) {
+          if (lane == 0 && d0 >= 0) red_add_release_sys(reinterpret_cast<uint32_t*>(fp.peer_counter[d0]), 32u);
+        } else if (valid) {
+          red_add_release_sys(reinterpret_cast<uint32_t*>(fp.peer_counter[d]), 1u);
         }
       }
       ptx::tc_fence_before();
@@ -292,9 +333,13 @@ bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC = 1>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int num_sms, cudaStream_t s) {
-  auto kern = gemm_tcgen05_kernel<BN, kAMN, kBMN, OutT, kFmt, kMC>;
+static const FusedParams kNoFused{};
+static const TmaArray kNoPeers{};
+
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, int kMC = 1, int kMode = 0>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int num_sms, cudaStream_t s,
+           const FusedParams& fp = kNoFused, const TmaArray& peers = kNoPeers) {
+  auto kern = gemm_tcgen05_kernel<BN, kAMN, kBMN, OutT, kFmt, kMC, kMode>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes) != cudaSuccess) return -2;
@@ -303,7 +348,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int nu
   const int tiles = RB_CEIL_DIV(p.M, BM) * RB_CEIL_DIV(p.N, BN);
   if constexpr (kMC == 1) {
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, p);
+    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, p, fp, peers);
   } else {
     const int padded = RB_CEIL_DIV(tiles, kMC) * kMC;
     const int cap = (num_sms / kMC) * kMC;
@@ -319,7 +364,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int nu
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return -3;
+    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p, fp, peers) != cudaSuccess) return -3;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -402,6 +447,49 @@ int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int
   }
 #undef RB_GO
   return -14;
+}
+
+// Fused tensor-parallel GEMMs (bf16, K-major A).  mode 1: GEMM -> reduce-scatter scatter phase; mode 2: all-gather -> GEMM.
+//   mode 1: A [M, K] local, output rows go to rank row / rows_per_rank (inbox slabs, see FusedParams); C is unused.
+//   mode 2: A is the concatenation over ranks of [rows_per_rank, K] buffers at `peer_a[r]` (row pitch lda); M = world*rows_per_rank.
+int rb_gemm_fused_tp(int mode, const void* A, const int64_t* peer_a, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
+                     int64_t ldc, int b_mn, const int64_t* peer_base, const int64_t* peer_counter, int rows_per_rank, int my_rank,
+                     int world, int num_sms, cudaStream_t s) {
+  if (world > kMaxTP || M <= 0 || N <= 0 || K <= 0) return -20;
+  if ((lda % 8) || (ldb % 8)) return -21;
+  if (num_sms <= 0) num_sms = rb::kNumSMs;
+  const int tm = RB_CEIL_DIV(M, BM);
+  int bn = ((int64_t)tm * RB_CEIL_DIV(N, 256) >= num_sms || N % 256 == 0) ? 256 : 128;
+  if (N < 256) bn = 128;
+  FusedParams fp{};
+  TmaArray peers{};
+  CUtensorMap ta{}, tb;
+  fp.rows_per_rank = rows_per_rank; fp.my_rank = my_rank; fp.world = world; fp.slab_elems = (int64_t)rows_per_rank * N;
+  bool ok = b_mn ? make_tmap(&tb, B, 1, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK)
+                 : make_tmap(&tb, B, 1, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn);
+  if (mode == 1) {
+    for (int r = 0; r < world; ++r) { fp.peer_base[r] = peer_base[r]; fp.peer_counter[r] = peer_counter[r]; }
+    ok = ok && make_tmap(&ta, A, 1, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM);
+  } else if (mode == 2) {
+    if (rows_per_rank % BM != 0 || M != rows_per_rank * world) return -22;
+    for (int r = 0; r < world; ++r)
+      ok = ok && make_tmap(&peers.m[r], reinterpret_cast<const void*>(peer_a[r]), 1, (uint64_t)rows_per_rank, (uint64_t)K, (uint64_t)lda, BK, BM);
+    ta = peers.m[my_rank];
+  } else {
+    return -23;
+  }
+  if (!ok) return -13;
+  Params p{C, nullptr, ldc, M, N, K, 0};
+#define RB_F(BNV, BMN, MODE) return launch<BNV, false, BMN, __nv_bfloat16, 1, 1, MODE>(ta, tb, p, num_sms, s, fp, peers)
+  if (mode == 1) {
+    if (bn == 256) { if (b_mn) RB_F(256, true, 1); else RB_F(256, false, 1); }
+    else { if (b_mn) RB_F(128, true, 1); else RB_F(128, false, 1); }
+  } else {
+    if (bn == 256) { if (b_mn) RB_F(256, true, 2); else RB_F(256, false, 2); }
+    else { if (b_mn) RB_F(128, true, 2); else RB_F(128, false, 2); }
+  }
+#undef RB_F
+  return -24;
 }
 
 }  // extern "C"

@@ -84,3 +84,37 @@ def test_gpt2_tied_embedding_pp2():
     for r in res:
         for a, b in zip(r["losses"], ref["losses"]):
             assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (r["losses"], ref["losses"])
+
+
+def _moe_worker(rank, world, layout, expert_parallel):
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    pp, dp, tp, sp = layout
+    cfg = hf_io.family("mixtral").make_test_config()
+    cfg.moe.expert_parallel = expert_parallel
+    cfg.moe.aux_loss_coeff = 0.0
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend="gloo", sequence_parallel=sp)
+    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
+                                        grad_dtype="fp32")).initialize(Model(ModelName("m", 0), m, tok, "cpu"), FinetuneSpec(1, 10, 10))
+    itf = basic.SFTInterface()
+    return [itf.train_step(model, _batch(8), n_mbs=1)["loss"] for _ in range(3)]
+
+
+@pytest.mark.parametrize("cfg", [((1, 1, 2, False), False), ((1, 1, 2, False), True), ((1, 1, 2, True), True), ((1, 1, 4, True), True)])
+def test_moe_tp_and_expert_parallel_match_single_process(cfg):
+    from realhf_b200.base.testing import run_distributed
+    layout, ep = cfg
+    ref = run_distributed(_moe_worker, 1, layout=(1, 1, 1, False), expert_parallel=False)[0]
+    res = run_distributed(_moe_worker, layout[2], layout=layout, expert_parallel=ep)
+    for r in res:
+        for a, b in zip(r, ref):
+            assert abs(a - b) < 3e-3 * max(1.0, abs(b)), (cfg, r, ref)
