@@ -84,7 +84,7 @@ class ReaLEngine(PipelinableEngine):
                     num_micro_batches: Optional[int] = None) -> Dict[str, Any]:
         assert self.optim is not None, "train_batch needs the `train` backend"
         n_mbs = num_micro_batches or 1
-        self.module.train() if self.module.training else None
+        self.optim.materialize()
         self.optim.zero_grad()
         if self._pipe is not None:
             stats = self._pipe.train_batch(input_, loss_fn, n_mbs)
@@ -98,6 +98,7 @@ class ReaLEngine(PipelinableEngine):
                 for k, v in st.items():
                     stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / len(mbs)
         ost = self.optim.step(version_steps)
+        self.optim.release()
         stats = dict(stats)
         stats.update(ost)
         return stats
@@ -122,13 +123,19 @@ class ReaLEngine(PipelinableEngine):
         """Inference over micro-batches; `post_hook(output, mb)` reduces each output (e.g. to log-probs)
         before aggregation so full logits never pile up (reference: backend/inference.py:96-124)."""
         n_mbs = num_micro_batches or 1
-        if self._pipe is not None:
-            return self._pipe.forward(input_, n_mbs, post_hook, aggregate_fn)
-        outs = []
-        for mb in input_.split(min(n_mbs, input_.bs)):
-            out = self._forward_mb(mb)
-            outs.append(post_hook(out, mb) if post_hook is not None else out.logits)
-        return aggregate_fn(outs) if len(outs) > 1 else outs[0]
+        if self.optim is not None:
+            self.optim.materialize()
+        try:
+            if self._pipe is not None:
+                return self._pipe.forward(input_, n_mbs, post_hook, aggregate_fn)
+            outs = []
+            for mb in input_.split(min(n_mbs, input_.bs)):
+                out = self._forward_mb(mb)
+                outs.append(post_hook(out, mb) if post_hook is not None else out.logits)
+            return aggregate_fn(outs) if len(outs) > 1 else outs[0]
+        finally:
+            if self.optim is not None:
+                self.optim.release()
 
     @torch.no_grad()
     def generate(self, input_: SequenceSample, tokenizer, gconfig: GenerationHyperparameters = None,
@@ -139,6 +146,8 @@ class ReaLEngine(PipelinableEngine):
         eos = getattr(tokenizer, "eos_token_id", None)
         pad = getattr(tokenizer, "pad_token_id", None)
         pad = pad if pad is not None else (eos if eos is not None else 0)
+        if self.optim is not None:
+            self.optim.materialize()  # ZeRO-3: the caller's next train/forward call releases again
         if self._pipe is not None:
             return self._pipe.generate(input_, gconfig, eos, pad, n_mbs)
         outs = []
@@ -177,6 +186,8 @@ class TrainBackend(ModelBackend):
                  offload_param: bool = False, enable_fp16: bool = False, enable_bf16: bool = True, **_ignored):
         cfg = optimizer if isinstance(optimizer, OptimizerConfig) else OptimizerConfig(**(optimizer or {}))
         cfg.offload = cfg.offload or offload_optimizer
+        cfg.zero_stage = max(cfg.zero_stage, zero_stage)
+        cfg.offload_param = cfg.offload_param or offload_param
         self.cfg = cfg
         self.zero_stage = zero_stage
         self.offload_param = offload_param
@@ -185,6 +196,7 @@ class TrainBackend(ModelBackend):
         m: ReaLModel = model.module
         total = spec.total_train_steps if spec is not None else 1000
         opt = FlatAdamW(m, self.cfg, total_steps=total)
+        opt.release()  # no-op unless ZeRO-3
         model.module = ReaLEngine(m, opt)
         model.backend_name = "train"
         return model

@@ -51,6 +51,8 @@ class OptimizerConfig:
     use_master_weights: bool = True
     grad_dtype: str = "bf16"       # dtype of the flat gradient buffer: bf16 | fp32
     share_grad_buffer: bool = False  # trainable models on one GPU that never train concurrently share one grad buffer
+    zero_stage: int = 1              # 1/2: optimizer state (+ reduced grads) sharded over DP; 3: parameters too, between calls
+    offload_param: bool = False      # ZeRO-3 only: park the parameter shard in pinned host memory between calls
 
 
 class LRScheduler:
@@ -291,6 +293,40 @@ class FlatAdamW:
             if self._good_steps >= c.loss_scale_window:
                 self.loss_scale *= 2
                 self._good_steps = 0
+
+    # ------------------------------------------------------------------ ZeRO-3: parameters sharded between calls
+    # Between model function calls only this rank's 1/dp slice of the flat parameter buffer stays resident (on the GPU,
+    # or in pinned host memory with `offload_param`); `materialize()` all-gathers the full buffer before a call and
+    # `release()` drops it afterwards.  (DeepSpeed gathers per layer inside the forward; gathering per call keeps the
+    # hot path identical to ZeRO-1 and is enough to fit e.g. 7B DPO with an offloaded reference on one GPU's budget.)
+    def release(self):
+        if self.cfg.zero_stage < 3 or not self.model.instantiated:
+            return
+        flat = self.model.flat_param.data
+        shard = flat[self.lo: self.hi]
+        if self.cfg.offload_param and flat.is_cuda:
+            if getattr(self, "_param_shard_host", None) is None:
+                self._param_shard_host = torch.empty(self.hi - self.lo, dtype=flat.dtype, device="cpu", pin_memory=True)
+            self._param_shard_host.copy_(shard, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self._param_shard = None
+        else:
+            self._param_shard = shard.clone()
+        self._dev = flat.device
+        self.model.release_params()
+
+    def materialize(self):
+        if self.cfg.zero_stage < 3 or self.model.instantiated:
+            return
+        n = self.model.flat_numel
+        buf = torch.empty(self.padded, dtype=self.model.dtype, device=self._dev)
+        src = self._param_shard if self._param_shard is not None else self._param_shard_host
+        buf[self.lo: self.hi].copy_(src, non_blocking=True)
+        if self.ctx.dp_size > 1:
+            dist.all_gather_into_tensor(buf, buf[self.lo: self.lo + self.shard_n].clone(), group=self.ctx.dp_group)
+        self.model.attach_flat(buf[:n])
+        self.model.attach_grad_buffer(self.flat_grad[:n])
+        self._param_shard = None
 
     # ------------------------------------------------------------------ state (recover saves what the reference drops)
     def state_dict(self):

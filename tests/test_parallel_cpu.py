@@ -118,3 +118,34 @@ def test_moe_tp_and_expert_parallel_match_single_process(cfg):
     for r in res:
         for a, b in zip(r, ref):
             assert abs(a - b) < 3e-3 * max(1.0, abs(b)), (cfg, r, ref)
+
+
+def _zero3_worker(rank, world, zero_stage):
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    cfg = hf_io.family("llama").make_test_config()
+    ctx = ParallelContext.build(ProcessTopology(1, world, 1), list(range(world)), rank, backend="gloo")
+    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant", grad_dtype="fp32"),
+                         zero_stage=zero_stage).initialize(Model(ModelName("m", 0), m, tok, "cpu"), FinetuneSpec(1, 10, 10))
+    resident = model.module.module.instantiated
+    mine = _batch(8).split(world)[rank]
+    losses = [basic.SFTInterface().train_step(model, mine, n_mbs=1)["loss"] for _ in range(3)]
+    return dict(losses=losses, resident_between_calls=resident and model.module.module.instantiated)
+
+
+def test_zero3_matches_zero1_and_releases_params():
+    from realhf_b200.base.testing import run_distributed
+    z1 = run_distributed(_zero3_worker, 2, zero_stage=1)
+    z3 = run_distributed(_zero3_worker, 2, zero_stage=3)
+    assert z1[0]["resident_between_calls"] and not z3[0]["resident_between_calls"]
+    for a, b in zip(z1[0]["losses"], z3[0]["losses"]):
+        assert abs(a - b) < 1e-5
