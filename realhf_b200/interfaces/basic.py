@@ -121,8 +121,11 @@ class PairedRewardInterface(ModelInterface):
         if scores is None:
             return None
         scores = (scores.float() - self.output_bias) * self.output_scaling
-        return SequenceSample.from_default(ids=data.ids, seqlens=data.flat_seqlens("packed_input_ids"),
-                                           data=dict(rewards=scores))
+        # one score per sequence; items that hold a group of sequences (GRPO, paired data) get a group of scores
+        with SequenceSample.disable_validation():
+            return SequenceSample(keys=["rewards"], ids=data.ids, trailing_shapes=dict(rewards=()), dtypes=dict(rewards=torch.float32),
+                                  seqlens=dict(rewards=[[1] * len(l) for l in data.seqlens["packed_input_ids"]]),
+                                  data=dict(rewards=scores))
 
     def train_step(self, model: Model, data: SequenceSample, n_mbs=None) -> Dict:
         eng = model.module

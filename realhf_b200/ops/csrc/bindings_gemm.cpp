@@ -8,7 +8,7 @@ using at::Tensor;
 
 extern "C" int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda,
                                int64_t ldb, int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn,
-                               int num_sms, cudaStream_t s);
+                               int num_sms, int mc_req, cudaStream_t s);
 
 static int dtc(at::ScalarType t) {
   switch (t) {
@@ -22,7 +22,7 @@ static int dtc(at::ScalarType t) {
 // a: a_mn ? [K, M] : [M, K];  b: b_mn ? [K, N] : [N, K].  Inner stride must be 1, row pitch a multiple of 8.
 // out: optional destination [M, N] (any supported dtype); with accumulate=True computes out += a x b.
 Tensor gemm(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, const c10::optional<Tensor>& bias, bool a_mn,
-            bool b_mn, bool accumulate, c10::optional<at::ScalarType> out_dtype, int64_t bn, int64_t num_sms) {
+            bool b_mn, bool accumulate, c10::optional<at::ScalarType> out_dtype, int64_t bn, int64_t num_sms, int64_t mc) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2, "gemm: 2-D CUDA tensors expected");
   TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1, "gemm: inner stride must be 1");
   TORCH_CHECK(a.scalar_type() == b.scalar_type(), "gemm: operand dtypes differ");
@@ -45,12 +45,12 @@ Tensor gemm(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, 
   }
   if (M == 0 || N == 0) return c;
   int rc = rb_gemm_tcgen05(a.data_ptr(), b.data_ptr(), c.data_ptr(), bp, (int)M, (int)N, (int)K, a.stride(0), b.stride(0),
-                           c.stride(0), a_mn, b_mn, dtc(a.scalar_type()), dtc(c.scalar_type()), accumulate, (int)bn, (int)num_sms,
+                           c.stride(0), a_mn, b_mn, dtc(a.scalar_type()), dtc(c.scalar_type()), accumulate, (int)bn, (int)num_sms, (int)mc,
                            at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, "rb_gemm_tcgen05 failed with code ", rc);
   return c;
 }
 
 void register_gemm_ops(torch::Library& m) {
-  m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms) -> Tensor", &gemm);
+  m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);
 }

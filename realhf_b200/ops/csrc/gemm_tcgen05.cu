@@ -406,8 +406,9 @@ extern "C" {
 // A: a_mn ? [K, M] : [M, K] with row pitch lda;  B: b_mn ? [K, N] : [N, K] with row pitch ldb.
 // bn = 0 picks the tile width from the problem size.
 int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
-                    int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, cudaStream_t s) {
-  static const int mc_mode = [] { const char* e = getenv("REAL_GEMM_MULTICAST"); return e ? atoi(e) : 1; }();
+                    int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, int mc_req, cudaStream_t s) {
+  static const int mc_env = [] { const char* e = getenv("REAL_GEMM_MULTICAST"); return e ? atoi(e) : 0; }();
+  const int mc_mode = mc_req >= 0 ? mc_req : mc_env;  // TMA-multicast clusters for small M: opt-in (measured slower than plain tiles so far)
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (in_dt != 1 && in_dt != 2) return -10;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;

@@ -20,9 +20,9 @@ def _sms(dev) -> int:
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-         a_mn: bool = False, b_mn: bool = False, accumulate: bool = False, out_dtype=None, bn: int = 0) -> torch.Tensor:
+         a_mn: bool = False, b_mn: bool = False, accumulate: bool = False, out_dtype=None, bn: int = 0, mc: int = -1) -> torch.Tensor:
     """D = A x B.  A is [M,K] (or [K,M] if a_mn), B is [N,K] (or [K,N] if b_mn)."""
-    return lib().gemm(a, b, out, bias, a_mn, b_mn, accumulate, out_dtype, bn, _sms(a.device))
+    return lib().gemm(a, b, out, bias, a_mn, b_mn, accumulate, out_dtype, bn, _sms(a.device), mc)
 
 
 def supported(x: torch.Tensor, w: torch.Tensor) -> bool:

@@ -59,7 +59,8 @@ def _ar_worker(rank, world):
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / n * 1e3
 
-    t_ours = timeit(lambda: sb.all_reduce(y, out=out[: y.numel()], algo=1))
+    out_y = torch.empty_like(y)
+    t_ours = timeit(lambda: sb.all_reduce(y, out=out_y, algo=1))
     t_nccl = timeit(lambda: dist.all_reduce(y))
     return dict(us_ours=t_ours, us_nccl=t_nccl)
 

@@ -29,8 +29,11 @@ def test_sample_matches_reference_filter(cfg, dtype):
     ref_removed = xf == torch.finfo(torch.float32).min
     removed = OF.unpack_mask_bits(mb, V)
     # ties / fp rounding at the top-p boundary may move a handful of tokens
-    diff = (removed != ref_removed).sum(1)
-    assert diff.max().item() <= 2, diff
+    # (bf16 logits have large tie groups; which members of the boundary group survive is sort-order dependent,
+    # so mismatches must be confined to at most two tied values per row: the top-k and the top-p boundary)
+    mism = removed != ref_removed
+    for r in torch.nonzero(mism.sum(1) > 2).flatten().tolist():
+        assert x[r][mism[r]].unique().numel() <= 2, (r, x[r][mism[r]])
     lp_ref = torch.log_softmax(xf.masked_fill(removed, float("-inf")), -1)
     rows = torch.arange(B, device=DEV)
     live = unfinished
