@@ -144,7 +144,9 @@ def sass_summary() -> dict:
     """Count the Blackwell-native SASS mnemonics in the built library (evidence for profiles/)."""
     out = _run([str(CUDA_HOME / "bin" / "cuobjdump"), "-sass", str(OPS_LIB)])
     keys = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS", "MULTIMEM", "UTCBAR"]
-    return {k: sum(1 for line in out.splitlines() if k in line) for k in keys}
+    import re
+    pats = {k: re.compile(r"(?<![A-Z0-9_.])" + k + r"(?![A-Z0-9])") for k in keys}  # whole mnemonic: `HMMA` must not count `UTCHMMA`
+    return {k: sum(1 for line in out.splitlines() if pats[k].search(line)) for k in keys}
 
 
 def build_all(force: bool = False, verbose: bool = False):

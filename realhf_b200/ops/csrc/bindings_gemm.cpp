@@ -10,6 +10,10 @@ extern "C" int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void
                                int64_t ldb, int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn,
                                int num_sms, int mc_req, cudaStream_t s);
 
+extern "C" int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda,
+                               int64_t ldb, int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
+                               cudaStream_t s);
+
 static int dtc(at::ScalarType t) {
   switch (t) {
     case at::kFloat: return 0;
@@ -51,6 +55,30 @@ Tensor gemm(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, 
   return c;
 }
 
+// Decode-shaped GEMM (M <= 128): y = a @ b^T (+ bias), stream-K over all SMs.  ws: fp32 [>= 2*num_sms*128*256], flags: int32 [8192] zeros.
+Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& bias, const Tensor& ws, const Tensor& flags,
+                    c10::optional<at::ScalarType> out_dtype, int64_t bn, int64_t split, int64_t num_sms, const c10::optional<Tensor>& dbg) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  TORCH_CHECK(a.scalar_type() == b.scalar_type() && a.size(1) == b.size(1), "gemm_streamk: operand mismatch");
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(M <= 128, "gemm_streamk: M <= 128");
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.numel() >= 2 * num_sms * 128 * 256 && flags.numel() >= 8192 && flags.element_size() == 4);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor c = at::empty({M, N}, a.options().dtype(out_dtype.value_or(a.scalar_type())));
+  const void* bp = nullptr;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->scalar_type() == c.scalar_type() && bias->numel() == N && bias->is_contiguous());
+    bp = bias->data_ptr();
+  }
+  if (M == 0 || N == 0) return c;
+  int rc = rb_gemm_streamk(a.data_ptr(), b.data_ptr(), c.data_ptr(), bp, (int)M, (int)N, (int)K, a.stride(0), b.stride(0), c.stride(0),
+                           dtc(a.scalar_type()), dtc(c.scalar_type()), (int)bn, (int)split, (int)num_sms, ws.data_ptr(), flags.data_ptr(), dbg.has_value() ? dbg->data_ptr() : nullptr,
+                           at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gemm_streamk failed with code ", rc);
+  return c;
+}
+
 void register_gemm_ops(torch::Library& m) {
+  m.def("gemm_streamk(Tensor a, Tensor b, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
   m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);
 }

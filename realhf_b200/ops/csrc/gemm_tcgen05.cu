@@ -292,6 +292,283 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- stream-K (decode shapes)
+// M <= 128 (one m-tile): the GEMM streams the weight matrix once and is bound by how evenly the weight bytes are
+// spread over the SMs (each SM ingests ~46-57 B/clk through TMA), not by the tensor cores.  Tiling only over N gives
+// tiles_n CTAs (16 for a 4096-wide projection with BN=256) and every CTA re-reads the whole activation panel.  Stream-K
+// instead cuts the flattened (n-tile, k-block) iteration space into gridDim.x equal contiguous ranges, so every SM
+// streams the same number of bytes whatever N and K are.  A range that covers only part of a tile produces a partial
+// accumulator: it is written as fp32 to one of the CTA's two workspace slots, the CTA bumps the tile's arrival counter,
+// and once all S CTAs that touched the tile have arrived each of them sums and stores 1/S of the tile's rows (a
+// serial "owner adds everything" fix-up measured 4-9x slower: 128 threads chasing S x 128 KB through L2).  While the
+// epilogue warps wait, the TMA / MMA warps already run the CTA's next segment (TMEM is double-buffered).  A CTA only
+// ever waits on tiles at or before its own, so with all CTAs resident (grid <= #SMs, 1 CTA/SM) the scheme cannot
+// deadlock.  The last reader re-arms the tile counters, so no per-call memset is needed and CUDA graphs can replay it.  A is loaded with a box of only round_up(M, 8) rows; the remaining rows
+// of the 128-row UMMA tile hold stale shared memory and only ever influence accumulator rows that are never stored.
+struct StreamKParams {
+  float* ws;         // [2 * gridDim.x][BM][BN] fp32 partials: slot 2g for CTA g's first segment, 2g+1 for its last
+  uint32_t* flags;   // [2 * tiles_n]: (arrived, done) per tile, zero at entry and exit
+  int a_box_rows;
+  int bn, stages;
+  long long* dbg;    // optional [gridDim.x][8] globaltimer stamps (profiling builds of the benchmark only)
+};
+
+RB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+RB_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+RB_DEVICE long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+RB_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <typename OutT, int kFmt>
+__global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                   const __grid_constant__ CUtensorMap tma_b, Params p,
+                                                                   StreamKParams sk) {
+  // tile width and pipeline depth are run-time values here: the host picks BN (any multiple of 16 up to 256) so that
+  // tiles_n x split lands just under the SM count, which matters more for these shapes than compile-time unrolling
+  const int BN = sk.bn, n_stages = sk.stages;
+  constexpr int kABytes = BM * BK * 2;
+  const int b_bytes = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + n_stages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + n_stages * b_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + n_stages;
+  uint64_t* tmem_full = bars + 2 * n_stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  __shared__ int slot_of[160];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = RB_CEIL_DIV(p.K, BK);
+  const int64_t units = (int64_t)RB_CEIL_DIV(p.N, BN) * num_kb;
+  const int G = gridDim.x, g = blockIdx.x;
+  const int u_begin = (int)(units * g / G), u_end = (int)(units * (g + 1) / G);
+  const uint32_t stage_tx = (uint32_t)sk.a_box_rows * 128u + (uint32_t)b_bytes;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tma_a);
+    ptx::prefetch_tensormap(&tma_b);
+    for (int i = 0; i < n_stages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tmem_empty[i]), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int tile = u / num_kb, kb = u - tile * num_kb;
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+        ptx::mbar_arrive_expect_tx(fb, stage_tx);
+        ptx::tma_load_2d(ptx::smem_u32(smem_a + stage * kABytes), &tma_a, fb, kb * BK, 0);
+        ptx::tma_load_2d(ptx::smem_u32(smem_b + stage * b_bytes), &tma_b, fb, kb * BK, tile * BN);
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(kFmt, BM, BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      int u = u_begin;
+      while (u < u_end) {
+        const int tile = u / num_kb;
+        const int seg_end = min(u_end, (tile + 1) * num_kb);
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty[as]), aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int first = 1; u < seg_end; ++u, first = 0) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * kABytes);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * b_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            ptx::tc_mma_f16(d_tmem, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024),
+                            idesc, (first && k == 0) ? 0u : 1u);
+          }
+          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(ptx::smem_u32(&tmem_full[as]));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int et = threadIdx.x - 64;  // 0..127 over the epilogue warps
+    int as = 0;
+    uint32_t aphase = 0;
+    OutT* Cp = reinterpret_cast<OutT*>(p.C);
+    const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
+    const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    auto cta_of = [&](int unit) { return (int)((((int64_t)unit + 1) * G - 1) / units); };
+    if (sk.dbg && et == 0) sk.dbg[g * 8 + 0] = gtimer();
+    int pending[2], n_pending = 0;  // a range has at most two partial segments: its first and its last
+    int u = u_begin;
+    while (u < u_end) {
+      const int tile = u / num_kb;
+      const int tile_u0 = tile * num_kb, tile_u1 = tile_u0 + num_kb;
+      const int seg_end = min(u_end, tile_u1);
+      const bool whole = u == tile_u0 && seg_end == tile_u1;
+      const int n0 = tile * BN;
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full[as]), aphase);
+      ptx::tc_fence_after();
+      if (sk.dbg && et == 0 && u == u_begin) sk.dbg[g * 8 + 1] = gtimer();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
+      float* my_slot = sk.ws + (int64_t)(2 * g + (u == u_begin ? 0 : 1)) * (BM * 256);
+#pragma unroll 1
+      const int n_end = min(p.N, n0 + BN);
+      for (int c = 0; c < (BN + 31) / 32; ++c) {
+        uint32_t r[32];
+        ptx::tc_ld_32x32(taddr + c * 32, r);  // a 16-column tail reads past the accumulator (inside the allocation); masked below
+        ptx::tc_wait_ld();
+        const int col = n0 + c * 32;
+        const int n_valid = min(32, n_end - col);
+        if (!row_ok || n_valid <= 0) continue;
+        if (!whole) {  // fp32 partial -> my workspace slot, laid out [col/4][row] in float4 units: a warp stores 512 contiguous bytes
+          float4* dst = reinterpret_cast<float4*>(my_slot) + (c * 8) * BM + row;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i * BM] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                      __uint_as_float(r[4 * i + 3]));
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(bias[col + i]);
+        }
+        store_chunk<OutT>(Cp + (int64_t)row * p.ldc + col, v, n_valid, vec_ok);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty[as]));  // the MMA warp may start the next segment now
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (!whole) {
+        epi_bar_sync();  // all four quadrants of my partial are written; the release below is cumulative over them
+        if (et == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sk.flags + 2 * tile), "r"(1u) : "memory");
+        pending[n_pending++] = tile;
+      }
+      u = seg_end;
+    }
+    if (sk.dbg && et == 0) sk.dbg[g * 8 + 2] = gtimer();
+    // ---- cooperative fix-up, deferred until every partial of this CTA is posted (waiting inside the loop would chain
+    // tile t's fix-up behind tile t-1's through the CTA that spans both): every CTA that touched a tile reduces 1/S of it
+    for (int pi = 0; pi < n_pending; ++pi) {
+      const int tile = pending[pi];
+      const int tile_u0 = tile * num_kb, tile_u1 = tile_u0 + num_kb;
+      const int n0 = tile * BN;
+      const int g_first = cta_of(tile_u0), g_last = cta_of(tile_u1 - 1);
+      const int S = g_last - g_first + 1, j = g - g_first;
+      uint32_t* arrived = sk.flags + 2 * tile;
+      if (et == 0) {
+        while (ld_acquire_gpu(arrived) < (uint32_t)S) {}
+      }
+      epi_bar_sync();
+      if (sk.dbg && et == 0) sk.dbg[g * 8 + 3 + 2 * pi] = gtimer();
+      // member j sums columns [c_lo, c_hi) (float4 units) of all rows.  A warp works on blocks of 8 rows x 4 float4-columns:
+      // its loads are four full 128-byte lines per member and its stores eight full 32-byte sectors.  Four blocks x eight
+      // members are in flight per thread, because this phase is bound by L2 round trips, not bytes.
+      for (int m = et; m < S; m += 128) {
+        const int gm = g_first + m;
+        slot_of[m] = 2 * gm + (((int)(units * gm / G) / num_kb) == tile ? 0 : 1);
+      }
+      epi_bar_sync();
+      const int kC4 = BN / 4;
+      const int c_lo = kC4 * j / S, c_hi = kC4 * (j + 1) / S;
+      const int n_rb = RB_CEIL_DIV(p.M, 8), n_cb = RB_CEIL_DIV(c_hi - c_lo, 4);
+      const int n_blocks = n_rb * n_cb;
+      const bool vec4 = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
+      const float4* ws4 = reinterpret_cast<const float4*>(sk.ws);
+      for (int bb = quad; bb < n_blocks; bb += 16) {
+        float4 acc[4];
+        int off[4];  // float4 offset inside a slot, or -1
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int blk = bb + 4 * q;
+          const int rr = (blk % n_rb) * 8 + (lane & 7), c4 = c_lo + (blk / n_rb) * 4 + (lane >> 3);
+          off[q] = (blk < n_blocks && rr < p.M && c4 < c_hi && n0 + c4 * 4 < p.N) ? c4 * BM + rr : -1;
+        }
+        for (int m0 = 0; m0 < S; m0 += 8) {
+          float4 t[8][4];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const bool mk = m0 + k < S;
+            const float4* slot = ws4 + (int64_t)slot_of[mk ? m0 + k : 0] * (BM * 256 / 4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[k][q] = (mk && off[q] >= 0) ? __ldcg(slot + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q].x += t[k][q].x; acc[q].y += t[k][q].y; acc[q].z += t[k][q].z; acc[q].w += t[k][q].w; }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (off[q] < 0) continue;
+          const int orow = off[q] % BM, col = n0 + (off[q] / BM) * 4;
+          float v[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
+          const int nv = min(4, p.N - col);
+          if (bias != nullptr) {
+            for (int i = 0; i < nv; ++i) v[i] += rb::to_f(bias[col + i]);
+          }
+          OutT* dst = Cp + (int64_t)orow * p.ldc + col;
+          if (nv == 4 && vec4) {
+            rb::Pack<OutT, 4> pk;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk.v[i] = rb::from_f<OutT>(v[i]);
+            *reinterpret_cast<rb::Pack<OutT, 4>*>(dst) = pk;
+          } else {
+            for (int i = 0; i < nv; ++i) dst[i] = rb::from_f<OutT>(v[i]);
+          }
+        }
+      }
+      epi_bar_sync();  // every thread of this CTA is done reading the group's slots
+      if (sk.dbg && et == 0) sk.dbg[g * 8 + 4 + 2 * pi] = gtimer();
+      if (et == 0) {
+        const uint32_t old = atomicAdd(arrived + 1, 1u);
+        if (old == (uint32_t)S - 1u) { arrived[1] = 0u; __threadfence(); arrived[0] = 0u; }  // last reader re-arms the tile
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -366,6 +643,21 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int nu
     cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p, fp, peers) != cudaSuccess) return -3;
   }
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+
+template <typename OutT, int kFmt>
+int launch_streamk(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, const StreamKParams& sk, int grid, cudaStream_t s) {
+  auto kern = gemm_streamk_kernel<OutT, kFmt>;
+  constexpr int kMaxSmem = 227 * 1024 - 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess) return -2;
+    configured = true;
+  }
+  const int smem = sk.stages * (BM * BK * 2 + sk.bn * BK * 2) + 1024 + 256;
+  kern<<<grid, kThreads, smem, s>>>(ta, tb, p, sk);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -447,6 +739,70 @@ int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int
     if (out_dt == 0) RB_GO(float, 0);
   }
 #undef RB_GO
+  return -14;
+}
+
+// Small-M GEMM (decode shapes): M <= 128, K-major operands, no accumulate.  `ws` holds 2 * num_sms * 128 * 256 floats,
+// `flags` 8192 zero-initialised words (persistent per device; calls sharing them must be stream-ordered).
+// bn = 0 / split = 0: pick the tile width (multiple of 16) and the K split from a byte-ingest cost model:
+//   t = max(weight bytes / HBM, bytes per CTA / ~70 GB/s per-SM TMA ingest) + fix-up(split > 1),
+// over the layouts with tiles_n * split <= #SMs (tile-aligned split: one fix-up round per CTA).
+int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
+                    cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M > BM || (in_dt != 1 && in_dt != 2)) return -30;
+  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
+  if (num_sms <= 0) num_sms = rb::kNumSMs;
+  if (num_sms > 160) num_sms = 160;
+  const int num_kb = RB_CEIL_DIV(K, BK);
+  const int box_rows = ((M + 7) / 8) * 8;
+  if (bn == 0) {
+    double best = 1e30;
+    for (int cand = 32; cand <= 256; cand += 16) {
+      const int tiles = RB_CEIL_DIV(N, cand);
+      if (tiles > num_sms && cand < 256) continue;
+      int smax = tiles <= num_sms ? num_sms / tiles : 1;
+      if (smax > num_kb) smax = num_kb;
+      for (int sp = 1; sp <= smax; ++sp) {
+        const double waves = (double)RB_CEIL_DIV(tiles * sp, num_sms);
+        const double cta_bytes = (double)(box_rows + cand) * 128.0 * RB_CEIL_DIV(num_kb, sp) * waves;
+        double t = cta_bytes / 70e3;                              // us
+        const double hbm = (double)N * K * 2.0 / 6.5e6;           // us
+        if (t < hbm) t = hbm;
+        if (sp > 1) t += 3.0 + 2.0 * (double)M * cand * 4.0 / 60e3;
+        if (t < best) { best = t; bn = cand; split = sp; }
+      }
+    }
+  }
+  if (bn % 16 || bn < 16 || bn > 256) return -5;
+  const int tiles_n = RB_CEIL_DIV(N, bn);
+  if (tiles_n > 4096) return -31;
+  const int64_t units = (int64_t)tiles_n * num_kb;
+  int grid;
+  if (split > 0 && (int64_t)tiles_n * split <= num_sms && split <= num_kb) {
+    grid = tiles_n * split;            // tile-aligned: CTA ranges never straddle a tile
+  } else {
+    grid = (int)(units < num_sms ? units : num_sms);  // general stream-K: equal contiguous ranges, up to two fix-ups per CTA
+  }
+  int stages = (227 * 1024 - 1024 - 1024 - 256) / (BM * BK * 2 + bn * BK * 2);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -32;
+  CUtensorMap ta, tb;
+  const int bf = in_dt == 1;
+  bool ok = make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)box_rows) &&
+            make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn);
+  if (!ok) return -13;
+  Params p{C, bias, ldc, M, N, K, 0};
+  StreamKParams sk{reinterpret_cast<float*>(ws), reinterpret_cast<uint32_t*>(flags), box_rows, bn, stages,
+                   reinterpret_cast<long long*>(dbg)};
+  if (in_dt == 1) {
+    if (out_dt == 1) return launch_streamk<__nv_bfloat16, 1>(ta, tb, p, sk, grid, s);
+    if (out_dt == 0) return launch_streamk<float, 1>(ta, tb, p, sk, grid, s);
+  } else {
+    if (out_dt == 2) return launch_streamk<__half, 0>(ta, tb, p, sk, grid, s);
+    if (out_dt == 0) return launch_streamk<float, 0>(ta, tb, p, sk, grid, s);
+  }
   return -14;
 }
 

@@ -94,3 +94,39 @@ def test_gemm_small_m_multicast(shape):
     for _ in range(3):  # repeated launches exercise barrier phase carry-over
         c = G.gemm(a, b)
     torch.testing.assert_close(c.float(), a.float() @ b.float().t(), atol=K ** 0.5 * 0.05, rtol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(128, 4096, 4096), (64, 4096, 11008), (17, 12288, 4096), (128, 22016, 4096), (1, 32000, 4096),
+                                   (100, 1000, 520), (128, 256, 256), (8, 4104, 264)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_streamk_decode_gemm(shape, dtype):
+    """Stream-K small-M GEMM vs fp32 reference; repeated calls check that the flags self-reset."""
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dtype)
+    b = (torch.randn(N, K, device=DEV) * 0.05).to(dtype)
+    bias = torch.randn(N, device=DEV).to(dtype)
+    ref = a.float() @ b.float().t()
+    for bn, split in ((0, 0), (128, 0), (48, 0), (96, 1), (256, 3), (32, 2)):
+        for it in range(3):
+            y = G.gemm_streamk(a, b, bn=bn, split=split)
+        torch.testing.assert_close(y.float(), ref, atol=2e-2 * (K / 4096) ** 0.5 + 1e-2, rtol=2e-2)
+    yb = G.gemm_streamk(a, b, bias=bias)
+    torch.testing.assert_close(yb.float(), ref + bias.float(), atol=2e-2 * (K / 4096) ** 0.5 + 2e-2, rtol=2e-2)
+    y32 = G.gemm_streamk(a, b, out_dtype=torch.float32)
+    torch.testing.assert_close(y32, ref, atol=5e-3 * (K / 4096) ** 0.5 + 1e-3, rtol=1e-3)
+    ws, flags = G.streamk_workspace(a.device)
+    assert int(flags.abs().sum()) == 0
+    # the default route for small M is the stream-K kernel, also under CUDA graph capture
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        G.gemm(a, b)
+        with torch.cuda.graph(g):
+            yg = G.gemm(a, b)
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(yg.float(), ref, atol=2e-2 * (K / 4096) ** 0.5 + 1e-2, rtol=2e-2)

@@ -34,7 +34,7 @@ def test_sample_matches_reference_filter(cfg, dtype):
     mism = removed != ref_removed
     for r in torch.nonzero(mism.sum(1) > 2).flatten().tolist():
         assert x[r][mism[r]].unique().numel() <= 2, (r, x[r][mism[r]])
-    lp_ref = torch.log_softmax(xf.masked_fill(removed, float("-inf")), -1)
+    lp_ref = torch.log_softmax(x.masked_fill(removed, float("-inf")), -1)  # log-probs under the kernel's own keep-set
     rows = torch.arange(B, device=DEV)
     live = unfinished
     assert (~removed[rows, tok])[live].all(), "sampled a filtered token"
