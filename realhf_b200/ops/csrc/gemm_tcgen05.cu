@@ -770,12 +770,16 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
         double t = cta_bytes / 70e3;                              // us
         const double hbm = (double)N * K * 2.0 / 6.5e6;           // us
         if (t < hbm) t = hbm;
-        if (sp > 1) t += 3.0 + 2.0 * (double)M * cand * 4.0 / 60e3;
+        const double kb_floor = 0.33 * RB_CEIL_DIV(num_kb, sp) * waves;  // measured per-k-block pipeline floor
+        if (t < kb_floor) t = kb_floor;
+        if (sp > 1) t += 5.0 + 4.5 * (double)M * cand * 4.0 / 60e3;  // partial write + barrier + cooperative reduce (measured)
         if (t < best) { best = t; bn = cand; split = sp; }
       }
     }
   }
   if (bn % 16 || bn < 16 || bn > 256) return -5;
+  static const bool verbose = getenv("REAL_GEMM_DEBUG") != nullptr;
+  if (verbose) fprintf(stderr, "[rb_gemm_smallm] M=%d N=%d K=%d -> bn=%d split=%d\n", M, N, K, bn, split);
   const int tiles_n = RB_CEIL_DIV(N, bn);
   if (tiles_n > 4096) return -31;
   const int64_t units = (int64_t)tiles_n * num_kb;
