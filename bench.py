@@ -250,7 +250,10 @@ def main():
                        "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes * world,
-                    "d2h_bytes_per_step": result_host.numel() * 4 * world},
+                    "d2h_bytes_per_step": result_host.numel() * 4 * world,
+                    "timer": "host wall clock (perf_counter) around the same K steps driven through SPMDExecutor.run_step: "
+                             "pinned-host prompt H2D, all six MFCs, loss/reward statistics D2H; `value` is the CUDA-event time",
+                    "wall_ms_per_step": round(wall * 1e3 / args.steps, 2), "device_ms_per_step": round(dev_s * 1e3 / args.steps, 2)},
             "gpu_launches": int(float(t[3]) if world > 1 else n_launch),
             "impl": "ours",
         }
