@@ -13,18 +13,9 @@
 // smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue), and a static
 // persistent tile loop (one CTA per SM).  The epilogue converts and stores straight from TMEM
 // registers with 16-byte stores, with optional bias and accumulate-into-C.
-#include <cuda.h>
-#include <stdio.h>
-#include <stdlib.h>
-
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kThreads = 192;
 
 template <int BN> struct Cfg {
   static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
@@ -33,14 +24,6 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-struct Params {
-  void* C;
-  const void* bias;
-  int64_t ldc;
-  int M, N, K;
-  int accumulate;  // C += result
 };
 
 // Fused tensor-parallel modes (kMode): 0 plain; 1 GEMM -> reduce-scatter: the epilogue stores every output row straight
@@ -57,30 +40,6 @@ struct TmaArray { CUtensorMap m[kMaxTP]; };
 
 RB_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok);
-
-template <> RB_DEVICE void store_chunk<float>(float* dst, const float* v, int n_valid, bool vec_ok) {
-  if (n_valid == 32 && vec_ok) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    for (int i = 0; i < n_valid; ++i) dst[i] = v[i];
-  }
-}
-template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok) {
-  if (n_valid == 32 && vec_ok) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      rb::Pack<T, 8> p;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) p.v[k] = rb::from_f<T>(v[8 * i + k]);
-      reinterpret_cast<rb::Pack<T, 8>*>(dst)[i] = p;
-    }
-  } else {
-    for (int i = 0; i < n_valid; ++i) dst[i] = rb::from_f<T>(v[i]);
-  }
 }
 
 // L2-friendly rasterisation: tiles are walked in bands of kGroupM m-tiles, m fastest inside a band, so the
@@ -319,7 +278,6 @@ RB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-RB_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 RB_DEVICE long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 RB_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -441,8 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
       if (sk.dbg && et == 0 && u == u_begin) sk.dbg[g * 8 + 1] = gtimer();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
       float* my_slot = sk.ws + (int64_t)(2 * g + (u == u_begin ? 0 : 1)) * (BM * 256);
-#pragma unroll 1
       const int n_end = min(p.N, n0 + BN);
+#pragma unroll 1
       for (int c = 0; c < (BN + 31) / 32; ++c) {
         uint32_t r[32];
         ptx::tc_ld_32x32(taddr + c * 32, r);  // a 16-column tail reads past the accumulator (inside the allocation); masked below
@@ -570,46 +528,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D row-major tensor [rows, cols] (cols contiguous, row pitch `ld` elements), 2-byte elements, 128B swizzle.
-int g_last_tmap_err = 0;
-bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-               uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  // The driver entry point needs a current context in *this* thread; autograd's backward threads only ever
-  // called cudaSetDevice, which does not bind the primary context for driver-API calls until a runtime call does.
-  static thread_local bool ctx_ready = false;
-  if (!ctx_ready) { cudaFree(nullptr); ctx_ready = true; }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    g_last_tmap_err = (int)r;
-    fprintf(stderr, "[rb_gemm] cuTensorMapEncodeTiled failed: %d ptr=%p rows=%llu cols=%llu ld=%llu box=(%u,%u)\n", (int)r, ptr,
-            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
-  }
-  return r == CUDA_SUCCESS;
-}
-
 static const FusedParams kNoFused{};
 static const TmaArray kNoPeers{};
 
@@ -692,6 +610,9 @@ int dispatch_bn(int bn, bool a_mn, bool b_mn, int mc, const CUtensorMap& ta, con
 
 }  // namespace
 
+extern "C" int rb_gemm_2cta(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                            int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, cudaStream_t s);
+
 extern "C" {
 
 // in_dt: 1 bf16, 2 fp16.  out_dt: 0 fp32, 1 bf16, 2 fp16.
@@ -700,6 +621,13 @@ extern "C" {
 int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
                     int64_t ldc, int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, int mc_req, cudaStream_t s) {
   static const int mc_env = [] { const char* e = getenv("REAL_GEMM_MULTICAST"); return e ? atoi(e) : 0; }();
+  static const int cta2_env = [] { const char* e = getenv("REAL_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  // CTA-pair kernel (gemm_2cta.cu) for everything with at least two m-tiles: mc_req == 2 forces it, -1 follows the env default
+  if ((mc_req == 2 || (mc_req < 0 && cta2_env != 0)) && M > BM && (bn == 0 || bn == 128 || bn == 256)) {
+    const int rc = rb_gemm_2cta(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, in_dt, out_dt, accumulate, bn, num_sms, s);
+    if (rc != -40) return rc;
+  }
+  if (mc_req == 2) mc_req = 0;
   const int mc_mode = mc_req >= 0 ? mc_req : mc_env;  // TMA-multicast clusters for small M: opt-in (measured slower than plain tiles so far)
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (in_dt != 1 && in_dt != 2) return -10;

@@ -130,3 +130,35 @@ def test_streamk_decode_gemm(shape, dtype):
         g.replay()
     torch.cuda.synchronize()
     torch.testing.assert_close(yg.float(), ref, atol=2e-2 * (K / 4096) ** 0.5 + 1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("majors", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 384, 256), (1000, 1032, 520), (4096, 4096, 1024), (2048, 11008, 512), (304, 128, 136)])
+@pytest.mark.parametrize("bn", [0, 128, 256])
+def test_gemm_cta_pair(shape, majors, bn):
+    """cta_group::2 kernel (256 x BN tiles on SM pairs), every operand-major combination, ragged edges."""
+    M, N, K = shape
+    a_mn, b_mn = majors
+    torch.manual_seed(3)
+    a = torch.randn((K, M) if a_mn else (M, K), device=DEV, dtype=torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), device=DEV, dtype=torch.bfloat16)
+    ref = _ref(a, b, a_mn, b_mn)
+    for _ in range(2):
+        c = G.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bn=bn, mc=2)
+    torch.testing.assert_close(c.float(), ref, atol=K ** 0.5 * 0.05, rtol=2e-2)
+
+
+def test_gemm_cta_pair_epilogues():
+    torch.manual_seed(4)
+    M, N, K = 600, 520, 264
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=DEV, dtype=torch.bfloat16)
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    c = G.gemm(a, b, bias=bias, mc=2)
+    torch.testing.assert_close(c.float(), _ref(a, b, False, False) + bias.float(), atol=1.0, rtol=2e-2)
+    acc = torch.randn(M, N, device=DEV, dtype=torch.float32)
+    acc0 = acc.clone()
+    G.gemm(a, b, out=acc, accumulate=True, mc=2)
+    torch.testing.assert_close(acc, acc0 + _ref(a, b, False, False), atol=1e-2, rtol=1e-3)
+    ah, bh = a.half(), b.half()
+    torch.testing.assert_close(G.gemm(ah, bh, mc=2).float(), _ref(ah, bh, False, False), atol=0.5, rtol=1e-2)
