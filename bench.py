@@ -76,6 +76,9 @@ def run_reference(args):
     return 0
 
 
+GEN_TP_DEFAULT = {1: 1, 2: 1, 4: 1, 8: 1}  # per-N generation layout (measured)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -88,6 +91,8 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=512)
     ap.add_argument("--gemm", default=os.environ.get("REAL_GEMM", "tcgen05"), choices=["tcgen05", "cublas"])
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--gen-tp", type=int, default=int(os.environ.get("REAL_BENCH_GEN_TP", "0")),
+                    help="tensor-parallel degree of the generation replica (0: default for this N; 1: generate on the dp layout)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,6 +181,14 @@ def main():
     interfaces = {"actor_gen": actor_itf, "ref_inf": actor_itf, "actor_train": actor_itf, "critic_inf": critic_itf,
                   "critic_train": critic_itf, "rew_inf": rw_itf}
     ex = SPMDExecutor(rpcs, models, interfaces, dev)
+    gen_tp = args.gen_tp if args.gen_tp > 0 else GEN_TP_DEFAULT.get(world, 1)
+    if world > 1 and gen_tp > 1:
+        # generation on a tp x dp replica of the actor: decode streams 1/tp of the weights per GPU per token; the replica is
+        # refreshed from the (dp-replicated) training layout by local segment copies before every generation
+        assert world % gen_tp == 0
+        gen_topo = ProcessTopology(1, world // gen_tp, gen_tp)
+        ctx_gen = ParallelContext.build(gen_topo, list(range(world)), rank, backend="nccl")
+        ex.add_layout_replica("actor_gen", models["actor"], ctx_gen, ProcessTopology(1, world, 1), gen_topo, list(range(world)), rank)
 
     # synthetic prompts of the dataset's padded shape, in pinned host memory
     gcpu = torch.Generator().manual_seed(1234 + rank)
@@ -243,7 +256,8 @@ def main():
             "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline else f" [DEBUG layers={args.layers}]"),
                        "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens,
                        "prompt_len": args.prompt_len, "new_tokens": args.new_tokens, "ppo_minibatches": 4,
-                       "parallelism": f"dp{world} (all 6 MFCs), ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
+                       "parallelism": (f"dp{world} (all 6 MFCs)" if not (world > 1 and gen_tp > 1) else
+                                       f"actor_gen tp{gen_tp}xdp{world // gen_tp} (realloc'd replica), other MFCs dp{world}") + ", ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
                        "optimizer": "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads",
                        "gemm": args.gemm, "attention": "flash-attn lib (varlen) + own split-KV decode kernel",
                        "l2": "working set >> L2 (54 GB weights per GPU); fresh inputs every step",
