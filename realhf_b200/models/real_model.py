@@ -331,9 +331,11 @@ class ReaLModel(nn.Module):
             o = F.dropout(o, c.resid_pdrop)
         return o
 
-    def _mlp(self, i: int, x):
+    def _mlp(self, i: int, x, h=None):
+        """h: the already-normalised input (decode path fuses residual add + norm), else computed from x."""
         c = self.config
-        h = self._norm(x, f"{i}.mlp.ln")
+        if h is None:
+            h = self._norm(x, f"{i}.mlp.ln")
         sp = self.sequence_parallel
         if c.mlp_type == "llama":
             gu = TP.col_linear(h, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, sp)
@@ -423,20 +425,39 @@ class ReaLModel(nn.Module):
         if c.apply_rotary:
             cos, sin = self.rope_tables(k_caches[0].shape[1] if k_caches else 2048)
         li = 0
+        rms = c.layer_norm_type is not None
+        w_off = 1.0 if c.layer_norm_type == "gemma" else 0.0
+        eps = c.layer_norm_epsilon
+        d = None  # branch output not yet added to the residual stream: every add is fused into the next RMSNorm kernel
         for i in self.layers:
             if i == 0:
                 x = self._embed(input_ids, cache_lens)
             elif i <= c.n_layers:
-                h = self._norm(x, f"{i}.attn.ln")
+                if rms and d is not None:
+                    h, x = OF.add_rmsnorm(d, x, self.p[f"{i}.attn.ln.weight"], eps, w_off)
+                else:
+                    if d is not None:
+                        x = x + d
+                    h = self._norm(x, f"{i}.attn.ln")
                 qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
                 o = attn_ops.decode_attention(qkv, k_caches[li], v_caches[li], cache_lens, nq, nkv, hd, self._attn_scale(i),
                                               cos, sin, hd, c.rotary_interleaved)
                 li += 1
                 o = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
-                x = x + o
-                x = x + self._mlp(i, x)
+                if rms:
+                    h2, x = OF.add_rmsnorm(o, x, self.p[f"{i}.mlp.ln.weight"], eps, w_off)
+                    d = self._mlp(i, x, h2)
+                else:
+                    x = x + o
+                    d = self._mlp(i, x)
                 if i == c.n_layers:
-                    x = self._norm(x, f"{i}.ln_f")
+                    if rms:
+                        x, _ = OF.add_rmsnorm(d, x, self.p[f"{i}.ln_f.weight"], eps, w_off)
+                    else:
+                        x = self._norm(x + d, f"{i}.ln_f")
+                    d = None
+        if d is not None:  # a pipeline stage that does not end with ln_f hands on the summed residual stream
+            x = x + d
         return x
 
     def n_local_blocks(self) -> int:

@@ -113,6 +113,42 @@ __global__ void __launch_bounds__(kThreads) allreduce_1shot_kernel(Peers P, cons
   block_barrier(P, rank, world);  // nobody restages before every peer finished reading
 }
 
+// One-shot over data that ALREADY lives in the symmetric buffers (the producing GEMM wrote its partial output there):
+// one barrier, then every rank sums the `world` copies at byte offset `off`.  No staging copy and no trailing barrier:
+// callers alternate between two regions, and a rank can only re-write region A in call k+2 after passing the barrier
+// of call k+1, which every peer reaches only after it finished reading A in call k.  All loads of a thread are issued
+// before the first add (the loop is bound by NVLink round trips).
+template <typename T, int kUnroll>
+__global__ void __launch_bounds__(kThreads) allreduce_symm_kernel(Peers P, int64_t off, int4* __restrict__ out, int64_t nvec, int rank,
+                                                                  int world) {
+  block_barrier(P, rank, world);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t base = i0; base < nvec; base += stride * kUnroll) {
+    int4 v[kUnroll][kMaxRanks];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = base + u * stride;
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) {
+        if (r < world && i < nvec) v[u][r] = reinterpret_cast<const int4*>(P.data[r] + off)[i];  // same order on every rank
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = base + u * stride;
+      if (i >= nvec) continue;
+      Acc8<T> acc;
+      acc.zero();
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) {
+        if (r < world) acc.add(v[u][r]);
+      }
+      out[i] = acc.pack();
+    }
+  }
+}
+
 // Two-shot: reduce-scatter into this rank's slice (kept in the second half of its data region), barrier, all-gather.
 // Block b owns vector range [b*chunk, (b+1)*chunk) in EVERY phase and on EVERY rank, so the same-index block barrier
 // is sufficient: block b only ever touches data staged / reduced by the peers' block b.
@@ -202,6 +238,16 @@ int rb_symm_allreduce(const int64_t* data_ptrs, const int64_t* pad_ptrs, const v
   int blocks = (int)((nvec + kThreads - 1) / kThreads);
   blocks = blocks < 1 ? 1 : (blocks > 36 ? 36 : blocks);  // few fat blocks: this op is latency / link bound, leave SMs to compute
   const int64_t half = (nvec + 63) / 64 * 64;
+  if (algo == 3) {  // `in` lives inside this rank's data region; the same offset is read on every peer
+    const int64_t off = reinterpret_cast<const uint8_t*>(in) - P.data[rank];
+    if (off < 0 || (off & 15)) return -3;
+    int nb = (int)((nvec + 2 * kThreads - 1) / (2 * kThreads));
+    nb = nb < 1 ? 1 : (nb > kMaxBlocks ? kMaxBlocks : nb);
+#define RB_GO3(T) allreduce_symm_kernel<T, 2><<<nb, kThreads, 0, s>>>(P, off, (int4*)out, nvec, rank, world)
+    if (dt == 0) RB_GO3(float); else if (dt == 1) RB_GO3(__nv_bfloat16); else if (dt == 2) RB_GO3(__half); else return -2;
+#undef RB_GO3
+    return 0;
+  }
 #define RB_GO(T)                                                                                                              \
   if (algo == 1) allreduce_1shot_kernel<T><<<blocks, kThreads, 0, s>>>(P, (const int4*)in, (int4*)out, nvec, rank, world);       \
   else allreduce_2shot_kernel<T><<<blocks, kThreads, 0, s>>>(P, (const int4*)in, (int4*)out, nvec, half, rank, world);

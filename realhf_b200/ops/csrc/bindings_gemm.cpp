@@ -56,7 +56,7 @@ Tensor gemm(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, 
 }
 
 // Decode-shaped GEMM (M <= 128): y = a @ b^T (+ bias), stream-K over all SMs.  ws: fp32 [>= 2*num_sms*128*256], flags: int32 [8192] zeros.
-Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& bias, const Tensor& ws, const Tensor& flags,
+Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& out, const c10::optional<Tensor>& bias, const Tensor& ws, const Tensor& flags,
                     c10::optional<at::ScalarType> out_dtype, int64_t bn, int64_t split, int64_t num_sms, const c10::optional<Tensor>& dbg) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
   TORCH_CHECK(a.scalar_type() == b.scalar_type() && a.size(1) == b.size(1), "gemm_streamk: operand mismatch");
@@ -64,7 +64,13 @@ Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor
   TORCH_CHECK(M <= 128, "gemm_streamk: M <= 128");
   TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.numel() >= 2 * num_sms * 128 * 256 && flags.numel() >= 8192 && flags.element_size() == 4);
   c10::cuda::CUDAGuard guard(a.device());
-  Tensor c = at::empty({M, N}, a.options().dtype(out_dtype.value_or(a.scalar_type())));
+  Tensor c;
+  if (out.has_value()) {
+    c = *out;
+    TORCH_CHECK(c.dim() == 2 && c.size(0) == M && c.size(1) == N && c.stride(1) == 1, "gemm_streamk: bad out shape");
+  } else {
+    c = at::empty({M, N}, a.options().dtype(out_dtype.value_or(a.scalar_type())));
+  }
   const void* bp = nullptr;
   if (bias.has_value()) {
     TORCH_CHECK(bias->scalar_type() == c.scalar_type() && bias->numel() == N && bias->is_contiguous());
@@ -79,6 +85,6 @@ Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor
 }
 
 void register_gemm_ops(torch::Library& m) {
-  m.def("gemm_streamk(Tensor a, Tensor b, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
+  m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
   m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);
 }

@@ -288,7 +288,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
   // tile width and pipeline depth are run-time values here: the host picks BN (any multiple of 16 up to 256) so that
   // tiles_n x split lands just under the SM count, which matters more for these shapes than compile-time unrolling
   const int BN = sk.bn, n_stages = sk.stages;
-  constexpr int kABytes = BM * BK * 2;
+  // A stages are packed to the rows that TMA actually writes (round_up(M, 8) x 128 B).  The MMA still addresses 128 rows
+  // from each stage base, so it reads on into the following stages / the B region (always inside the allocation, see
+  // the host-side layout): those rows only feed accumulator rows >= M, which are never stored.  With M = 16 a stage
+  // shrinks from 28 KB to 14 KB and twice as many loads are in flight per SM, which is what bounds these shapes.
+  const int kABytes = sk.a_box_rows * 128;
   const int b_bytes = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -574,7 +578,7 @@ int launch_streamk(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess) return -2;
     configured = true;
   }
-  const int smem = sk.stages * (BM * BK * 2 + sk.bn * BK * 2) + 1024 + 256;
+  const int smem = sk.stages * (sk.a_box_rows * 128 + sk.bn * BK * 2) + 1024 + 512;
   kern<<<grid, kThreads, smem, s>>>(ta, tb, p, sk);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -717,9 +721,14 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
   } else {
     grid = (int)(units < num_sms ? units : num_sms);  // general stream-K: equal contiguous ranges, up to two fix-ups per CTA
   }
-  int stages = (227 * 1024 - 1024 - 1024 - 256) / (BM * BK * 2 + bn * BK * 2);
-  if (stages > 8) stages = 8;
+  // smem: [stages x A(box_rows x 128 B)] [stages x B(bn x 128 B)] [barriers, 512 B]; the last A stage is read up to 16 KB
+  // past its base, which must still fall inside the allocation -> require stages * b_bytes >= 16 KB (true for stages >= 2)
+  const int a_bytes = box_rows * 128, b_bytes = bn * BK * 2;
+  int stages = (227 * 1024 - 1024 - 1024 - 512) / (a_bytes + b_bytes);
+  if (stages > 16) stages = 16;
   if (stages < 2) return -32;
+  while (stages * b_bytes < BM * BK * 2 && stages < 16) ++stages;
+  if (stages * b_bytes < BM * BK * 2) return -33;
   CUtensorMap ta, tb;
   const int bf = in_dt == 1;
   bool ok = make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)box_rows) &&

@@ -39,20 +39,21 @@ def streamk_workspace(dev, create: bool = True):
 
 
 def gemm_streamk(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, out_dtype=None, bn: int = 0,
+                 out: Optional[torch.Tensor] = None,
                  split: int = 0, dbg: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Decode-shaped y = a @ b^T (M <= 128): stream-K over every SM (see gemm_tcgen05.cu)."""
     ws, flags = streamk_workspace(a.device)
-    return lib().gemm_streamk(a, b, bias, ws, flags, out_dtype, bn, split, _sms(a.device), dbg)
+    return lib().gemm_streamk(a, b, out, bias, ws, flags, out_dtype, bn, split, _sms(a.device), dbg)
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          a_mn: bool = False, b_mn: bool = False, accumulate: bool = False, out_dtype=None, bn: int = 0, mc: int = -1) -> torch.Tensor:
     """D = A x B.  A is [M,K] (or [K,M] if a_mn), B is [N,K] (or [K,N] if b_mn)."""
-    if (_SK_ENABLED and out is None and not (a_mn or b_mn or accumulate) and bn == 0 and mc < 0 and a.shape[0] <= 128
+    if (_SK_ENABLED and not (a_mn or b_mn or accumulate) and bn == 0 and mc < 0 and a.shape[0] <= 128
             and 256 <= b.shape[0] <= 256 * _sms(a.device) and a.shape[1] >= 256):
         wsf = streamk_workspace(a.device)
         if wsf is not None:
-            return lib().gemm_streamk(a, b, bias, wsf[0], wsf[1], out_dtype, 0, 0, _sms(a.device), None)
+            return lib().gemm_streamk(a, b, out, bias, wsf[0], wsf[1], out_dtype, 0, 0, _sms(a.device), None)
     return lib().gemm(a, b, out, bias, a_mn, b_mn, accumulate, out_dtype, bn, _sms(a.device), mc)
 
 

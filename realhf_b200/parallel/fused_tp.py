@@ -54,6 +54,7 @@ class FusedTP:
         # a dedicated all-reduce view over the tail of the buffer
         self._ar_data_ptrs = [p + self.ar_off for p in self.symm.data_ptrs]
         self._ar_bytes = ar_bytes
+        self._ar_calls = 0
 
     # ------------------------------------------------------------------ eligibility
     def _ok(self, x, w) -> bool:
@@ -93,6 +94,23 @@ class FusedTP:
             return x
         out = torch.empty_like(x)
         lib().symm_allreduce(x, out, self._ar_data_ptrs, self.symm.pad_ptrs, self.rank, algo)
+        return out
+
+    def symm_out(self, rows: int, cols: int, dtype) -> Optional[torch.Tensor]:
+        """A [rows, cols] view inside this rank's all-reduce region (regions alternate per call) for a producer that
+        writes its partial result straight into symmetric memory; pass it to `all_reduce_symm`."""
+        nbytes = rows * cols * torch.tensor([], dtype=dtype).element_size()
+        half = self._ar_bytes // 2
+        if nbytes > half or nbytes % 16 != 0:
+            return None
+        off = self.ar_off + (self._ar_calls & 1) * half
+        self._ar_calls += 1
+        return self.symm.data()[off: off + nbytes].view(dtype).view(rows, cols)
+
+    def all_reduce_symm(self, y_sym: torch.Tensor) -> torch.Tensor:
+        """Sum over ranks of a tensor obtained from `symm_out` (one barrier, no staging copy)."""
+        out = torch.empty(y_sym.shape, dtype=y_sym.dtype, device=y_sym.device)
+        lib().symm_allreduce(y_sym, out, self.symm.data_ptrs, self.symm.pad_ptrs, self.rank, 3)
         return out
 
     # ------------------------------------------------------------------ autograd-aware entry points used by parallel/tp.py
@@ -172,6 +190,13 @@ class _GemmAR(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, f: FusedTP):
         ctx.save_for_backward(x, w)
+        from realhf_b200.ops import gemm as G
+        x2 = x.reshape(-1, x.shape[-1])
+        if G.supported(x2, w) and x2.stride(-1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0:
+            y_sym = f.symm_out(x2.shape[0], w.shape[0], x.dtype)
+            if y_sym is not None:  # the GEMM writes its partial sums straight into symmetric memory
+                G.gemm(x2, w, out=y_sym)
+                return f.all_reduce_symm(y_sym).view(*x.shape[:-1], w.shape[0])
         y = OF.linear(x, w)
         return f.all_reduce(y)
 

@@ -32,7 +32,7 @@ def timeit(f, n=20, warm=3):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
 
-for B in (64, 128):
+for B in ((16, 32) if os.environ.get("SMALL_B") else (64, 128)):
     st = gen.DecodeState(m, B, 640)
     for ctx in (128, 384, 639):
         st.cache_lens.fill_(ctx)

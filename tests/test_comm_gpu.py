@@ -27,6 +27,19 @@ def _ar_worker(rank, world):
                 err = (out.float() - ref).abs().max().item()
                 tol = 1e-4 if dtype == torch.float32 else 0.1
                 assert err <= tol * max(1.0, ref.abs().max().item()), (dtype, n, algo, err)
+    # in-place variant: the producer writes into symmetric memory, regions alternate per call, one barrier per call
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.parallel.fused_tp import FusedTP
+    from realhf_b200.ops import gemm as G
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl")
+    f = FusedTP(ctx, max_tokens=256, max_features=4096, device=dev)
+    for it in range(5):
+        xs = (torch.randn(128, 2048, device=dev) * 0.3).to(torch.bfloat16)
+        ws = (torch.randn(4096, 2048, device=dev) * 0.05).to(torch.bfloat16)
+        ref = xs.float() @ ws.float().t()
+        dist.all_reduce(ref)
+        y = f.gemm_ar(xs, ws)
+        torch.testing.assert_close(y.float(), ref, atol=0.15, rtol=3e-2)
     # repeated calls + CUDA graph capture
     x = torch.ones(1 << 16, device=dev, dtype=torch.bfloat16) * (rank + 1)
     out = torch.empty_like(x)
@@ -62,7 +75,17 @@ def _ar_worker(rank, world):
     out_y = torch.empty_like(y)
     t_ours = timeit(lambda: sb.all_reduce(y, out=out_y, algo=1))
     t_nccl = timeit(lambda: dist.all_reduce(y))
-    return dict(us_ours=t_ours, us_nccl=t_nccl)
+    ysym = f.symm_out(128, 1024, torch.bfloat16)
+
+    def symm_call():
+        f._ar_calls += 1  # alternate regions as a producer would
+        f.all_reduce_symm(ysym)
+    t_symm = timeit(symm_call)
+    xs = torch.randn(128, 2048, device=dev, dtype=torch.bfloat16)
+    ws = torch.randn(4096, 2048, device=dev, dtype=torch.bfloat16)
+    t_gemm_ar = timeit(lambda: f.gemm_ar(xs, ws))
+    t_gemm = timeit(lambda: G.gemm(xs, ws))
+    return dict(us_ours=t_ours, us_nccl=t_nccl, us_symm_inplace=t_symm, us_gemm_ar_1MB=t_gemm_ar, us_gemm_alone=t_gemm)
 
 
 def test_symmetric_allreduce_matches_nccl():
