@@ -12,6 +12,8 @@ concat_prompt_to_generation_output :451-530) and `utils/logits_warper.py`.  Diff
 
 from __future__ import annotations
 
+import os
+
 import dataclasses
 from typing import List, Optional, Tuple
 
@@ -170,6 +172,11 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         h = model.decode_step(state.input_ids, state.k, state.v, state.cache_lens)
         return _final_logits(model, h)
 
+    # programmatic dependent launch pays off for short decode kernels only (measured: +2% at B=16, -1..4% at B>=64)
+    pdl_prev = None
+    if dev.type == "cuda" and os.environ.get("REAL_PDL") is None:
+        from realhf_b200.ops import lib as _lib
+        pdl_prev = int(_lib().set_pdl(1 if B <= 32 else 0))
     if use_graph and state.graph is None:
         state.input_ids.copy_(nxt)
         lens_backup = state.cache_lens.clone()
@@ -200,6 +207,8 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         step += 1
         if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(unfinished.any()):
             break
+    if pdl_prev is not None:
+        _lib().set_pdl(pdl_prev)
     tokens = torch.stack(toks, 1)
     logprobs = torch.stack(lps, 1)
     mask_bits = torch.stack(masks, 1) if masks[0] is not None else None

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(DecodeParams p) {
   const int b = blockIdx.x, hkv = blockIdx.y, split = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rsel = lane / LPR;
+  rb::pdl_wait();
+  rb::pdl_trigger();
   const int pos = p.cache_lens[b];   // position of the new token; attends to [0, pos]
   const int n_ctx = pos + 1;
   const T* qkv = reinterpret_cast<const T*>(p.qkv) + (int64_t)b * p.qkv_stride;
@@ -228,6 +230,8 @@ __global__ void decode_attn_reduce_kernel(const float* __restrict__ part_acc, co
                                           T* __restrict__ out, int splits) {
   const int64_t bh = blockIdx.x;  // b * nq + hq
   const int d = threadIdx.x;
+  rb::pdl_wait();
+  rb::pdl_trigger();
   float mg = -INFINITY;
   for (int s = 0; s < splits; ++s) mg = fmaxf(mg, part_ml[(bh * splits + s) * 2]);
   float lg = 0.f, ag = 0.f;
@@ -244,7 +248,7 @@ template <typename T, int HD>
 int launch_decode(const DecodeParams& p, cudaStream_t s) {
   const int rep = p.nq / p.nkv;
   dim3 grid(p.B, p.nkv, p.splits);
-#define RB_L(REP) decode_attn_kernel<T, HD, REP><<<grid, kThreads, 0, s>>>(p)
+#define RB_L(REP) rb::launch_pdl(decode_attn_kernel<T, HD, REP>, grid, dim3(kThreads), 0, s, p)
   switch (rep) {
     case 1: RB_L(1); break;
     case 2: RB_L(2); break;
@@ -254,7 +258,8 @@ int launch_decode(const DecodeParams& p, cudaStream_t s) {
   }
 #undef RB_L
   if (p.splits > 1)
-    decode_attn_reduce_kernel<T, HD><<<p.B * p.nq, HD, 0, s>>>(p.part_acc, p.part_ml, reinterpret_cast<T*>(p.out), p.splits);
+    rb::launch_pdl(decode_attn_reduce_kernel<T, HD>, dim3(p.B * p.nq), dim3(HD), 0, s, (const float*)p.part_acc, (const float*)p.part_ml,
+                   reinterpret_cast<T*>(p.out), p.splits);
   return 0;
 }
 

@@ -29,6 +29,8 @@ template <typename T> static inline T* optp(const c10::optional<Tensor>& t) {
 }
 
 extern "C" {
+void rb_set_pdl(int on);
+int rb_get_pdl();
 void rb_gae_1d_misalign(const float*, const float*, const int*, const bool*, float*, float*, int, float, float, cudaStream_t);
 void rb_ppo_rewards_gae(const float*, const float*, const float*, const float*, const int*, const bool*, float*, float*,
                         float*, float*, int, float, float, float, float, cudaStream_t);
@@ -264,7 +266,10 @@ void register_gemm_ops(torch::Library& m);     // bindings_gemm.cpp
 void register_attn_ops(torch::Library& m);     // bindings_attn.cpp
 void register_comm_ops(torch::Library& m);     // bindings_comm.cpp
 
+static int64_t set_pdl(int64_t on) { const int old = rb_get_pdl(); if (on >= 0) rb_set_pdl((int)on); return old; }
+
 TORCH_LIBRARY(realhf_b200, m) {
+  m.def("set_pdl(int on) -> int", &set_pdl);
   m.def("gae_1d_misalign(Tensor rewards, Tensor values, Tensor cu_seqlens, Tensor bootstrap, float gamma, float lam) -> Tensor[]", &gae_1d_misalign);
   m.def("ppo_rewards_gae(Tensor logp, Tensor ref_logp, Tensor scores, Tensor values, Tensor cu_seqlens, Tensor no_eos, float gamma, float lam, float kl_ctl, float clip_reward) -> Tensor[]", &ppo_rewards_gae);
   m.def("gae_2d(Tensor rewards, Tensor values, Tensor dones, Tensor truncs, float gamma, float lam, int mode) -> Tensor[]", &gae_2d);

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define RB_DEVICE __device__ __forceinline__
 #define RB_CEIL_DIV(a, b) (((a) + (b)-1) / (b))
@@ -59,5 +60,32 @@ RB_DEVICE void st_stream(void* p, const int4& v) {
 }
 
 template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
+
+// Programmatic dependent launch (PDL).  A kernel launched with `launch_pdl` may become resident while its predecessor in
+// the stream is still running (hiding launch latency and its own prologue); it must execute `pdl_wait()` before it
+// touches any global memory the predecessor may read or write.  `pdl_trigger()` lets the successor start launching.
+// Both are no-ops for kernels launched the ordinary way, so kernels can call them unconditionally.
+RB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+RB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Process-wide switch (set through `rb_set_pdl`): measured inside CUDA graphs, PDL wins ~2% of a decode step at 16
+// sequences per GPU and loses 1-4% at 64-128 (long attention kernels), so the generation loop turns it on per batch size.
+extern "C" int rb_get_pdl();
+inline bool pdl_enabled() { return rb_get_pdl() != 0; }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 }  // namespace rb

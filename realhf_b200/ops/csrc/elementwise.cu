@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const T* __restrict_
                                                             int F, int kind) {
   const int vec_per_row = F / 8;
   const int64_t total = n_tok * vec_per_row;
+  rb::pdl_wait();
+  rb::pdl_trigger();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = idx / vec_per_row;
     const int c = (int)(idx % vec_per_row);
@@ -128,6 +130,11 @@ inline int grid_for(int64_t total) {
 
 extern "C" {
 
+static int g_rb_pdl = [] { const char* e = getenv("REAL_PDL"); return (e != nullptr && atoi(e) != 0) ? 1 : 0; }();
+int rb_get_pdl() { return g_rb_pdl; }
+void rb_set_pdl(int on) { g_rb_pdl = on ? 1 : 0; }
+
+
 int rb_rope_inplace(void* x, const float* cs, const float* sn, const int* pos, int64_t n_tok, int n_heads, int hd,
                     int64_t row_stride, int rot_dim, int interleaved, int inverse, int dt, cudaStream_t s) {
   if (n_tok == 0) return 0;
@@ -145,8 +152,8 @@ int rb_gated_act_fwd(const void* gu, void* out, int64_t n_tok, int F, int kind, 
   if (n_tok == 0) return 0;
   if (F % 8 != 0) return -1;
   const int64_t total = n_tok * (F / 8);
-  if (dt == 1) gated_act_fwd_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)gu, (__nv_bfloat16*)out, n_tok, F, kind);
-  else if (dt == 2) gated_act_fwd_kernel<__half><<<grid_for(total), 256, 0, s>>>((const __half*)gu, (__half*)out, n_tok, F, kind);
+  if (dt == 1) rb::launch_pdl(gated_act_fwd_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, s, (const __nv_bfloat16*)gu, (__nv_bfloat16*)out, n_tok, F, kind);
+  else if (dt == 2) rb::launch_pdl(gated_act_fwd_kernel<__half>, dim3(grid_for(total)), dim3(256), 0, s, (const __half*)gu, (__half*)out, n_tok, F, kind);
   else return -1;
   return 0;
 }

@@ -334,12 +334,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: the prologue above (barrier init, TMEM allocation, descriptor prefetch) already
+  // overlapped the previous kernel's tail.  The weight operand B does not depend on the predecessor either, so the
+  // producer below fills the whole smem ring with weight tiles BEFORE `griddepcontrol.wait` -- HBM keeps streaming
+  // weights while the preceding norm / activation / attention kernel drains -- and only the activation loads (A), the
+  // output stores and the stream-K workspace wait for the predecessor.
+  rb::pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = u_begin; u < u_end; ++u) {
+      // first pass over the ring: weights now, activations after the dependency wait
+      const int n_pre = min(n_stages, u_end - u_begin);
+      for (int i = 0; i < n_pre; ++i) {
+        const int u = u_begin + i;
+        const int tile = u / num_kb, kb = u - tile * num_kb;
+        const uint32_t fb = ptx::smem_u32(&full_bar[i]);
+        ptx::mbar_arrive_expect_tx(fb, stage_tx);
+        ptx::tma_load_2d(ptx::smem_u32(smem_b + i * b_bytes), &tma_b, fb, kb * BK, tile * BN);
+      }
+      rb::pdl_wait();
+      for (int i = 0; i < n_pre; ++i) {
+        const int u = u_begin + i;
+        const int kb = u - (u / num_kb) * num_kb;
+        ptx::tma_load_2d(ptx::smem_u32(smem_a + i * kABytes), &tma_a, ptx::smem_u32(&full_bar[i]), kb * BK, 0);
+      }
+      int stage = n_pre == n_stages ? 0 : n_pre;
+      uint32_t phase = n_pre == n_stages ? 1 : 0;
+      for (int u = u_begin + n_pre; u < u_end; ++u) {
         const int tile = u / num_kb, kb = u - tile * num_kb;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
@@ -383,6 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
     const int row = quad * 32 + lane;
     const bool row_ok = row < p.M;
     const int et = threadIdx.x - 64;  // 0..127 over the epilogue warps
+    rb::pdl_wait();  // output buffer, bias and the stream-K workspace may still be in use by the predecessor
     int as = 0;
     uint32_t aphase = 0;
     OutT* Cp = reinterpret_cast<OutT*>(p.C);
@@ -579,7 +601,7 @@ int launch_streamk(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p
     configured = true;
   }
   const int smem = sk.stages * (sk.a_box_rows * 128 + sk.bn * BK * 2) + 1024 + 512;
-  kern<<<grid, kThreads, smem, s>>>(ta, tb, p, sk);
+  if (rb::launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, s, ta, tb, p, sk) != cudaSuccess) return -3;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const T* __restri
   constexpr int V = 8;
   const int64_t row = blockIdx.x;
   const int nvec = H / V;
+  rb::pdl_wait();
+  rb::pdl_trigger();
   const rb::Pack<T, V>* xr = reinterpret_cast<const rb::Pack<T, V>*>(x + row * H);
   const rb::Pack<T, V>* rr = kResidual ? reinterpret_cast<const rb::Pack<T, V>*>(res_in + row * H) : nullptr;
   float vals[kMaxVec][V];
@@ -146,10 +148,10 @@ int rb_rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* y, vo
   if (rows == 0) return 0;
   if (H % 8 != 0 || H > kThreads * 8 * 8) return -1;
 #define RB_L2(T, NV)                                                                                               \
-  if (res_in) rmsnorm_fwd_kernel<T, true, NV><<<(unsigned)rows, kThreads, 0, s>>>(                                     \
+  if (res_in) rb::launch_pdl(rmsnorm_fwd_kernel<T, true, NV>, dim3((unsigned)rows), dim3(kThreads), 0, s,                \
       (const T*)x, (const T*)res_in, (const T*)w, (T*)y, (T*)res_out, rstd, H, eps, w_offset);                         \
-  else rmsnorm_fwd_kernel<T, false, NV><<<(unsigned)rows, kThreads, 0, s>>>((const T*)x, nullptr, (const T*)w, (T*)y,  \
-                                                                           nullptr, rstd, H, eps, w_offset);
+  else rb::launch_pdl(rmsnorm_fwd_kernel<T, false, NV>, dim3((unsigned)rows), dim3(kThreads), 0, s, (const T*)x,       \
+                      (const T*)nullptr, (const T*)w, (T*)y, (T*)nullptr, rstd, H, eps, w_offset);
 #define RB_L(T)                                                            \
   { const int nv = RB_CEIL_DIV(H, kThreads * 8);                            \
     if (nv <= 1) { RB_L2(T, 1) } else if (nv <= 2) { RB_L2(T, 2) } else if (nv <= 4) { RB_L2(T, 4) } else { RB_L2(T, 8) } }
