@@ -1,4 +1,4 @@
-"""`python -m realhf_b200.apps.quickstart <sft|rw|dpo|ppo|gen> key=value ...`
+"""`python -m realhf_b200.apps.quickstart <sft|rw|dpo|ppo|gen|profile> key=value ...`
 
 Parity: `realhf/apps/quickstart.py` + `api/quickstart/entrypoint.py`: the first argument selects a registered
 experiment dataclass, the remaining `a.b.c=value` arguments override its (nested) fields.
@@ -13,6 +13,7 @@ from realhf_b200.api.quickstart import QUICKSTART_EXPERIMENTS, parse_overrides
 
 def build_experiment(argv):
     import realhf_b200.experiments.algos  # noqa: F401  (registers sft / rw / dpo / ppo / gen)
+    import realhf_b200.experiments.profile  # noqa: F401  (registers profile)
     if not argv or argv[0] in ("-h", "--help"):
         print("usage: python -m realhf_b200.apps.quickstart {" + ",".join(sorted(QUICKSTART_EXPERIMENTS)) + "} key=value ...")
         sys.exit(0)
@@ -30,6 +31,8 @@ def build_experiment(argv):
 def main(argv=None):
     from realhf_b200.apps.main import main_start
     cfg = build_experiment(sys.argv[1:] if argv is None else argv)
+    if hasattr(cfg, "run_local"):  # in-process experiments (profile sweeps)
+        return cfg.run_local()
     return main_start(cfg)
 
 

@@ -172,11 +172,11 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         h = model.decode_step(state.input_ids, state.k, state.v, state.cache_lens)
         return _final_logits(model, h)
 
-    # programmatic dependent launch pays off for short decode kernels only (measured: +2% at B=16, -1..4% at B>=64)
+    # programmatic dependent launch pays off for short decode kernels only (measured per decode step: +2.5% at B=16, +1% at B=64, -1..4% at B=128 where attention dominates)
     pdl_prev = None
     if dev.type == "cuda" and os.environ.get("REAL_PDL") is None:
         from realhf_b200.ops import lib as _lib
-        pdl_prev = int(_lib().set_pdl(1 if B <= 32 else 0))
+        pdl_prev = int(_lib().set_pdl(1 if B <= 64 else 0))
     if use_graph and state.graph is None:
         state.input_ids.copy_(nxt)
         lens_backup = state.cache_lens.clone()
@@ -265,3 +265,93 @@ def concat_prompt_to_generation_output(prompt_ids: torch.Tensor, prompt_cu: torc
         mask_bits = torch.zeros(total1, out.mask_bits.shape[-1], dtype=torch.uint8, device=dev)
         mask_bits[is_gen1] = out.mask_bits[seq1[is_gen1], gp1[is_gen1]]
     return packed, slens, lp, mask_bits, in_prompt
+
+
+class InflightBatchingGenerator:
+    """Continuous (in-flight) batching over a fixed number of decode slots.
+
+    Parity: `InflightBatchingGenerator` (nn/real_llm_generate.py:664-882; not used by the reference's interfaces either).
+    Prompts wait in a queue; whenever a slot's sequence ends (EOS or `max_new_tokens`) its result is emitted and the slot
+    is refilled by a prefill of the next prompt, so short answers do not hold the batch hostage.  The KV cache, the
+    per-slot lengths and the next-token buffer are the same static `DecodeState` buffers the plain loop uses, i.e. a
+    decode step is one `decode_step` call (CUDA-graph capturable: refills only rewrite buffer contents)."""
+
+    def __init__(self, model: ReaLModel, g: GenerationHyperparameters, eos_id: Optional[int], pad_id: int, n_slots: int,
+                 max_prompt_len: int):
+        assert model.is_first_stage and model.is_last_stage
+        self.model, self.g, self.eos_id, self.pad_id, self.B = model, g, eos_id, pad_id, n_slots
+        self.state = DecodeState(model, n_slots, max_prompt_len + g.max_new_tokens)
+        self.slot_seq = [-1] * n_slots                 # which request a slot serves
+        self.slot_tokens: List[List[int]] = [[] for _ in range(n_slots)]
+        self.slot_logprobs: List[List[float]] = [[] for _ in range(n_slots)]
+        self.unfinished = torch.zeros(n_slots, dtype=torch.bool, device=model.device)
+
+    @torch.no_grad()
+    def _refill(self, slot: int, req_id: int, prompt: torch.Tensor):
+        m, st = self.model, self.state
+        cu = torch.tensor([0, prompt.numel()], dtype=torch.int32, device=m.device)
+        kv: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        out = m(input_ids=prompt, cu_seqlens=cu, max_seqlen=int(prompt.numel()), kv_sink=kv)
+        logits = _final_logits(m, out.hidden[-1:])
+        n = prompt.numel()
+        for li, (k, v) in enumerate(kv):
+            st.k[li][slot, :n] = k
+            st.v[li][slot, :n] = v
+        st.cache_lens[slot] = n
+        one = torch.ones(1, dtype=torch.bool, device=m.device)
+        nxt, lp, _, _ = genstep(logits, self.g, 0, self.eos_id, self.pad_id, one, want_mask=False)
+        st.input_ids[slot] = nxt[0]
+        self.slot_seq[slot] = req_id
+        self.slot_tokens[slot] = [int(nxt[0])]
+        self.slot_logprobs[slot] = [float(lp[0])]
+        self.unfinished[slot] = True
+
+    @torch.no_grad()
+    def generate(self, prompts: List[torch.Tensor]):
+        """prompts: list of 1-D token tensors.  Returns per request (tokens, logprobs, ended_with_eos) in request order."""
+        m, st, g = self.model, self.state, self.g
+        was_training = m.training
+        m.eval()
+        sp_saved, m.sequence_parallel = m.sequence_parallel, False
+        results: List[Optional[Tuple[List[int], List[float], bool]]] = [None] * len(prompts)
+        queue = list(range(len(prompts)))
+        n_done = 0
+
+        def retire(slot: int):
+            nonlocal n_done
+            rid = self.slot_seq[slot]
+            toks = self.slot_tokens[slot]
+            ended = self.eos_id is not None and len(toks) > 0 and toks[-1] == self.eos_id
+            results[rid] = (toks, self.slot_logprobs[slot], ended)
+            self.slot_seq[slot] = -1
+            self.unfinished[slot] = False
+            n_done += 1
+
+        while n_done < len(prompts):
+            for slot in range(self.B):
+                if self.slot_seq[slot] < 0 and queue:
+                    rid = queue.pop(0)
+                    self._refill(slot, rid, prompts[rid].to(m.device))
+                    toks = self.slot_tokens[slot]
+                    if (self.eos_id is not None and toks[-1] == self.eos_id and g.min_new_tokens <= 1) or g.max_new_tokens <= 1:
+                        retire(slot)
+            active = [s for s in range(self.B) if self.slot_seq[s] >= 0]
+            if not active:
+                continue
+            h = m.decode_step(st.input_ids, st.k, st.v, st.cache_lens)
+            logits = _final_logits(m, h)
+            st.cache_lens += self.unfinished.int()
+            # per-slot step index decides whether EOS is still suppressed
+            nxt, lp, _, _ = genstep(logits, g, min(len(self.slot_tokens[s]) for s in active), self.eos_id, self.pad_id,
+                                    self.unfinished, want_mask=False)
+            st.input_ids.copy_(nxt)
+            nxt_h, lp_h = nxt.tolist(), lp.tolist()
+            for s in active:
+                self.slot_tokens[s].append(nxt_h[s])
+                self.slot_logprobs[s].append(lp_h[s])
+                n = len(self.slot_tokens[s])
+                if n >= g.max_new_tokens or (self.eos_id is not None and nxt_h[s] == self.eos_id and n >= g.min_new_tokens):
+                    retire(s)
+        m.train(was_training)
+        m.sequence_parallel = sp_saved
+        return results

@@ -47,6 +47,7 @@ class MasterWorker:
         self._pending: Dict[str, asyncio.Future] = {}
         self.step = self.epoch = self.epoch_step = 0
         self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
+        self.rpc_mem: Dict[str, dict] = {}
         self.stats_log: List[Dict] = []
         self._consumed_ids_this_epoch: List[Hashable] = []
 
@@ -203,6 +204,10 @@ class MasterWorker:
         self.rpc_secs[rpc.name] += time.perf_counter() - t0
         heads = set(self._dp_heads(rpc.model_name))
         stats = []
+        mems = [r.data["mem"] for r in replies if isinstance(r.data, dict) and r.data.get("mem")]
+        if mems:  # max over the workers of this MFC, with the worker that holds it (reference: model_worker.py:999-1094)
+            top = max(mems, key=lambda m: m.get("peak_allocated_gb", 0.0))
+            self.rpc_mem[rpc.name] = top
         for r in replies:
             if r.handler not in heads or not isinstance(r.data, dict):
                 continue
@@ -243,6 +248,10 @@ class MasterWorker:
         dt = time.perf_counter() - t0
         logger.info(f"step {self.step} (epoch {self.epoch}, {self.epoch_step}/{self.ft_spec.steps_per_epoch}) e2e {dt:.3f}s; "
                     + ", ".join(f"{k} {v:.2f}s" for k, v in self.rpc_secs.items()))
+        if self.rpc_mem:
+            logger.info("peak memory: " + ", ".join(
+                f"{k} {m.get('peak_allocated_gb', 0):.1f}/{m.get('peak_reserved_gb', 0):.1f} GB alloc/reserved @worker{m.get('worker')}"
+                for k, m in self.rpc_mem.items()))
         self.rpc_secs.clear()
         return dt
 

@@ -21,7 +21,7 @@ from realhf_b200.api import system as system_api
 from realhf_b200.api.config import ModelName, ModelShardID
 from realhf_b200.api.data import SequenceSample
 from realhf_b200.api.dfg import OffloadHook, ParamReallocHook
-from realhf_b200.base import constants, logging, name_resolve, seeding
+from realhf_b200.base import constants, logging, monitor, name_resolve, seeding
 from realhf_b200.base.topology import ParallelContext
 from realhf_b200.parallel import realloc
 from realhf_b200.system.stream import Payload, WorkerStream
@@ -187,9 +187,11 @@ class ModelWorker:
 
     def _run_hook(self, h: str, d: Any):
         if h == "data_transfer":
-            self._data_transfer(d)
+            with monitor.cuda_tmarked("data_transfer", monitor.CUDATimeMarkType.comm):
+                self._data_transfer(d)
         elif h == "param_realloc":
-            self._param_realloc(d)
+            with monitor.cuda_tmarked("param_realloc", monitor.CUDATimeMarkType.mem_layout):
+                self._param_realloc(d)
         elif h == "offload":
             m = self.models.get(d["model"])
             if m is not None:
@@ -224,6 +226,8 @@ class ModelWorker:
                 self.data_storage.pop(i, None)
             if self.device.type == "cuda" and self.cfg.cuda_cache_cleanliness:
                 torch.cuda.empty_cache()
+            if monitor.TIME_MARK_DB:
+                monitor.dump_tmark_db(os.path.join(constants.run_dirs(self.exp, self.trial)["log"], f"time_marks{self.index}.pkl"))
             return None
         name = req.model_name
         model = self.models[name]
@@ -255,11 +259,15 @@ class ModelWorker:
             if rpc.input_key_remap:
                 inp.remap_keys_(rpc.input_key_remap)
             t0 = time.perf_counter()
-            res = getattr(self.interfaces[rpc.name], h)(model, inp, n_mbs=rpc.n_mbs)
+            if self.device.type == "cuda":
+                torch.cuda.reset_peak_memory_stats(self.device)
+            with self._mfc_profile(rpc.name), monitor.cuda_tmarked(rpc.name, _TMARK_OF[h], str(name)):
+                res = getattr(self.interfaces[rpc.name], h)(model, inp, n_mbs=rpc.n_mbs)
             if self.device.type == "cuda":
                 torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             ctx = self.ctxs[name]
+            mem = self._memory_stats()
             if isinstance(res, SequenceSample):
                 if rpc.output_key_remap:
                     res.remap_keys_(rpc.output_key_remap)
@@ -269,9 +277,58 @@ class ModelWorker:
                             self.data_storage[it.ids[0]].update_(it)
                         else:
                             self.data_storage[it.ids[0]] = it
-                return dict(meta=res.meta() if ctx.is_dp_head else None, secs=dt)
-            return dict(stats=res if ctx.is_dp_head else None, secs=dt)
+                return dict(meta=res.meta() if ctx.is_dp_head else None, secs=dt, mem=mem)
+            return dict(stats=res if ctx.is_dp_head else None, secs=dt, mem=mem)
         raise NotImplementedError(f"unknown request `{h}`")
+
+    # ------------------------------------------------------------------ observability
+    def _mfc_profile(self, rpc_name: str):
+        """`REAL_DUMP_TRACE=1`: one torch.profiler chrome trace per MFC call under <log>/trace/; `REAL_DUMP_MEMORY=1`: allocator
+        history snapshot per call (reference: model_worker.py:65-78, :663-721)."""
+        import contextlib
+        trace = os.environ.get("REAL_DUMP_TRACE", "0") == "1"
+        memory = os.environ.get("REAL_DUMP_MEMORY", "0") == "1" and self.device.type == "cuda"
+        if not trace and not memory:
+            return contextlib.nullcontext()
+        worker = self
+
+        @contextlib.contextmanager
+        def cm():
+            out_dir = os.path.join(constants.run_dirs(worker.exp, worker.trial)["log"], "trace")
+            os.makedirs(out_dir, exist_ok=True)
+            worker._n_profiled = getattr(worker, "_n_profiled", 0) + 1
+            tag = f"{rpc_name}_r{worker.index}_c{worker._n_profiled}"
+            if memory:
+                torch.cuda.memory._record_memory_history(max_entries=100000)
+            prof = None
+            if trace:
+                acts = [torch.profiler.ProfilerActivity.CPU] + ([torch.profiler.ProfilerActivity.CUDA] if worker.device.type == "cuda" else [])
+                prof = torch.profiler.profile(activities=acts, record_shapes=True, profile_memory=True, with_stack=False)
+                prof.__enter__()
+            try:
+                yield
+            finally:
+                if prof is not None:
+                    prof.__exit__(None, None, None)
+                    prof.export_chrome_trace(os.path.join(out_dir, tag + ".json"))
+                if memory:
+                    torch.cuda.memory._dump_snapshot(os.path.join(out_dir, tag + ".mem.pkl"))
+                    torch.cuda.memory._record_memory_history(enabled=None)
+        return cm()
+
+    def _memory_stats(self) -> Dict[str, float]:
+        """Peak allocator numbers of the MFC that just ran; travels with the reply (the reference all-gathers these over the
+        model group after every MFC, model_worker.py:1031-1040 -- here they ride on the control plane instead)."""
+        if self.device.type != "cuda":
+            return {}
+        st = dict(peak_allocated_gb=torch.cuda.max_memory_allocated(self.device) / 2 ** 30,
+                  peak_reserved_gb=torch.cuda.max_memory_reserved(self.device) / 2 ** 30, worker=self.index)
+        try:
+            free, total = torch.cuda.mem_get_info(self.device)
+            st["device_used_gb"] = (total - free) / 2 ** 30
+        except Exception:
+            pass
+        return st
 
     # ------------------------------------------------------------------ main loop
     def run(self):
@@ -310,6 +367,10 @@ class ModelWorker:
                 if rpc is not None:
                     self.interfaces[rpc.name].save(model, os.path.join(root, name.role))
                     self.backends[name].save(model, os.path.join(root, name.role, "optim"))
+
+
+_TMARK_OF = {"generate": monitor.CUDATimeMarkType.forward, "inference": monitor.CUDATimeMarkType.forward,
+             "train_step": monitor.CUDATimeMarkType.backward}
 
 
 def _real(model: model_api.Model):

@@ -1,0 +1,1 @@
+"""Small reusable utilities: CUDA-graph registry, logits warpers, the global stats tracker."""

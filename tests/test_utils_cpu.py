@@ -1,0 +1,69 @@
+"""Utilities and aux subsystems: logits warpers, stats tracker, in-flight batching, profile experiment, trace summary."""
+import json
+
+import torch
+
+from realhf_b200.api.model import GenerationHyperparameters
+from realhf_b200.base import monitor
+from realhf_b200.models import generation as gen
+from realhf_b200.models import hf_io
+from realhf_b200.models.real_model import ReaLModel
+from realhf_b200.utils import logits_warper as LW
+from realhf_b200.utils.stats_tracker import StatsTracker
+
+
+def test_logits_warpers_match_generation_filter():
+    torch.manual_seed(0)
+    x = torch.randn(6, 200) * 3
+    g = GenerationHyperparameters(top_k=20, top_p=0.7, temperature=0.9)
+    ref = gen._filter_logits((x / g.temperature).clone(), g)
+    out = LW.chained_logits_wraper([LW.TemperatureLogitsWarper(0.9), LW.TopKLogitsWarper(20), LW.TopPLogitsWarper(0.7)])(None, x)
+    kept_ref = ref > torch.finfo(ref.dtype).min
+    kept = out > -float("inf")
+    assert torch.equal(kept, kept_ref)
+    assert (kept.sum(-1) >= 1).all() and (kept.sum(-1) <= 20).all()
+    eps = LW.EpsilonLogitsWarper(0.01)(None, x)
+    assert ((eps > -float("inf")).sum(-1) >= 1).all()
+
+
+def test_stats_tracker_reduce_hook():
+    t = StatsTracker()
+    t.log("aux", torch.tensor(1.0))
+    t.log("aux", torch.tensor(2.5), hook=lambda v: v * 2)
+    assert t.pop("aux").item() == 7.0
+    assert t.pop("aux") is None
+
+
+def test_inflight_batching_matches_batched_generation():
+    cfg = hf_io.family("llama").make_test_config()
+    m = ReaLModel(cfg, dtype=torch.float32).instantiate(seed=3)
+    g = GenerationHyperparameters(max_new_tokens=6, min_new_tokens=6, greedy=True)
+    torch.manual_seed(0)
+    prompts = [torch.randint(2, 128, (n,)) for n in (5, 9, 4, 7, 6)]
+    res = gen.InflightBatchingGenerator(m, g, eos_id=1, pad_id=0, n_slots=2, max_prompt_len=16).generate(prompts)
+    ids = torch.cat(prompts)
+    cu = torch.zeros(len(prompts) + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor([p.numel() for p in prompts]).cumsum(0)
+    out, _ = gen.generate(m, ids, cu, g, 1, 0)
+    for i, (toks, lps, _ended) in enumerate(res):
+        assert toks == out.tokens[i].tolist()
+        torch.testing.assert_close(torch.tensor(lps), out.logprobs[i], atol=1e-4, rtol=1e-3)
+
+
+def test_profile_experiment_cpu(tmp_path):
+    from realhf_b200.apps.quickstart import build_experiment
+    out = tmp_path / "prof.json"
+    cfg = build_experiment(["profile", "device=cpu", "batch_sizes=[2]", "seqlens=[12]", "handles=[inference,train_step]", "repeats=1",
+                            f"output_file={out}"])
+    rows = cfg.run_local()
+    assert {r["handle"] for r in rows} == {"inference", "train_step"} and all(r["secs"] > 0 for r in rows)
+    assert json.load(open(out))[0]["bs"] == 2
+
+
+def test_kernel_trace_categorisation():
+    ev = [dict(cat="kernel", name="ncclDevKernel_AllReduce_Sum_bf16", dur=10.0), dict(cat="kernel", name="gemm_2cta_kernel<256>", dur=30.0),
+          dict(cat="gpu_memcpy", name="Memcpy DtoD", dur=5.0), dict(cat="cpu_op", name="aten::add", dur=99.0)]
+    s = monitor.summarize_chrome_trace(ev)
+    assert s == {"collective": 10.0, "compute": 30.0, "memory": 5.0}
+    f = monitor.calculate_llama_forward_flops(2, [16, 16], 2, 64, 128, 100)
+    assert monitor.calculate_llama_train_flops(3, 2, [16, 16], 2, 64, 128, 100) == 3 * f
