@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(DecodeParams p) {
   const int b = blockIdx.x, hkv = blockIdx.y, split = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rsel = lane / LPR;
+  rb::pdl_trigger();  // successors may start launching (and prefetching weights) while this kernel still waits below
   rb::pdl_wait();
-  rb::pdl_trigger();
   const int pos = p.cache_lens[b];   // position of the new token; attends to [0, pos]
   const int n_ctx = pos + 1;
   const T* qkv = reinterpret_cast<const T*>(p.qkv) + (int64_t)b * p.qkv_stride;
@@ -230,8 +230,8 @@ __global__ void decode_attn_reduce_kernel(const float* __restrict__ part_acc, co
                                           T* __restrict__ out, int splits) {
   const int64_t bh = blockIdx.x;  // b * nq + hq
   const int d = threadIdx.x;
+  rb::pdl_trigger();  // successors may start launching (and prefetching weights) while this kernel still waits below
   rb::pdl_wait();
-  rb::pdl_trigger();
   float mg = -INFINITY;
   for (int s = 0; s < splits; ++s) mg = fmaxf(mg, part_ml[(bh * splits + s) * 2]);
   float lg = 0.f, ag = 0.f;

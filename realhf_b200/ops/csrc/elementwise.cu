@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const T* __restrict_
                                                             int F, int kind) {
   const int vec_per_row = F / 8;
   const int64_t total = n_tok * vec_per_row;
+  rb::pdl_trigger();  // successors may start launching (and prefetching weights) while this kernel still waits below
   rb::pdl_wait();
-  rb::pdl_trigger();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = idx / vec_per_row;
     const int c = (int)(idx % vec_per_row);

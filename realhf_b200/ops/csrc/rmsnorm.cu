@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const T* __restri
   constexpr int V = 8;
   const int64_t row = blockIdx.x;
   const int nvec = H / V;
+  rb::pdl_trigger();  // successors may start launching (and prefetching weights) while this kernel still waits below
   rb::pdl_wait();
-  rb::pdl_trigger();
   const rb::Pack<T, V>* xr = reinterpret_cast<const rb::Pack<T, V>*>(x + row * H);
   const rb::Pack<T, V>* rr = kResidual ? reinterpret_cast<const rb::Pack<T, V>*>(res_in + row * H) : nullptr;
   float vals[kMaxVec][V];
