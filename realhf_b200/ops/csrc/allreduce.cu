@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(kThreads) reduce_slabs_kernel(const uint8_t* _
   }
 }
 
+__global__ void spin_wait_kernel(const uint32_t* flag, uint32_t target) {
+  while ((int32_t)(ld_acquire_sys(flag) - target) < 0) {}
+}
+
 Peers make_peers(const int64_t* data_ptrs, const int64_t* pad_ptrs, int world) {
   Peers P;
   for (int i = 0; i < kMaxRanks; ++i) {
@@ -253,6 +257,11 @@ int rb_symm_allreduce(const int64_t* data_ptrs, const int64_t* pad_ptrs, const v
   else allreduce_2shot_kernel<T><<<blocks, kThreads, 0, s>>>(P, (const int4*)in, (int4*)out, nvec, half, rank, world);
   if (dt == 0) { RB_GO(float) } else if (dt == 1) { RB_GO(__nv_bfloat16) } else if (dt == 2) { RB_GO(__half) } else return -2;
 #undef RB_GO
+  return 0;
+}
+
+int rb_spin_wait(const uint32_t* flag, uint32_t target, cudaStream_t s) {
+  spin_wait_kernel<<<1, 1, 0, s>>>(flag, target);
   return 0;
 }
 

@@ -16,6 +16,10 @@ int rb_symm_barrier(const int64_t*, const int64_t*, int, int, cudaStream_t);
 int rb_symm_allreduce(const int64_t*, const int64_t*, const void*, void*, int64_t, int, int, int, int, cudaStream_t);
 int rb_reduce_slabs(const void*, void*, int64_t, int64_t, int, const uint32_t*, uint32_t*, uint32_t, int, cudaStream_t);
 int rb_symm_calls_word(int);
+int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
+                       int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, const uint32_t* ready_flags,
+                       uint32_t ready_epoch, int rows_per_flag, int m_rot_rows, uint32_t* done_counters, cudaStream_t s);
+int rb_spin_wait(const uint32_t* flag, uint32_t target, cudaStream_t s);
 int rb_gemm_fused_tp(int mode, const void* A, const int64_t* peer_a, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                      int64_t ldc, int b_mn, const int64_t* peer_base, const int64_t* peer_counter, int rows_per_rank, int my_rank,
                      int world, int num_sms, cudaStream_t s);
@@ -47,6 +51,37 @@ void symm_allreduce(const Tensor& in, Tensor out, std::vector<int64_t> data_ptrs
   int rc = rb_symm_allreduce(data_ptrs.data(), pad_ptrs.data(), in.data_ptr(), out.data_ptr(), in.nbytes(), (int)rank,
                              (int)data_ptrs.size(), dtc(in.scalar_type()), (int)algo, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, "symm_allreduce failed: ", rc);
+}
+
+// y = a @ w^T (or a @ w if b_mn) on the CTA-pair kernel, reading row-block i of `a` only after flags[i] >= epoch: the
+// all-gather -> GEMM path fills `a` chunk by chunk on a copy stream while the tensor cores already work on the local rows.
+Tensor gemm_gated(const Tensor& a, const Tensor& w, bool b_mn, const c10::optional<Tensor>& flags, int64_t epoch, int64_t rows_per_flag,
+                  int64_t first_row, int64_t num_sms, const c10::optional<Tensor>& done) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && w.dim() == 2 && a.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.stride(1) == 1 && w.stride(1) == 1);
+  const int64_t M = a.size(0), K = a.size(1), N = b_mn ? w.size(1) : w.size(0);
+  for (const auto* t : {&flags, &done}) {
+    if (t->has_value())
+      TORCH_CHECK((*t)->scalar_type() == at::kInt && (*t)->is_contiguous() && (*t)->numel() * rows_per_flag >= M, "gemm_gated: bad flag tensor");
+  }
+  c10::cuda::CUDAGuard g(a.device());
+  auto y = at::empty({M, N}, a.options());
+  int rc = rb_gemm_2cta_gated(a.data_ptr(), w.data_ptr(), y.data_ptr(), nullptr, (int)M, (int)N, (int)K, a.stride(0), w.stride(0), N, 0,
+                              b_mn, 1, 1, 0, 0, (int)num_sms, flags.has_value() ? reinterpret_cast<const uint32_t*>(flags->data_ptr()) : nullptr,
+                              (uint32_t)epoch, (int)rows_per_flag, (int)first_row,
+                              done.has_value() ? reinterpret_cast<uint32_t*>(done->data_ptr()) : nullptr,
+                              at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "gemm_gated failed: ", rc);
+  return y;
+}
+
+// Blocks the current stream until flags[index] >= target (device-side spin of one thread; the flag is written by another
+// stream, a copy engine or a peer GPU).
+void spin_wait(const Tensor& flags, int64_t index, int64_t target) {
+  TORCH_CHECK(flags.is_cuda() && flags.scalar_type() == at::kInt && index >= 0 && index < flags.numel());
+  c10::cuda::CUDAGuard g(flags.device());
+  TORCH_CHECK(rb_spin_wait(reinterpret_cast<const uint32_t*>(flags.data_ptr()) + index, (uint32_t)target,
+                           at::cuda::getCurrentCUDAStream().stream()) == 0);
 }
 
 int64_t symm_calls_word(int64_t parity) { return rb_symm_calls_word((int)parity); }
@@ -131,5 +166,7 @@ void register_comm_ops(torch::Library& m) {
   m.def("symm_allreduce(Tensor inp, Tensor(a!) out, int[] data_ptrs, int[] pad_ptrs, int rank, int algo) -> ()", &symm_allreduce);
   m.def("symm_calls_word(int parity) -> int", &symm_calls_word);
   m.def("gemm_rs(Tensor x, Tensor w, bool b_mn, int[] peer_inbox, int[] peer_counter, int my_calls_ptr, int rank, int num_sms) -> Tensor", &gemm_rs);
+  m.def("gemm_gated(Tensor a, Tensor w, bool b_mn, Tensor? flags, int epoch, int rows_per_flag, int first_row, int num_sms, Tensor? done) -> Tensor", &gemm_gated);
+  m.def("spin_wait(Tensor flags, int index, int target) -> ()", &spin_wait);
   m.def("ag_gemm(int[] peer_a, int rows, int K, Tensor w, bool b_mn, int rank, int num_sms) -> Tensor", &ag_gemm);
 }

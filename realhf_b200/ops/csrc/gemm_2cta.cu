@@ -70,13 +70,18 @@ RB_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t cols) {
 
 // Tiles are 256 rows tall here; bands of 8 pair-tiles keep the in-flight set roughly square (see tile_coords in gemm_tcgen05.cu).
 constexpr int kGroupM2 = 8;
-RB_DEVICE void tile_coords2(int tile, int tiles_m, int tiles_n, int bn, int& m0, int& n0) {
+RB_DEVICE void tile_coords2(int tile, int tiles_m, int tiles_n, int bn, int m_rot, int& m0, int& n0) {
   const int per_group = kGroupM2 * tiles_n;
   const int group = tile / per_group, within = tile - group * per_group;
   const int gm0 = group * kGroupM2;
   const int gsize = min(kGroupM2, tiles_m - gm0);
-  m0 = (gm0 + within % gsize) * (2 * BM);
+  m0 = ((gm0 + within % gsize + m_rot) % tiles_m) * (2 * BM);
   n0 = (within / gsize) * bn;
+}
+RB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
@@ -132,9 +137,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         int m0, n0;
-        tile_coords2(tile, tiles_m, tiles_n, BN, m0, n0);
+        tile_coords2(tile, tiles_m, tiles_n, BN, p.m_rot, m0, n0);
         m0 += (int)rank * BM;          // my 128 rows of A (and of the output)
         n0 += (int)rank * (BN / 2);    // my half of the B tile
+        if (p.ready_flags != nullptr && m0 < p.M) {  // A rows of this tile may still be in flight from a peer
+          const uint32_t* f = p.ready_flags + m0 / p.rows_per_flag;
+          while ((int32_t)(ld_acquire_gpu_u32(f) - p.ready_epoch) < 0) {}
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_local = ptx::smem_u32(&full_bar[stage]);
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
     const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m0, n0;
-      tile_coords2(tile, tiles_m, tiles_n, BN, m0, n0);
+      tile_coords2(tile, tiles_m, tiles_n, BN, p.m_rot, m0, n0);
       ptx::mbar_wait(ptx::smem_u32(&tmem_full[as]), aphase);
       ptx::tc_fence_after();
       const int row = m0 + (int)rank * BM + quad * 32 + lane;
@@ -226,6 +235,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
           }
           store_chunk<OutT>(dst, v, n_valid, vec_ok);
         }
+      }
+      if (p.done_counters != nullptr) {
+        __threadfence();
+        __syncwarp();
+        const int wrow = m0 + (int)rank * BM + quad * 32;
+        if (lane == 0 && wrow < p.M) atomicAdd(p.done_counters + wrow / p.rows_per_flag, 1u);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -283,17 +298,31 @@ extern "C" {
 
 // Same contract as rb_gemm_tcgen05 (gemm_tcgen05.cu); bn must be 128 or 256 (0 picks).  Returns -40 when the problem is
 // better served by the single-CTA kernel (one m-tile) so the caller can fall through.
+int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
+                       int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, const uint32_t* ready_flags,
+                       uint32_t ready_epoch, int rows_per_flag, int m_rot_rows, uint32_t* done_counters, cudaStream_t s);
+
 int rb_gemm_2cta(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
                  int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, cudaStream_t s) {
+  return rb_gemm_2cta_gated(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, in_dt, out_dt, accumulate, bn, num_sms, nullptr, 0, 1, 0, nullptr, s);
+}
+
+// ready_flags != nullptr: rows [i * rows_per_flag, (i+1) * rows_per_flag) of A may only be read once flag[i] >= ready_epoch
+// (rows_per_flag must be a multiple of 128); m_rot_rows: process the m-tiles starting at this row first.
+int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
+                       int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, const uint32_t* ready_flags,
+                       uint32_t ready_epoch, int rows_per_flag, int m_rot_rows, uint32_t* done_counters, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (in_dt != 1 && in_dt != 2) return -10;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
-  if (M <= BM) return -40;
+  const bool gated = ready_flags != nullptr || done_counters != nullptr;
+  if (M <= BM && !gated) return -40;
+  if (gated && (rows_per_flag <= 0 || rows_per_flag % BM != 0 || a_mn)) return -41;
   if (num_sms <= 0) num_sms = rb::kNumSMs;
   if (bn == 0) {
     // 256x256 pair tiles, unless they would leave most SM pairs idle (then the single-CTA kernel's smaller tiles win)
     const int64_t pair_tiles = (int64_t)RB_CEIL_DIV(M, 2 * BM) * RB_CEIL_DIV(N, 256);
-    if (pair_tiles * 10 < (int64_t)(num_sms / 2) * 7) return -40;
+    if (!gated && pair_tiles * 10 < (int64_t)(num_sms / 2) * 7) return -40;
     bn = N > 128 ? 256 : 128;
   }
   if (bn != 128 && bn != 256) return -5;
@@ -304,7 +333,8 @@ int rb_gemm_2cta(const void* A, const void* B, void* C, const void* bias, int M,
   ok = ok && (b_mn ? make_tmap(&tb, B, bf, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK)
                    : make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)(bn / 2)));
   if (!ok) return -13;
-  Params p{C, bias, ldc, M, N, K, accumulate};
+  Params p{C, bias, ldc, M, N, K, accumulate, ready_flags, ready_epoch, rows_per_flag > 0 ? rows_per_flag : 1,
+           (m_rot_rows / (2 * BM)) % RB_CEIL_DIV(M, 2 * BM), done_counters};
 #define RB_GO2(OutT, FMT)                                                                     \
   return bn == 256 ? dispatch_major2<256, OutT, FMT>(a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s) \
                    : dispatch_major2<128, OutT, FMT>(a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s)

@@ -19,6 +19,15 @@ struct Params {
   int64_t ldc;
   int M, N, K;
   int accumulate;  // C += result
+  // optional gating of A row-blocks on arrival flags (all-gather -> GEMM: a copy stream fills A chunk by chunk and bumps
+  // flag[row / rows_per_flag] to `ready_epoch`); m_rot rotates the m-tile order so the rows that are already local go first
+  const uint32_t* ready_flags;
+  uint32_t ready_epoch;
+  int rows_per_flag;
+  int m_rot;
+  // optional completion counters (GEMM -> reduce-scatter): every epilogue warp bumps done[row / rows_per_flag] once its 32
+  // rows x BN columns of a tile are stored, so a copy stream can ship finished row-blocks while later tiles still compute
+  uint32_t* done_counters;
 };
 
 template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok);

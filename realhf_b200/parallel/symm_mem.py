@@ -49,6 +49,10 @@ class SymmetricBuffer:
         t = self.peers[self.rank if rank is None else rank][: self.nbytes]
         return t.view(dtype)
 
+    def pad(self, rank: Optional[int] = None) -> torch.Tensor:
+        """int32 view of a rank's signal pad (words >= 960 are free for host-orchestrated protocols)."""
+        return self.peers[self.rank if rank is None else rank][self.nbytes:].view(torch.int32)
+
     def barrier(self):
         lib().symm_barrier(self.local, self.data_ptrs, self.pad_ptrs, self.rank)
 
