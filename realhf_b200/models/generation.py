@@ -172,11 +172,6 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         h = model.decode_step(state.input_ids, state.k, state.v, state.cache_lens)
         return _final_logits(model, h)
 
-    # programmatic dependent launch pays off for short decode kernels only (measured per decode step: +2.5% at B=16, +1% at B=64, -1..4% at B=128 where attention dominates)
-    pdl_prev = None
-    if dev.type == "cuda" and os.environ.get("REAL_PDL") is None:
-        from realhf_b200.ops import lib as _lib
-        pdl_prev = int(_lib().set_pdl(1 if B <= 64 else 0))
     if use_graph and state.graph is None:
         state.input_ids.copy_(nxt)
         lens_backup = state.cache_lens.clone()
@@ -207,8 +202,6 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         step += 1
         if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(unfinished.any()):
             break
-    if pdl_prev is not None:
-        _lib().set_pdl(pdl_prev)
     tokens = torch.stack(toks, 1)
     logprobs = torch.stack(lps, 1)
     mask_bits = torch.stack(masks, 1) if masks[0] is not None else None

@@ -68,8 +68,9 @@ template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
 RB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 RB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Process-wide switch (set through `rb_set_pdl`): measured inside CUDA graphs, PDL wins ~2% of a decode step at 16
-// sequences per GPU and loses 1-4% at 64-128 (long attention kernels), so the generation loop turns it on per batch size.
+// Process-wide switch (`REAL_PDL=0` / `rb_set_pdl`).  Measured on the LLaMA-7B generation MFC inside CUDA graphs with the
+// trigger issued before the wait in the small kernels and the weight prefetch in the small-M GEMM: -4.5% time at 16
+// sequences per GPU, neutral at 128 (attention-bound).
 extern "C" int rb_get_pdl();
 inline bool pdl_enabled() { return rb_get_pdl() != 0; }
 

@@ -130,7 +130,7 @@ inline int grid_for(int64_t total) {
 
 extern "C" {
 
-static int g_rb_pdl = [] { const char* e = getenv("REAL_PDL"); return (e != nullptr && atoi(e) != 0) ? 1 : 0; }();
+static int g_rb_pdl = [] { const char* e = getenv("REAL_PDL"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
 int rb_get_pdl() { return g_rb_pdl; }
 void rb_set_pdl(int on) { g_rb_pdl = on ? 1 : 0; }
 
