@@ -81,7 +81,9 @@ def remote_worker_cmd(expr_name: str, trial_name: str, debug: bool, worker_type:
 
 
 class LocalSchedulerClient(SchedulerClient):
-    """One OS process per worker; model worker i sees only GPU i (CUDA_VISIBLE_DEVICES)."""
+    """One OS process per worker.  Model worker i drives GPU i (`REAL_LOCAL_GPU`) but keeps every GPU of the node visible:
+    peer-mapped symmetric memory (CUDA IPC: custom all-reduce, fused TP GEMMs, direct-store realloc) needs the peers' devices
+    in the process.  `REAL_ISOLATE_GPUS=1` restores the reference's one-visible-GPU-per-worker behaviour."""
 
     def __init__(self, expr_name, trial_name):
         super().__init__(expr_name, trial_name)
@@ -95,8 +97,11 @@ class LocalSchedulerClient(SchedulerClient):
             env = dict(os.environ)
             env.update(env_vars or {})
             if gpu > 0 and n_gpus > 0:
-                env["CUDA_VISIBLE_DEVICES"] = str(i % n_gpus)
-                env["REAL_LOCAL_GPU"] = "0"
+                if os.environ.get("REAL_ISOLATE_GPUS", "0") == "1":
+                    env["CUDA_VISIBLE_DEVICES"] = str(i % n_gpus)
+                    env["REAL_LOCAL_GPU"] = "0"
+                else:
+                    env["REAL_LOCAL_GPU"] = str(i % n_gpus)
             c = cmd.format(jobstep_id=i, n_jobsteps=count, worker_submission_index=0, wprocs_per_jobstep=1, wprocs_in_job=count,
                            wproc_offset=0)
             name = f"{worker_type}/{i}"

@@ -81,6 +81,18 @@ class ModelWorker:
                                         gradient_checkpointing=getattr(topo, "gradient_checkpointing", False))
             if ctx.is_member:
                 self.ctxs[name] = ctx
+        # fused tensor-parallel GEMM + collective kernels over peer memory (one node, GPUs mutually visible); construction is
+        # collective over each TP group, so every member decides from the same config / env
+        if cfg.device == "cuda" and os.environ.get("REAL_FUSED_TP", "1") != "0" and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1":
+            for name in sorted(self.ctxs, key=str):
+                ctx = self.ctxs[name]
+                if ctx.tp_size > 1 and getattr(ctx, "symm", None) is None:
+                    try:
+                        from realhf_b200.parallel.fused_tp import FusedTP
+                        ctx.symm = FusedTP(ctx, max_tokens=int(os.environ.get("REAL_FUSED_TP_MAX_TOKENS", "32768")),
+                                           max_features=int(os.environ.get("REAL_FUSED_TP_MAX_HIDDEN", "8192")), device=self.device)
+                    except Exception as e:  # e.g. IPC not permitted in this container: plain GEMM + NCCL stays in place
+                        logger.warning(f"fused TP kernels disabled for {name}: {e}")
         # models / backends / interfaces
         for shard in cfg.shards:
             name = shard.id.model_name
