@@ -36,36 +36,80 @@ BASELINE_TOKENS_PER_S = 128 * 640 / (574.312 / 39)  # reference quickstart log: 
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of this rank's GPU with nvidia-smi during the timed region."""
+    """Samples SM clocks / throttle reasons of the node's GPUs during the timed region.
 
-    def __init__(self, index: int, period: float = 0.5):
+    One sampler per node (local rank 0) through NVML in-process (`nvidia_ml_py`); spawning `nvidia-smi` from every rank
+    twice a second perturbed the 8-GPU runs (each invocation initialises NVML on all GPUs).  Falls back to one
+    `nvidia-smi` query per period when NVML is unavailable."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
+
+    def __init__(self, n_gpus: int, period: float = 0.5):
         super().__init__(daemon=True)
-        self.index, self.period = index, period
+        self.n_gpus, self.period = n_gpus, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop_ev = threading.Event()
 
-    def run(self):
+    def _sample_nvml(self, nv, handles):
+        for h in handles:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self._REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=10).stdout.strip().splitlines()
+        for line in out[: self.n_gpus]:
+            f = line.split(",")
+            self.samples.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for n, v in zip(names, f[2:]):
+                if v.strip().lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def run(self):
+        nv = handles = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = [int(x) for x in vis.split(",")][: self.n_gpus] if vis and all(x.strip().isdigit() for x in vis.split(",")) else list(range(self.n_gpus))
+            handles = [nv.nvmlDeviceGetHandleByIndex(i) for i in idx]
+        except Exception:
+            nv = None
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                if nv is not None:
+                    self._sample_nvml(nv, handles)
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_ev.wait(self.period)
+            self._stop_ev.wait(self.period if nv is not None else max(self.period, 2.0))
 
     def stop(self):
         self._stop_ev.set()
-        self.join(timeout=5)
+        self.join(timeout=10)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "n_samples": len(s), "gpus_sampled": self.n_gpus}
+
+
+class _NoSampler:
+    def start(self):
+        pass
+
+    def stop(self):
+        return None
 
 
 def run_reference(args):
@@ -97,6 +141,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # four 7B models + optimizer state + a 43 GB KV cache leave little slack on one GPU: expandable segments keep the caching
+    # allocator from fragmenting (a failed 43 GB request makes it free and re-cudaMalloc its whole cache inside the timed region)
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     import torch
     import torch.distributed as dist
 
@@ -216,7 +263,7 @@ def main():
         rec, st_a, st_c = one_step(i)
         if args.verbose and rank == 0:
             print(f"[warmup {i}] " + " ".join(f"{k}={v.device_ms:.0f}ms" for k, v in rec.items()), file=sys.stderr, flush=True)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(world) if local_rank == 0 else _NoSampler()
     barrier()
     sampler.start()
     launches.reset()
@@ -269,6 +316,10 @@ def main():
                              "pinned-host prompt H2D, all six MFCs, loss/reward statistics D2H; `value` is the CUDA-event time",
                     "wall_ms_per_step": round(wall * 1e3 / args.steps, 2), "device_ms_per_step": round(dev_s * 1e3 / args.steps, 2)},
             "gpu_launches": int(float(t[3]) if world > 1 else n_launch),
+            "memory": {"peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                       "peak_reserved_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1),
+                       "alloc_retries": int(torch.cuda.memory_stats().get("num_alloc_retries", 0)),
+                       "allocator": os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "")},
             "impl": "ours",
         }
         print(json.dumps(out), flush=True)

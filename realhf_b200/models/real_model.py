@@ -318,13 +318,10 @@ class ReaLModel(nn.Module):
             cos, sin = self.rope_tables(max_seqlen)
             qkv = OF.apply_rope(qkv, cos, sin, position_ids, nq + nkv, hd, hd, c.rotary_interleaved)
         T = qkv.shape[0]
-        q = qkv[:, : nq * hd].view(T, nq, hd)
-        k = qkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd)
-        v = qkv[:, (nq + nkv) * hd:].view(T, nkv, hd)
         if kv_sink is not None:
-            kv_sink.append((k, v))
-        o = attn_ops.varlen_attention(q, k, v, cu_seqlens, max_seqlen, self._attn_scale(i), True,
-                                      c.attn_pdrop if self.training else 0.0)
+            kv_sink.append((qkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd), qkv[:, (nq + nkv) * hd:].view(T, nkv, hd)))
+        o = attn_ops.varlen_attention_qkv(qkv, cu_seqlens, max_seqlen, nq, nkv, hd, self._attn_scale(i), True,
+                                          c.attn_pdrop if self.training else 0.0)
         o = TP.row_linear(o.reshape(T, nq * hd), self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx,
                           self.sequence_parallel)
         if self.training and c.resid_pdrop > 0:
