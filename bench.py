@@ -38,13 +38,13 @@ BASELINE_TOKENS_PER_S = 128 * 640 / (574.312 / 39)  # reference quickstart log: 
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons of the node's GPUs during the timed region.
 
-    One sampler per node (local rank 0) through NVML in-process (`nvidia_ml_py`); spawning `nvidia-smi` from every rank
-    twice a second perturbed the 8-GPU runs (each invocation initialises NVML on all GPUs).  Falls back to one
-    `nvidia-smi` query per period when NVML is unavailable."""
+    One sampler per node (local rank 0) through NVML in-process (`nvidia_ml_py`), one sample every 3 s: driver queries
+    contend with CUDA-graph launches -- sampling every 0.5 s made the generation MFC 10-25% slower inside the timed region
+    than in the (unsampled) warm-up steps.  Falls back to one `nvidia-smi` query per period when NVML is unavailable."""
 
     _REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
-    def __init__(self, n_gpus: int, period: float = 0.5):
+    def __init__(self, n_gpus: int, period: float = 3.0):
         super().__init__(daemon=True)
         self.n_gpus, self.period = n_gpus, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -53,7 +53,8 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self, nv, handles):
         for h in handles:
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            if self.max_mhz is None:
+                self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             try:
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
@@ -94,7 +95,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_ev.wait(self.period if nv is not None else max(self.period, 2.0))
+            self._stop_ev.wait(self.period)
 
     def stop(self):
         self._stop_ev.set()
