@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=512)
     ap.add_argument("--gemm", default=os.environ.get("REAL_GEMM", "tcgen05"), choices=["tcgen05", "cublas"])
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--ckpt", default="auto", type=lambda v: {"auto": "auto", "all": True, "none": False}[v],
+                    help="activation checkpointing: auto (recompute only what the free HBM requires), all (every block, the reference default), none")
     ap.add_argument("--gen-tp", type=int, default=int(os.environ.get("REAL_BENCH_GEN_TP", "0")),
                     help="tensor-parallel degree of the generation replica (0: default for this N; 1: generate on the dp layout)")
     args = ap.parse_args()
@@ -170,10 +172,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         ctx = ParallelContext.build(ProcessTopology(1, world, 1), list(range(world)), rank, backend="nccl",
-                                    gradient_checkpointing=True)
+                                    gradient_checkpointing=args.ckpt)
     else:
         ctx = ParallelContext.single()
-        ctx.gradient_checkpointing = True
+        ctx.gradient_checkpointing = args.ckpt
     if args.gemm == "tcgen05":
         from realhf_b200.ops import gemm as G
         OF.set_gemm_impl(G.linear)
@@ -283,6 +285,7 @@ def main():
     dev_s = e0.elapsed_time(e1) / 1e3
     clocks = sampler.stop()
     n_launch = launches.total
+    unckpt = {r: getattr(getattr(models[r].module, "module", None), "last_unckpt_blocks", 0) for r in ("actor", "critic")}
     pool = ex.last_pool
     tokens_this_rank = float(sum(pool.flat_seqlens("packed_input_ids")))
     t = torch.tensor([dev_s, wall, tokens_this_rank, float(n_launch)], dtype=torch.float64, device=dev)
@@ -307,6 +310,8 @@ def main():
                        "parallelism": (f"dp{world} (all 6 MFCs)" if not (world > 1 and gen_tp > 1) else
                                        f"actor_gen tp{gen_tp}xdp{world // gen_tp} (realloc'd replica), other MFCs dp{world}") + ", ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
                        "optimizer": "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads",
+                       "activation_checkpointing": (f"auto: {unckpt} of {args.layers} blocks keep activations (free-HBM budget)" if args.ckpt == "auto"
+                                                    else ("every block" if args.ckpt else "none")),
                        "gemm": args.gemm, "attention": "flash-attn lib (varlen) + own split-KV decode kernel",
                        "l2": "working set >> L2 (54 GB weights per GPU); fresh inputs every step",
                        "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}},
