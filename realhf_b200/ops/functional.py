@@ -303,7 +303,13 @@ class _LMHeadLogProb(torch.autograd.Function):
         T = hidden.shape[0]
         dlogp = dlogp.float().contiguous()
         dh = torch.empty_like(hidden) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            mg = getattr(weight, "main_grad", None)
+            if mg is not None and mg.dtype == torch.float32 and _native_gemm(hidden, weight) is not None:
+                dw = mg  # same contract as ops.gemm._Linear: wgrad accumulates into the fp32 main-grad view
+            else:
+                dw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
         for s in range(0, T, ctx.chunk):
             e = min(T, s + ctx.chunk)
             logits = linear(hidden[s:e], weight)
@@ -320,11 +326,31 @@ class _LMHeadLogProb(torch.autograd.Function):
                 dlogits = ((onehot - p) * (dlogp[s:e] * ctx.inv_temp).unsqueeze(-1)).to(logits.dtype)
                 if mb is not None:
                     dlogits = dlogits.masked_fill(unpack_mask_bits(mb, x.shape[1]), 0)
+            G = _native_gemm(dlogits, weight)
             if dh is not None:
-                dh[s:e] = dlogits @ weight
+                if G is not None:
+                    G.gemm(dlogits, weight, out=dh[s:e], b_mn=True)                    # [t,V] x [V,H]
+                else:
+                    dh[s:e] = dlogits @ weight
             if dw is not None:
-                dw += (dlogits.t() @ hidden[s:e]).float()
+                if G is not None:
+                    G.gemm(dlogits, hidden[s:e], out=dw, a_mn=True, b_mn=True, accumulate=True)  # [t,V]^T x [t,H] += into fp32
+                else:
+                    dw += (dlogits.t() @ hidden[s:e]).float()
+        if dw is not None and dw is getattr(weight, "main_grad", None):
+            dw = None  # accumulated straight into the flat gradient bucket
         return dh, (dw.to(weight.dtype) if dw is not None else None), None, None, None, None
+
+
+def _native_gemm(x, w):
+    """The tcgen05 GEMM module when it is installed as the projection matmul and the operands qualify, else None."""
+    if _GEMM_IMPL["fn"] is None or not x.is_cuda:
+        return None
+    from realhf_b200.ops import gemm as G
+    ok = (x.dtype in (torch.bfloat16, torch.float16) and w.dtype == x.dtype and x.dim() == 2 and x.stride(-1) == 1 and w.stride(-1) == 1
+          and x.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and x.shape[0] % 8 == 0 and x.shape[1] % 8 == 0 and w.shape[0] % 8 == 0
+          and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0)
+    return G if ok else None
 
 
 def lm_head_logprobs(hidden, weight, labels, mask_bits=None, temperature: float = 1.0, chunk: int = 8192):
