@@ -220,6 +220,7 @@ class ReaLModel(nn.Module):
             g = flat_grad[slot.offset: slot.offset + slot.numel].view(slot.shape)
             if flat_grad.dtype == self.p[name].dtype:
                 self.p[name].grad = g
+                self.p[name]._grad_in_flat_buffer = True  # lets the GEMM wgrad accumulate into it in place
             else:
                 p = self.p[name]
                 p.main_grad = g  # fp32 bucket: the GEMM wgrad kernel accumulates into it directly

@@ -26,6 +26,12 @@ RB_DEVICE __nv_bfloat16 sr_bf16(float x, uint32_t rnd16) {
   return __ushort_as_bfloat16((unsigned short)(u >> 16));
 }
 
+RB_DEVICE float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <typename TP, typename TG, typename TS, bool kMaster, bool kStochastic>
 __global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p, const TG* __restrict__ g, TS* __restrict__ m,
                                                     TS* __restrict__ v, float* __restrict__ master, int64_t n, float lr,
@@ -34,6 +40,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p, const TG
                                                     uint32_t seed) {
   if (skip_ptr != nullptr && *skip_ptr != 0) return;
   const float gscale = scale_ptr ? *scale_ptr : 1.f;
+  const float inv_bc1 = 1.f / bc1, inv_bc2 = 1.f / bc2;
   constexpr int V = 8;
   const int64_t nvec = n / V;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -50,7 +57,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p, const TG
       float w = kMaster ? ms.v[k] : rb::to_f(pp.v[k]);
       float mk = b1 * rb::to_f(mm.v[k]) + (1.f - b1) * grad;
       float vk = b2 * rb::to_f(vv.v[k]) + (1.f - b2) * grad * grad;
-      const float upd = (mk / bc1) / (sqrtf(vk / bc2) + eps) + wd * w;
+      const float upd = __fdividef(mk * inv_bc1, sqrt_approx(vk * inv_bc2) + eps) + wd * w;  // IEEE div/sqrt made this kernel ALU-bound
       w -= lr * upd;
       mm.v[k] = rb::from_f<TS>(mk);
       vv.v[k] = rb::from_f<TS>(vk);

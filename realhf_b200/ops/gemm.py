@@ -85,6 +85,8 @@ class _Linear(torch.autograd.Function):
             dx = gemm(dy2, w, b_mn=True).view(ctx.x_shape)            # [T,N] x [N,K] -> [T,K]
         if ctx.needs_input_grad[1]:
             main_grad = getattr(w, "main_grad", None)
+            if main_grad is None and getattr(w, "_grad_in_flat_buffer", False) and w.grad is not None and w.grad.dtype == dy2.dtype:
+                main_grad = w.grad                                      # same-dtype flat gradient buffer: no temp dW + add
             if main_grad is not None:                                   # accumulate straight into the flat grad bucket
                 gemm(dy2, x2, out=main_grad.view(w.shape), a_mn=True, b_mn=True, accumulate=True)
                 dw = None

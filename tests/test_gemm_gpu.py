@@ -162,3 +162,21 @@ def test_gemm_cta_pair_epilogues():
     torch.testing.assert_close(acc, acc0 + _ref(a, b, False, False), atol=1e-2, rtol=1e-3)
     ah, bh = a.half(), b.half()
     torch.testing.assert_close(G.gemm(ah, bh, mc=2).float(), _ref(ah, bh, False, False), atol=0.5, rtol=1e-2)
+
+
+def test_linear_wgrad_accumulates_into_flat_grad_view():
+    """With a same-dtype flat gradient buffer the wgrad GEMM adds into the parameter's .grad view (two micro-batches)."""
+    torch.manual_seed(5)
+    T, K, N = 512, 256, 384
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    flat = torch.zeros(N * K, device=DEV, dtype=torch.bfloat16)
+    w.grad = flat.view(N, K)
+    w._grad_in_flat_buffer = True
+    ref = torch.zeros(N, K, device=DEV)
+    for _ in range(2):
+        x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
+        dy = torch.randn(T, N, device=DEV, dtype=torch.bfloat16) * 0.1
+        G.linear(x, w).backward(dy)
+        ref += dy.float().t() @ x.float()
+    assert w.grad.data_ptr() == flat.data_ptr()
+    torch.testing.assert_close(flat.view(N, K).float(), ref, atol=0.2, rtol=3e-2)
