@@ -84,6 +84,23 @@ def _apply_capacity(probs, idx, n_experts: int, mcfg):
     return probs * keep.view(T, k).to(probs.dtype)
 
 
+def grouped_mlp_device(x_sorted: torch.Tensor, counts_dev: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor, act: str):
+    """Expert MLP over tokens sorted by expert with the counts left on the DEVICE: two grouped tcgen05 GEMM launches and the
+    gated activation, no `tokens_per_expert.cpu()` (reference: moe/experts.py:186) and no per-expert Python loop."""
+    from realhf_b200.ops import gemm as G
+    offsets = torch.zeros(counts_dev.numel() + 1, dtype=torch.int32, device=x_sorted.device)
+    offsets[1:] = counts_dev.cumsum(0)
+    h = G.grouped_linear(x_sorted, w_gate_up, offsets)
+    return G.grouped_linear(OF.gated_act(h, act), w_down, offsets)
+
+
+def _use_grouped_kernel(x: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> bool:
+    if OF._GEMM_IMPL["fn"] is None or not x.is_cuda:
+        return False
+    from realhf_b200.ops import gemm as G
+    return G.grouped_supported(x, w_gate_up) and G.grouped_supported(x, w_down)
+
+
 def grouped_mlp(x_sorted: torch.Tensor, counts: List[int], w_gate_up: torch.Tensor, w_down: torch.Tensor, act: str):
     """Tokens sorted by expert; expert e owns rows [sum(counts[:e]), +counts[e]).  w_gate_up [E,2F,H], w_down [E,H,F]."""
     outs, off = [], 0
@@ -138,8 +155,11 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
             0, tok[sel], (y_sorted * w_sorted[sel].to(y_sorted.dtype).unsqueeze(-1)).to(h.dtype))
         return TP.reduce_from_tp(out, ctx)
     x_sorted = h.index_select(0, tok)
-    counts = torch.bincount(flat_e, minlength=E).tolist()
-    y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)
+    if _use_grouped_kernel(x_sorted, w_gu, w_dn):
+        y_sorted = grouped_mlp_device(x_sorted, torch.bincount(flat_e, minlength=E), w_gu, w_dn, c.activation_function)
+    else:
+        counts = torch.bincount(flat_e, minlength=E).tolist()
+        y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)
     out = torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
     if ctx.tp_size > 1:  # experts are F-sharded over TP: partial sums
         out = TP.reduce_scatter_to_sp(out, ctx) if sp else TP.reduce_from_tp(out, ctx)

@@ -14,6 +14,9 @@ extern "C" int rb_gemm_streamk(const void* A, const void* B, void* C, const void
                                int64_t ldb, int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
                                cudaStream_t s);
 
+extern "C" int rb_gemm_grouped(const void* A, const void* B, void* C, const int* group_offsets, int G, int M, int N, int K, int64_t lda,
+                               int64_t ldb, int64_t ldc, int b_mn, int num_sms, cudaStream_t s);
+
 static int dtc(at::ScalarType t) {
   switch (t) {
     case at::kFloat: return 0;
@@ -84,7 +87,25 @@ Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor
   return c;
 }
 
+// Grouped GEMM over row groups (MoE experts): a [M, K] sorted by group, offsets int32 [G+1] on the device,
+// w [G, N, K] (b_mn = false: y = a_g @ w_g^T) or [G, K, N] (b_mn = true: y = a_g @ w_g).  One launch, no host sync.
+Tensor gemm_grouped(const Tensor& a, const Tensor& w, const Tensor& offsets, bool b_mn, int64_t num_sms) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && w.dim() == 3 && a.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.stride(1) == 1 && w.is_contiguous() && offsets.scalar_type() == at::kInt && offsets.is_contiguous() && offsets.is_cuda());
+  const int64_t G = w.size(0), M = a.size(0), K = a.size(1);
+  const int64_t N = b_mn ? w.size(2) : w.size(1);
+  TORCH_CHECK((b_mn ? w.size(1) : w.size(2)) == K && offsets.numel() == G + 1, "gemm_grouped: shape mismatch");
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor c = at::empty({M, N}, a.options());
+  if (M == 0) return c;
+  int rc = rb_gemm_grouped(a.data_ptr(), w.data_ptr(), c.data_ptr(), offsets.data_ptr<int>(), (int)G, (int)M, (int)N, (int)K, a.stride(0),
+                           w.stride(1), c.stride(0), b_mn, (int)num_sms, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gemm_grouped failed with code ", rc);
+  return c;
+}
+
 void register_gemm_ops(torch::Library& m) {
+  m.def("gemm_grouped(Tensor a, Tensor w, Tensor offsets, bool b_mn, int num_sms) -> Tensor", &gemm_grouped);
   m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
   m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);
 }

@@ -35,7 +35,11 @@ struct FusedParams {
   int64_t peer_counter[kMaxTP];  // mode 1: byte address of the arrival counter on every rank
   int64_t slab_elems;            // mode 1: rows_per_rank * N
   int rows_per_rank, my_rank, world;
+  const int* group_offsets;      // mode 3 (grouped / MoE): device prefix sums of rows per group, [num_groups + 1]
+  int num_groups;
+  int group_b_rows;              // mode 3: rows of the stacked B tensor that belong to one group
 };
+constexpr int kMaxGroups = 256;
 struct TmaArray { CUtensorMap m[kMaxTP]; };
 
 RB_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
@@ -66,6 +70,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
   static_assert(kMC == 1 || !kAMN, "A multicast is implemented for K-major A");
   static_assert(kMode == 0 || (kMC == 1 && !kAMN), "fused TP modes: K-major A, no cluster");
   using C = Cfg<BN>;
+  // mode 3: tiles of group g are [s_tile_prefix[g], s_tile_prefix[g+1]); inside a group n-tiles are outer, m-tiles inner
+  __shared__ int s_tile_prefix[kMode == 3 ? kMaxGroups + 1 : 1];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -79,8 +85,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = RB_CEIL_DIV(p.M, BM), tiles_n = RB_CEIL_DIV(p.N, BN);
+  if constexpr (kMode == 3) {
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      s_tile_prefix[0] = 0;
+      for (int g = 0; g < fp.num_groups; ++g) {
+        acc += RB_CEIL_DIV(fp.group_offsets[g + 1] - fp.group_offsets[g], BM) * tiles_n;
+        s_tile_prefix[g + 1] = acc;
+      }
+    }
+    __syncthreads();
+  }
   // with multicast every CTA of a cluster runs the same number of iterations (padded tiles load zeros, store nothing)
-  const int num_tiles = kMC == 1 ? tiles_m * tiles_n : RB_CEIL_DIV(tiles_m * tiles_n, kMC) * kMC;
+  const int num_tiles = kMode == 3 ? s_tile_prefix[fp.num_groups]
+                                   : (kMC == 1 ? tiles_m * tiles_n : RB_CEIL_DIV(tiles_m * tiles_n, kMC) * kMC);
+  // grouped tile -> (row start, row end, n0, B row offset)
+  auto group_tile = [&](int tile, int& m0, int& m_end, int& n0, int& b_row0) {
+    int g = 0;
+    while (g + 1 < fp.num_groups && s_tile_prefix[g + 1] <= tile) ++g;
+    const int r0 = fp.group_offsets[g], r1 = fp.group_offsets[g + 1];
+    const int mt = RB_CEIL_DIV(r1 - r0, BM);
+    const int local = tile - s_tile_prefix[g];
+    m0 = r0 + (local % mt) * BM;
+    m_end = r1;
+    n0 = (local / mt) * BN;
+    b_row0 = g * fp.group_b_rows;
+  };
   const int num_kb = RB_CEIL_DIV(p.K, BK);
   const uint32_t cta_rank = kMC == 1 ? 0u : (blockIdx.x % kMC);
   constexpr uint16_t kMcMask = (uint16_t)((1u << kMC) - 1u);
@@ -114,8 +144,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m0, n0;
-        tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
+        int m0, n0, m_end = 0, b_row0 = 0;
+        if constexpr (kMode == 3) group_tile(tile, m0, m_end, n0, b_row0);
+        else tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
@@ -137,9 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           }
           if constexpr (kBMN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n0 + 64 * j, k0 + b_row0);
           } else {
-            ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);
+            ptx::tma_load_2d(sb, &tma_b, fb, k0, n0 + b_row0);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -188,8 +219,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     const bool vec_ok = kMode == 1 ? (p.N % (16 / sizeof(OutT)) == 0)
                                    : ((p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int m0, n0;
-        tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
+      int m0, n0, m_end = p.M, b_row0 = 0;
+      if constexpr (kMode == 3) group_tile(tile, m0, m_end, n0, b_row0);
+      else tile_coords(tile, tiles_m, tiles_n, BN, m0, n0);
       ptx::mbar_wait(ptx::smem_u32(&tmem_full[as]), aphase);
       ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
@@ -201,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         ptx::tc_wait_ld();
         const int col = n0 + c * 32;
         const int n_valid = min(32, p.N - col);
-        if (row < p.M && n_valid > 0) {
+        if (row < m_end && n_valid > 0) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -767,6 +799,37 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
     if (out_dt == 0) return launch_streamk<float, 0>(ta, tb, p, sk, grid, s);
   }
   return -14;
+}
+
+// Grouped GEMM (MoE experts) in ONE launch: rows [off[g], off[g+1]) of A are multiplied by group g's weight.
+//   A [M, K] K-major (tokens sorted by group), group_offsets: device int32 [G + 1] (no host copy of the counts needed).
+//   b_mn == 0: B is [G * N, K] (weights [G, N, K]):  C[rows_g] = A[rows_g] @ W_g^T
+//   b_mn == 1: B is [G * K, N] (weights [G, K, N]): C[rows_g] = A[rows_g] @ W_g      (dgrad of the first form)
+// Tile -> (group, m, n) is resolved on the device from the prefix sums; a tile never crosses a group boundary (its tail rows
+// are computed and masked in the epilogue).
+int rb_gemm_grouped(const void* A, const void* B, void* C, const int* group_offsets, int G, int M, int N, int K, int64_t lda,
+                    int64_t ldb, int64_t ldc, int b_mn, int num_sms, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return 0;
+  if (G > kMaxGroups) return -50;
+  if ((lda % 8) || (ldb % 8)) return -21;
+  if (num_sms <= 0) num_sms = rb::kNumSMs;
+  const int bn = N >= 256 ? 256 : 128;
+  FusedParams fp{};
+  fp.group_offsets = group_offsets; fp.num_groups = G; fp.group_b_rows = b_mn ? K : N;
+  CUtensorMap ta, tb;
+  bool ok = make_tmap(&ta, A, 1, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM);
+  ok = ok && (b_mn ? make_tmap(&tb, B, 1, (uint64_t)G * K, (uint64_t)N, (uint64_t)ldb, 64, BK)
+                   : make_tmap(&tb, B, 1, (uint64_t)G * N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn));
+  if (!ok) return -13;
+  Params p{C, nullptr, ldc, M, N, K, 0};
+  // upper bound of the tile count (the exact number is only known on the device): grid = persistent CTAs
+  const int64_t max_tiles = ((int64_t)RB_CEIL_DIV(M, BM) + G) * RB_CEIL_DIV(N, bn);
+  const int grid_sms = (int)(max_tiles < num_sms ? max_tiles : num_sms);
+#define RB_G(BNV, BMN) return launch<BNV, false, BMN, __nv_bfloat16, 1, 1, 3>(ta, tb, p, grid_sms, s, fp, kNoPeers)
+  if (bn == 256) { if (b_mn) RB_G(256, true); else RB_G(256, false); }
+  else { if (b_mn) RB_G(128, true); else RB_G(128, false); }
+#undef RB_G
+  return -24;
 }
 
 // Fused tensor-parallel GEMMs (bf16, K-major A).  mode 1: GEMM -> reduce-scatter scatter phase; mode 2: all-gather -> GEMM.

@@ -101,3 +101,42 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if not supported(x, w):
         return torch.nn.functional.linear(x, w, bias)
     return _Linear.apply(x, w, bias)
+
+
+class _GroupedLinear(torch.autograd.Function):
+    """y[rows of group g] = x[rows of group g] @ w[g]^T for rows sorted by group (MoE experts), one kernel launch."""
+
+    @staticmethod
+    def forward(ctx, x, w, offsets):
+        ctx.save_for_backward(x, w, offsets)
+        return lib().gemm_grouped(x, w, offsets, False, _sms(x.device))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, offsets = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = lib().gemm_grouped(dy, w, offsets, True, _sms(x.device))        # [rows_g, N] x [N, K]
+        if ctx.needs_input_grad[1]:
+            # per-group wgrad: the reduction runs over a data-dependent row range, so it stays one GEMM per group
+            dw = torch.zeros_like(w)
+            off = offsets.tolist()
+            for g in range(w.shape[0]):
+                a, b = off[g], off[g + 1]
+                if b - a >= 8 and (b - a) % 8 == 0:
+                    gemm(dy[a:b], x[a:b], out=dw[g], a_mn=True, b_mn=True)
+                elif b > a:
+                    dw[g] = (dy[a:b].float().t() @ x[a:b].float()).to(w.dtype)
+        return dx, dw, None
+
+
+def grouped_linear(x: torch.Tensor, w: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """x [M, K] sorted by group, w [G, N, K], offsets int32 [G + 1] (device) -> [M, N]."""
+    return _GroupedLinear.apply(x, w, offsets)
+
+
+def grouped_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.dim() == 3 and w.is_contiguous()
+            and x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and w.shape[1] % 8 == 0 and w.shape[2] % 8 == 0
+            and w.shape[0] <= 256)

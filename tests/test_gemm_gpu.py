@@ -180,3 +180,27 @@ def test_linear_wgrad_accumulates_into_flat_grad_view():
         ref += dy.float().t() @ x.float()
     assert w.grad.data_ptr() == flat.data_ptr()
     torch.testing.assert_close(flat.view(N, K).float(), ref, atol=0.2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("counts", [[130, 0, 257, 64, 5, 1024], [8, 8, 8, 8], [0, 0, 300, 0], [513]])
+def test_grouped_gemm_moe(counts):
+    """One-launch grouped GEMM over expert row groups (empty and ragged groups) incl. its backward."""
+    torch.manual_seed(7)
+    E, K, N = len(counts), 256, 384
+    M = sum(counts)
+    x = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(E, N, K, device=DEV) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), device=DEV, dtype=torch.int32)
+    y = G.grouped_linear(x, w, off)
+    dy = (torch.randn(M, N, device=DEV) * 0.1).to(torch.bfloat16)
+    y.backward(dy)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    outs, o = [], 0
+    for e, n in enumerate(counts):
+        outs.append(xr[o:o + n] @ wr[e].t())
+        o += n
+    yr = torch.cat(outs)
+    yr.backward(dy.float())
+    torch.testing.assert_close(y.float(), yr, atol=0.1, rtol=2e-2)
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.05, rtol=3e-2)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.3, rtol=3e-2)
