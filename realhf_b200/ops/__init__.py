@@ -80,9 +80,16 @@ def lib():
     global _lib
     if _lib is None:
         if not _LIB_PATH.exists():
-            raise RuntimeError(
-                f"{_LIB_PATH} is missing. Build it with `python -m realhf_b200.ops.build` "
-                "(or `python -c 'import __graft_entry__ as g; g.build()'`).")
+            # a checkout without build artefacts (the .so files are git-ignored): build in-tree once, loudly
+            try:
+                import sys
+                print(f"[realhf_b200] {_LIB_PATH.name} missing: building the sm_100a kernels in-tree (takes a few minutes)", file=sys.stderr)
+                from realhf_b200.ops import build as _build
+                _build.build_all()
+            except Exception as e:
+                raise RuntimeError(
+                    f"{_LIB_PATH} is missing and building it failed ({e}). Build it with `python -m realhf_b200.ops.build` "
+                    "(or `python -c 'import __graft_entry__ as g; g.build()'`).") from e
         torch.ops.load_library(str(_LIB_PATH))
         _lib = _CountingLib(torch.ops.realhf_b200)
     return _lib
