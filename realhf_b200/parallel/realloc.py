@@ -188,7 +188,7 @@ class ReallocExecutor:
         return self.plan.dst_numel.get(self.me)
 
     def run(self, src_flat: Optional[torch.Tensor], dst_flat: Optional[torch.Tensor], eta: float = 1.0,
-            peer_dst_ptrs: Optional[Dict[int, int]] = None, group=None):
+            peer_dst_ptrs: Optional[Dict[int, int]] = None, group=None, notify: bool = False):
         """peer_dst_ptrs: dst worker -> device address of its destination flat buffer mapped into this process.
         When given for every send, transfers are direct peer stores; else pack + isend/irecv + unpack."""
         for pl in self.local_plans:
@@ -197,6 +197,17 @@ class ReallocExecutor:
         if direct:
             for t, pl in zip(self.sends, self.direct_plans):
                 pl.run(src_flat, None, dst_ptr=peer_dst_ptrs[t.dst_worker], eta=eta)
+            if notify:
+                # completion tokens: a 4-byte send ordered after each store kernel, a matching recv on the destination, so the
+                # destination's stream continues only once every sender's stores have landed (no group / barrier needed)
+                dev = self.device
+                tok = torch.ones(1, dtype=torch.int32, device=dev)
+                ops = [dist.P2POp(dist.isend, tok, self.w2r(t.dst_worker), group) for t in self.sends]
+                bufs = [torch.empty(1, dtype=torch.int32, device=dev) for _ in self.recvs]
+                ops += [dist.P2POp(dist.irecv, b, self.w2r(t.src_worker), group) for b, t in zip(bufs, self.recvs)]
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
             return
         ops, staged = [], []
         for t, pl in zip(self.sends, self.pack_plans):

@@ -48,6 +48,8 @@ class ModelWorker:
         self.data_iter = None
         self.epoch = 0
         self._realloc_cache: Dict[Tuple[ModelName, ModelName], realloc.ReallocExecutor] = {}
+        self._ipc_owned: Dict[ModelName, torch.Tensor] = {}
+        self._ipc_peers: Dict[Tuple[ModelName, int], torch.Tensor] = {}
         self._exiting = False
 
     # ------------------------------------------------------------------ setup
@@ -176,17 +178,61 @@ class ModelWorker:
         ex = self._realloc_cache[key]
         src_flat = _real(src_model).flat_param.data if src_model is not None and _real(src_model).instantiated else None
         dst_flat = None
+        # receive-only replicas (replica_id > 0, created by the allocation for another layout) live in IPC-shareable
+        # memory on GPUs: senders store the destination layout straight into them over NVLink, one kernel per transfer
+        direct = self._direct_realloc_ok(dst_name)
         if dst_model is not None:
             m = _real(dst_model)
             if not m.instantiated:
-                m.attach_flat(torch.zeros(m.flat_numel, dtype=m.dtype, device=self.device))
-                for p in m.parameters():
-                    p.requires_grad_(False)
+                self._alloc_recv_flat(dst_name, m)
             dst_flat = m.flat_param.data
-        ex.run(src_flat, dst_flat, eta=eta)
+        if direct:
+            es = torch.tensor([], dtype=(src_model or dst_model).dtype).element_size()
+            ptrs = {t.dst_worker: self._peer_flat_ptr(dst_name, t.dst_worker, ex.plan.dst_numel[t.dst_worker] * es) for t in ex.sends}
+            ex.run(src_flat, dst_flat, eta=eta, peer_dst_ptrs=ptrs, notify=True)
+        else:
+            ex.run(src_flat, dst_flat, eta=eta)
         # a non-trainable source replica is dropped after handing its weights back
         if spec.get("release_src") and src_model is not None:
             _real(src_model).release_params()
+
+    # ------------------------------------------------------------------ direct (peer-store) reallocation plumbing
+    def _direct_realloc_ok(self, dst_name: ModelName) -> bool:
+        return (self.device.type == "cuda" and dst_name.replica_id > 0 and os.environ.get("REAL_REALLOC_DIRECT", "1") != "0"
+                and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1")
+
+    def _ipc_key(self, name: ModelName, worker: int) -> str:
+        return f"{self.exp}/{self.trial}/realloc_ipc/{name}/{worker}"
+
+    def _alloc_recv_flat(self, name: ModelName, m):
+        """Flat buffer of a replica that only ever receives weights by reallocation."""
+        nbytes = m.flat_numel * torch.tensor([], dtype=m.dtype).element_size()
+        if self._direct_realloc_ok(name):
+            from realhf_b200.ops import lib
+            buf = self._ipc_owned.get(name)
+            if buf is None:  # allocated once: peers keep their mapping of it across release / re-attach cycles
+                buf, handle = lib().symm_alloc(max(nbytes, 16), self.device.index)
+                self._ipc_owned[name] = buf
+                name_resolve.add(self._ipc_key(name, self.index), bytes(handle.tolist()).hex(), replace=True)
+            flat = buf[:nbytes].view(m.dtype)
+        else:
+            flat = torch.zeros(m.flat_numel, dtype=m.dtype, device=self.device)
+        m.attach_flat(flat)
+        for p in m.parameters():
+            p.requires_grad_(False)
+
+    def _peer_flat_ptr(self, name: ModelName, worker: int, nbytes: int) -> int:
+        """Device address (in this process) of `worker`'s flat buffer of replica `name`."""
+        k = (name, worker)
+        if k not in self._ipc_peers:
+            if worker == self.index:
+                self._ipc_peers[k] = self._ipc_owned[name]
+            else:
+                from realhf_b200.ops import lib
+                hexs = name_resolve.wait(self._ipc_key(name, worker), timeout=300)
+                handle = torch.tensor(list(bytes.fromhex(hexs)), dtype=torch.uint8)
+                self._ipc_peers[k] = lib().symm_open(handle, max(nbytes, 16), self.device.index)
+        return int(self._ipc_peers[k].data_ptr())
 
     # ------------------------------------------------------------------ request handling
     def _handle(self, req: Payload) -> Any:
@@ -248,7 +294,7 @@ class ModelWorker:
         if h == "initialize":
             m = _real(model)
             if not m.instantiated:  # replica that only ever receives weights by realloc
-                m.attach_flat(torch.zeros(m.flat_numel, dtype=m.dtype, device=self.device))
+                self._alloc_recv_flat(name, m)
             self.models[name] = self.backends[name].initialize(model, req.data)
             return None
         if h == "save":

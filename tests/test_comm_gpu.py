@@ -176,3 +176,86 @@ def test_fused_tp_gemm_collectives():
     world = 2
     res = run_distributed(_fused_worker, world, backend="nccl", timeout=400)
     print("fused TP (ms), rank 0:", res[0])
+
+
+def _realloc_direct_worker(rank, world):
+    """tp2 -> dp2 (and back) parameter reallocation where every transfer is ONE segment-copy kernel storing straight into
+    the destination GPU's flat buffer (CUDA IPC), checked against the exact destination shards."""
+    import torch.distributed as dist
+
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.parallel import realloc
+    from realhf_b200.parallel.symm_mem import SymmetricBuffer
+    dev = torch.device("cuda", rank)
+    cfg = hf_io.family("llama").make_test_config()
+    cfg.n_layers = 4
+    for (src_dims, dst_dims) in (((1, 1, 2), (1, 2, 1)), ((1, 2, 1), (1, 1, 2))):
+        s_topo, d_topo = ProcessTopology(*src_dims), ProcessTopology(*dst_dims)
+        src = ReaLModel(cfg, ParallelContext.fake(s_topo, rank), dtype=torch.bfloat16, device=dev).instantiate(seed=9)
+        ref = ReaLModel(cfg, ParallelContext.fake(d_topo, rank), dtype=torch.bfloat16, device=dev).instantiate(seed=9)
+        plan = realloc.derive_plan(cfg, s_topo, [0, 1], d_topo, [0, 1])
+        exe = realloc.ReallocExecutor(plan, rank, 2, dev)
+        sb = SymmetricBuffer(plan.dst_numel[rank] * 2, device=dev)
+        dst_flat = sb.data()[: plan.dst_numel[rank] * 2].view(torch.bfloat16)
+        dst_flat.fill_(float("nan"))
+        torch.cuda.synchronize(); dist.barrier()
+        exe.run(src.flat_param.data, dst_flat, peer_dst_ptrs={w: sb.data_ptrs[w] for w in range(world)})
+        torch.cuda.synchronize(); dist.barrier()   # every peer's stores have landed
+        assert torch.equal(dst_flat, ref.flat_param.data), (src_dims, dst_dims, (dst_flat != ref.flat_param.data).sum())
+        # same plan through the pack / isend-irecv / unpack fallback
+        dst2 = torch.full_like(ref.flat_param.data, float("nan"))
+        exe.run(src.flat_param.data, dst2)
+        torch.cuda.synchronize()
+        assert torch.equal(dst2, ref.flat_param.data)
+    return True
+
+
+def test_realloc_direct_peer_stores():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from realhf_b200.base.testing import run_distributed
+    assert all(run_distributed(_realloc_direct_worker, 2, backend="nccl", timeout=300))
+
+
+def test_full_runtime_ppo_with_direct_realloc(tmp_path):
+    """Launcher -> master + 2 model workers on 2 GPUs (NCCL): PPO where generation (dp2) and actor training (tp2) use
+    different layouts, so the actor's weights are reallocated around every generation by direct peer stores."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import os
+    import uuid
+
+    import importlib
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import fixtures
+    os.environ["PYTHONPATH"] = os.path.dirname(here) + os.pathsep + os.environ.get("PYTHONPATH", "")
+    os.environ["REAL_FILEROOT"] = str(tmp_path / "fileroot")
+    os.environ["REAL_NAME_RESOLVE_ROOT"] = str(tmp_path / "nr")
+    from realhf_b200.base import constants, name_resolve
+    importlib.reload(constants)
+    name_resolve.reconfigure("nfs", record_root=str(tmp_path / "nr"))
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    actor, critic = str(tmp_path / "actor"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(actor, "llama")
+    fixtures.make_checkpoint(critic, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    args = ["ppo", f"experiment_name=ppo-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cuda", "dtype=bf16", "n_gpus_per_node=2",
+            "allocation_mode=manual", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2"]
+    for role, path in (("actor", actor), ("ref", actor), ("critic", critic), ("rew", critic)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.gradient_checkpointing=false"]
+    args += ["actor_gen.parallel.data_parallel_size=2", "actor_train.parallel.model_parallel_size=2",
+             "critic_train.parallel.data_parallel_size=2", "critic_inf.parallel.data_parallel_size=2",
+             "ref_inf.parallel.data_parallel_size=2", "rew_inf.parallel.data_parallel_size=2"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=600)
+    root = os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0")
+    log = open(os.path.join(root, "master_worker-0")).read()
+    assert log.count("[actor_train]") == 2 and "benchmark finished" in log, log[-3000:]
