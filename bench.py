@@ -179,6 +179,8 @@ def main():
     if args.gemm == "tcgen05":
         from realhf_b200.ops import gemm as G
         OF.set_gemm_impl(G.linear)
+    else:
+        OF.set_gemm_impl(False)  # library matmul, for A/B runs only
 
     def llama7b(is_critic):
         return ReaLModelConfig(n_layers=args.layers, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008,

@@ -95,7 +95,7 @@ def grouped_mlp_device(x_sorted: torch.Tensor, counts_dev: torch.Tensor, w_gate_
 
 
 def _use_grouped_kernel(x: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> bool:
-    if OF._GEMM_IMPL["fn"] is None or not x.is_cuda:
+    if not x.is_cuda or OF.gemm_impl() is None:
         return False
     from realhf_b200.ops import gemm as G
     return G.grouped_supported(x, w_gate_up) and G.grouped_supported(x, w_down)

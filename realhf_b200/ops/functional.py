@@ -5,6 +5,8 @@ The `*_ref` functions are the numerics oracle used by `tests/` (fp32 PyTorch of 
 
 from __future__ import annotations
 
+import os
+
 import math
 from typing import List, Optional, Tuple
 
@@ -344,7 +346,7 @@ class _LMHeadLogProb(torch.autograd.Function):
 
 def _native_gemm(x, w):
     """The tcgen05 GEMM module when it is installed as the projection matmul and the operands qualify, else None."""
-    if _GEMM_IMPL["fn"] is None or not x.is_cuda:
+    if not x.is_cuda or gemm_impl() is None:
         return None
     from realhf_b200.ops import gemm as G
     ok = (x.dtype in (torch.bfloat16, torch.float16) and w.dtype == x.dtype and x.dim() == 2 and x.stride(-1) == 1 and w.stride(-1) == 1
@@ -365,19 +367,32 @@ def lm_head_logprobs_ref(hidden, weight, labels, mask_bits=None, temperature: fl
 
 # ------------------------------------------------------------------------------------------------ GEMM
 
-_GEMM_IMPL = {"fn": None}
+_GEMM_IMPL = {"fn": None}  # None: auto (tcgen05 on CUDA unless REAL_GEMM=cublas); False: library matmul; callable: that
 
 
 def set_gemm_impl(fn):
-    """Install the tcgen05 GEMM (`ops.gemm.linear`) as the matmul used by every projection."""
+    """Choose the matmul behind every projection: a callable (`ops.gemm.linear`), None for the default (the tcgen05 GEMM on
+    CUDA tensors), or False to force the library matmul (cuBLAS; used by the A/B benchmarks)."""
     _GEMM_IMPL["fn"] = fn
+
+
+def gemm_impl():
+    """The active projection matmul for CUDA tensors, or None when the library path is selected."""
+    fn = _GEMM_IMPL["fn"]
+    if fn is None:
+        if os.environ.get("REAL_GEMM", "tcgen05") == "cublas":
+            return None
+        from realhf_b200.ops import gemm as G
+        fn = _GEMM_IMPL["fn"] = G.linear
+    return fn or None
 
 
 def linear(x, w, bias=None):
     """y = x @ w.T (+ bias), w is [out, in] (torch layout)."""
-    fn = _GEMM_IMPL["fn"]
-    if fn is not None and x.is_cuda:
-        return fn(x, w, bias)
+    if x.is_cuda:
+        fn = gemm_impl()
+        if fn is not None:
+            return fn(x, w, bias)
     return F.linear(x, w, bias)
 
 

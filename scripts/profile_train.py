@@ -14,8 +14,7 @@ from realhf_b200.ops import gemm as G
 
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 impl = sys.argv[2] if len(sys.argv) > 2 else "tcgen05"
-if impl == "tcgen05":
-    OF.set_gemm_impl(G.linear)
+OF.set_gemm_impl(G.linear if impl == "tcgen05" else False)
 dev = torch.device("cuda")
 ctx = ParallelContext.single(); ctx.gradient_checkpointing = True
 cfg = ReaLModelConfig(n_layers=layers, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008, vocab_size=32000,
