@@ -329,7 +329,39 @@ def make_dataset(cfg: Union[str, config_api.DatasetAbstraction], seed: int, dp_r
         cfg = config_api.DatasetAbstraction(type_=cfg)
     tokenizer = load_hf_tokenizer(tokenizer_or_path) if isinstance(tokenizer_or_path, str) else tokenizer_or_path
     util = DatasetUtility(seed, dp_rank, world_size, tokenizer)
-    return ALL_DATASET_CLASSES[cfg.type_](util=util, **cfg.args)
+    if cache_root is None:
+        return ALL_DATASET_CLASSES[cfg.type_](util=util, **cfg.args)
+    # optional on-disk cache of the tokenised shard (parity: data_api.py:677-741): keyed by everything that determines it
+    import hashlib
+    import pickle
+    tok_id = tokenizer_or_path if isinstance(tokenizer_or_path, str) else getattr(tokenizer, "name_or_path", type(tokenizer).__name__)
+    src_stamp = []
+    for v in cfg.args.values():
+        if isinstance(v, str) and os.path.exists(v):
+            st = os.stat(v)
+            src_stamp.append((v, st.st_size, int(st.st_mtime)))
+    key = hashlib.sha1(repr((cfg.type_, sorted(cfg.args.items(), key=str), seed, dp_rank, world_size, tok_id, src_stamp)).encode()).hexdigest()[:20]
+    path = os.path.join(cache_root, "datasets", f"{cfg.type_}-{key}.pkl")
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as f:
+                ds = pickle.load(f)
+            ds.util = util
+            return ds
+        except Exception:
+            pass  # stale / incompatible cache entry: rebuild
+    ds = ALL_DATASET_CLASSES[cfg.type_](util=util, **cfg.args)
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + f".tmp{os.getpid()}"
+        saved_util, ds.util = getattr(ds, "util", None), None  # the tokenizer is not part of the cached payload
+        with open(tmp, "wb") as f:
+            pickle.dump(ds, f)
+        ds.util = saved_util
+        os.replace(tmp, path)
+    except Exception:
+        ds.util = util
+    return ds
 
 
 def make_dataloader(cfg: Union[str, config_api.DataLoaderAbstraction], dataset) -> torch.utils.data.DataLoader:

@@ -111,7 +111,8 @@ class ModelWorker:
         if cfg.datasets:
             src = next(r for r in cfg.model_rpcs if r.is_src)
             ctx = self.ctxs[src.model_name]
-            ds = [data_api.make_dataset(d, cfg.seed, ctx.dp_rank, ctx.dp_size, cfg.tokenizer_name_or_path, self.exp, self.trial)
+            cache_root = os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "..", "..", "cache") if os.environ.get("REAL_DATASET_CACHE", "0") == "1" else None
+            ds = [data_api.make_dataset(d, cfg.seed, ctx.dp_rank, ctx.dp_size, cfg.tokenizer_name_or_path, self.exp, self.trial, cache_root)
                   for d in cfg.datasets]
             dataset = ds[0] if len(ds) == 1 else torch.utils.data.ConcatDataset(ds)
             self.dataset = dataset

@@ -189,3 +189,35 @@ def test_datasets_through_packed_loader(tmp_path):
     assert all(len(l) == 4 for l in b.seqlens["packed_input_ids"])
     parts = b.meta().split(2)
     assert sum(p.bs for p in parts) == 4
+
+
+def test_dataset_disk_cache(tmp_path):
+    """make_dataset(cache_root=...) reuses the tokenised shard and rebuilds it when the source file changes."""
+    import json
+    import types
+
+    import realhf_b200.datasets  # noqa: F401
+    from realhf_b200.api import data as data_api
+    from realhf_b200.api.config import DatasetAbstraction
+
+    class Tok:
+        name_or_path = "toy"
+        eos_token_id, pad_token_id, eos_token = 1, 0, "</s>"
+        calls = 0
+
+        def __call__(self, texts, **kw):
+            Tok.calls += 1
+            ids = [[3 + (ord(c) % 50) for c in t][: kw.get("max_length") or 10 ** 9] for t in texts]
+            return types.SimpleNamespace(input_ids=ids) if False else {"input_ids": ids, "length": [len(i) for i in ids]}
+
+    path = tmp_path / "p.jsonl"
+    path.write_text("\n".join(json.dumps({"id": i, "prompt": "hello world %d" % i}) for i in range(8)))
+    cfg = DatasetAbstraction("prompt", args=dict(dataset_path=str(path), max_length=16))
+    d1 = data_api.make_dataset(cfg, 1, 0, 1, Tok(), cache_root=str(tmp_path / "cache"))
+    n_calls = Tok.calls
+    d2 = data_api.make_dataset(cfg, 1, 0, 1, Tok(), cache_root=str(tmp_path / "cache"))
+    assert Tok.calls == n_calls, "second construction must come from the cache"
+    assert len(d1) == len(d2) == 8 and d2[0].ids == d1[0].ids
+    path.write_text(path.read_text() + "\n" + json.dumps({"id": 99, "prompt": "one more"}))
+    d3 = data_api.make_dataset(cfg, 1, 0, 1, Tok(), cache_root=str(tmp_path / "cache"))
+    assert len(d3) == 9 and Tok.calls > n_calls
