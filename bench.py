@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--ckpt", default="auto", type=lambda v: {"auto": "auto", "all": True, "none": False}[v],
                     help="activation checkpointing: auto (recompute only what the free HBM requires), all (every block, the reference default), none")
+    ap.add_argument("--offload-frozen", default="auto", choices=["auto", "on", "off"],
+                    help="drop the idle reference / reward weights during training and stream them back during generation "
+                         "(auto: on for a single GPU with --ckpt auto, where the freed HBM buys un-recomputed blocks)")
     ap.add_argument("--gen-tp", type=int, default=int(os.environ.get("REAL_BENCH_GEN_TP", "0")),
                     help="tensor-parallel degree of the generation replica (0: default for this N; 1: generate on the dp layout)")
     args = ap.parse_args()
@@ -233,6 +236,17 @@ def main():
     interfaces = {"actor_gen": actor_itf, "ref_inf": actor_itf, "actor_train": actor_itf, "critic_inf": critic_itf,
                   "critic_train": critic_itf, "rew_inf": rw_itf}
     ex = SPMDExecutor(rpcs, models, interfaces, dev)
+    if args.offload_frozen == "on" or (args.offload_frozen == "auto" and world == 1 and args.ckpt == "auto"):
+        # The reference and reward models idle from the end of their inference MFC until the next step's: their device copies
+        # are dropped there (the pinned host copy of frozen weights stays valid) and streamed back on a side stream while the
+        # actor generates.  The ~27 GB this frees during training go to the activation budget (fewer recomputed blocks); the
+        # reference does the same with its OffloadHook (experiments/common/utils.py:182-198).
+        side = torch.cuda.Stream(dev)
+        frozen = {"ref": models["ref"].module.module, "reward": models["reward"].module.module}
+        for mfc, role in (("ref_inf", "ref"), ("rew_inf", "reward")):
+            ex.post_hooks.setdefault(mfc, []).append(lambda m=frozen[role]: m.offload(frozen=True))
+            ex.hooks.setdefault(mfc, []).append(lambda: torch.cuda.current_stream(dev).wait_stream(side))
+        ex.hooks.setdefault("actor_gen", []).append(lambda: [m.reload(stream=side) for m in frozen.values()])
     gen_tp = args.gen_tp if args.gen_tp > 0 else GEN_TP_DEFAULT.get(world, 1)
     if world > 1 and gen_tp > 1:
         # generation on a tp x dp replica of the actor: decode streams 1/tp of the weights per GPU per token; the replica is
@@ -312,6 +326,7 @@ def main():
                        "parallelism": (f"dp{world} (all 6 MFCs)" if not (world > 1 and gen_tp > 1) else
                                        f"actor_gen tp{gen_tp}xdp{world // gen_tp} (realloc'd replica), other MFCs dp{world}") + ", ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
                        "optimizer": "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads",
+                       "frozen_model_offload": args.offload_frozen == "on" or (args.offload_frozen == "auto" and world == 1 and args.ckpt == "auto"),
                        "activation_checkpointing": (f"auto: {unckpt} of {args.layers} blocks keep activations (free-HBM budget)" if args.ckpt == "auto"
                                                     else ("every block" if args.ckpt else "none")),
                        "gemm": args.gemm, "attention": "flash-attn lib (varlen) + own split-KV decode kernel",

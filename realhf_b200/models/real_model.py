@@ -246,23 +246,34 @@ class ReaLModel(nn.Module):
         return missing, unexpected
 
     # ------------------------------------------------------------------ host offload (non-trainable roles)
-    def offload(self):
-        """Async D2H of the whole shard into one pinned buffer (reference: real_llm_api.py:274-306)."""
+    def offload(self, frozen: bool = False):
+        """D2H of the whole shard into one pinned buffer, then drop the device copy (reference: real_llm_api.py:274-306).
+        frozen=True: the weights never change (reference / reward models), so after the first call the host copy is still
+        valid and offloading is just freeing the device buffer."""
         if self.flat_param is None or not self.flat_param.is_cuda:
             return
-        if self._offloaded is None:
-            self._offloaded = torch.empty(self.flat_numel, dtype=self.dtype, device="cpu", pin_memory=True)
-        self._offloaded.copy_(self.flat_param.data, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if self._offloaded is None or not frozen:
+            if self._offloaded is None:
+                self._offloaded = torch.empty(self.flat_numel, dtype=self.dtype, device="cpu", pin_memory=True)
+            self._offloaded.copy_(self.flat_param.data, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         dev = self.flat_param.device
         self.release_params()
         self._offload_dev = dev
 
-    def reload(self):
+    def reload(self, stream: Optional["torch.cuda.Stream"] = None):
+        """H2D of an offloaded shard.  With `stream` the copy runs there (the caller makes its compute stream wait on it before
+        the first use, e.g. `SPMDExecutor` hooks): the reload of an idle model overlaps another model's generation."""
         if self._offloaded is None or self.flat_param is not None:
             return
-        flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self._offload_dev)
-        flat.copy_(self._offloaded, non_blocking=True)
+        if stream is None:
+            flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self._offload_dev)
+            flat.copy_(self._offloaded, non_blocking=True)
+        else:
+            stream.wait_stream(torch.cuda.current_stream(self._offload_dev))  # blocks freed by the compute stream are reusable
+            with torch.cuda.stream(stream):
+                flat = torch.empty(self.flat_numel, dtype=self.dtype, device=self._offload_dev)
+                flat.copy_(self._offloaded, non_blocking=True)
         self.attach_flat(flat)
         for p in self.p.values():
             p.requires_grad_(False)
@@ -421,7 +432,8 @@ class ReaLModel(nn.Module):
 
         The reference checkpoints every block (`nn/real_llm_base.py:194-204`); with 180 GB per GPU that wastes a quarter of
         the training FLOPs whenever the model states leave room.  In "auto" mode the budget is the HBM that is free right
-        now (driver-free + cached-but-unused allocator blocks) minus a safety margin, divided by the saved-tensor footprint
+        now (driver-free + cached-but-unused allocator blocks) minus a safety margin (max(24 GB, 15%): backward transients, logits
+        chunks, workspace), divided by the saved-tensor footprint
         of one block for this micro-batch: x, two normalised inputs, qkv (+ its rotated copy), attention output and LSE,
         gate_up and the gated activation = (11 + 3 F/H) * T * H * 2 bytes."""
         if not self.ckpt_auto or self.device.type != "cuda":
@@ -429,10 +441,10 @@ class ReaLModel(nn.Module):
         c = self.config
         free, total = torch.cuda.mem_get_info(self.device)
         cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-        margin = self.ckpt_margin_bytes if self.ckpt_margin_bytes is not None else max(16 << 30, total // 10)
+        margin = self.ckpt_margin_bytes if self.ckpt_margin_bytes is not None else max(24 << 30, (total * 3) // 20)
         tp = max(1, self.ctx.tp_size)
         inter = c.intermediate_dim if c.mlp_type != "moe" else c.intermediate_dim * max(1, getattr(c.moe, "top_k", 1))
-        per_block = int(n_tokens * c.hidden_dim * 2 * (5 + (6 + 3 * inter / c.hidden_dim) / tp))
+        per_block = int(1.1 * n_tokens * c.hidden_dim * 2 * (5 + (6 + 3 * inter / c.hidden_dim) / tp))  # +10%: allocator rounding
         n = max(0, int((free + cached - margin) // max(per_block, 1)))
         self.last_unckpt_blocks = min(n, self.n_local_blocks())
         return self.last_unckpt_blocks
