@@ -36,3 +36,24 @@ def test_moe_model_forward_backward_matches_cpu_reference():
     torch.testing.assert_close(m.p[k].grad.float().cpu(), ref.p[k].grad, atol=2e-2, rtol=0.2)
     from realhf_b200.ops import launches
     assert launches.by_op.get("gemm_grouped", 0) > 0, "the grouped kernel was not used"
+
+
+def test_frozen_offload_and_async_reload_roundtrip():
+    """Dropping a frozen model's device copy (pinned host copy stays valid) and streaming it back on a side stream."""
+    cfg = hf_io.family("llama").make_test_config()
+    dev = torch.device("cuda")
+    m = ReaLModel(cfg, dtype=torch.bfloat16, device=dev).instantiate(seed=6)
+    m.eval()
+    ids = torch.randint(2, cfg.vocab_size, (50,), device=dev)
+    cu = torch.tensor([0, 20, 50], dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        ref = m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits.clone()
+    side = torch.cuda.Stream(dev)
+    for _ in range(3):
+        m.offload(frozen=True)
+        assert not m.instantiated
+        m.reload(stream=side)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():
+            out = m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits
+        assert torch.equal(out, ref)
