@@ -403,6 +403,8 @@ class ReaLModel(nn.Module):
         Returns a ModelOutput on the last stage, else the hidden-state tensor for the next stage.
         """
         c = self.config
+        if self.flat_param is None and self._offloaded is not None:
+            self.reload()  # offloaded by an OffloadHook after its last call: bring the weights back on first use
         cu_seqlens = cu_seqlens.int()
         if max_seqlen is None:
             max_seqlen = int((cu_seqlens[1:] - cu_seqlens[:-1]).max())

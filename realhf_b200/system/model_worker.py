@@ -48,6 +48,7 @@ class ModelWorker:
         self.data_iter = None
         self.epoch = 0
         self._realloc_cache: Dict[Tuple[ModelName, ModelName], realloc.ReallocExecutor] = {}
+        self._host_copy_stale: set = set()  # models written by a realloc (e.g. reference EMA) since their last offload
         self._ipc_owned: Dict[ModelName, torch.Tensor] = {}
         self._ipc_peers: Dict[Tuple[ModelName, int], torch.Tensor] = {}
         self._exiting = False
@@ -187,6 +188,8 @@ class ModelWorker:
             if not m.instantiated:
                 self._alloc_recv_flat(dst_name, m)
             dst_flat = m.flat_param.data
+        if dst_model is not None:
+            self._host_copy_stale.add(dst_name)
         if direct:
             es = torch.tensor([], dtype=(src_model or dst_model).dtype).element_size()
             ptrs = {t.dst_worker: self._peer_flat_ptr(dst_name, t.dst_worker, ex.plan.dst_numel[t.dst_worker] * es) for t in ex.sends}
@@ -254,7 +257,9 @@ class ModelWorker:
         elif h == "offload":
             m = self.models.get(d["model"])
             if m is not None:
-                _real(m).offload()
+                # weights that did not change since the last offload keep a valid pinned host copy: just free the device copy
+                _real(m).offload(frozen=d["model"] not in self._host_copy_stale)
+                self._host_copy_stale.discard(d["model"])
         else:
             raise NotImplementedError(h)
 

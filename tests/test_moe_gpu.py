@@ -57,3 +57,6 @@ def test_frozen_offload_and_async_reload_roundtrip():
         with torch.no_grad():
             out = m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits
         assert torch.equal(out, ref)
+    m.offload(frozen=True)
+    with torch.no_grad():  # implicit reload on first use (what the runtime's OffloadHook relies on)
+        assert torch.equal(m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits, ref)
