@@ -23,7 +23,7 @@ def _batch(bs=8, seed=0, vocab=128):
     return SequenceSample.from_default(seqlens=lens, ids=list(range(bs)), data=dict(packed_input_ids=ids, prompt_mask=pm))
 
 
-def _worker(rank, world, layout, fam, n_steps, n_mbs=1):
+def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torch.float32, backend="gloo"):
     import types
 
     from realhf_b200.api.config import ModelName
@@ -37,21 +37,25 @@ def _worker(rank, world, layout, fam, n_steps, n_mbs=1):
     pp, dp, tp, sp = layout
     cfg = hf_io.family(fam).make_test_config()
     cfg.n_layers = 4
-    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend="gloo", sequence_parallel=sp)
-    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    if device == "cuda":
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=backend, sequence_parallel=sp)
+    m = ReaLModel(cfg, ctx, dtype=dtype, device=torch.device(device)).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
-                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, "cpu"),
+                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, device),
                                                                                                FinetuneSpec(1, 10, 10))
     full = _batch(8)
     mine = full.split(dp)[ctx.dp_rank] if dp > 1 else full
+    mine.to_device(device)
     itf = basic.SFTInterface()
     losses = [itf.train_step(model, mine, n_mbs=n_mbs)["loss"] for _ in range(n_steps)]
     # greedy generation from the updated weights
     g = GenerationHyperparameters(max_new_tokens=5, min_new_tokens=5, greedy=True)
     plens = [4, 6, 5, 3][: max(2, 4)]
     prompts = SequenceSample.from_default(seqlens=plens, ids=list(range(len(plens))),
-                                          data=dict(packed_input_ids=torch.arange(2, 2 + sum(plens)) % cfg.vocab_size))
+                                          data=dict(packed_input_ids=(torch.arange(2, 2 + sum(plens)) % cfg.vocab_size).to(device)))
     outs = model.module.generate(prompts, tok, g, num_micro_batches=1)
     gen_tokens = torch.cat([o.tokens for o in outs]).tolist() if outs is not None else None
     return dict(losses=losses, gen=gen_tokens, coord=tuple(ctx.coord))
@@ -100,8 +104,11 @@ def _moe_worker(rank, world, layout, expert_parallel):
     cfg = hf_io.family("mixtral").make_test_config()
     cfg.moe.expert_parallel = expert_parallel
     cfg.moe.aux_loss_coeff = 0.0
-    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend="gloo", sequence_parallel=sp)
-    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    if device == "cuda":
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=backend, sequence_parallel=sp)
+    m = ReaLModel(cfg, ctx, dtype=dtype, device=torch.device(device)).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
                                         grad_dtype="fp32")).initialize(Model(ModelName("m", 0), m, tok, "cpu"), FinetuneSpec(1, 10, 10))
