@@ -23,7 +23,7 @@ def _batch(bs=8, seed=0, vocab=128):
     return SequenceSample.from_default(seqlens=lens, ids=list(range(bs)), data=dict(packed_input_ids=ids, prompt_mask=pm))
 
 
-def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torch.float32, backend="gloo"):
+def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torch.float32, pg_backend="gloo"):
     import types
 
     from realhf_b200.api.config import ModelName
@@ -40,7 +40,7 @@ def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torc
     if device == "cuda":
         torch.cuda.set_device(rank)
         device = torch.device("cuda", rank)
-    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=backend, sequence_parallel=sp)
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=pg_backend, sequence_parallel=sp)
     m = ReaLModel(cfg, ctx, dtype=dtype, device=torch.device(device)).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
@@ -107,7 +107,7 @@ def _moe_worker(rank, world, layout, expert_parallel):
     if device == "cuda":
         torch.cuda.set_device(rank)
         device = torch.device("cuda", rank)
-    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=backend, sequence_parallel=sp)
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend=pg_backend, sequence_parallel=sp)
     m = ReaLModel(cfg, ctx, dtype=dtype, device=torch.device(device)).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",

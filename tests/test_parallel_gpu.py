@@ -16,7 +16,7 @@ def test_two_gpu_layout_tracks_single_gpu(layout):
     import test_parallel_cpu as T
     from realhf_b200.base.testing import run_distributed
     pp, dp, tp, sp = layout
-    kw = dict(fam="llama", n_steps=3, device="cuda", dtype=torch.bfloat16, backend="nccl")
+    kw = dict(fam="llama", n_steps=3, device="cuda", dtype=torch.bfloat16, pg_backend="nccl")
     ref = run_distributed(T._worker, 1, backend="nccl", layout=(1, 1, 1, False), n_mbs=dp * (2 * pp if pp > 1 else 1), **kw)[0]
     res = run_distributed(T._worker, 2, backend="nccl", layout=layout, **kw)
     for r in res:
