@@ -226,6 +226,8 @@ class ReaLModel(nn.Module):
                 p.main_grad = g  # fp32 bucket: the GEMM wgrad kernel accumulates into it directly
                 if not getattr(p, "_main_grad_hooked", False):
                     def _fold(param):  # params whose grad comes from autograd (norms, embeddings, biases)
+                        if param.grad is None:  # the GEMM wgrad already accumulated into main_grad and returned no gradient
+                            return
                         param.main_grad.add_(param.grad.view_as(param.main_grad))
                         param.grad = None
                     p.register_post_accumulate_grad_hook(_fold)
