@@ -60,3 +60,30 @@ def test_frozen_offload_and_async_reload_roundtrip():
     m.offload(frozen=True)
     with torch.no_grad():  # implicit reload on first use (what the runtime's OffloadHook relies on)
         assert torch.equal(m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits, ref)
+
+
+def test_train_step_bf16_params_fp32_main_grad():
+    """bf16 weights with an fp32 flat gradient buffer: GEMM wgrads accumulate into `main_grad` in place, autograd gradients of
+    norms / embeddings are folded in by the post-accumulate hook."""
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.data import SequenceSample
+    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    cfg = hf_io.family("llama").make_test_config()
+    cfg.n_layers = 2
+    dev = torch.device("cuda")
+    m = ReaLModel(cfg, dtype=torch.bfloat16, device=dev).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
+                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, dev),
+                                                                                               FinetuneSpec(1, 10, 10))
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(5, 14, (8,), generator=g).tolist()
+    ids = torch.randint(2, cfg.vocab_size, (sum(lens),), generator=g).to(dev)
+    batch = SequenceSample.from_default(seqlens=lens, ids=list(range(8)), data=dict(packed_input_ids=ids, prompt_mask=torch.zeros(sum(lens), dtype=torch.bool, device=dev)))
+    itf = basic.SFTInterface()
+    losses = [itf.train_step(model, batch, n_mbs=n)["loss"] for n in (1, 2, 4, 1)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
