@@ -90,7 +90,7 @@ def test_gpt2_tied_embedding_pp2():
             assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (r["losses"], ref["losses"])
 
 
-def _moe_worker(rank, world, layout, expert_parallel):
+def _moe_worker(rank, world, layout, expert_parallel, device="cpu", dtype=torch.float32, pg_backend="gloo"):
     import types
 
     from realhf_b200.api.config import ModelName
