@@ -34,9 +34,16 @@ class Controller:
                     out[f"{wt}/{i}"] = "UNKNOWN"
         return out
 
-    def wait(self, timeout: Optional[float] = None, poll: float = 0.5):
+    def wait(self, timeout: Optional[float] = None, poll: float = 0.5, status_poll: float = 5.0):
         t0 = time.monotonic()
+        last_status = t0
         while True:
+            if time.monotonic() - last_status > status_poll:
+                # a worker that caught its own exception publishes ERROR before the scheduler sees the process exit
+                last_status = time.monotonic()
+                bad = {k: v for k, v in self.statuses().items() if v == "ERROR"}
+                if bad:
+                    raise sched_client.JobException(self.sched.run_name, sorted(bad)[0], "localhost", sched_client.JobState.FAILED)
             infos = self.sched.find_all()
             master = next((i for i in infos if i.name.startswith("master_worker")), None)
             failed = [i for i in infos if i.state == sched_client.JobState.FAILED]

@@ -231,8 +231,14 @@ class MasterWorker:
     # ------------------------------------------------------------------ main loop
     async def _run_step(self):
         t0 = time.perf_counter()
-        if self.buffer.n_ready_for(self.src_rpc) < self.src_rpc.n_seqs:
+        # usually one fetch; after a recover run whole batches may be filtered out (ids consumed before the failure)
+        attempts = 0
+        while self.buffer.n_ready_for(self.src_rpc) < self.src_rpc.n_seqs:
             await self._load_data()
+            attempts += 1
+            if attempts > 2 * self.ft_spec.steps_per_epoch + 2:
+                raise RuntimeError(f"dataset cannot supply {self.src_rpc.n_seqs} fresh sequences "
+                                   f"({self.buffer.n_ready_for(self.src_rpc)} ready after {attempts} fetches)")
         results = await asyncio.gather(*[self._run_rpc_once(r) for r in self.rpcs])
         done = self.buffer.pop_fully_consumed()
         if done:

@@ -100,8 +100,16 @@ class ModelWorker:
         for shard in cfg.shards:
             name = shard.id.model_name
             self.shard_ids[name] = shard.id
+            model_cfg = shard.model
+            rdir = self._recover_dir(name)
+            if rdir is not None and shard.should_instantiate:
+                # recover run: weights come from the states saved at the failure (reference: model_worker.py:308-313)
+                import copy
+                model_cfg = copy.deepcopy(shard.model)
+                model_cfg.args.update(model_path=rdir, init_from_scratch=False, init_critic_from_actor=False)
+                logger.info(f"recover run: loading {name} from {rdir}")
             with constants.model_scope(name, self.ctxs[name], instantiate=shard.should_instantiate):
-                model = model_api.make_model(shard.model, name=name, device=self.device)
+                model = model_api.make_model(model_cfg, name=name, device=self.device)
             self.models[name] = model
             self.backends[name] = model_api.make_backend(shard.backend)
             self._eval_dataset_cfg = shard.eval_dataset
@@ -302,6 +310,15 @@ class ModelWorker:
             if not m.instantiated:  # replica that only ever receives weights by realloc
                 self._alloc_recv_flat(name, m)
             self.models[name] = self.backends[name].initialize(model, req.data)
+            rdir = self._recover_dir(name)
+            if rdir is not None and os.path.isdir(os.path.join(rdir, "optim")):
+                self.backends[name].load(self.models[name], os.path.join(rdir, "optim"))  # optimizer moments + loss scale
+            if rdir is not None:
+                from realhf_b200.base import recover
+                info = recover.load_recover_info(self.exp, self.trial)
+                if info is not None:  # the version counter drives the LR schedule and the checkpoint names
+                    v = self.models[name].version
+                    v.epoch, v.epoch_step, v.global_step = info.recover_start.epoch, info.recover_start.epoch_step, info.recover_start.global_step
             return None
         if h == "save":
             rpc = next(r for r in self.cfg.model_rpcs if r.model_name == name)
@@ -422,6 +439,12 @@ class ModelWorker:
         except Exception:
             pass
         self.stream.close()
+
+    def _recover_dir(self, name: ModelName) -> Optional[str]:
+        if os.environ.get("REAL_RECOVER_RUN", "0") != "1":
+            return None
+        d = os.path.join(constants.RECOVER_ROOT, self.exp, self.trial, "ckpt", name.role)
+        return d if os.path.exists(os.path.join(d, "config.json")) else None
 
     def save_recover_states(self):
         root = os.path.join(constants.RECOVER_ROOT, self.exp, self.trial, "ckpt")

@@ -76,3 +76,49 @@ def test_ppo_with_realloc_gloo(tmp_path):
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "master_worker-0")).read()
     assert log.count("[actor_train]") == 2 and log.count("[critic_train]") == 2, log[-3000:]
     assert "benchmark finished" in log
+
+
+def test_failure_detection_raises_instead_of_hanging(tmp_path):
+    """A worker that dies during setup (missing dataset) must surface as a JobException from the launcher."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    from realhf_b200.scheduler.client import JobException
+    ckpt = str(tmp_path / "gpt2")
+    fixtures.make_checkpoint(ckpt, "gpt2")
+    exp = build_experiment([
+        "sft", f"experiment_name=bad-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1",
+        "n_gpus_per_node=1", "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}",
+        f"dataset.train_path={tmp_path / 'does-not-exist.jsonl'}", "dataset.train_bs_n_seqs=8", "exp_ctrl.total_train_epochs=1"])
+    with pytest.raises((JobException, TimeoutError)) as ei:
+        main_start(exp, timeout=180)
+    assert isinstance(ei.value, JobException), "the launcher should notice the failed worker long before the timeout"
+
+
+def test_recover_resume_continues_from_saved_step(tmp_path):
+    """recover_mode=save dumps RecoverInfo + model states at exit; a `resume` run restarts counting from there."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    from realhf_b200.base import recover
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=32)
+    name = f"rec-{uuid.uuid4().hex[:6]}"
+    common = ["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1", "n_gpus_per_node=1",
+              "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}",
+              "dataset.train_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=2", "model.optimizer.grad_dtype=fp32",
+              "model.gradient_checkpointing=false"]
+    main_start(build_experiment(common + ["recover_mode=save", "exp_ctrl.benchmark_steps=3"]), timeout=600)
+    info = recover.load_recover_info(name, "t0")
+    assert info is not None and info.last_step_info.global_step >= 2, info
+    main_start(build_experiment(common + ["recover_mode=resume", "exp_ctrl.benchmark_steps=5"]), timeout=300)
+    root = os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0")
+    log = open(os.path.join(root, "master_worker-0")).read()
+    steps = [int(l.split("] step ")[1].split(":")[0]) for l in log.splitlines() if "[trainDefault] step" in l]
+    assert steps == [0, 1, 2, 3, 4], steps                       # the resumed run continues the global step count
+    lrs = [float(l.split("lr=")[1].split(",")[0].split()[0]) for l in log.splitlines() if "[trainDefault] step" in l]
+    assert lrs[3] < lrs[2], lrs                                   # LR schedule position restored with the optimizer state
+    wlog = open(os.path.join(root, "model_worker-0")).read()
+    assert "recover run: loading" in wlog, wlog[-1500:]
