@@ -334,6 +334,7 @@ class ModelWorker:
             dl = data_api.make_dataloader("packed_eval", ds)
             return self.interfaces[rpc.name].evaluate(model, dl)
         if h in ("generate", "inference", "train_step"):
+            self._maybe_inject_fault(h)
             rpc = next(r for r in self.cfg.model_rpcs if r.name == req.data["rpc_name"])
             ids = req.data["ids"]
             inp = SequenceSample.gather([self.data_storage[i] for i in ids], keys=rpc.input_keys)
@@ -439,6 +440,19 @@ class ModelWorker:
         except Exception:
             pass
         self.stream.close()
+
+    def _maybe_inject_fault(self, handle: str):
+        """Fault injection for recovery tests (the reference has none): `REAL_FAULT_INJECT=<worker>:<handle>:<n>` makes that
+        worker raise on its n-th call of `handle` -- only in the original run, never in a recover run."""
+        spec = os.environ.get("REAL_FAULT_INJECT")
+        if not spec or os.environ.get("REAL_RECOVER_RUN", "0") == "1":
+            return
+        w, hname, n = spec.split(":")
+        if int(w) != self.index or hname != handle:
+            return
+        self._fault_calls = getattr(self, "_fault_calls", 0) + 1
+        if self._fault_calls == int(n):
+            raise RuntimeError(f"injected fault: worker {self.index}, call {n} of {handle}")
 
     def _recover_dir(self, name: ModelName) -> Optional[str]:
         if os.environ.get("REAL_RECOVER_RUN", "0") != "1":

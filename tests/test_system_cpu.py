@@ -122,3 +122,30 @@ def test_recover_resume_continues_from_saved_step(tmp_path):
     assert lrs[3] < lrs[2], lrs                                   # LR schedule position restored with the optimizer state
     wlog = open(os.path.join(root, "model_worker-0")).read()
     assert "recover run: loading" in wlog, wlog[-1500:]
+
+
+def test_auto_recover_after_injected_fault(tmp_path):
+    """recover_mode=auto: a model worker dies in its 3rd train step (fault injection), the launcher saves the recover states,
+    restarts everything as a recover run and the experiment finishes with a continuous step count."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=32)
+    name = f"auto-{uuid.uuid4().hex[:6]}"
+    exp = build_experiment(["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1", "n_gpus_per_node=1",
+                            "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}",
+                            "dataset.train_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=2",
+                            "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false", "recover_mode=auto", "recover_retries=1"])
+    os.environ["REAL_FAULT_INJECT"] = "0:train_step:3"
+    try:
+        main_start(exp, timeout=600)
+    finally:
+        os.environ.pop("REAL_FAULT_INJECT", None)
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
+    steps = [int(l.split("] step ")[1].split(":")[0]) for l in log.splitlines() if "[trainDefault] step" in l]
+    assert steps[:2] == [0, 1] and steps[-1] == 7 and len(steps) >= 8, steps
+    wlog = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "model_worker-0")).read()
+    assert "injected fault" in wlog and "recover run: loading" in wlog
