@@ -73,3 +73,35 @@ def test_generation_experiment_writes_jsonl(tmp_path):
     main_start(exp, timeout=600)
     rows = [json.loads(l) for l in open(out)]
     assert len(rows) == 16 and all("answer" in r or "generated" in r or len(r) >= 2 for r in rows), rows[:2]
+
+
+@pytest.mark.parametrize("case", [("search", "ppo", 2), ("d2m2p1", "sft", 4)])
+def test_allocation_modes_through_runtime(tmp_path, case):
+    """`allocation_mode=search` (C++ MCMC search) for PPO and a regex layout with TP x DP on 4 workers for SFT."""
+    mode, algo, n = case
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    fixtures.make_checkpoint(crit, "llama", is_critic=True, seed=5)
+    name = f"m-{uuid.uuid4().hex[:6]}"
+    if algo == "sft":
+        data = str(tmp_path / "sft.jsonl")
+        fixtures.write_sft_dataset(data, words, n=32)
+        args = ["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1", f"n_gpus_per_node={n}",
+                f"allocation_mode={mode}", "model.type._class=llama", f"model.path={ckpt}", f"dataset.train_path={data}",
+                "dataset.train_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2",
+                "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"]
+    else:
+        data = str(tmp_path / "prompts.jsonl")
+        fixtures.write_prompt_dataset(data, words, n=32)
+        args = ["ppo", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", f"n_gpus_per_node={n}", f"allocation_mode={mode}",
+                f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16", "ppo.gen.max_new_tokens=6",
+                "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2", "exp_ctrl.total_train_epochs=1",
+                "exp_ctrl.benchmark_steps=2"]
+        for role, path in (("actor", ckpt), ("ref", ckpt), ("critic", crit), ("rew", crit)):
+            args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=600)
+    assert "benchmark finished" in _master_log(exp)
