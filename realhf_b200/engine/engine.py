@@ -106,15 +106,21 @@ class ReaLEngine(PipelinableEngine):
     @torch.no_grad()
     def eval_batch(self, input_: SequenceSample, loss_fn: Callable, num_micro_batches: Optional[int] = None):
         n_mbs = num_micro_batches or 1
-        if self._pipe is not None:
-            return self._pipe.eval_batch(input_, loss_fn, n_mbs)
-        stats: Dict[str, Any] = collections.defaultdict(float)
-        mbs = input_.split(min(n_mbs, input_.bs))
-        for mb in mbs:
-            _, st = loss_fn(self._forward_mb(mb), mb)
-            for k, v in st.items():
-                stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / len(mbs)
-        return dict(stats)
+        if self.optim is not None:
+            self.optim.materialize()
+        try:
+            if self._pipe is not None:
+                return self._pipe.eval_batch(input_, loss_fn, n_mbs)
+            stats: Dict[str, Any] = collections.defaultdict(float)
+            mbs = input_.split(min(n_mbs, input_.bs))
+            for mb in mbs:
+                _, st = loss_fn(self._forward_mb(mb), mb)
+                for k, v in st.items():
+                    stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / len(mbs)
+            return dict(stats)
+        finally:
+            if self.optim is not None:
+                self.optim.release()
 
     @torch.no_grad()
     def forward(self, input_: SequenceSample, num_micro_batches: Optional[int] = None,

@@ -39,7 +39,14 @@ def _save_hf(model: Model, save_dir: str):
     eng = model.module
     m = getattr(eng, "module", eng)
     fam = getattr(model, "hf_family", None) or getattr(m, "hf_family", "llama")
-    hf_io.save_to_hf(m, fam, save_dir, tokenizer=model.tokenizer)
+    optim = getattr(eng, "optim", None)
+    if optim is not None:
+        optim.materialize()  # ZeRO-3 keeps only this rank's parameter shard between calls (collective over DP: all ranks save)
+    try:
+        hf_io.save_to_hf(m, fam, save_dir, tokenizer=model.tokenizer)
+    finally:
+        if optim is not None:
+            optim.release()
 
 
 def _actor_loss_from_output(out: ModelOutput, mb: SequenceSample, *, kl_adapter, eps_clip: float, temperature: float,

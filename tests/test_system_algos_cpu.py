@@ -105,3 +105,25 @@ def test_allocation_modes_through_runtime(tmp_path, case):
     exp = build_experiment(args)
     main_start(exp, timeout=600)
     assert "benchmark finished" in _master_log(exp)
+
+
+@pytest.mark.parametrize("opt", ["model.zero_stage=3", "model.offload=true"])
+def test_sharded_optimizer_variants_save_hf_checkpoint(tmp_path, opt):
+    """ZeRO-3 (parameters sharded between calls) and host-offloaded optimizer state through the runtime, incl. a periodic
+    HuggingFace checkpoint that `transformers` can load."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "llama")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=32)
+    exp = build_experiment(["sft", f"experiment_name=o-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1",
+                            "n_gpus_per_node=2", "allocation_mode=d2m1p1", "model.type._class=llama", f"model.path={ckpt}", f"dataset.train_path={data}",
+                            "dataset.train_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=3",
+                            "exp_ctrl.save_freq_steps=2", "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false", opt])
+    main_start(exp, timeout=600)
+    found = [os.path.join(d, f) for d, _, fs in os.walk(os.path.join(os.environ["REAL_FILEROOT"], "checkpoints")) for f in fs if f == "config.json"]
+    assert found, "no checkpoint written"
+    import transformers
+    transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
