@@ -34,6 +34,7 @@ def main_worker(args):
         import importlib.util
         spec = importlib.util.spec_from_file_location("real_user_code", user_code)
         mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod  # dataclasses / pickling resolve classes through sys.modules[cls.__module__]
         spec.loader.exec_module(mod)
     with open(config_path(args.experiment_name, args.trial_name), "rb") as f:
         cfg = pickle.load(f)

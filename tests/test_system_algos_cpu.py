@@ -127,3 +127,25 @@ def test_sharded_optimizer_variants_save_hf_checkpoint(tmp_path, opt):
     assert found, "no checkpoint written"
     import transformers
     transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
+
+
+def test_custom_experiment_script_through_runtime(tmp_path):
+    """`python examples/new_algorithms/grpo.py grpo ...`: the user's file registers an interface + experiment, the launcher
+    starts workers that re-import it (REAL_USER_CODE) and the run completes."""
+    import subprocess
+    _env(tmp_path)
+    ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    fixtures.make_checkpoint(crit, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    name = f"ex-{uuid.uuid4().hex[:6]}"
+    args = [sys.executable, os.path.join(ROOT, "examples", "new_algorithms", "grpo.py"), "grpo", f"experiment_name={name}", "trial_name=t0",
+            "device=cpu", "dtype=fp32", "n_gpus_per_node=2", "allocation_mode=heuristic", f"dataset.path={data}", "dataset.train_bs_n_seqs=8",
+            "dataset.max_prompt_len=16", "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2", "actor.type._class=llama",
+            f"actor.path={ckpt}", "ref.type._class=llama", f"ref.path={ckpt}", "rew.type._class=llama", f"rew.path={crit}",
+            "actor.optimizer.grad_dtype=fp32", "actor.gradient_checkpointing=false"]
+    r = subprocess.run(args, cwd=ROOT, env=dict(os.environ), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
+    assert "benchmark finished" in log, log[-2000:]
