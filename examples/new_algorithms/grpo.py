@@ -71,7 +71,7 @@ class GRPOInterface(ModelInterface):
         if outs is None:
             return None
         parts = []
-        for mb, o in zip(x.split(min(n_mbs or 1, x.bs)), outs):
+        for mb, o in IF.pair_generation_outputs(x, outs):
             ids, c, _ = _mb_prompt(mb, dev)
             parts.append(gen.concat_prompt_to_generation_output(ids, c, o) + (o.no_eos,))
         packed = torch.cat([p[0] for p in parts])

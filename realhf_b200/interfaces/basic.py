@@ -240,8 +240,7 @@ class GenerationInterface(ModelInterface):
             return None
         dev = data.data["packed_prompts"].device
         records, all_tokens, all_lens = [], [], []
-        mbs = x.split(min(n_mbs or 1, x.bs))
-        for mb, o in zip(mbs, outs):
+        for mb, o in IF.pair_generation_outputs(x, outs):
             ids, cu, _ = _mb_prompt(mb, dev)
             cu_l = cu.tolist()
             toks, glens = o.tokens.tolist(), o.gen_lens.tolist()

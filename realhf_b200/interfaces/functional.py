@@ -230,3 +230,16 @@ def packed_rewards_and_gae(old_logp, ref_logp, scores, values, seqlens: Sequence
     old/ref log-probs [sum (L-1)], values [sum L].  Returns (advantages, returns, kl_rewards, rewards)."""
     cu = short1_cu_seqlens(seqlens, old_logp.device)
     return OF.ppo_rewards_gae(old_logp, ref_logp, scores, values, cu, no_eos, gamma, lam, kl_ctl, clip_reward)
+
+
+def pair_generation_outputs(x, outs):
+    """[(micro-batch of `x`, GenerationOutput)]: the engine may use more micro-batches than requested (a pipeline needs at least
+    pp of them), so the contiguous partition of `x` is rebuilt from the number of sequences in every output."""
+    from realhf_b200.api.data import SequenceSample
+    items, off, pairs = x.unpack(), 0, []
+    for o in outs:
+        nb = int(o.tokens.shape[0])
+        pairs.append((SequenceSample.gather(items[off: off + nb]), o))
+        off += nb
+    assert off == x.bs, f"generation returned {off} sequences for {x.bs} prompts"
+    return pairs

@@ -117,9 +117,7 @@ class PPOActorInterface(ModelInterface):
             return None
         dev = input_.data["packed_prompts"].device
         parts = []
-        off = 0
-        mbs = x.split(min(n_mbs or 1, x.bs))
-        for mb, o in zip(mbs, outs):
+        for mb, o in IF.pair_generation_outputs(x, outs):
             ids, cu, _ = _mb_prompt(mb, dev)
             packed, slens, lp, mask_bits, in_prompt = gen.concat_prompt_to_generation_output(ids, cu, o)
             parts.append((packed, slens, lp, mask_bits, in_prompt, o.no_eos))

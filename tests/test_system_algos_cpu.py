@@ -149,3 +149,34 @@ def test_custom_experiment_script_through_runtime(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
     assert "benchmark finished" in log, log[-2000:]
+
+
+def test_ppo_pipeline_generation_and_mixed_layouts(tmp_path):
+    """PPO where generation and actor training are pipelined (pp2: more micro-batches than requested), critic training is
+    tp2, critic inference pp2, reference dp2, reward tp2: realloc + data transfer between all of them, and the periodic
+    actor checkpoint (saved from a pipeline layout) loads in `transformers`."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    fixtures.make_checkpoint(crit, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    args = ["ppo", f"experiment_name=pp-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=2",
+            "allocation_mode=manual", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2", "exp_ctrl.save_freq_steps=1",
+            "actor_gen.parallel.pipeline_parallel_size=2", "actor_train.parallel.pipeline_parallel_size=2",
+            "critic_train.parallel.model_parallel_size=2", "critic_inf.parallel.pipeline_parallel_size=2",
+            "ref_inf.parallel.data_parallel_size=2", "rew_inf.parallel.model_parallel_size=2"]
+    for role, path in (("actor", ckpt), ("ref", ckpt), ("critic", crit), ("rew", crit)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=600)
+    assert "benchmark finished" in _master_log(exp)
+    found = [os.path.join(d, f) for d, _, fs in os.walk(os.path.join(os.environ["REAL_FILEROOT"], "checkpoints")) for f in fs
+             if f == "config.json" and "/actor/" in d + "/"]
+    assert found
+    import transformers
+    transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
