@@ -90,9 +90,12 @@ def estimate(rpc: MFCDef, shape: Dict[str, float], par: ParallelismConfig, hw: H
         kv_per_tok = 2 * 2 * h * L / (tp * pp)
         # one token round: every stage runs its pp micro-batches, re-reading its weight shard for each of them
         m = pp
-        step = (wbytes * m + bs * (seq_len + gen_len / 2) * kv_per_tok) / hw.hbm_bw + m * (L / pp) * 9 * hw.launch_us * 1e-6 / 8
+        # calibrated on B200 decode profiles (profiles/decode_step_breakdown_*, bench logs): weight streaming reaches ~85% and
+        # the KV-cache reads ~87% of the HBM copy peak; every layer adds ~45 us of per-kernel fixed cost (4 small-M GEMMs,
+        # attention, norms / activation) and, under TP, two all-reduces that cost ~40 us each end to end inside the graph
+        step = wbytes * m / (0.85 * hw.hbm_bw) + bs * (seq_len + gen_len / 2) * kv_per_tok / (0.87 * hw.hbm_bw) + m * (L / pp) * 45e-6
         if tp > 1:
-            step += m * (L / pp) * 2 * (8e-6)  # small all-reduce latency per layer
+            step += m * (L / pp) * 2 * 40e-6
         if pp > 1:
             step += pp * 10e-6                 # p2p hops of the token ring
         t = prefill + gen_len * step
