@@ -96,6 +96,8 @@ class LocalSchedulerClient(SchedulerClient):
         for i in range(count):
             env = dict(os.environ)
             env.update(env_vars or {})
+            # co-located workers must not each spin up one OpenMP thread per core (the reference forwards OMP_NUM_THREADS too)
+            env.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // (count + 1))))
             if gpu > 0 and n_gpus > 0:
                 if os.environ.get("REAL_ISOLATE_GPUS", "0") == "1":
                     env["CUDA_VISIBLE_DEVICES"] = str(i % n_gpus)
