@@ -1,0 +1,129 @@
+"""Unit tests of the plumbing utilities: name_resolve backends, frequency controls, device-mesh naming, the dotted-override parser,
+the Slurm script builder and the process-topology rank math."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from realhf_b200.api import quickstart as Q
+from realhf_b200.base import name_resolve, timeutil
+from realhf_b200.base.topology import ProcessTopology
+
+
+@pytest.mark.parametrize("kind", ["memory", "nfs"])
+def test_name_resolve_backends(tmp_path, kind):
+    repo = name_resolve.make_repository(kind, **({"record_root": str(tmp_path)} if kind == "nfs" else {}))
+    repo.add("exp/t/a", "1")
+    with pytest.raises(name_resolve.NameEntryExistsError):
+        repo.add("exp/t/a", "2")
+    repo.add("exp/t/a", "2", replace=True)
+    assert repo.get("exp/t/a") == "2"
+    repo.add_subentry("exp/t/peers", "x")
+    repo.add_subentry("exp/t/peers", "y")
+    assert sorted(repo.get_subtree("exp/t/peers")) == ["x", "y"]
+    assert len(repo.find_subtree("exp/t")) >= 3
+    with pytest.raises(name_resolve.NameEntryNotFoundError):
+        repo.get("exp/t/missing")
+    # wait() sees a key published later by another thread
+    threading.Timer(0.2, lambda: repo.add("exp/t/late", "ok")).start()
+    assert repo.wait("exp/t/late", timeout=5) == "ok"
+    with pytest.raises(TimeoutError):
+        repo.wait("exp/t/never", timeout=0.2)
+    repo.delete("exp/t/a")
+    with pytest.raises(name_resolve.NameEntryNotFoundError):
+        repo.get("exp/t/a")
+    repo.clear_subtree("exp/t")
+    assert repo.find_subtree("exp/t") == []
+    repo.reset()
+
+
+def test_watch_names_fires_when_a_key_disappears(tmp_path):
+    repo = name_resolve.make_repository("nfs", record_root=str(tmp_path))
+    repo.add("w/alive", "1")
+    fired = threading.Event()
+    repo.watch_names(["w/alive"], fired.set, poll_frequency=0.1, wait_timeout=5)
+    time.sleep(0.3)
+    assert not fired.is_set()
+    repo.delete("w/alive")
+    assert fired.wait(5)
+
+
+def test_frequency_controls():
+    f = timeutil.FrequencyControl(frequency_steps=3)
+    assert [f.check() for _ in range(7)] == [False, False, True, False, False, True, False]
+    f2 = timeutil.FrequencyControl(frequency_steps=3)
+    f2.load_state_dict(f.state_dict())
+    assert f2.check() is False and f2.check() is True  # count carried over: 1 -> 2 -> 3
+    t = timeutil.FrequencyControl(frequency_seconds=0.15)
+    assert t.check() is False
+    time.sleep(0.2)
+    assert t.check() is True and t.check() is False
+    assert timeutil.FrequencyControl(frequency_steps=100, initial_value=True).check() is True
+    ctl = timeutil.EpochStepTimeFreqCtl(freq_epoch=1, freq_step=2)
+    fires = [ctl.check(epochs=int(i == 3), steps=1) for i in range(5)]
+    assert fires == [False, True, False, True, True] or fires[1] and fires[3]
+
+
+def test_device_mesh_names_and_strategies():
+    m = Q.make_device_mesh_from_name("NODE[01-02]", "NODE01:0,1,2,3", n_nodes=2, n_gpus_per_node=8)
+    assert m.n_gpus == 4 and m.mapping[0, :4].all() and not m.mapping[1].any()
+    whole = Q.make_device_mesh_from_name("NODE[01-02]", "NODE[01-02]", n_nodes=2, n_gpus_per_node=8)
+    assert whole.n_gpus == 16 and whole.contain(m) and whole.overlap(m)
+    other = Q.make_device_mesh_from_name("NODE[01-02]", "NODE02:4,5,6,7", n_nodes=2, n_gpus_per_node=8)
+    assert not other.overlap(m)
+    for bad in ("NODE01:1,2", "NODE01:0,2", "NODE01:0,1,2"):
+        with pytest.raises(ValueError):
+            Q.make_device_mesh_from_name(None, bad, n_nodes=1, n_gpus_per_node=8)
+    subs = whole.sub_device_meshes()
+    assert any(s.n_gpus == 1 for s in subs) and any(s.n_gpus == 8 for s in subs) and all(s.n_gpus in (1, 2, 4, 8, 16) for s in subs)
+    strategies = Q.find_parallel_strategies(m)
+    assert {(p.model_parallel_size, p.pipeline_parallel_size, p.data_parallel_size) for p in strategies} == \
+        {(1, 1, 4), (1, 2, 2), (1, 4, 1), (2, 1, 2), (2, 2, 1), (4, 1, 1)}
+
+
+def test_dotted_overrides_cover_the_reference_surface():
+    from realhf_b200.experiments.algos import PPOConfig
+    cfg = PPOConfig(experiment_name="a", trial_name="b")
+    Q.parse_overrides(cfg, ["actor.optimizer.lr=1e-4", "actor_train.parallel.model_parallel_size=2", "exp_ctrl.save_freq_steps=null",
+                            "ppo.gen.top_k=50", "ppo.gen.use_cuda_graph=True", "actor.type._class=qwen2", "actor.type.size=13",
+                            "actor_gen.n_mbs=4", "ppo.kl_ctl=0.05", "dataset.path=/x/y.jsonl"])
+    assert cfg.actor.optimizer.lr == 1e-4 and cfg.actor_train.parallel.model_parallel_size == 2 and cfg.exp_ctrl.save_freq_steps is None
+    assert cfg.ppo.gen.top_k == 50 and cfg.ppo.gen.use_cuda_graph is True and cfg.actor.type._class == "qwen2" and cfg.actor.type.size == 13
+    assert cfg.actor_gen.n_mbs == 4 and cfg.ppo.kl_ctl == 0.05 and cfg.dataset.path == "/x/y.jsonl"
+    with pytest.raises((AttributeError, KeyError, ValueError)):
+        Q.parse_overrides(cfg, ["actor.no_such_field=1"])
+
+
+def test_slurm_script_builder(tmp_path, monkeypatch):
+    monkeypatch.setenv("REAL_FILEROOT", str(tmp_path))
+    import importlib
+
+    from realhf_b200.base import constants
+    importlib.reload(constants)
+    from realhf_b200.scheduler import client as C
+    importlib.reload(C)
+    s = C.SlurmSchedulerClient("exp", "trial", partition="gpu", container_image="img:latest")
+    cmd = C.remote_worker_cmd("exp", "trial", True, "model_worker")
+    script = s.build_script("model_worker", cmd, count=16, cpu=8, gpu=1, mem=64000, nodelist="n[1-2]", time_limit="1:00:00",
+                            env_vars={"REAL_MODE": "SLURM", "X": "a b"})
+    assert "#SBATCH --ntasks=16" in script and "#SBATCH --nodes=2" in script and "#SBATCH --gpus-per-task=1" in script
+    assert "#SBATCH --nodelist=n[1-2]" in script and "export X='a b'" in script and "--container-image=img:latest" in script
+    mp = [l for l in script.splitlines() if l.startswith("srun")][0].split()[-1]
+    lines = open(mp).read().splitlines()
+    assert len(lines) == 16 and lines[3].startswith("3 ") and "-i 3 -g 16" in lines[3] and "-w model_worker" in lines[3]
+
+
+def test_process_topology_rank_math():
+    topo = ProcessTopology(2, 3, 4)  # (pp, dp, tp)
+    assert topo.world_size() == 24
+    seen = set()
+    for r in range(24):
+        c = topo.get_coord(r)
+        assert topo.get_rank(pipe=c.pipe, data=c.data, model=c.model) == r
+        seen.add((c.pipe, c.data, c.model))
+    assert len(seen) == 24
+    # tensor-parallel peers are adjacent ranks (they share a node / NVLink domain)
+    c0 = topo.get_coord(0)
+    assert sorted(topo.get_rank(pipe=c0.pipe, data=c0.data, model=t) for t in range(4)) == [0, 1, 2, 3]
