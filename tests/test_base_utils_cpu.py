@@ -127,3 +127,53 @@ def test_process_topology_rank_math():
     # tensor-parallel peers are adjacent ranks (they share a node / NVLink domain)
     c0 = topo.get_coord(0)
     assert sorted(topo.get_rank(pipe=c0.pipe, data=c0.data, model=t) for t in range(4)) == [0, 1, 2, 3]
+
+
+def test_layer_profiler_cpu(tmp_path, monkeypatch):
+    """The layer profiler that feeds the allocation search runs on CPU (wall clock) and writes its table."""
+    import torch
+
+    from realhf_b200.models import hf_io
+    from realhf_b200.search import layers
+    monkeypatch.setattr(layers.constants, "PROFILER_CACHE_PATH", str(tmp_path))
+    cfg = hf_io.family("llama").make_test_config()
+    rows = layers.profile_layers(cfg, [2], [16, 32], device="cpu", dtype=torch.float32)
+    assert {(r["layer"], r["op"]) for r in rows} == {("block", "fwd"), ("block", "fwd_bwd"), ("embedding", "fwd")}
+    assert all(r["time_us"] == r["time_us"] for r in rows)
+    p = layers.dump_profile(rows, "llama-test")
+    assert os.path.exists(p)
+
+
+def test_sequence_buffer_readiness_and_reuse():
+    """AsyncIOSequenceBuffer: a batch is ready for an MFC when all its input keys are present; slots are freed once every
+    consumer has read them."""
+    import asyncio
+
+    import torch
+
+    from realhf_b200.api.config import ModelInterfaceAbstraction, ModelInterfaceType
+    from realhf_b200.api.data import SequenceSample
+    from realhf_b200.api.dfg import MFCDef, build_graph
+    from realhf_b200.system.buffer import AsyncIOSequenceBuffer
+    A = lambda t: ModelInterfaceAbstraction(t, {})
+    gen = MFCDef("gen", 2, ModelInterfaceType.GENERATE, A("x"), "actor", input_keys=("packed_prompts",), output_keys=("packed_input_ids",))
+    train = MFCDef("train", 2, ModelInterfaceType.TRAIN_STEP, A("x"), "actor", input_keys=("packed_input_ids",))
+    build_graph([gen, train])
+    buf = AsyncIOSequenceBuffer([gen, train], max_size=16)
+
+    def meta(i, key):
+        return SequenceSample.from_default(seqlens=[3], ids=[i], data={key: torch.zeros(3)}).meta()
+
+    async def run():
+        await buf.put_batch([meta(i, "packed_prompts") for i in range(3)])
+        assert buf.n_ready_for(gen) == 3 and buf.n_ready_for(train) == 0
+        ids, _ = await buf.get_batch_for_rpc(gen)
+        assert len(ids) == 2
+        await buf.amend_batch(ids, [meta(i, "packed_input_ids") for i in ids])
+        assert buf.n_ready_for(train) == 2
+        ids2, _ = await buf.get_batch_for_rpc(train)
+        assert sorted(ids2) == sorted(ids)
+        done = buf.pop_fully_consumed()
+        assert sorted(done) == sorted(ids) and buf.n_ready_for(gen) == 1
+
+    asyncio.run(run())
