@@ -159,6 +159,32 @@ class PairedRewardInterface(ModelInterface):
         if self.enable_save:
             _save_hf(model, save_dir)
 
+    def _mock_train_step(self, model: Model, data: SequenceSample):
+        return _mock_pairs(data)
+
+
+def _mock_pairs(data: SequenceSample, with_seqlogp: bool = False) -> SequenceSample:
+    """Profiling inputs for the paired interfaces: consecutive sequences become (chosen, rejected) pairs of one item."""
+    lens = data.flat_seqlens("packed_input_ids")
+    if len(lens) % 2:
+        raise ValueError("paired interfaces are profiled with an even number of sequences")
+    ids = data.data["packed_input_ids"]
+    dev = ids.device
+    n = len(lens) // 2
+    grouped = [[lens[2 * i], lens[2 * i + 1]] for i in range(n)]
+    pm = torch.zeros(sum(lens), dtype=torch.bool, device=dev)
+    off = 0
+    for l in lens:
+        pm[off: off + max(1, l // 4)] = True
+        off += l
+    keys = dict(packed_input_ids=(ids, grouped), prompt_mask=(pm, grouped))
+    if with_seqlogp:
+        keys["seqlogp"] = (-torch.rand(len(lens), device=dev) * 10, [[1, 1]] * n)
+    with SequenceSample.disable_validation():
+        return SequenceSample(keys=list(keys), ids=[f"pair{i}" for i in range(n)], seqlens={k: v[1] for k, v in keys.items()},
+                              trailing_shapes={k: () for k in keys}, dtypes={k: v[0].dtype for k, v in keys.items()},
+                              data={k: v[0] for k, v in keys.items()})
+
 
 # ------------------------------------------------------------------------------------------- DPO
 
@@ -212,6 +238,12 @@ class DPOInterface(ModelInterface):
         return dict(loss=g["loss"] / n, pos_score=g["pos_score"] / n, neg_score=g["neg_score"] / n, kl=g["kl"] / (2 * n),
                     grad_norm=float(st["grad_norm"]))
 
+    def _mock_inference(self, model: Model, data: SequenceSample):
+        return _mock_pairs(data)
+
+    def _mock_train_step(self, model: Model, data: SequenceSample):
+        return _mock_pairs(data, with_seqlogp=True)
+
     def save(self, model: Model, save_dir: str):
         if self.enable_save:
             _save_hf(model, save_dir)
@@ -248,7 +280,7 @@ class GenerationInterface(ModelInterface):
                 p = ids[cu_l[i]:cu_l[i + 1]].tolist()
                 a = toks[i][: glens[i]]
                 rec = dict(id=sid, prompt_ids=p, answer_ids=a)
-                if model.tokenizer is not None:
+                if hasattr(model.tokenizer, "decode"):
                     rec["prompt"] = model.tokenizer.decode(p, skip_special_tokens=True)
                     rec["answer"] = model.tokenizer.decode(a, skip_special_tokens=True)
                 records.append(rec)

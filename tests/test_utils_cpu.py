@@ -67,3 +67,14 @@ def test_kernel_trace_categorisation():
     assert s == {"collective": 10.0, "compute": 30.0, "memory": 5.0}
     f = monitor.calculate_llama_forward_flops(2, [16, 16], 2, 64, 128, 100)
     assert monitor.calculate_llama_train_flops(3, 2, [16, 16], 2, 64, 128, 100) == 3 * f
+
+
+def test_profile_experiment_mocks_cover_every_interface():
+    """`quickstart profile` fabricates valid inputs for every built-in interface through their `_mock_*` hooks."""
+    from realhf_b200.apps.quickstart import build_experiment
+    for itf, handles, extra in (("sft", "[train_step]", []), ("paired_rw", "[inference,train_step]", ["model.type.is_critic=True"]),
+                                ("dpo", "[inference,train_step]", []), ("ppo_critic", "[inference,train_step]", ["model.type.is_critic=True"]),
+                                ("generation", "[generate]", ["gen.max_new_tokens=3", "gen.min_new_tokens=3"])):
+        cfg = build_experiment(["profile", "device=cpu", "batch_sizes=[4]", "seqlens=[12]", f"handles={handles}", f"interface={itf}", "repeats=1"] + extra)
+        rows = cfg.run_local()
+        assert rows and all(r["secs"] > 0 for r in rows), (itf, rows)
