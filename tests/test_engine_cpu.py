@@ -146,3 +146,30 @@ def test_partial_activation_checkpointing_matches_full():
     for l, g in grads[1:]:
         assert abs(l - grads[0][0]) < 1e-6
         torch.testing.assert_close(g, grads[0][1], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("variant", [
+    dict(adaptive_kl_ctl=True), dict(value_norm=True, value_norm_type="ma"), dict(value_norm=True, adv_norm=False),
+    dict(early_stop_imp_ratio=1.0001, early_stop_kl=1e-9), dict(discount=0.99, gae_lambda=0.95, eps_clip=0.1, max_reward_clip=0.5),
+    dict(n_minibatches=3), dict(generation_config=dict(max_new_tokens=8, min_new_tokens=0, greedy=True)),
+    dict(generation_config=dict(max_new_tokens=8, min_new_tokens=1, top_p=0.5, temperature=0.7, force_no_logits_mask=True))])
+def test_ppo_hyperparameter_variants(variant):
+    """Two PPO iterations under the option combinations of the reference's PPOHyperparameters (adaptive KL, both value
+    normalisers, early stopping, GAE parameters, odd minibatch counts, greedy / unmasked generation)."""
+    torch.manual_seed(0)
+    actor, critic = make_model("actor"), make_model("critic", critic=True)
+    ref, rew = make_model("ref", train=False), make_model("reward", critic=True, train=False, seed=7)
+    kw = dict(n_minibatches=2, generation_config=dict(max_new_tokens=8, min_new_tokens=2, top_k=50, top_p=0.9))
+    kw.update(variant)
+    a = ppo.PPOActorInterface(**kw)
+    c = ppo.PPOCriticInterface(**{k: v for k, v in kw.items() if k in ("n_minibatches", "kl_ctl", "discount", "gae_lambda", "value_eps_clip",
+                                                                         "max_reward_clip", "adaptive_kl_ctl", "value_norm", "value_norm_type")})
+    plens = [5, 7, 4, 6, 5, 8]
+    prompts = SequenceSample.from_default(seqlens=plens, ids=list(range(6)), data=dict(packed_prompts=torch.randint(2, 128, (sum(plens),))))
+    for _ in range(2):
+        d = a.generate(actor, prompts, n_mbs=2)
+        d.update_(a.inference(ref, d))
+        d.update_(c.inference(critic, d))
+        d.update_(basic.PairedRewardInterface().inference(rew, d))
+        sa, sc = a.train_step(actor, d, n_mbs=2), c.train_step(critic, d, n_mbs=2)
+        assert all(x == x for x in list(sa.values()) + list(sc.values()) if isinstance(x, float)), (sa, sc)
