@@ -49,6 +49,7 @@ class MasterWorker:
         self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
         self.rpc_mem: Dict[str, dict] = {}
         self.stats_log: List[Dict] = []
+        self._stats_file = None
         self._consumed_ids_this_epoch: List[Hashable] = []
 
     # ------------------------------------------------------------------ transport helpers
@@ -223,7 +224,9 @@ class MasterWorker:
         if stats and rpc.log_return_value:
             merged = {k: float(np.mean([s[k] for s in stats if k in s])) for k in stats[0] if isinstance(stats[0][k], (int, float))}
             logger.info(f"[{rpc.name}] step {self.step}: " + ", ".join(f"{k}={v:.4g}" for k, v in merged.items()))
-            self.stats_log.append({"rpc": rpc.name, "step": self.step, **merged})
+            rec = {"rpc": rpc.name, "step": self.step, "epoch": self.epoch, "time": time.time(), **merged}
+            self.stats_log.append(rec)
+            self._write_stats(rec)
         if rpc.is_src:
             self._consumed_ids_this_epoch += ids
         return ids
@@ -300,6 +303,19 @@ class MasterWorker:
             self._pump_task.cancel()
             self.stream.close()
         return times
+
+    def _write_stats(self, rec: Dict):
+        """Training statistics as JSON lines under the run's log directory (`stats.jsonl`): machine-readable twin of the log
+        lines (the reference carries wandb / tensorboard fields but never writes anything, system_api.py:96-104)."""
+        try:
+            if self._stats_file is None:
+                import json as _json
+                self._json = _json
+                self._stats_file = open(os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "stats.jsonl"), "a")
+            self._stats_file.write(self._json.dumps(rec) + "\n")
+            self._stats_file.flush()
+        except Exception:
+            pass
 
     def _dump_recover(self):
         info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),

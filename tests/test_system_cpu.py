@@ -43,6 +43,9 @@ def test_gpt2_sft_dp2_gloo(tmp_path):
     losses = [float(l.split("loss=")[1].split(",")[0]) for l in log.splitlines() if "[trainDefault]" in l and "loss=" in l]
     assert len(losses) == 8, log[-3000:]
     assert losses[-1] < losses[0], losses
+    import json
+    stats = [json.loads(l) for l in open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "stats.jsonl"))]
+    assert [r["step"] for r in stats] == list(range(8)) and abs(stats[0]["loss"] - losses[0]) < 1e-3
     save_root = os.path.join(os.environ["REAL_FILEROOT"], "checkpoints")
     found = [os.path.join(d, f) for d, _, fs in os.walk(save_root) for f in fs if f == "config.json"]
     assert found, "no checkpoint was written"
