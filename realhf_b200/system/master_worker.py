@@ -48,6 +48,8 @@ class MasterWorker:
         self.step = self.epoch = self.epoch_step = 0
         self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
         self.rpc_mem: Dict[str, dict] = {}
+        self._rpc_batch_lens: Dict[str, List[int]] = {}
+        self._t_start = time.time()
         self.stats_log: List[Dict] = []
         self._stats_file = None
         self._consumed_ids_this_epoch: List[Hashable] = []
@@ -96,6 +98,14 @@ class MasterWorker:
         for nm in names:
             await self._group_request(self.workers_of[nm], "initialize", data=self.ft_spec, model_name=nm)
         self.buffer = AsyncIOSequenceBuffer(self.rpcs)
+        # model shapes for the analytic FLOP accounting of the step log (reference: master_worker.py:1407-1488)
+        self.model_cfgs = {}
+        for nm in names:
+            try:
+                r = await self._group_request(self.workers_of[nm][:1], "model_config", model_name=nm)
+                self.model_cfgs[nm] = r[0].data
+            except Exception:
+                pass
         ec = cfg.exp_ctrl
         self.save_ctl = timeutil.EpochStepTimeFreqCtl(ec.save_freq_epochs, ec.save_freq_steps, ec.save_freq_secs)
         self.eval_ctl = timeutil.EpochStepTimeFreqCtl(ec.eval_freq_epochs, ec.eval_freq_steps, ec.eval_freq_secs)
@@ -158,6 +168,7 @@ class MasterWorker:
         else:
             parts = meta.get_split_spec(dp, min_size=max(1, (rpc.n_mbs or 1) * (2 * pp if pp > 1 else 1))).partitions
         part = {d: ids[a:b] for d, (a, b) in enumerate(parts)}
+        self._rpc_batch_lens[rpc.name] = self._batch_lens(meta)
         plan = self._transfer_plan(rpc, part, meta)
         involved = set(self.workers_of[rpc.model_name])
         for e in plan:
@@ -257,6 +268,7 @@ class MasterWorker:
         dt = time.perf_counter() - t0
         logger.info(f"step {self.step} (epoch {self.epoch}, {self.epoch_step}/{self.ft_spec.steps_per_epoch}) e2e {dt:.3f}s; "
                     + ", ".join(f"{k} {v:.2f}s" for k, v in self.rpc_secs.items()))
+        self._log_throughput(dt)
         if self.rpc_mem:
             logger.info("peak memory: " + ", ".join(
                 f"{k} {m.get('peak_allocated_gb', 0):.1f}/{m.get('peak_reserved_gb', 0):.1f} GB alloc/reserved @worker{m.get('worker')}"
@@ -303,6 +315,40 @@ class MasterWorker:
             self._pump_task.cancel()
             self.stream.close()
         return times
+
+    @staticmethod
+    def _batch_lens(meta: SequenceSample) -> List[int]:
+        for k in ("packed_input_ids", "packed_prompts"):
+            if k in meta.keys:
+                return meta.flat_seqlens(k)
+        return []
+
+    def _log_throughput(self, step_secs: float):
+        """Tokens per batch, analytic TFLOP/s (x3 for a training MFC, x4 with activation recomputation) and ETA."""
+        try:
+            flops, n_tokens = 0.0, 0
+            for rpc in self.rpcs:
+                lens = self._rpc_batch_lens.get(rpc.name) or []
+                mc = self.model_cfgs.get(rpc.model_name)
+                if not lens or mc is None:
+                    continue
+                args = (len(lens), lens, mc.n_layers, mc.hidden_dim, mc.intermediate_dim, mc.vocab_size)
+                if rpc.interface_type == ModelInterfaceType.TRAIN_STEP:
+                    flops += monitor.calculate_llama_train_flops(4 if getattr(self.topos[rpc.model_name], "gradient_checkpointing", False) else 3, *args)
+                    n_tokens = max(n_tokens, sum(lens))
+                elif rpc.interface_type == ModelInterfaceType.GENERATE:
+                    g = (rpc.interface_impl.args or {}).get("generation_config", {}) or {}
+                    flops += monitor.calculate_llama_gen_flops(len(lens), lens, int(g.get("max_new_tokens", 256)), *args[2:])
+                else:
+                    flops += monitor.calculate_llama_forward_flops(*args)
+                    n_tokens = max(n_tokens, sum(lens))
+            done = max(self.step, 1)
+            eta = (self.ft_spec.total_train_steps - self.step) * (time.time() - self._t_start) / done
+            n_gpus = max(1, self.cfg.n_model_workers)
+            logger.info(f"throughput: {n_tokens} tokens in the batch, {flops / step_secs / 1e12:.2f} TFLOP/s total, "
+                        f"{flops / step_secs / 1e12 / n_gpus:.2f} per worker; ETA {eta / 60:.1f} min")
+        except Exception as e:  # accounting must never take the run down
+            logger.debug(f"throughput accounting skipped: {e}")
 
     def _write_stats(self, rec: Dict):
         """Training statistics as JSON lines under the run's log directory (`stats.jsonl`): machine-readable twin of the log

@@ -79,6 +79,7 @@ def test_ppo_with_realloc_gloo(tmp_path):
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "master_worker-0")).read()
     assert log.count("[actor_train]") == 2 and log.count("[critic_train]") == 2, log[-3000:]
     assert "benchmark finished" in log
+    assert log.count("throughput:") == 2 and "TFLOP/s total" in log, log[-2000:]
 
 
 def test_failure_detection_raises_instead_of_hanging(tmp_path):
