@@ -62,7 +62,6 @@ class FusedTP:
         self._ag_epoch = 0
         self._ag_bufs = {}
         self._rs_state = {}
-        self._epoch_src = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._epoch_ring = [torch.zeros(1, dtype=torch.int32, device=self.device) for _ in range(64)]
 
     # ------------------------------------------------------------------ eligibility
