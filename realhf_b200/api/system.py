@@ -9,12 +9,12 @@ from __future__ import annotations
 
 import dataclasses
 import os
-from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+from typing import Callable, Dict, List, Optional, Tuple, Union
 
 from realhf_b200.api.config import (DataLoaderAbstraction, DatasetAbstraction, ModelName, ModelShardID,
                                     StandaloneModelShardAbstraction)
 from realhf_b200.api.dfg import MFCDef, ParamReallocHook, build_graph
-from realhf_b200.base.topology import PipeModelDataParallelTopology, ProcessTopology
+from realhf_b200.base.topology import ProcessTopology
 
 
 @dataclasses.dataclass

@@ -11,7 +11,7 @@ import enum
 import os
 import pickle
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

@@ -9,7 +9,6 @@ across nodes on any shared mount, and `realhf_b200.system.rendezvous` offers a T
 
 from __future__ import annotations
 
-import dataclasses
 import os
 import random
 import shutil

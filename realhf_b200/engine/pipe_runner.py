@@ -20,7 +20,7 @@ import torch.distributed as dist
 from realhf_b200.api.data import SequenceSample
 from realhf_b200.api.model import GenerationHyperparameters
 from realhf_b200.models import generation as gen
-from realhf_b200.models.real_model import ModelOutput, ReaLModel
+from realhf_b200.models.real_model import ReaLModel
 
 
 def _mb_inputs(mb: SequenceSample, device, key: str = "packed_input_ids"):

@@ -8,14 +8,13 @@ from __future__ import annotations
 
 import copy
 import dataclasses
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
-from realhf_b200.api.config import DatasetAbstraction, ModelFamily, ModelInterfaceAbstraction, ModelInterfaceType, ModelName
-from realhf_b200.api.dfg import MFCDef, ParamReallocHook
+from realhf_b200.api.config import DatasetAbstraction, ModelInterfaceAbstraction, ModelInterfaceType
+from realhf_b200.api.dfg import MFCDef
 from realhf_b200.api.model import GenerationHyperparameters
 from realhf_b200.api.quickstart import (MFCConfig, ModelTrainEvalConfig, PairedComparisonDatasetConfig, PromptAnswerDatasetConfig,
                                         PromptOnlyDatasetConfig, register_quickstart_exp)
-from realhf_b200.api.system import register_experiment
 from realhf_b200.experiments.common import CommonExperimentConfig
 
 T = ModelInterfaceType

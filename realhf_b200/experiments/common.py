@@ -10,7 +10,6 @@ data-parallel on every GPU instead of being cut by TP/PP.
 from __future__ import annotations
 
 import dataclasses
-import itertools
 import re
 from typing import Any, Dict, List, Optional, Tuple
 

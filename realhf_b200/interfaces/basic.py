@@ -11,7 +11,7 @@ import fcntl
 import functools
 import json
 import os
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F

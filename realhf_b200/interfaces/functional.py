@@ -7,8 +7,7 @@ masked normalisation :226-293) and `modules/rms.py` (running mean/std value norm
 
 from __future__ import annotations
 
-import dataclasses
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -9,7 +9,7 @@ ranks and tokens travel by all-to-all (`dispatch -> grouped GEMM -> combine`); t
 
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.distributed as dist

@@ -10,7 +10,7 @@ CPU tensors: plain PyTorch reference (also the numerics oracle for the tests).
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import os
 
-import math
 from typing import List, Optional, Tuple
 
 import torch

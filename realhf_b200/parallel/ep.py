@@ -12,7 +12,7 @@ partitions the experts over the tensor-parallel group (rank r owns experts [r*E/
 
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List
 
 import torch
 import torch.distributed as dist

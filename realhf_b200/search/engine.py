@@ -12,7 +12,7 @@ from __future__ import annotations
 import dataclasses
 import json
 import os
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 from realhf_b200.api.config import ModelInterfaceType
 from realhf_b200.api.dfg import MFCDef, build_graph

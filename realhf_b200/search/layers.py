@@ -11,7 +11,7 @@ import dataclasses
 import json
 import os
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

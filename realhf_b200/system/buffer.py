@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import asyncio
 import dataclasses
-from typing import Any, Dict, Hashable, List, Optional, Set
+from typing import Dict, Hashable, List, Set
 
 from realhf_b200.api.data import SequenceSample
 from realhf_b200.api.dfg import MFCDef

@@ -12,12 +12,12 @@ import asyncio
 import collections
 import os
 import time
-from typing import Any, Dict, Hashable, List, Optional, Tuple
+from typing import Dict, Hashable, List, Tuple
 
 import numpy as np
 
 from realhf_b200.api import system as system_api
-from realhf_b200.api.config import ModelInterfaceType, ModelName, ModelShardID
+from realhf_b200.api.config import ModelInterfaceType, ModelName
 from realhf_b200.api.data import DataBatchMeta, SequenceSample
 from realhf_b200.api.dfg import MFCDef, OffloadHook, ParamReallocHook
 from realhf_b200.api.model import FinetuneSpec

@@ -20,7 +20,6 @@ from realhf_b200.api import model as model_api
 from realhf_b200.api import system as system_api
 from realhf_b200.api.config import ModelName, ModelShardID
 from realhf_b200.api.data import SequenceSample
-from realhf_b200.api.dfg import OffloadHook, ParamReallocHook
 from realhf_b200.base import constants, logging, monitor, name_resolve, seeding
 from realhf_b200.base.topology import ParallelContext
 from realhf_b200.parallel import realloc

@@ -15,7 +15,7 @@ import pickle
 import socket
 import time
 import uuid
-from typing import Any, Dict, List, Optional
+from typing import Any, List, Optional
 
 import zmq
 
