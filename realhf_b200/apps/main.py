@@ -11,11 +11,30 @@ import time
 from typing import Optional
 
 from realhf_b200.api.system import Experiment
-from realhf_b200.apps.remote import config_path, status_key
+from realhf_b200.apps.remote import config_path, control_key, status_key
 from realhf_b200.base import constants, logging, name_resolve
 from realhf_b200.scheduler import client as sched_client
 
 logger = logging.getLogger("main", "system")
+
+
+def _command(exp: str, trial: str, cmd: str):
+    name_resolve.add(control_key(exp, trial, "master_worker", 0), cmd, replace=True)
+
+
+def pause_experiment(exp: str, trial: str):
+    """The master finishes its current step, publishes PAUSED and stops issuing MFCs until `resume_experiment`; model workers
+    idle on their request streams (parity: WorkerControlPanel pause / resume, system/worker_base.py:217-455)."""
+    _command(exp, trial, "pause")
+
+
+def resume_experiment(exp: str, trial: str):
+    _command(exp, trial, "resume")
+
+
+def stop_experiment(exp: str, trial: str):
+    """Graceful stop after the current step: recover states are saved if the run was launched with recover_mode save / auto."""
+    _command(exp, trial, "exit")
 
 
 class Controller:
@@ -23,6 +42,15 @@ class Controller:
 
     def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int):
         self.exp, self.trial, self.sched, self.n = exp, trial, sched, n_model_workers
+
+    def pause(self):
+        pause_experiment(self.exp, self.trial)
+
+    def resume(self):
+        resume_experiment(self.exp, self.trial)
+
+    def stop(self):
+        stop_experiment(self.exp, self.trial)
 
     def statuses(self):
         out = {}

@@ -22,6 +22,11 @@ def status_key(exp, trial, worker_type, index):
     return f"{exp}/{trial}/status/{worker_type}/{index}"
 
 
+def control_key(exp, trial, worker_type, index):
+    """Commands for a worker: `pause` / `resume` / `exit` (written by the controller, polled by the worker between steps)."""
+    return f"{exp}/{trial}/control/{worker_type}/{index}"
+
+
 def main_worker(args):
     # register everything the configs may name
     import realhf_b200.datasets  # noqa: F401

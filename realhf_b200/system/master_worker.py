@@ -297,6 +297,9 @@ class MasterWorker:
         total = self.ft_spec.total_train_steps
         try:
             while self.step < total:
+                if not await self._check_control():
+                    logger.info(f"stop requested by the controller at step {self.step}")
+                    break
                 times.append(await self._run_step())
                 if self.save_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
                     await self._save()
@@ -349,6 +352,28 @@ class MasterWorker:
                         f"{flops / step_secs / 1e12 / n_gpus:.2f} per worker; ETA {eta / 60:.1f} min")
         except Exception as e:  # accounting must never take the run down
             logger.debug(f"throughput accounting skipped: {e}")
+
+    async def _check_control(self) -> bool:
+        """Controller commands between steps: `pause` (publish PAUSED, wait for `resume`), `exit` (stop gracefully)."""
+        from realhf_b200.apps.remote import control_key, status_key
+        from realhf_b200.base import name_resolve
+        ckey, skey = control_key(self.exp, self.trial, "master_worker", 0), status_key(self.exp, self.trial, "master_worker", 0)
+
+        def cmd():
+            try:
+                return name_resolve.get(ckey)
+            except name_resolve.NameEntryNotFoundError:
+                return None
+        c = cmd()
+        if c == "pause":
+            name_resolve.add(skey, "PAUSED", replace=True, keepalive_ttl=30)
+            logger.info(f"paused by the controller at step {self.step}")
+            while c == "pause":
+                await asyncio.sleep(0.2)
+                c = cmd()
+            name_resolve.add(skey, "RUNNING", replace=True, keepalive_ttl=30)
+            logger.info("resumed")
+        return c != "exit"
 
     def _write_stats(self, rec: Dict):
         """Training statistics as JSON lines under the run's log directory (`stats.jsonl`): machine-readable twin of the log

@@ -153,3 +153,68 @@ def test_auto_recover_after_injected_fault(tmp_path):
     assert steps[:2] == [0, 1] and steps[-1] == 7 and len(steps) >= 8, steps
     wlog = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "model_worker-0")).read()
     assert "injected fault" in wlog and "recover run: loading" in wlog
+
+
+def test_pause_resume_and_stop_through_the_controller(tmp_path):
+    """pause: the master publishes PAUSED and no further step runs; resume continues; stop ends the run early and cleanly."""
+    import threading
+    import time
+    _env(tmp_path)
+    from realhf_b200.apps import main as M
+    from realhf_b200.apps.quickstart import build_experiment
+    from realhf_b200.apps.remote import status_key
+    from realhf_b200.base import name_resolve
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=64)
+    name = f"ctl-{uuid.uuid4().hex[:6]}"
+    exp = build_experiment(["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1", "n_gpus_per_node=1",
+                            "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}",
+                            "dataset.train_bs_n_seqs=4", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=40",
+                            "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"])
+    err = []
+
+    def runner():
+        try:
+            M.main_start(exp, timeout=600)
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+    th = threading.Thread(target=runner, daemon=True)
+    th.start()
+    log_path = os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")
+    skey = status_key(name, "t0", "master_worker", 0)
+
+    def wait_for(pred, what, timeout=180):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            if pred():
+                return
+            time.sleep(0.2)
+        raise AssertionError(f"timed out waiting for {what}")
+
+    def status():
+        try:
+            return name_resolve.get(skey)
+        except name_resolve.NameEntryNotFoundError:
+            return None
+
+    n_steps = lambda: open(log_path).read().count("[trainDefault] step") if os.path.exists(log_path) else 0
+    wait_for(lambda: status() == "RUNNING", "the master to come up")  # main_start wipes the trial's keys before launching
+    M.pause_experiment(name, "t0")
+    wait_for(lambda: status() == "PAUSED", "PAUSED status")
+    frozen = n_steps()
+    time.sleep(1.5)
+    assert n_steps() == frozen
+    M.resume_experiment(name, "t0")
+    wait_for(lambda: n_steps() >= frozen + 3, "steps after resume")
+    M.pause_experiment(name, "t0")
+    wait_for(lambda: status() == "PAUSED", "second pause")
+    frozen = n_steps()
+    time.sleep(1.0)
+    assert n_steps() == frozen
+    M.stop_experiment(name, "t0")
+    th.join(timeout=120)
+    assert not th.is_alive() and not err, err
+    log = open(log_path).read()
+    assert "stop requested by the controller" in log and n_steps() < 16 * 40
