@@ -2,8 +2,11 @@
 single-token decode attention over a dense KV cache.
 
 CUDA tensors: decode runs the split-KV sm_100a kernel in `csrc/attn_decode.cu` (with fused RoPE and
-in-place KV append); varlen forward/backward currently calls the flash-attn library kernel (a library
-call on this path, recorded as such in DESIGN.md) until the tcgen05 varlen kernel lands.
+in-place KV append); varlen forward/backward calls the flash-attn library kernel by default (a library
+call on this path, recorded as such in DESIGN.md).  `REAL_ATTN=tcgen05` switches the varlen FORWARD to
+`csrc/attn_fwd_tcgen05.cu` (TMA + tcgen05 + TMEM; head dim 64 / 128, no dropout / sliding window); its LSE
+has the layout the library backward consumes.  That kernel is compiled and SASS-checked but has not run on
+hardware yet, hence opt-in.
 CPU tensors: plain PyTorch reference (also the numerics oracle for the tests).
 """
 
@@ -14,7 +17,18 @@ from typing import Optional
 
 import torch
 
+import os
+
 from realhf_b200.ops import lib, use_native
+
+
+def attn_impl() -> str:
+    """`flash` (library kernel, default) or `tcgen05` (own forward kernel, experimental)."""
+    return os.environ.get("REAL_ATTN", "flash")
+
+
+def _own_fwd_ok(hd: int, dropout_p: float) -> bool:
+    return attn_impl() == "tcgen05" and hd in (64, 128) and dropout_p == 0.0
 
 
 def varlen_attention_ref(q, k, v, cu_seqlens, scale: float, causal: bool = True, sliding_window: Optional[int] = None):
@@ -50,6 +64,9 @@ def varlen_attention(q, k, v, cu_seqlens, max_seqlen: int, scale: Optional[float
     if use_native(q) and q.dtype in (torch.bfloat16, torch.float16):
         from flash_attn import flash_attn_varlen_func
         cu = cu_seqlens.int()
+        if _own_fwd_ok(q.shape[-1], dropout_p) and not torch.is_grad_enabled() and all(
+                t.stride(-1) == 1 and t.stride(1) == t.shape[-1] for t in (q, k, v)):
+            return lib().attn_fwd(q, k, v, cu, max_seqlen, scale, causal)[0]
         return flash_attn_varlen_func(q, k, v, cu, cu, max_seqlen, max_seqlen, dropout_p=dropout_p,
                                       softmax_scale=scale, causal=causal)
     return varlen_attention_ref(q, k, v, cu_seqlens, scale, causal)
@@ -69,6 +86,11 @@ class _PackedQKVAttention(torch.autograd.Function):
         q = qkv[:, : nq * hd].view(T, nq, hd)
         k = qkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd)
         v = qkv[:, (nq + nkv) * hd:].view(T, nkv, hd)
+        if _own_fwd_ok(hd, dropout_p):
+            out, lse = lib().attn_fwd(q, k, v, cu, max_seqlen, scale, causal)
+            ctx.save_for_backward(qkv, out, lse, cu, torch.empty(2, dtype=torch.int64, device=qkv.device))
+            ctx.meta = (max_seqlen, nq, nkv, hd, scale, causal, dropout_p)
+            return out
         out, lse, _, rng = _wrapped_flash_attn_varlen_forward(q, k, v, cu, cu, max_seqlen, max_seqlen, dropout_p, scale, causal=causal,
                                                               window_size_left=-1, window_size_right=-1, softcap=0.0, alibi_slopes=None,
                                                               return_softmax=False, block_table=None)

@@ -81,7 +81,32 @@ std::vector<Tensor> sample(const Tensor& logits, const c10::optional<Tensor>& un
   return {tok, lp, mask};
 }
 
+extern "C" int rb_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* cu_seqlens, int64_t q_ld,
+                           int64_t k_ld, int64_t v_ld, int64_t out_ld, int T, int B, int nq, int nkv, int hd, int max_seqlen,
+                           float scale, int causal, int dt, cudaStream_t s);
+
+// q [T, nq, hd], k / v [T, nkv, hd]: views with unit stride over hd and heads packed (stride(1) == hd), any row pitch.
+// Returns (out [T, nq, hd], lse [nq, T] fp32).
+std::vector<Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& cu_seqlens, int64_t max_seqlen,
+                             double scale, bool causal) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 3 && k.dim() == 3 && v.dim() == 3);
+  const int64_t T = q.size(0), nq = q.size(1), hd = q.size(2), nkv = k.size(1);
+  for (const Tensor* t : {&q, &k, &v}) TORCH_CHECK(t->stride(2) == 1 && t->stride(1) == hd && t->size(0) == T && t->size(2) == hd);
+  TORCH_CHECK(v.size(1) == nkv && k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type());
+  TORCH_CHECK(cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous() && cu_seqlens.is_cuda());
+  c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty({T, nq, hd}, q.options());
+  auto lse = at::empty({nq, T}, q.options().dtype(at::kFloat));
+  const int dt = q.scalar_type() == at::kBFloat16 ? 1 : (q.scalar_type() == at::kHalf ? 2 : -1);
+  int rc = rb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), cu_seqlens.data_ptr<int>(),
+                       q.stride(0), k.stride(0), v.stride(0), out.stride(0), (int)T, (int)cu_seqlens.numel() - 1, (int)nq, (int)nkv,
+                       (int)hd, (int)max_seqlen, (float)scale, causal ? 1 : 0, dt, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "attn_fwd: unsupported configuration (", rc, ")");
+  return {out, lse};
+}
+
 void register_attn_ops(torch::Library& m) {
+  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> Tensor[]", &attn_fwd);
   m.def("sample(Tensor logits, Tensor? unfinished, int top_k, float top_p, float inv_temp, int eos_id, bool suppress_eos, bool greedy, int pad_id, int seed, int step, bool want_mask) -> Tensor[]", &sample);
   m.def("decode_attention(Tensor qkv, Tensor(a!) k_cache, Tensor(b!) v_cache, Tensor cache_lens, int nq, int nkv, int hd, float scale, Tensor? cos, Tensor? sin, int rot_dim, bool interleaved) -> Tensor", &decode_attention);
 }

@@ -69,3 +69,33 @@ def test_packed_qkv_attention_forward_backward(heads):
     ref.backward(dout.float())
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(g.float(), x.grad, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="tcgen05 varlen attention forward has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
+@pytest.mark.parametrize("hd,nq,nkv,causal", [(128, 8, 8, True), (128, 8, 2, True), (64, 4, 4, True), (128, 4, 4, False)])
+def test_attn_fwd_tcgen05_matches_reference(hd, nq, nkv, causal):
+    import math
+
+    import numpy as np
+
+    from realhf_b200.ops import lib
+    torch.manual_seed(0)
+    lens = [1, 37, 128, 129, 300, 640, 5]
+    T = sum(lens)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    qkv = torch.randn(T, (nq + 2 * nkv) * hd, device=DEV, dtype=torch.bfloat16)
+    q = qkv[:, : nq * hd].view(T, nq, hd)
+    k = qkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd)
+    v = qkv[:, (nq + nkv) * hd:].view(T, nkv, hd)
+    scale = 1.0 / math.sqrt(hd)
+    out, lse = lib().attn_fwd(q, k, v, cu, max(lens), scale, causal)
+    ref = A.varlen_attention_ref(q.float(), k.float(), v.float(), cu, scale, causal)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    # LSE [nq, T]: natural log of the softmax denominator with the scale applied
+    rep = nq // nkv
+    for s, e in zip(cu[:-1].tolist(), cu[1:].tolist()):
+        att = torch.einsum("qhd,khd->hqk", q[s:e].float(), k[s:e].float().repeat_interleave(rep, 1)) * scale
+        if causal:
+            att = att.masked_fill(torch.ones(e - s, e - s, device=DEV, dtype=torch.bool).triu(1), float("-inf"))
+        torch.testing.assert_close(lse[:, s:e], torch.logsumexp(att, -1), atol=2e-2, rtol=2e-2)
