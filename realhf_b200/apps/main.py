@@ -11,7 +11,7 @@ import time
 from typing import Optional
 
 from realhf_b200.api.system import Experiment
-from realhf_b200.apps.remote import config_path, control_key, status_key
+from realhf_b200.apps.remote import config_path, control_key, status_key, status_ttl
 from realhf_b200.base import constants, logging, name_resolve
 from realhf_b200.scheduler import client as sched_client
 
@@ -42,6 +42,9 @@ class Controller:
 
     def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int):
         self.exp, self.trial, self.sched, self.n = exp, trial, sched, n_model_workers
+        self._seen = set()
+        # liveness lease of the launcher itself: workers exit when it expires (apps/remote.py::_watch_controller)
+        name_resolve.add(status_key(exp, trial, "controller", 0), "RUNNING", replace=True, keepalive_ttl=status_ttl())
 
     def pause(self):
         pause_experiment(self.exp, self.trial)
@@ -56,10 +59,13 @@ class Controller:
         out = {}
         for wt, cnt in (("master_worker", 1), ("model_worker", self.n)):
             for i in range(cnt):
+                k = f"{wt}/{i}"
                 try:
-                    out[f"{wt}/{i}"] = name_resolve.get(status_key(self.exp, self.trial, wt, i))
+                    out[k] = name_resolve.get(status_key(self.exp, self.trial, wt, i))
+                    self._seen.add(k)
                 except name_resolve.NameEntryNotFoundError:
-                    out[f"{wt}/{i}"] = "UNKNOWN"
+                    # a status that was published and whose lease then ran out: the worker (or its node) died without a word
+                    out[k] = "LOST" if k in self._seen else "UNKNOWN"
         return out
 
     def wait(self, timeout: Optional[float] = None, poll: float = 0.5, status_poll: float = 5.0):
@@ -69,7 +75,7 @@ class Controller:
             if time.monotonic() - last_status > status_poll:
                 # a worker that caught its own exception publishes ERROR before the scheduler sees the process exit
                 last_status = time.monotonic()
-                bad = {k: v for k, v in self.statuses().items() if v == "ERROR"}
+                bad = {k: v for k, v in self.statuses().items() if v in ("ERROR", "LOST")}
                 if bad:
                     raise sched_client.JobException(self.sched.run_name, sorted(bad)[0], "localhost", sched_client.JobState.FAILED)
             infos = self.sched.find_all()

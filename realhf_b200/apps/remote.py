@@ -27,6 +27,21 @@ def control_key(exp, trial, worker_type, index):
     return f"{exp}/{trial}/control/{worker_type}/{index}"
 
 
+def status_ttl() -> float:
+    return float(os.environ.get("REAL_STATUS_TTL", "60"))
+
+
+def _watch_controller(exp: str, trial: str):
+    """Exit when the launcher's liveness key disappears (controller killed / its node lost): orphaned workers would otherwise
+    hold their GPUs forever (reference: `watch_names`, system/worker_base.py:660-666)."""
+    ttl = status_ttl()
+
+    def _die():
+        logger.error("the controller's liveness key expired: exiting")
+        os._exit(3)
+    name_resolve.watch_names([status_key(exp, trial, "controller", 0)], _die, poll_frequency=max(0.5, ttl / 3), wait_timeout=300)
+
+
 def main_worker(args):
     # register everything the configs may name
     import realhf_b200.datasets  # noqa: F401
@@ -44,7 +59,9 @@ def main_worker(args):
     with open(config_path(args.experiment_name, args.trial_name), "rb") as f:
         cfg = pickle.load(f)
     key = status_key(args.experiment_name, args.trial_name, args.worker_type, args.jobstep_id)
-    name_resolve.add(key, "RUNNING", replace=True, keepalive_ttl=30)
+    name_resolve.add(key, "RUNNING", replace=True, keepalive_ttl=status_ttl())
+    if os.environ.get("REAL_WATCH_CONTROLLER", "1") == "1":
+        _watch_controller(args.experiment_name, args.trial_name)
     try:
         if args.worker_type == "model_worker":
             from realhf_b200.system.model_worker import ModelWorker

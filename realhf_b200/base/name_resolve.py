@@ -107,6 +107,7 @@ class MemoryNameRecordRepository(NameRecordRepository):
             if name in self._store and not replace:
                 raise NameEntryExistsError(name)
             self._store[name] = str(value)
+            # the owner lives in this process, so a TTL'd key of the in-memory store can never go stale
 
     def delete(self, name):
         with self._lock:
@@ -158,6 +159,19 @@ class NfsNameRecordRepository(NameRecordRepository):
     def _file(self, name):
         return os.path.join(self._dir(name), "ENTRY")
 
+    def _ttl_file(self, name):
+        return os.path.join(self._dir(name), "TTL")
+
+    def _expired(self, name) -> bool:
+        """A key written with `keepalive_ttl` is live only while its owner keeps touching it: once the entry has not been
+        refreshed for a full TTL (owner killed, node lost) readers treat it as gone (reference: etcd / redis lease expiry)."""
+        try:
+            with open(self._ttl_file(name)) as fh:
+                ttl = float(fh.read())
+            return time.time() - os.path.getmtime(self._file(name)) > ttl
+        except (OSError, ValueError):
+            return False
+
     def add(self, name, value, delete_on_exit=True, keepalive_ttl=None, replace=False):
         if not name.strip("/"):
             raise ArgumentError("empty name")
@@ -172,8 +186,16 @@ class NfsNameRecordRepository(NameRecordRepository):
         if delete_on_exit:
             self._to_delete.add(name)
         if keepalive_ttl is not None:
+            with open(self._ttl_file(name), "w") as fh:
+                fh.write(str(float(keepalive_ttl)))
             self._keepalive[name] = keepalive_ttl
             self._ensure_keepalive()
+        else:
+            self._keepalive.pop(name, None)
+            try:
+                os.remove(self._ttl_file(name))
+            except OSError:
+                pass
 
     def _ensure_keepalive(self):
         if self._ka_thread is not None:
@@ -196,6 +218,10 @@ class NfsNameRecordRepository(NameRecordRepository):
         if not os.path.isfile(f):
             raise NameEntryNotFoundError(name)
         os.remove(f)
+        try:
+            os.remove(self._ttl_file(name))
+        except OSError:
+            pass
         self._to_delete.discard(name)
         self._keepalive.pop(name, None)
         d = os.path.dirname(f)
@@ -211,6 +237,8 @@ class NfsNameRecordRepository(NameRecordRepository):
 
     def get(self, name):
         f = self._file(name)
+        if self._expired(name):
+            raise NameEntryNotFoundError(f"{name} (lease expired)")
         for _ in range(3):
             try:
                 with open(f) as fh:

@@ -355,7 +355,7 @@ class MasterWorker:
 
     async def _check_control(self) -> bool:
         """Controller commands between steps: `pause` (publish PAUSED, wait for `resume`), `exit` (stop gracefully)."""
-        from realhf_b200.apps.remote import control_key, status_key
+        from realhf_b200.apps.remote import control_key, status_key, status_ttl
         from realhf_b200.base import name_resolve
         ckey, skey = control_key(self.exp, self.trial, "master_worker", 0), status_key(self.exp, self.trial, "master_worker", 0)
 
@@ -366,12 +366,12 @@ class MasterWorker:
                 return None
         c = cmd()
         if c == "pause":
-            name_resolve.add(skey, "PAUSED", replace=True, keepalive_ttl=30)
+            name_resolve.add(skey, "PAUSED", replace=True, keepalive_ttl=status_ttl())
             logger.info(f"paused by the controller at step {self.step}")
             while c == "pause":
                 await asyncio.sleep(0.2)
                 c = cmd()
-            name_resolve.add(skey, "RUNNING", replace=True, keepalive_ttl=30)
+            name_resolve.add(skey, "RUNNING", replace=True, keepalive_ttl=status_ttl())
             logger.info("resumed")
         return c != "exit"
 

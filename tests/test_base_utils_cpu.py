@@ -177,3 +177,42 @@ def test_sequence_buffer_readiness_and_reuse():
         assert sorted(done) == sorted(ids) and buf.n_ready_for(gen) == 1
 
     asyncio.run(run())
+
+
+def test_name_resolve_lease_expires_when_the_owner_dies(tmp_path):
+    """A key written with a TTL is kept alive by its owner's background thread and reads as missing once the owner is gone."""
+    import subprocess
+    import sys
+    import time
+    from realhf_b200.base import name_resolve
+    root = str(tmp_path / "nr")
+    code = ("import sys, time\n"
+            "from realhf_b200.base import name_resolve\n"
+            f"r = name_resolve.NfsNameRecordRepository({root!r})\n"
+            "r.add('a/b/status', 'RUNNING', keepalive_ttl=1.5)\n"
+            "r.add('a/b/final', 'COMPLETED')\n"
+            "print('up', flush=True)\n"
+            "time.sleep(120)\n")
+    p = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, text=True)
+    try:
+        assert p.stdout.readline().strip() == "up"
+        repo = name_resolve.NfsNameRecordRepository(root)
+        time.sleep(3.0)   # two TTLs: the owner's keep-alive thread must have refreshed the lease
+        assert repo.get("a/b/status") == "RUNNING"
+        p.kill()
+        p.wait()
+        gone = []
+        repo.watch_names(["a/b/status"], lambda: gone.append(1), poll_frequency=0.2)
+        t0 = time.time()
+        while not gone and time.time() - t0 < 10:
+            time.sleep(0.1)
+        assert gone, "watch_names did not fire after the lease expired"
+        with pytest.raises(name_resolve.NameEntryNotFoundError):
+            repo.get("a/b/status")
+        assert repo.get("a/b/final") == "COMPLETED"   # keys without a lease never expire
+        repo.add("a/b/status", "COMPLETED", replace=True)  # a terminal status drops the lease
+        time.sleep(2.0)
+        assert repo.get("a/b/status") == "COMPLETED"
+    finally:
+        if p.poll() is None:
+            p.kill()

@@ -218,3 +218,77 @@ def test_pause_resume_and_stop_through_the_controller(tmp_path):
     assert not th.is_alive() and not err, err
     log = open(log_path).read()
     assert "stop requested by the controller" in log and n_steps() < 16 * 40
+
+
+def test_workers_exit_when_the_controller_is_killed_and_lost_status(tmp_path):
+    """Orphan protection: SIGKILL the launcher -> its liveness lease expires -> master and model workers exit on their own.
+    Also the controller-side view: a status whose lease ran out reads LOST."""
+    import re
+    import subprocess
+    import sys
+    import time
+
+    import psutil
+    _env(tmp_path)
+    from realhf_b200.apps import main as M
+    from realhf_b200.apps.remote import status_key
+    from realhf_b200.base import name_resolve
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=64)
+    name = f"orphan-{uuid.uuid4().hex[:6]}"
+    env = dict(os.environ, REAL_STATUS_TTL="3")
+    launcher_log = str(tmp_path / "launcher.log")
+    with open(launcher_log, "w") as lf:
+        p = subprocess.Popen([sys.executable, "-m", "realhf_b200.apps.quickstart", "sft", f"experiment_name={name}", "trial_name=t0",
+                              "device=cpu", "dtype=fp32", "n_nodes=1", "n_gpus_per_node=1", "allocation_mode=manual",
+                              "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}", "dataset.train_bs_n_seqs=4",
+                              "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=200", "model.optimizer.grad_dtype=fp32",
+                              "model.gradient_checkpointing=false"], env=env, stdout=lf, stderr=subprocess.STDOUT)
+    pids = []
+    try:
+        master_log = os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")
+        t0 = time.time()
+        while time.time() - t0 < 240:
+            if os.path.exists(master_log) and "[trainDefault] step" in open(master_log).read():
+                break
+            assert p.poll() is None, open(launcher_log).read()[-3000:]
+            time.sleep(0.5)
+        else:
+            raise AssertionError("the run never started stepping")
+        pids = [int(x) for x in re.findall(r"started (?:master|model)_worker/\d+ \(pid (\d+)\)", open(launcher_log).read())]
+        assert len(pids) == 2, open(launcher_log).read()[-2000:]
+        p.kill()   # SIGKILL: no cleanup handler runs, the workers are in their own sessions and keep running
+        p.wait()
+
+        def dead(pid):
+            try:
+                return psutil.Process(pid).status() == psutil.STATUS_ZOMBIE
+            except psutil.NoSuchProcess:
+                return True
+        t0 = time.time()
+        while time.time() - t0 < 60 and not all(dead(x) for x in pids):
+            time.sleep(0.5)
+        assert all(dead(x) for x in pids), "workers survived the controller"
+        assert "liveness key expired" in open(master_log).read()
+    finally:
+        if p.poll() is None:
+            p.kill()
+        for x in pids:
+            try:
+                os.kill(x, 9)
+            except OSError:
+                pass
+
+    # controller-side: a published status whose lease is stale reads LOST, an unpublished one UNKNOWN
+    class _Sched:
+        run_name = "x"
+    ctl = M.Controller(name, "t1", _Sched(), 2)
+    repo = name_resolve.DEFAULT_REPOSITORY
+    repo.add(status_key(name, "t1", "model_worker", 0), "RUNNING", replace=True, keepalive_ttl=600)
+    assert ctl.statuses() == {"master_worker/0": "UNKNOWN", "model_worker/0": "RUNNING", "model_worker/1": "UNKNOWN"}
+    repo._keepalive.pop(status_key(name, "t1", "model_worker", 0))   # stop refreshing, then age the entry past its TTL
+    old = time.time() - 3600
+    os.utime(repo._file(status_key(name, "t1", "model_worker", 0)), (old, old))
+    assert ctl.statuses()["model_worker/0"] == "LOST"
