@@ -218,6 +218,14 @@ class ModelInterface(abc.ABC):
     def save(self, model: Model, save_dir: str):
         pass
 
+    def state_dict(self) -> Dict:
+        """Algorithm state that lives outside the model (KL controller, value normaliser, ...): written with the recover
+        states and restored on a recover run.  (The reference loses this state on recovery)"""
+        return {}
+
+    def load_state_dict(self, sd: Dict):
+        pass
+
     def evaluate(self, model: Model, eval_dataloader) -> Dict:
         return {}
 

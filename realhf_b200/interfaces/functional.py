@@ -109,6 +109,10 @@ class ExponentialRunningMeanStd:
             self.mean = torch.zeros((), dtype=self.dtype, device=device)
             self.mean_sq = torch.zeros((), dtype=self.dtype, device=device)
             self.debias = torch.zeros((), dtype=self.dtype, device=device)
+        elif self.mean.device != torch.device(device):  # restored from a checkpoint (host tensors)
+            for k in ("mean", "mean_sq", "debias", "count"):
+                if getattr(self, k, None) is not None:
+                    setattr(self, k, getattr(self, k).to(device))
 
     @torch.no_grad()
     def update(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, group=None):
@@ -140,11 +144,11 @@ class ExponentialRunningMeanStd:
         return (x.to(self.dtype) * std + mean).float()
 
     def state_dict(self):
-        return {k: (None if getattr(self, k) is None else getattr(self, k).cpu()) for k in ("mean", "mean_sq", "debias")}
+        return {k: getattr(self, k).cpu() for k in ("mean", "mean_sq", "debias", "count") if getattr(self, k, None) is not None}
 
     def load_state_dict(self, sd):
         for k, v in sd.items():
-            setattr(self, k, v)
+            setattr(self, k, None if v is None else v.to(self.dtype))
 
 
 class MovingAverageRunningMeanStd(ExponentialRunningMeanStd):

@@ -104,6 +104,14 @@ class PPOActorInterface(ModelInterface):
         if self.enable_save:
             _save_hf(model, save_dir)
 
+    def state_dict(self):
+        return {"kl": self.kl_adapter.state_dict(), "rms": None if self.rms is None else self.rms.state_dict()}
+
+    def load_state_dict(self, sd):
+        self.kl_adapter.load_state_dict(sd["kl"])
+        if self.rms is not None and sd.get("rms") is not None:
+            self.rms.load_state_dict(sd["rms"])
+
     # ------------------------------------------------------------------ generate
     @torch.no_grad()
     def generate(self, model: Model, input_: SequenceSample, n_mbs=None) -> Optional[SequenceSample]:
@@ -266,6 +274,14 @@ class PPOCriticInterface(ModelInterface):
     def save(self, model: Model, save_dir: str):
         if self.enable_save:
             _save_hf(model, save_dir)
+
+    def state_dict(self):
+        return {"kl": self.kl_adapter.state_dict(), "rms": None if self.rms is None else self.rms.state_dict()}
+
+    def load_state_dict(self, sd):
+        self.kl_adapter.load_state_dict(sd["kl"])
+        if self.rms is not None and sd.get("rms") is not None:
+            self.rms.load_state_dict(sd["rms"])
 
     @torch.no_grad()
     def inference(self, model: Model, input_: SequenceSample, n_mbs=None) -> Optional[SequenceSample]:

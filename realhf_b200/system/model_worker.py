@@ -115,6 +115,8 @@ class ModelWorker:
         for rpc in cfg.model_rpcs:
             if rpc.model_name in self.models:
                 self.interfaces[rpc.name] = model_api.make_interface(rpc.interface_impl)
+                if os.environ.get("REAL_RECOVER_RUN", "0") == "1":
+                    load_interface_state(rpc.name, self.interfaces[rpc.name], os.path.join(constants.RECOVER_ROOT, self.exp, self.trial, "ckpt"))
         # dataset (only on data-owner workers)
         if cfg.datasets:
             src = next(r for r in cfg.model_rpcs if r.is_src)
@@ -467,6 +469,28 @@ class ModelWorker:
                 if rpc is not None:
                     self.interfaces[rpc.name].save(model, os.path.join(root, name.role))
                     self.backends[name].save(model, os.path.join(root, name.role, "optim"))
+        save_interface_states(self.interfaces, root, tag=str(self.index))
+
+
+def save_interface_states(interfaces: Dict, root: str, tag: str = "0"):
+    """KL controller / value-normaliser state of every interface (identical on every rank of a model: the statistics are
+    all-reduced), one file per MFC, written atomically so concurrent ranks cannot leave a torn file."""
+    for rpc_name, itf in interfaces.items():
+        sd = itf.state_dict()
+        if sd:
+            os.makedirs(root, exist_ok=True)
+            tmp = os.path.join(root, f".interface_{rpc_name}.{tag}.tmp")
+            torch.save(sd, tmp)
+            os.replace(tmp, os.path.join(root, f"interface_{rpc_name}.pt"))
+
+
+def load_interface_state(rpc_name: str, itf, root: str) -> bool:
+    f = os.path.join(root, f"interface_{rpc_name}.pt")
+    if not os.path.exists(f):
+        return False
+    itf.load_state_dict(torch.load(f, weights_only=False))
+    logger.info(f"recover run: restored the interface state of {rpc_name}")
+    return True
 
 
 _TMARK_OF = {"generate": monitor.CUDATimeMarkType.forward, "inference": monitor.CUDATimeMarkType.forward,

@@ -1,6 +1,7 @@
 """RLHF functionals against literal re-implementations of the textbook formulas (CPU): PPO clipped losses, DPO loss, KL-shaped
 rewards + GAE on packed sequences, masked normalisation, running mean/std, KL controllers."""
 import math
+import os
 
 import pytest
 import torch
@@ -109,3 +110,46 @@ def test_kl_controllers():
     assert abs(ad.value - 0.1 * (1 + 0.2 * 10 / 100)) < 1e-9
     ad.update(0.0, 10)
     assert ad.value < 0.1 * (1 + 0.2 * 10 / 100)
+
+
+def test_interface_state_roundtrip_kl_controller_and_value_normaliser():
+    """What a recover run restores: the adaptive KL coefficient and the running value statistics."""
+    from realhf_b200.interfaces import functional as IF
+    from realhf_b200.interfaces.ppo import PPOActorInterface, PPOCriticInterface
+    a = PPOActorInterface(adaptive_kl_ctl=True, kl_ctl=0.1, adaptive_kl_target=6.0, adaptive_kl_horizon=100)
+    a.kl_adapter.update(12.0, n_steps=10)
+    assert a.kl_adapter.value != 0.1
+    b = PPOActorInterface(adaptive_kl_ctl=True, kl_ctl=0.1, adaptive_kl_target=6.0, adaptive_kl_horizon=100)
+    b.load_state_dict(a.state_dict())
+    assert b.kl_adapter.value == a.kl_adapter.value
+    for kind in ("exp", "ma"):
+        c = PPOCriticInterface(value_norm=True, value_norm_type=kind)
+        x = torch.randn(257) * 3 + 5
+        c.rms.update(x)
+        c.rms.update(x * 0.5)
+        d = PPOCriticInterface(value_norm=True, value_norm_type=kind)
+        d.load_state_dict(c.state_dict())
+        y = torch.randn(33)
+        torch.testing.assert_close(d.rms.normalize(y), c.rms.normalize(y))
+        c.rms.update(y)
+        d.rms.update(y)    # updates keep working on restored (host) tensors
+        torch.testing.assert_close(d.rms.denormalize(y), c.rms.denormalize(y))
+    assert isinstance(c.rms, IF.MovingAverageRunningMeanStd)
+
+
+def test_interface_states_are_written_with_the_recover_states_and_restored(tmp_path):
+    from realhf_b200.interfaces.ppo import PPOActorInterface, PPOCriticInterface
+    from realhf_b200.interfaces.basic import SFTInterface
+    from realhf_b200.system.model_worker import load_interface_state, save_interface_states
+    a = PPOActorInterface(adaptive_kl_ctl=True, kl_ctl=0.1)
+    a.kl_adapter.update(20.0, n_steps=50)
+    c = PPOCriticInterface(value_norm=True)
+    c.rms.update(torch.arange(10.0))
+    root = str(tmp_path / "ckpt")
+    save_interface_states({"actor_train": a, "critic_train": c, "sft": SFTInterface()}, root, tag="3")
+    assert sorted(os.listdir(root)) == ["interface_actor_train.pt", "interface_critic_train.pt"]  # stateless interfaces write nothing
+    a2, c2 = PPOActorInterface(adaptive_kl_ctl=True, kl_ctl=0.1), PPOCriticInterface(value_norm=True)
+    assert load_interface_state("actor_train", a2, root) and load_interface_state("critic_train", c2, root)
+    assert not load_interface_state("ref_inf", PPOActorInterface(), root)
+    assert a2.kl_adapter.value == a.kl_adapter.value
+    torch.testing.assert_close(c2.rms.normalize(torch.ones(3)), c.rms.normalize(torch.ones(3)))
