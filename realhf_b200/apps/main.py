@@ -108,10 +108,14 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
     env = {k: os.environ[k] for k in constants.FORWARDED_ENV if k in os.environ}
     env.update(env_vars or {})
     debug = getattr(exp_cfg, "debug", True)
-    sched.submit_array("master_worker", sched_client.remote_worker_cmd(exp, trial, debug, "master_worker"), count=1, env_vars=env)
+    def res(s):  # scheduler resources of a task group (the local scheduler ignores everything but `gpu`)
+        return dict(cpu=s.cpu, gpu=s.gpu, mem=s.mem, nodelist=s.nodelist, exclude=s.exclude, time_limit=s.time_limit,
+                    container_image=s.container_image, env_vars={**env, **s.env_vars})
+    sched.submit_array("master_worker", sched_client.remote_worker_cmd(exp, trial, debug, "master_worker"), count=1,
+                       **res(sched_cfg.master_worker.scheduling))
     mw = sched_cfg.model_worker
     sched.submit_array("model_worker", sched_client.remote_worker_cmd(exp, trial, debug, "model_worker"), count=mw.count,
-                       gpu=mw.scheduling.gpu, env_vars=env)
+                       **res(mw.scheduling))
     ctl = Controller(exp, trial, sched, mw.count)
     try:
         ctl.wait(timeout=timeout)

@@ -12,7 +12,17 @@ import os
 from typing import Optional
 
 USER = os.environ.get("USER") or getpass.getuser()
-FILEROOT = os.environ.get("REAL_FILEROOT", f"/tmp/realhf_b200/{USER}")
+
+
+def _default_fileroot() -> str:
+    # REAL_FILEROOT > the cluster spec's shared filesystem ($CLUSTER_SPEC_PATH) > a per-user directory under /tmp
+    if os.environ.get("REAL_FILEROOT"):
+        return os.environ["REAL_FILEROOT"]
+    from realhf_b200.base import cluster
+    return cluster.spec().fileroot or f"/tmp/realhf_b200/{USER}"
+
+
+FILEROOT = _default_fileroot()
 LOG_ROOT = os.path.join(FILEROOT, "logs")
 MODEL_SAVE_ROOT = os.path.join(FILEROOT, "checkpoints")
 RECOVER_ROOT = os.path.join(FILEROOT, "recover")

@@ -97,8 +97,9 @@ class CommonExperimentConfig(Experiment):
 
     def scheduling_setup(self) -> ExperimentScheduling:
         return ExperimentScheduling(
-            model_worker=TasksGroup(self.n_workers, Scheduling.model_worker_default(gpu=0 if self.device == "cpu" else 1)),
-            master_worker=TasksGroup(1, Scheduling.master_worker_default()))
+            model_worker=TasksGroup(self.n_workers, Scheduling.model_worker_default(gpu=0 if self.device == "cpu" else 1,
+                                                                                    nodelist=self.nodelist, container_image=self.image_name)),
+            master_worker=TasksGroup(1, Scheduling.master_worker_default(container_image=self.image_name)))
 
     # ---- allocation
     def _heuristic_rpc_allocation(self) -> List[RPCAllocation]:

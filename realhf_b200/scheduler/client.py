@@ -178,14 +178,23 @@ class SlurmSchedulerClient(SchedulerClient):
     """Builds one sbatch script per worker type with `srun --multi-prog` (reference: scheduler/slurm/utils.py:357-471).
     Submission needs a Slurm cluster; command construction is unit-testable offline."""
 
-    def __init__(self, expr_name, trial_name, partition: str = "dev", container_image: Optional[str] = None):
+    def __init__(self, expr_name, trial_name, partition: Optional[str] = None, container_image: Optional[str] = None,
+                 container_mounts: Optional[str] = None):
         super().__init__(expr_name, trial_name)
-        self.partition, self.image = partition, container_image
+        from realhf_b200.base import cluster
+        cs = cluster.spec()  # partition / images / mounts default to the cluster spec ($CLUSTER_SPEC_PATH)
+        self.partition = partition or cs.partition or "dev"
+        self.image, self.cpu_image = container_image or cs.gpu_image, container_image or cs.cpu_image
+        self.mounts = container_mounts or cs.default_mount or "/:/host"
         self._job_ids: Dict[str, str] = {}
 
     def build_script(self, worker_type: str, cmd: str, count: int, cpu: int = 4, gpu: int = 0, mem: int = 10000,
                      nodelist: Optional[str] = None, exclude: Optional[str] = None, time_limit: Optional[str] = None,
-                     env_vars: Optional[Dict[str, str]] = None, gpus_per_node: int = 8) -> str:
+                     env_vars: Optional[Dict[str, str]] = None, gpus_per_node: Optional[int] = None,
+                     container_image: Optional[str] = None) -> str:
+        if gpus_per_node is None:
+            from realhf_b200.base import cluster
+            gpus_per_node = cluster.spec().n_gpus_per_node
         log_dir = constants.run_dirs(self.expr_name, self.trial_name)["log"]
         n_nodes = max(1, (count * max(gpu, 0) + gpus_per_node - 1) // gpus_per_node) if gpu else 1
         lines = ["#!/bin/bash", f"#SBATCH --job-name={self.run_name}:{worker_type}", f"#SBATCH --partition={self.partition}",
@@ -206,12 +215,14 @@ class SlurmSchedulerClient(SchedulerClient):
             for i in range(count):
                 f.write(f"{i} " + cmd.format(jobstep_id=i, n_jobsteps=count, worker_submission_index=0, wprocs_per_jobstep=1,
                                              wprocs_in_job=count, wproc_offset=0) + "\n")
-        container = f"--container-image={self.image} --container-mounts=/:/host " if self.image else ""
+        image = container_image or (self.image if gpu else self.cpu_image)
+        container = f"--container-image={image} --container-mounts={self.mounts} " if image else ""
         lines.append(f"srun {container}--multi-prog {multiprog}")
         return "\n".join(lines) + "\n"
 
     def submit_array(self, worker_type, cmd, count, **kw):
-        script = self.build_script(worker_type, cmd, count, **kw)
+        allowed = ("cpu", "gpu", "mem", "nodelist", "exclude", "time_limit", "env_vars", "gpus_per_node", "container_image")
+        script = self.build_script(worker_type, cmd, count, **{k: v for k, v in kw.items() if k in allowed and v is not None})
         path = os.path.join(constants.run_dirs(self.expr_name, self.trial_name)["log"], f"{worker_type}.sbatch")
         with open(path, "w") as f:
             f.write(script)

@@ -34,6 +34,8 @@ class HardwareModel:
     @classmethod
     def from_measured(cls) -> "HardwareModel":
         hw = cls()
+        from realhf_b200.base import cluster
+        hw.mem_cap = cluster.spec().gpu_memory_gb * 1e9
         p = os.path.join(_ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(p):
             try:

@@ -216,3 +216,47 @@ def test_name_resolve_lease_expires_when_the_owner_dies(tmp_path):
     finally:
         if p.poll() is None:
             p.kill()
+
+
+def test_cluster_spec_drives_fileroot_slurm_defaults_and_search_memory(tmp_path, monkeypatch):
+    import importlib
+    import json
+
+    from realhf_b200.base import cluster
+    example = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "cluster_config.json")
+    raw = json.load(open(example))
+    raw.update(fileroot=str(tmp_path / "shared"), gpu_memory_gb=141, n_gpus_per_node=4)
+    path = str(tmp_path / "cluster.json")
+    json.dump(raw, open(path, "w"))
+    monkeypatch.setenv("CLUSTER_SPEC_PATH", path)
+    monkeypatch.delenv("REAL_FILEROOT", raising=False)
+    cs = cluster.spec()
+    assert cs.cluster_name == "my_b200_cluster" and cs.node_type("NODE07") == "b200x8" and cs.gpu_type("NODE12") == "b200"
+    assert cluster.node_name_is_node_type("NODE01", ["x", "b200x8"]) and not cluster.node_name_is_node_type("NODE01", "a100")
+    assert cs.node_names([1, 12]) == ["NODE01", "NODE12"]
+    with pytest.raises(KeyError):
+        cs.node_type("login-1")
+    from realhf_b200.base import constants
+    importlib.reload(constants)
+    try:
+        assert constants.FILEROOT == str(tmp_path / "shared")
+        from realhf_b200.scheduler import client as C
+        importlib.reload(C)
+        s = C.SlurmSchedulerClient("exp", "trial")
+        script = s.build_script("model_worker", C.remote_worker_cmd("exp", "trial", True, "model_worker"), count=8, gpu=1)
+        assert "#SBATCH --partition=gpu" in script and "#SBATCH --nodes=2" in script          # 8 workers on 4-GPU nodes
+        assert "--container-image=my-registry/realhf-b200-gpu" in script and "/dev/infiniband:/dev/infiniband" in script
+        script = s.build_script("master_worker", C.remote_worker_cmd("exp", "trial", True, "master_worker"), count=1, gpu=0)
+        assert "--container-image=my-registry/realhf-b200-cpu" in script
+        from realhf_b200.search.engine import HardwareModel
+        assert HardwareModel.from_measured().mem_cap == 141e9
+        # malformed specs fail loudly
+        bad = str(tmp_path / "bad.json")
+        json.dump({"cluster_type": "slurm", "cluster_name": "x", "fileroot": "/x", "gpu_count": 8}, open(bad, "w"))
+        with pytest.raises(ValueError, match="unknown keys"):
+            cluster.ClusterSpec.from_file(bad)
+    finally:
+        monkeypatch.delenv("CLUSTER_SPEC_PATH")
+        monkeypatch.setenv("REAL_FILEROOT", str(tmp_path / "fr"))
+        importlib.reload(constants)
+    assert cluster.spec().cluster_type == "local" and cluster.spec().gpu_memory_gb == 180
