@@ -104,7 +104,7 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
     sched_cfg = exp_cfg.scheduling_setup()
     with open(config_path(exp, trial), "wb") as f:
         pickle.dump(sys_cfg, f)
-    sched = sched_client.make(mode, exp, trial)
+    sched = sched_client.make(mode, exp, trial, **({"partition": getattr(exp_cfg, "partition", None)} if mode == "slurm" else {}))
     env = {k: os.environ[k] for k in constants.FORWARDED_ENV if k in os.environ}
     env.update(env_vars or {})
     debug = getattr(exp_cfg, "debug", True)

@@ -148,10 +148,17 @@ class NfsNameRecordRepository(NameRecordRepository):
     """One file per key under a shared directory; writes are atomic renames."""
 
     def __init__(self, record_root: Optional[str] = None):
-        self.root = record_root or os.environ.get("REAL_NAME_RESOLVE_ROOT", "/tmp/realhf_b200/name_resolve")
+        self.root = record_root or os.environ.get("REAL_NAME_RESOLVE_ROOT") or self._default_root()
         self._to_delete = set()
         self._keepalive: Dict[str, float] = {}
         self._ka_thread: Optional[threading.Thread] = None
+
+    @staticmethod
+    def _default_root() -> str:
+        # multi-node runs need the store on the shared filesystem: follow the cluster spec's fileroot when there is one
+        from realhf_b200.base import cluster
+        fr = cluster.spec().fileroot
+        return os.path.join(fr, "name_resolve") if fr else "/tmp/realhf_b200/name_resolve"
 
     def _dir(self, name):
         return os.path.join(self.root, name.strip("/"))

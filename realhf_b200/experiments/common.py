@@ -31,7 +31,7 @@ class CommonExperimentConfig(Experiment):
     trial_name: str = "default-trial"
     mode: str = "local"  # local | slurm
     debug: bool = True
-    partition: str = "dev"
+    partition: Optional[str] = None  # Slurm partition; None: the cluster spec's, else "dev"
     wandb_mode: str = "disabled"
     image_name: Optional[str] = None
     recover_mode: str = "disabled"  # disabled | auto | save | resume

@@ -260,3 +260,12 @@ def test_cluster_spec_drives_fileroot_slurm_defaults_and_search_memory(tmp_path,
         monkeypatch.setenv("REAL_FILEROOT", str(tmp_path / "fr"))
         importlib.reload(constants)
     assert cluster.spec().cluster_type == "local" and cluster.spec().gpu_memory_gb == 180
+
+
+def test_config_reference_doc_is_up_to_date():
+    """docs/expconfig.md is generated from the dataclasses; a renamed or added option must be regenerated with the code."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_config_docs.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
