@@ -144,6 +144,10 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     """Generate for a packed batch of prompts on a single pipeline stage (pp == 1)."""
     assert model.is_first_stage and model.is_last_stage, "pipelined generation goes through engine.pipe_runner"
     dev = model.device
+    if generator is None and dev.type != "cuda" and model.ctx.tp_size > 1 and not g.greedy:
+        # every TP rank samples from the same (gathered) distribution and must draw the same token: the PyTorch sampling
+        # path needs a stream shared by the group (the fused CUDA sampler is seeded identically on all ranks already)
+        generator = model.shared_generator(dev)
     cu = cu_seqlens.int()
     B = cu.numel() - 1
     lens = (cu[1:] - cu[:-1])

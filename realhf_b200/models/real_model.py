@@ -128,6 +128,7 @@ class ReaLModel(nn.Module):
         self.ckpt_margin_bytes: Optional[int] = None
         self.last_unckpt_blocks = 0
         self.sequence_parallel = bool(self.ctx.sequence_parallel) and self.ctx.tp_size > 1
+        self._shared_gens: Dict[torch.device, torch.Generator] = {}
         self._offloaded: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ construction
@@ -322,9 +323,52 @@ class ReaLModel(nn.Module):
             x = x + pe
         if c.normalize_embed:
             x = x * torch.tensor(c.hidden_dim ** 0.5, dtype=x.dtype, device=x.device)
-        if self.training and c.embd_pdrop > 0:
-            x = F.dropout(x, c.embd_pdrop)
-        return x
+        return self._dropout(x, c.embd_pdrop)
+
+    # ------------------------------------------------------------------ dropout under tensor parallelism
+    def shared_generator(self, device) -> torch.Generator:
+        """A generator whose stream is identical on all TP ranks of this replica (same dp / pp coordinates) and different
+        elsewhere: randomness applied to activations that are REPLICATED over the TP group (residual / embedding dropout
+        without sequence parallelism, CPU sampling) must agree across the group, while each worker's global generator is
+        seeded per rank.  (Reference: the model-parallel RNG tracker, impl/model/utils/random.py:76-286.)"""
+        device = torch.device(device)
+        g = self._shared_gens.get(device)
+        if g is None:
+            from realhf_b200.base import seeding
+            g = torch.Generator(device=device)
+            g.manual_seed(seeding.derive_seed("tp-shared", self.ctx.dp_rank, self.ctx.pp_rank))
+            self._shared_gens[device] = g
+        return g
+
+    def _dropout(self, x, p: float):
+        if not self.training or p <= 0:
+            return x
+        if self.ctx.tp_size == 1 or self.sequence_parallel:
+            return F.dropout(x, p)  # x is rank-local (or token-sharded): rank-local randomness is what we want
+        keep = torch.empty_like(x).bernoulli_(1.0 - p, generator=self.shared_generator(x.device))
+        return x * keep * (1.0 / (1.0 - p))
+
+    def _ckpt_block(self, i, x, position_ids, cu_seqlens, max_seqlen):
+        """Activation checkpointing of one block.  torch's checkpoint replays the GLOBAL generators; the TP-shared generator
+        is ours to replay: the recomputation must see the state the first pass saw, and must not disturb the live state."""
+        uses_shared = self.training and self.ctx.tp_size > 1 and not self.sequence_parallel and self.config.resid_pdrop > 0
+        if not uses_shared:
+            return checkpoint(self._block_packed, i, x, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
+        g = self.shared_generator(x.device)
+        at_forward = g.get_state()
+        calls = [0]
+
+        def run(x_):
+            calls[0] += 1
+            if calls[0] == 1:
+                return self._block_packed(i, x_, position_ids, cu_seqlens, max_seqlen)
+            live = g.get_state()
+            g.set_state(at_forward)
+            try:
+                return self._block_packed(i, x_, position_ids, cu_seqlens, max_seqlen)
+            finally:
+                g.set_state(live)
+        return checkpoint(run, x, use_reentrant=False)
 
     def _attention_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink: Optional[list]):
         c = self.config
@@ -342,9 +386,7 @@ class ReaLModel(nn.Module):
                                           c.attn_pdrop if self.training else 0.0)
         o = TP.row_linear(o.reshape(T, nq * hd), self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx,
                           self.sequence_parallel)
-        if self.training and c.resid_pdrop > 0:
-            o = F.dropout(o, c.resid_pdrop)
-        return o
+        return self._dropout(o, c.resid_pdrop)
 
     def _mlp(self, i: int, x, h=None):
         """h: the already-normalised input (decode path fuses residual add + norm), else computed from x."""
@@ -363,9 +405,7 @@ class ReaLModel(nn.Module):
             a = TP.col_linear(h, self.p[f"{i}.mlp.fc.weight"], self._w(f"{i}.mlp.fc.bias"), self.ctx, sp)
             a = _ACT[c.activation_function](a)
             o = TP.row_linear(a, self.p[f"{i}.mlp.proj.weight"], self._w(f"{i}.mlp.proj.bias"), self.ctx, sp)
-        if self.training and c.resid_pdrop > 0:
-            o = F.dropout(o, c.resid_pdrop)
-        return o
+        return self._dropout(o, c.resid_pdrop)
 
     def _block_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink=None):
         x = x + self._attention_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
@@ -422,7 +462,7 @@ class ReaLModel(nn.Module):
                 x = self._embed(input_ids, position_ids)
             elif i <= c.n_layers:
                 if ckpt and i < first_kept:
-                    x = checkpoint(self._block_packed, i, x, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
+                    x = self._ckpt_block(i, x, position_ids, cu_seqlens, max_seqlen)
                 else:
                     x = self._block_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
         if not self.is_last_stage:

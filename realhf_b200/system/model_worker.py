@@ -55,7 +55,7 @@ class ModelWorker:
     # ------------------------------------------------------------------ setup
     def setup(self):
         cfg = self.cfg
-        seeding.set_random_seed(cfg.seed + self.index)
+        seeding.set_random_seed(cfg.seed, offset=self.index)
         if cfg.device == "cuda":
             torch.cuda.set_device(int(os.environ.get("REAL_LOCAL_GPU", self.index % max(torch.cuda.device_count(), 1))))
             self.device = torch.device("cuda", torch.cuda.current_device())

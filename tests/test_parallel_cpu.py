@@ -156,3 +156,54 @@ def test_zero3_matches_zero1_and_releases_params():
     assert z1[0]["resident_between_calls"] and not z3[0]["resident_between_calls"]
     for a, b in zip(z1[0]["losses"], z3[0]["losses"]):
         assert abs(a - b) < 1e-5
+
+
+def _dropout_worker(rank, world, ckpt):
+    """GPT-2 with dropout 0.2 in training mode, tp=2 without sequence parallelism: activations are replicated over the TP
+    group, so the dropout masks (and hence losses / updated weights / sampled tokens) must agree across the group."""
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, GenerationHyperparameters, Model
+    from realhf_b200.base import seeding
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.api.data import SequenceSample
+    seeding.set_random_seed(3, offset=rank)          # what a model worker does: per-rank global generators
+    cfg = hf_io.family("gpt2").make_test_config()
+    cfg.n_layers = 3
+    cfg.resid_pdrop = cfg.embd_pdrop = 0.2
+    cfg.attn_pdrop = 0.0
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="gloo", sequence_parallel=False,
+                                gradient_checkpointing=ckpt)
+    m = ReaLModel(cfg, ctx, dtype=torch.float32, device=torch.device("cpu")).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
+                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, "cpu"),
+                                                                                               FinetuneSpec(1, 10, 10))
+    batch = _batch(8)
+    itf = basic.SFTInterface()
+    losses = [itf.train_step(model, batch, n_mbs=1)["loss"] for _ in range(3)]
+    # a replicated (not TP-sharded) parameter after three dropout-perturbed updates
+    ln = m.p["1.attn.ln.weight"].detach().tolist()   # plain lists: tensors in an mp.Queue need the sender alive
+    g = GenerationHyperparameters(max_new_tokens=6, min_new_tokens=6, greedy=False, top_k=50, temperature=1.0)
+    plens = [4, 6, 5]
+    prompts = SequenceSample.from_default(seqlens=plens, ids=list(range(len(plens))),
+                                          data=dict(packed_input_ids=(torch.arange(2, 2 + sum(plens)) % cfg.vocab_size)))
+    outs = model.module.generate(prompts, tok, g, num_micro_batches=1)
+    return dict(losses=losses, ln=ln, gen=torch.cat([o.tokens for o in outs]).tolist())
+
+
+@pytest.mark.parametrize("ckpt", [False, True])
+def test_replicated_dropout_and_sampling_agree_across_tp_ranks(ckpt):
+    from realhf_b200.base.testing import run_distributed
+    a, b = run_distributed(_dropout_worker, 2, ckpt=ckpt)
+    assert a["losses"] == b["losses"], (a["losses"], b["losses"])
+    assert a["ln"] == b["ln"]
+    assert a["gen"] == b["gen"]
+    if ckpt:   # recomputation replays the same masks: identical training trajectory with and without checkpointing
+        c, _ = run_distributed(_dropout_worker, 2, ckpt=False)
+        assert c["losses"] == pytest.approx(a["losses"], rel=1e-5)
