@@ -177,9 +177,8 @@ def make_device_mesh_from_name(global_mesh_name: Optional[str], name: str, n_nod
             raise ValueError(f"invalid device mesh `{name}`: need 1/2/4/8 consecutive, aligned GPUs")
         m[node_idx(node), gl] = 1
     else:
-        rng = re.match(r"^(.*)\[(\d+)-(\d+)\]$", name)
-        nodes = ([f"{rng.group(1)}{i:02d}" for i in range(int(rng.group(2)), int(rng.group(3)) + 1)] if rng else name.split(","))
-        for nd in nodes:
+        from realhf_b200.base.cluster import parse_nodelist
+        for nd in parse_nodelist(name):  # full Slurm hostlist syntax: NODE[01-02,05],NODE07
             m[node_idx(nd)] = 1
     return DeviceMesh(n_nodes, n_gpus_per_node, m, global_mesh_name, name)
 

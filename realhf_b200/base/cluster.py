@@ -77,6 +77,54 @@ class ClusterSpec:
         return self.gpu_image if gpu else self.cpu_image
 
 
+def parse_nodelist(nodelist: str) -> List[str]:
+    """Slurm hostlist syntax -> node names: `NODE[01-03,07],gpu12` -> NODE01 NODE02 NODE03 NODE07 gpu12 (zero padding kept).
+    (Reference: base/slurm_utils.py:13-32, which shells out to `scontrol show hostnames`.)"""
+    out: List[str] = []
+    for item in re.findall(r"[^,\[]+(?:\[[^\]]*\])?", nodelist.replace(" ", "")):
+        m = re.fullmatch(r"(.*)\[([^\]]*)\]", item)
+        if not m:
+            out.append(item)
+            continue
+        prefix, body = m.groups()
+        for part in body.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                if int(hi) < int(lo):
+                    raise ValueError(f"descending range `{part}` in nodelist `{nodelist}`")
+                out.extend(f"{prefix}{i:0{len(lo)}d}" for i in range(int(lo), int(hi) + 1))
+            elif part:
+                out.append(prefix + part)
+    if not out or len(set(out)) != len(out):
+        raise ValueError(f"empty or repeated nodes in nodelist `{nodelist}`")
+    return out
+
+
+def format_nodelist(nodes: List[str]) -> str:
+    """Inverse of `parse_nodelist` for names of the form <prefix><digits>: consecutive numbers are folded into ranges."""
+    groups: Dict[tuple, List[int]] = {}
+    plain: List[str] = []
+    for n in nodes:
+        m = re.fullmatch(r"(.*?)(\d+)", n)
+        if m:
+            groups.setdefault((m.group(1), len(m.group(2))), []).append(int(m.group(2)))
+        else:
+            plain.append(n)
+    parts = []
+    for (prefix, width), nums in groups.items():
+        nums = sorted(set(nums))
+        runs, start, prev = [], nums[0], nums[0]
+        for x in nums[1:] + [None]:
+            if x is not None and x == prev + 1:
+                prev = x
+                continue
+            runs.append(f"{start:0{width}d}" if start == prev else f"{start:0{width}d}-{prev:0{width}d}")
+            if x is not None:
+                start = prev = x
+        parts.append(f"{prefix}{runs[0]}" if len(runs) == 1 and "-" not in runs[0] else f"{prefix}[{','.join(runs)}]")
+    return ",".join(parts + plain)
+
+
 _SPEC: Optional[ClusterSpec] = None
 _SPEC_PATH: Optional[str] = None
 

@@ -269,3 +269,18 @@ def test_config_reference_doc_is_up_to_date():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_config_docs.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_nodelist_parsing_and_formatting_roundtrip():
+    from realhf_b200.api.quickstart import make_device_mesh_from_name
+    from realhf_b200.base.cluster import format_nodelist, parse_nodelist
+    assert parse_nodelist("NODE[01-03,07],gpu12") == ["NODE01", "NODE02", "NODE03", "NODE07", "gpu12"]
+    assert parse_nodelist("NODE01,NODE02") == ["NODE01", "NODE02"] and parse_nodelist("n[9-11]") == ["n9", "n10", "n11"]
+    assert format_nodelist(["NODE01", "NODE02", "NODE03", "NODE07"]) == "NODE[01-03,07]" and format_nodelist(["NODE05"]) == "NODE05"
+    for s in ("NODE[01-04]", "NODE[01-02,05]", "a1,b[3-4]"):
+        assert parse_nodelist(format_nodelist(parse_nodelist(s))) == parse_nodelist(s)
+    for bad in ("NODE[03-01]", "NODE01,NODE01", ""):
+        with pytest.raises(ValueError):
+            parse_nodelist(bad)
+    m = make_device_mesh_from_name("NODE[01-04]", "NODE[01-02,04]", n_nodes=4, n_gpus_per_node=8)
+    assert m.mapping.sum(1).tolist() == [8, 8, 0, 8]
