@@ -4,9 +4,10 @@ single-token decode attention over a dense KV cache.
 CUDA tensors: decode runs the split-KV sm_100a kernel in `csrc/attn_decode.cu` (with fused RoPE and
 in-place KV append); varlen forward/backward calls the flash-attn library kernel by default (a library
 call on this path, recorded as such in DESIGN.md).  `REAL_ATTN=tcgen05` switches the varlen FORWARD to
-`csrc/attn_fwd_tcgen05.cu` (TMA + tcgen05 + TMEM; head dim 64 / 128, no dropout / sliding window); its LSE
-has the layout the library backward consumes.  That kernel is compiled and SASS-checked but has not run on
-hardware yet, hence opt-in.
+`csrc/attn_fwd_tcgen05.cu` (TMA + tcgen05 + TMEM; head dim 64 / 128, no dropout / sliding window) and
+`REAL_ATTN_BWD=tcgen05` the BACKWARD to `csrc/attn_bwd_tcgen05.cu`; both use the LSE layout of the library, so
+they can be switched independently.  These kernels are compiled and SASS-checked but have not run on hardware
+yet, hence opt-in.
 CPU tensors: plain PyTorch reference (also the numerics oracle for the tests).
 """
 
@@ -29,6 +30,12 @@ def attn_impl() -> str:
 
 def _own_fwd_ok(hd: int, dropout_p: float) -> bool:
     return attn_impl() == "tcgen05" and hd in (64, 128) and dropout_p == 0.0
+
+
+def _own_bwd_ok(hd: int, dropout_p: float) -> bool:
+    """`REAL_ATTN_BWD=tcgen05`: own backward (`csrc/attn_bwd_tcgen05.cu`), independent of the forward switch (both produce /
+    consume the same LSE layout).  Experimental for the same reason as the forward."""
+    return os.environ.get("REAL_ATTN_BWD", "flash") == "tcgen05" and hd in (64, 128) and dropout_p == 0.0
 
 
 def varlen_attention_ref(q, k, v, cu_seqlens, scale: float, causal: bool = True, sliding_window: Optional[int] = None):
@@ -111,6 +118,9 @@ class _PackedQKVAttention(torch.autograd.Function):
         dq = dqkv[:, : nq * hd].view(T, nq, hd)
         dk = dqkv[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd)
         dv = dqkv[:, (nq + nkv) * hd:].view(T, nkv, hd)
+        if _own_bwd_ok(hd, dropout_p):
+            lib().attn_bwd(dout.contiguous().view(T, nq, hd), q, k, v, out.view(T, nq, hd), lse, dq, dk, dv, cu, max_seqlen, scale, causal)
+            return dqkv, None, None, None, None, None, None, None, None
         _wrapped_flash_attn_varlen_backward(dout.contiguous(), q, k, v, out, lse, dq, dk, dv, cu, cu, max_seqlen, max_seqlen, dropout_p,
                                             scale, causal, -1, -1, 0.0, None, False, rng_state=rng)
         return dqkv, None, None, None, None, None, None, None, None

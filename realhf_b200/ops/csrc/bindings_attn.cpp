@@ -105,7 +105,35 @@ std::vector<Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, 
   return {out, lse};
 }
 
+extern "C" int rb_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                           float* delta, void* dq, void* dk, void* dv, const int* cu_seqlens, int64_t q_ld, int64_t k_ld, int64_t v_ld,
+                           int64_t o_ld, int64_t do_ld, int64_t dq_ld, int64_t dk_ld, int64_t dv_ld, int T, int B, int nq, int nkv,
+                           int hd, int max_seqlen, float scale, int causal, int dt, cudaStream_t s);
+
+// Writes dq / dk / dv (views with the same layout rules as q / k / v, e.g. column ranges of one d(qkv) buffer).
+void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse, Tensor dq,
+              Tensor dk, Tensor dv, const Tensor& cu_seqlens, int64_t max_seqlen, double scale, bool causal) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 3);
+  const int64_t T = q.size(0), nq = q.size(1), hd = q.size(2), nkv = k.size(1);
+  for (const Tensor* t : std::initializer_list<const Tensor*>{&q, &k, &v, &out, &dout, &dq, &dk, &dv})
+    TORCH_CHECK(t->dim() == 3 && t->stride(2) == 1 && t->stride(1) == hd && t->size(0) == T && t->size(2) == hd &&
+                t->scalar_type() == q.scalar_type());
+  TORCH_CHECK(out.size(1) == nq && dout.size(1) == nq && dq.size(1) == nq && v.size(1) == nkv && dk.size(1) == nkv && dv.size(1) == nkv);
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.size(0) == nq && lse.size(1) == T);
+  TORCH_CHECK(cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous() && cu_seqlens.is_cuda());
+  c10::cuda::CUDAGuard guard(q.device());
+  auto delta = at::empty({nq, T}, q.options().dtype(at::kFloat));
+  const int dt = q.scalar_type() == at::kBFloat16 ? 1 : (q.scalar_type() == at::kHalf ? 2 : -1);
+  int rc = rb_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(),
+                       delta.data_ptr<float>(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), cu_seqlens.data_ptr<int>(), q.stride(0),
+                       k.stride(0), v.stride(0), out.stride(0), dout.stride(0), dq.stride(0), dk.stride(0), dv.stride(0), (int)T,
+                       (int)cu_seqlens.numel() - 1, (int)nq, (int)nkv, (int)hd, (int)max_seqlen, (float)scale, causal ? 1 : 0, dt,
+                       at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "attn_bwd: unsupported configuration (", rc, ")");
+}
+
 void register_attn_ops(torch::Library& m) {
+  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
   m.def("attn_fwd(Tensor q, Tensor k, Tensor v, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> Tensor[]", &attn_fwd);
   m.def("sample(Tensor logits, Tensor? unfinished, int top_k, float top_p, float inv_temp, int eos_id, bool suppress_eos, bool greedy, int pad_id, int seed, int step, bool want_mask) -> Tensor[]", &sample);
   m.def("decode_attention(Tensor qkv, Tensor(a!) k_cache, Tensor(b!) v_cache, Tensor cache_lens, int nq, int nkv, int hd, float scale, Tensor? cos, Tensor? sin, int rot_dim, bool interleaved) -> Tensor", &decode_attention);

@@ -99,3 +99,44 @@ def test_attn_fwd_tcgen05_matches_reference(hd, nq, nkv, causal):
         if causal:
             att = att.masked_fill(torch.ones(e - s, e - s, device=DEV, dtype=torch.bool).triu(1), float("-inf"))
         torch.testing.assert_close(lse[:, s:e], torch.logsumexp(att, -1), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="tcgen05 varlen attention backward has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
+@pytest.mark.parametrize("hd,nq,nkv,causal", [(128, 8, 8, True), (128, 8, 2, True), (64, 4, 4, True), (128, 4, 4, False)])
+def test_attn_bwd_tcgen05_matches_autograd_of_the_reference(hd, nq, nkv, causal):
+    """dq / dk / dv written into the three column ranges of one d(qkv) buffer vs autograd through the fp32 reference."""
+    import math
+
+    import numpy as np
+
+    from realhf_b200.ops import lib
+    torch.manual_seed(0)
+    lens = [1, 37, 128, 129, 300, 640, 5]
+    T = sum(lens)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    W = (nq + 2 * nkv) * hd
+    qkv = torch.randn(T, W, device=DEV, dtype=torch.bfloat16)
+    dout = torch.randn(T, nq, hd, device=DEV, dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(hd)
+
+    def views(t):
+        return (t[:, : nq * hd].view(T, nq, hd), t[:, nq * hd:(nq + nkv) * hd].view(T, nkv, hd), t[:, (nq + nkv) * hd:].view(T, nkv, hd))
+    # reference: fp32 autograd, forward statistics from the same math
+    x = qkv.float().requires_grad_(True)
+    qf, kf, vf = views(x)
+    ref = A.varlen_attention_ref(qf, kf, vf, cu, scale, causal)
+    ref.backward(dout.float())
+    q, k, v = views(qkv)
+    rep = nq // nkv
+    lse = torch.empty(nq, T, device=DEV, dtype=torch.float32)
+    for s, e in zip(cu[:-1].tolist(), cu[1:].tolist()):
+        att = torch.einsum("qhd,khd->hqk", q[s:e].float(), k[s:e].float().repeat_interleave(rep, 1)) * scale
+        if causal:
+            att = att.masked_fill(torch.ones(e - s, e - s, device=DEV, dtype=torch.bool).triu(1), float("-inf"))
+        lse[:, s:e] = torch.logsumexp(att, -1)
+    dqkv = torch.full_like(qkv, float("nan"))   # every element must be written
+    dq, dk, dv = views(dqkv)
+    lib().attn_bwd(dout, q, k, v, ref.detach().to(torch.bfloat16), lse, dq, dk, dv, cu, max(lens), scale, causal)
+    assert torch.isfinite(dqkv.float()).all()
+    torch.testing.assert_close(dqkv.float(), x.grad, atol=6e-2, rtol=6e-2)
