@@ -42,8 +42,9 @@ class HardwareModel:
                 d = json.load(open(p))
                 hw.bf16_flops = d.get("bf16_tflops_sustained", hw.bf16_flops / 1e12) * 1e12
                 hw.hbm_bw = d.get("hbm_gbs", hw.hbm_bw / 1e9) * 1e9
-            except Exception:
-                pass
+            except (OSError, ValueError, TypeError) as e:  # unreadable / malformed file: keep the documented defaults
+                import warnings
+                warnings.warn(f"ignoring {p}: {e}")
         return hw
 
 

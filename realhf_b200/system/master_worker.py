@@ -104,8 +104,8 @@ class MasterWorker:
             try:
                 r = await self._group_request(self.workers_of[nm][:1], "model_config", model_name=nm)
                 self.model_cfgs[nm] = r[0].data
-            except Exception:
-                pass
+            except Exception as e:  # only the TFLOP/s column of the step log depends on it
+                logger.warning(f"no model config for {nm} ({e}): FLOP accounting disabled for it")
         ec = cfg.exp_ctrl
         self.save_ctl = timeutil.EpochStepTimeFreqCtl(ec.save_freq_epochs, ec.save_freq_steps, ec.save_freq_secs)
         self.eval_ctl = timeutil.EpochStepTimeFreqCtl(ec.eval_freq_epochs, ec.eval_freq_steps, ec.eval_freq_secs)
@@ -313,8 +313,8 @@ class MasterWorker:
                 self._dump_recover()
             try:
                 await asyncio.wait_for(self._group_request(list(range(self.cfg.n_model_workers)), "exit"), timeout=30)
-            except Exception:
-                pass
+            except Exception as e:  # workers that already died cannot acknowledge; the launcher stops them anyway
+                logger.warning(f"not every model worker acknowledged `exit`: {e!r}")
             self._pump_task.cancel()
             self.stream.close()
         return times
@@ -385,8 +385,10 @@ class MasterWorker:
                 self._stats_file = open(os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "stats.jsonl"), "a")
             self._stats_file.write(self._json.dumps(rec) + "\n")
             self._stats_file.flush()
-        except Exception:
-            pass
+        except (OSError, TypeError, ValueError) as e:  # statistics must never stop a training run
+            if not getattr(self, "_stats_warned", False):
+                self._stats_warned = True
+                logger.warning(f"cannot write stats.jsonl: {e}")
 
     def _dump_recover(self):
         info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),

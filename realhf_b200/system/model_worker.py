@@ -409,7 +409,7 @@ class ModelWorker:
         try:
             free, total = torch.cuda.mem_get_info(self.device)
             st["device_used_gb"] = (total - free) / 2 ** 30
-        except Exception:
+        except RuntimeError:  # driver query unavailable (e.g. inside some containers): the allocator numbers are enough
             pass
         return st
 
@@ -438,8 +438,8 @@ class ModelWorker:
             self.save_recover_states()
         try:
             dist.destroy_process_group()
-        except Exception:
-            pass
+        except Exception as e:  # peers may already be gone at teardown
+            logger.debug(f"destroy_process_group: {e!r}")
         self.stream.close()
 
     def _maybe_inject_fault(self, handle: str):
