@@ -180,3 +180,29 @@ def test_ppo_pipeline_generation_and_mixed_layouts(tmp_path):
     assert found
     import transformers
     transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
+
+
+@pytest.mark.parametrize("mode", ["heuristic", "pipe_model"])
+def test_two_node_cluster_shape_through_runtime(tmp_path, mode):
+    """n_nodes=2 x n_gpus_per_node=2 (four workers on this host standing in for two nodes): per-MFC device meshes that are node
+    halves / whole nodes, pipeline stages across the node boundary, and data / parameter movement between them."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    fixtures.make_checkpoint(crit, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    name = f"mn-{uuid.uuid4().hex[:6]}"
+    args = ["ppo", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=2", "n_gpus_per_node=2",
+            f"allocation_mode={mode}", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2"]
+    for role, path in (("actor", ckpt), ("ref", ckpt), ("critic", crit), ("rew", crit)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    exp = build_experiment(args)
+    sys_cfg = exp.initial_setup()
+    assert len(sys_cfg.model_worker) == 4
+    main_start(exp, timeout=900)
+    assert "benchmark finished" in _master_log(exp)
