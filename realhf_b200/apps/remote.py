@@ -28,7 +28,7 @@ def control_key(exp, trial, worker_type, index):
 
 
 def status_ttl() -> float:
-    return float(os.environ.get("REAL_STATUS_TTL", "60"))
+    return float(os.environ.get("REAL_STATUS_TTL", "120"))
 
 
 def _watch_controller(exp: str, trial: str):
