@@ -135,3 +135,69 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
     finally:
         sched.stop_all()
     return sys_cfg
+
+
+# ------------------------------------------------------------------------------------------- command line
+def main(argv=None):
+    """`python -m realhf_b200.apps.main <cmd>`: operate on a trial from another shell (parity: apps/main.py:233-257,330-450;
+    experiments are STARTED with `python -m realhf_b200.apps.quickstart <experiment> key=value ...`).
+
+      status -e EXP -f TRIAL            worker statuses (RUNNING / PAUSED / COMPLETED / ERROR / LOST)
+      pause | resume -e EXP -f TRIAL    the master stops issuing model function calls after its current step / continues
+      stop -e EXP -f TRIAL [--mode M]   graceful stop through the master; with --mode slurm also `scancel` the trial's jobs
+      find_config -r REGEX              list the registered experiment names that match
+      profile_layers ...                forwards to `realhf_b200.apps.profile_layers`
+    """
+    import argparse
+    import re
+    ap = argparse.ArgumentParser(prog="realhf_b200.apps.main")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    for name in ("status", "pause", "resume", "stop"):
+        sp = sub.add_parser(name)
+        sp.add_argument("--experiment_name", "-e", required=True)
+        sp.add_argument("--trial_name", "-f", required=True)
+        if name == "stop":
+            sp.add_argument("--mode", default="local", choices=["local", "slurm"])
+        if name == "status":
+            sp.add_argument("--n_model_workers", "-n", type=int, default=None)
+    sp = sub.add_parser("find_config")
+    sp.add_argument("--regex", "-r", required=True)
+    sub.add_parser("profile_layers", add_help=False)
+    args, rest = ap.parse_known_args(argv)
+    if args.cmd == "profile_layers":
+        from realhf_b200.apps import profile_layers
+        return profile_layers.main(rest)
+    if rest:
+        ap.error(f"unrecognized arguments: {rest}")
+    if args.cmd == "find_config":
+        import realhf_b200.experiments.algos  # noqa: F401
+        import realhf_b200.experiments.profile  # noqa: F401
+        from realhf_b200.api.quickstart import QUICKSTART_EXPERIMENTS
+        names = sorted(n for n in QUICKSTART_EXPERIMENTS if re.match(args.regex, n))
+        print("\n".join(names) if names else "No matched experiment names.")
+        return names
+    exp, trial = args.experiment_name, args.trial_name
+    if args.cmd == "status":
+        keys = name_resolve.find_subtree(f"{exp}/{trial}/status")
+        out = {}
+        for k in keys:
+            try:
+                out[k.split("/status/", 1)[1]] = name_resolve.get(k)
+            except name_resolve.NameEntryNotFoundError:
+                out[k.split("/status/", 1)[1]] = "LOST"
+        for k in sorted(out):
+            print(f"{k}: {out[k]}")
+        return out
+    if args.cmd == "pause":
+        return pause_experiment(exp, trial)
+    if args.cmd == "resume":
+        return resume_experiment(exp, trial)
+    if args.cmd == "stop":
+        stop_experiment(exp, trial)
+        if args.mode == "slurm":
+            sched_client.make("slurm", exp, trial).stop_all()
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ import json
 import torch
 
 
-def main():
+def main(argv=None):
     from realhf_b200.api.quickstart import ModelTrainEvalConfig
     from realhf_b200.api.config import ModelFamily
     from realhf_b200.api.model import ReaLModelConfig
@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--bs", type=int, nargs="+", default=[1, 8])
     ap.add_argument("--seqlen", type=int, nargs="+", default=[256, 1024])
     ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     sh = model_shape(ModelTrainEvalConfig(type=ModelFamily(a.family, a.size, False)))
     cfg = ReaLModelConfig(n_layers=2, n_kv_heads=int(sh["h"]) // 128, n_q_heads=int(sh["h"]) // 128, hidden_dim=int(sh["h"]),
                           intermediate_dim=int(sh["f"]), vocab_size=int(sh["v"]), n_positions=4096, embd_pdrop=0.0, resid_pdrop=0.0,

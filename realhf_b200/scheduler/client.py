@@ -252,8 +252,13 @@ class SlurmSchedulerClient(SchedulerClient):
             time.sleep(poll)
 
     def stop_all(self, signal_=None):
-        for jid in self._job_ids.values():
-            subprocess.run(["scancel"] + (["-s", "INT"] if signal_ == signal.SIGINT else []) + [jid])
+        sig = ["-s", "INT"] if signal_ == signal.SIGINT else []
+        if self._job_ids:
+            for jid in self._job_ids.values():
+                subprocess.run(["scancel"] + sig + [jid])
+        else:  # a fresh client (`apps.main stop` from another shell): address the trial's jobs by name
+            for wt in ("master_worker", "model_worker"):
+                subprocess.run(["scancel"] + sig + ["--name", f"{self.run_name}:{wt}"])
 
 
 def make(mode: str, expr_name: str, trial_name: str, **kw) -> SchedulerClient:

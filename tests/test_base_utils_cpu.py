@@ -284,3 +284,28 @@ def test_nodelist_parsing_and_formatting_roundtrip():
             parse_nodelist(bad)
     m = make_device_mesh_from_name("NODE[01-04]", "NODE[01-02,04]", n_nodes=4, n_gpus_per_node=8)
     assert m.mapping.sum(1).tolist() == [8, 8, 0, 8]
+
+
+def test_operations_cli_status_pause_stop_find_config(tmp_path, monkeypatch, capsys):
+    """`python -m realhf_b200.apps.main ...` from another shell: talks to a trial only through the name-resolve store."""
+    from realhf_b200.apps import main as M
+    from realhf_b200.apps.remote import control_key, status_key
+    from realhf_b200.base import name_resolve
+    name_resolve.reconfigure("nfs", record_root=str(tmp_path / "nr"))
+    name_resolve.add(status_key("e1", "t1", "master_worker", 0), "RUNNING", replace=True)
+    name_resolve.add(status_key("e1", "t1", "model_worker", 0), "ERROR", replace=True)
+    out = M.main(["status", "-e", "e1", "-f", "t1"])
+    assert out == {"master_worker/0": "RUNNING", "model_worker/0": "ERROR"} and "model_worker/0: ERROR" in capsys.readouterr().out
+    M.main(["pause", "-e", "e1", "-f", "t1"])
+    assert name_resolve.get(control_key("e1", "t1", "master_worker", 0)) == "pause"
+    M.main(["resume", "-e", "e1", "-f", "t1"])
+    assert name_resolve.get(control_key("e1", "t1", "master_worker", 0)) == "resume"
+    calls = []
+    import subprocess
+    monkeypatch.setattr(subprocess, "run", lambda cmd, **kw: calls.append(cmd))
+    M.main(["stop", "-e", "e1", "-f", "t1", "--mode", "slurm"])
+    assert name_resolve.get(control_key("e1", "t1", "master_worker", 0)) == "exit"
+    assert calls == [["scancel", "--name", "e1_t1:master_worker"], ["scancel", "--name", "e1_t1:model_worker"]]
+    assert M.main(["find_config", "-r", "p"]) == ["ppo", "profile"]
+    with pytest.raises(SystemExit):
+        M.main(["status", "-e", "e1"])   # trial name is required
