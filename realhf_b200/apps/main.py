@@ -106,6 +106,10 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
         pickle.dump(sys_cfg, f)
     sched = sched_client.make(mode, exp, trial, **({"partition": getattr(exp_cfg, "partition", None)} if mode == "slurm" else {}))
     env = {k: os.environ[k] for k in constants.FORWARDED_ENV if k in os.environ}
+    if getattr(exp_cfg, "wandb_mode", "disabled") != "disabled":
+        env["WANDB_MODE"] = exp_cfg.wandb_mode
+    if getattr(exp_cfg, "tensorboard", False):
+        env["REAL_TENSORBOARD"] = "1"
     env.update(env_vars or {})
     debug = getattr(exp_cfg, "debug", True)
     def res(s):  # scheduler resources of a task group (the local scheduler ignores everything but `gpu`)

@@ -32,7 +32,8 @@ class CommonExperimentConfig(Experiment):
     mode: str = "local"  # local | slurm
     debug: bool = True
     partition: Optional[str] = None  # Slurm partition; None: the cluster spec's, else "dev"
-    wandb_mode: str = "disabled"
+    wandb_mode: str = "disabled"  # disabled | online | offline (exported as WANDB_MODE to the master worker)
+    tensorboard: bool = False     # TensorBoard event files under <log dir>/tensorboard
     image_name: Optional[str] = None
     recover_mode: str = "disabled"  # disabled | auto | save | resume
     recover_retries: int = 1

@@ -376,19 +376,11 @@ class MasterWorker:
         return c != "exit"
 
     def _write_stats(self, rec: Dict):
-        """Training statistics as JSON lines under the run's log directory (`stats.jsonl`): machine-readable twin of the log
-        lines (the reference carries wandb / tensorboard fields but never writes anything, system_api.py:96-104)."""
-        try:
-            if self._stats_file is None:
-                import json as _json
-                self._json = _json
-                self._stats_file = open(os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "stats.jsonl"), "a")
-            self._stats_file.write(self._json.dumps(rec) + "\n")
-            self._stats_file.flush()
-        except (OSError, TypeError, ValueError) as e:  # statistics must never stop a training run
-            if not getattr(self, "_stats_warned", False):
-                self._stats_warned = True
-                logger.warning(f"cannot write stats.jsonl: {e}")
+        """Per-step statistics -> stats.jsonl (+ TensorBoard / wandb when enabled), see `system/metrics.py`."""
+        if self._stats_file is None:
+            from realhf_b200.system.metrics import MetricSinks
+            self._stats_file = MetricSinks(self.exp, self.trial, constants.run_dirs(self.exp, self.trial)["log"])
+        self._stats_file.log(rec)
 
     def _dump_recover(self):
         info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),

@@ -1,5 +1,6 @@
 """Utilities and aux subsystems: logits warpers, stats tracker, in-flight batching, profile experiment, trace summary."""
 import json
+import os
 
 import torch
 
@@ -78,3 +79,39 @@ def test_profile_experiment_mocks_cover_every_interface():
         cfg = build_experiment(["profile", "device=cpu", "batch_sizes=[4]", "seqlens=[12]", f"handles={handles}", f"interface={itf}", "repeats=1"] + extra)
         rows = cfg.run_local()
         assert rows and all(r["secs"] > 0 for r in rows), (itf, rows)
+
+
+def test_metric_sinks_jsonl_tensorboard_and_failing_sink(tmp_path, monkeypatch):
+    import glob
+    import json
+    import sys
+    import types
+    from realhf_b200.system.metrics import MetricSinks
+    monkeypatch.setenv("REAL_TENSORBOARD", "1")
+    monkeypatch.setenv("WANDB_MODE", "offline")
+    logged = []
+
+    class _Run:
+        def log(self, d, step):
+            if step == 2:
+                raise RuntimeError("quota")
+            logged.append((step, d))
+
+        def finish(self):
+            logged.append("finished")
+    monkeypatch.setitem(sys.modules, "wandb", types.SimpleNamespace(init=lambda **kw: _Run()))
+    m = MetricSinks("exp", "trial", str(tmp_path))
+    assert m.active == ["jsonl", "tensorboard", "wandb"]
+    for step in (1, 2, 3):
+        m.log({"rpc": "actor_train", "step": step, "epoch": 0, "time": 1.0 * step, "loss": 0.5 / step, "n_tokens": 100, "note": "x", "ok": True})
+    assert m.active == ["jsonl", "tensorboard"]          # the failing sink was switched off, the others kept going
+    m.close()
+    rows = [json.loads(l) for l in open(tmp_path / "stats.jsonl")]
+    assert [r["step"] for r in rows] == [1, 2, 3] and rows[0]["loss"] == 0.5
+    assert logged[0] == (1, {"actor_train/loss": 0.5, "actor_train/n_tokens": 100.0, "epoch": 0})
+    ev = glob.glob(str(tmp_path / "tensorboard" / "events.out.tfevents.*"))
+    assert ev and os.path.getsize(ev[0]) > 0
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(tmp_path / "tensorboard"))
+    acc.Reload()
+    assert [e.step for e in acc.Scalars("actor_train/loss")] == [1, 2, 3]
