@@ -37,9 +37,12 @@ def test_gpt2_sft_dp2_gloo(tmp_path):
         "n_gpus_per_node=2", "allocation_mode=manual", "allocation.parallel.data_parallel_size=2", "model.type._class=gpt2",
         f"model.path={ckpt}", f"dataset.train_path={data}", "dataset.train_bs_n_seqs=16", "dataset.max_seqlen=64",
         "exp_ctrl.total_train_epochs=2", "exp_ctrl.save_freq_steps=4", "model.optimizer.lr=1e-3",
-        "model.optimizer.warmup_steps_proportion=0.0", "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"])
+        "model.optimizer.warmup_steps_proportion=0.0", "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false",
+        "tensorboard=True"])
     main_start(exp, timeout=600)
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "master_worker-0")).read()
+    import glob
+    assert glob.glob(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "tensorboard", "events.out.tfevents.*"))
     losses = [float(l.split("loss=")[1].split(",")[0]) for l in log.splitlines() if "[trainDefault]" in l and "loss=" in l]
     assert len(losses) == 8, log[-3000:]
     assert losses[-1] < losses[0], losses
