@@ -155,6 +155,10 @@ class CommonExperimentConfig(Experiment):
 
     # ---- system config
     def initial_setup(self) -> ExperimentConfig:
+        for role, m in self.models.items():
+            if getattr(m, "lora", None) is not None or any(getattr(self, f, False) for f in ("is_sft_lora", "is_rew_lora")):
+                # the option names exist for command-line compatibility; silently training full weights instead would be worse
+                raise NotImplementedError(f"LoRA is not supported (model `{role}`; the reference rejects it too, ppo_exp.py:199-202)")
         rpc_allocs = self._get_rpc_allocations()
         for a in rpc_allocs:
             if isinstance(a.rpc, str):

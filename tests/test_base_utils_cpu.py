@@ -309,3 +309,11 @@ def test_operations_cli_status_pause_stop_find_config(tmp_path, monkeypatch, cap
     assert M.main(["find_config", "-r", "p"]) == ["ppo", "profile"]
     with pytest.raises(SystemExit):
         M.main(["status", "-e", "e1"])   # trial name is required
+
+
+def test_lora_options_are_rejected_loudly(tmp_path, monkeypatch):
+    monkeypatch.setenv("REAL_FILEROOT", str(tmp_path))
+    from realhf_b200.apps.quickstart import build_experiment
+    exp = build_experiment(["rw", "experiment_name=e", "trial_name=t", "device=cpu", "n_gpus_per_node=1", "is_sft_lora=True"])
+    with pytest.raises(NotImplementedError, match="LoRA"):
+        exp.initial_setup()
