@@ -129,9 +129,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_
           ptx::tma_load_2d(sK + st * C::kKVBytes + kb * (kBKV * 128), &tma_k, bar(K_FULL + st), hk * kD + kb * 64, row);
         ptx::mbar_wait(bar(V_EMPTY + st), par ^ 1);
         ptx::mbar_arrive_expect_tx(bar(V_FULL + st), C::kKVBytes);
+        // V is the MN-major B operand of P V: it is staged as two 64-key halves, each [d chunk][64 keys][128 B], i.e. exactly
+        // the stage format (and the 8 KB chunk stride) of the GEMM's MN-major operands
 #pragma unroll
-        for (int kb = 0; kb < C::kDBlocks; ++kb)
-          ptx::tma_load_2d(sV + st * C::kKVBytes + kb * (kBKV * 128), &tma_v, bar(V_FULL + st), hk * kD + kb * 64, row);
+        for (int half = 0; half < kBKV / 64; ++half)
+#pragma unroll
+          for (int kb = 0; kb < C::kDBlocks; ++kb)
+            ptx::tma_load_2d(sV + st * C::kKVBytes + half * (64 * kD * 2) + kb * (64 * 128), &tma_v, bar(V_FULL + st),
+                             hk * kD + kb * 64, row + half * 64);
       }
     }
   } else if (warp == 1) {
@@ -166,11 +171,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kBKV / 16; ++kk) {
-          // A: 16 keys = 32 B inside the 128 B row of key block kk/4; B: 16 key rows = 2048 B down every 64-wide d chunk
+          // A: 16 keys = 32 B inside the 128 B row of key block kk/4; B: 16 key rows = 2048 B down every 64-wide d chunk of
+          // key half kk/4
           ptx::tc_mma_f16(tmem_base + 256 + st * 128,
                           ptx::make_smem_desc_sw128(sP + (kk >> 2) * (kBQ * 128) + (kk & 3) * 32, 16, 1024),
-                          ptx::make_smem_desc_sw128(sV + st * C::kKVBytes + kk * 2048, kBKV * 128, 1024), idesc_o,
-                          kk != 0 ? 1u : 0u);
+                          ptx::make_smem_desc_sw128(sV + st * C::kKVBytes + (kk >> 2) * (64 * kD * 2) + (kk & 3) * 2048, 64 * 128, 1024),
+                          idesc_o, kk != 0 ? 1u : 0u);
         }
         ptx::tc_commit(bar(V_EMPTY + st));
         ptx::tc_commit(bar(P_EMPTY));
@@ -329,7 +335,7 @@ extern "C" int rb_attn_fwd(const void* q, const void* k, const void* v, void* ou
   const int bf = dt == 1;
   if (!make_tmap(&mq, q, bf, T, (uint64_t)nq * hd, q_ld, 64, kBQ)) return -10;
   if (!make_tmap(&mk, k, bf, T, (uint64_t)nkv * hd, k_ld, 64, kBKV)) return -11;
-  if (!make_tmap(&mv, v, bf, T, (uint64_t)nkv * hd, v_ld, 64, kBKV)) return -12;
+  if (!make_tmap(&mv, v, bf, T, (uint64_t)nkv * hd, v_ld, 64, 64)) return -12;  // 64-key halves, see the producer
   AttnParams p{cu_seqlens, out, lse, out_ld, T, nq, nkv, scale, causal};
   if (hd == 128) {
     return bf ? launch_attn_fwd<128, __nv_bfloat16, 1>(mq, mk, mv, p, B, max_seqlen, s)
