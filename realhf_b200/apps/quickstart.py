@@ -11,6 +11,23 @@ import sys
 from realhf_b200.api.quickstart import QUICKSTART_EXPERIMENTS, parse_overrides
 
 
+def option_table(cls, prefix=""):
+    """(dotted option, type, default) for every leaf field of an experiment dataclass (also feeds docs/expconfig.md)."""
+    import dataclasses
+    rows = []
+    for f in dataclasses.fields(cls):
+        if f.name.startswith("_"):
+            continue
+        default = f.default if f.default is not dataclasses.MISSING else (
+            f.default_factory() if f.default_factory is not dataclasses.MISSING else None)
+        if dataclasses.is_dataclass(default):
+            rows.extend(option_table(type(default), prefix + f.name + "."))
+        else:
+            t = f.type if isinstance(f.type, str) else (str(f.type).replace("typing.", "") if "[" in str(f.type) else getattr(f.type, "__name__", str(f.type)))
+            rows.append((prefix + f.name, t, repr(default)))
+    return rows
+
+
 def build_experiment(argv):
     import realhf_b200.experiments.algos  # noqa: F401  (registers sft / rw / dpo / ppo / gen)
     import realhf_b200.experiments.profile  # noqa: F401  (registers profile)
@@ -21,6 +38,11 @@ def build_experiment(argv):
     if name not in QUICKSTART_EXPERIMENTS:
         raise SystemExit(f"unknown experiment `{name}`; choices: {sorted(QUICKSTART_EXPERIMENTS)}")
     cfg = QUICKSTART_EXPERIMENTS[name]()
+    if any(o in ("-h", "--help", "help") for o in overrides):
+        print(f"usage: python -m realhf_b200.apps.quickstart {name} key=value ...\n\noptions (dotted name, type, default):")
+        for opt, typ, default in option_table(type(cfg)):
+            print(f"  {opt:<55} {typ:<28} {default}")
+        sys.exit(0)
     parse_overrides(cfg, overrides)
     for n in (cfg.experiment_name, cfg.trial_name):
         if "_" in n:

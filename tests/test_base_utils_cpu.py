@@ -317,3 +317,13 @@ def test_lora_options_are_rejected_loudly(tmp_path, monkeypatch):
     exp = build_experiment(["rw", "experiment_name=e", "trial_name=t", "device=cpu", "n_gpus_per_node=1", "is_sft_lora=True"])
     with pytest.raises(NotImplementedError, match="LoRA"):
         exp.initial_setup()
+
+
+def test_quickstart_help_lists_every_option(capsys):
+    from realhf_b200.apps.quickstart import build_experiment
+    with pytest.raises(SystemExit) as e:
+        build_experiment(["ppo", "--help"])
+    out = capsys.readouterr().out
+    assert e.value.code == 0 and "actor_train.parallel.model_parallel_size" in out and "ppo.gen.max_new_tokens" in out
+    with pytest.raises(SystemExit):
+        build_experiment(["no-such-experiment"])
