@@ -231,7 +231,7 @@ def test_cluster_spec_drives_fileroot_slurm_defaults_and_search_memory(tmp_path,
     monkeypatch.setenv("CLUSTER_SPEC_PATH", path)
     monkeypatch.delenv("REAL_FILEROOT", raising=False)
     cs = cluster.spec()
-    assert cs.cluster_name == "my_b200_cluster" and cs.node_type("NODE07") == "b200x8" and cs.gpu_type("NODE12") == "b200"
+    assert cs.cluster_name == "blackwell-pod-a" and cs.node_type("NODE07") == "b200x8" and cs.gpu_type("NODE12") == "b200"
     assert cluster.node_name_is_node_type("NODE01", ["x", "b200x8"]) and not cluster.node_name_is_node_type("NODE01", "a100")
     assert cs.node_names([1, 12]) == ["NODE01", "NODE12"]
     with pytest.raises(KeyError):
@@ -244,10 +244,10 @@ def test_cluster_spec_drives_fileroot_slurm_defaults_and_search_memory(tmp_path,
         importlib.reload(C)
         s = C.SlurmSchedulerClient("exp", "trial")
         script = s.build_script("model_worker", C.remote_worker_cmd("exp", "trial", True, "model_worker"), count=8, gpu=1)
-        assert "#SBATCH --partition=gpu" in script and "#SBATCH --nodes=2" in script          # 8 workers on 4-GPU nodes
-        assert "--container-image=my-registry/realhf-b200-gpu" in script and "/dev/infiniband:/dev/infiniband" in script
+        assert "#SBATCH --partition=b200" in script and "#SBATCH --nodes=2" in script          # 8 workers on 4-GPU nodes
+        assert "--container-image=registry.example.com/rlhf/realhf-b200:gpu" in script and "/dev/infiniband:/dev/infiniband" in script
         script = s.build_script("master_worker", C.remote_worker_cmd("exp", "trial", True, "master_worker"), count=1, gpu=0)
-        assert "--container-image=my-registry/realhf-b200-cpu" in script
+        assert "--container-image=registry.example.com/rlhf/realhf-b200:cpu" in script
         from realhf_b200.search.engine import HardwareModel
         assert HardwareModel.from_measured().mem_cap == 141e9
         # malformed specs fail loudly
