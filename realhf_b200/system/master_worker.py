@@ -51,7 +51,7 @@ class MasterWorker:
         self._rpc_batch_lens: Dict[str, List[int]] = {}
         self._t_start = time.time()
         self.stats_log: List[Dict] = []
-        self._stats_file = None
+        self._metrics = None
         self._consumed_ids_this_epoch: List[Hashable] = []
 
     # ------------------------------------------------------------------ transport helpers
@@ -317,6 +317,8 @@ class MasterWorker:
                 logger.warning(f"not every model worker acknowledged `exit`: {e!r}")
             self._pump_task.cancel()
             self.stream.close()
+            if self._metrics is not None:
+                self._metrics.close()  # flushes TensorBoard / finishes the wandb run
         return times
 
     @staticmethod
@@ -377,10 +379,10 @@ class MasterWorker:
 
     def _write_stats(self, rec: Dict):
         """Per-step statistics -> stats.jsonl (+ TensorBoard / wandb when enabled), see `system/metrics.py`."""
-        if self._stats_file is None:
+        if self._metrics is None:
             from realhf_b200.system.metrics import MetricSinks
-            self._stats_file = MetricSinks(self.exp, self.trial, constants.run_dirs(self.exp, self.trial)["log"])
-        self._stats_file.log(rec)
+            self._metrics = MetricSinks(self.exp, self.trial, constants.run_dirs(self.exp, self.trial)["log"])
+        self._metrics.log(rec)
 
     def _dump_recover(self):
         info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),
