@@ -298,7 +298,7 @@ class ReaLModel(nn.Module):
         c = self.config
         w = self.p[f"{prefix}.weight"]
         if c.layer_norm_type is None:
-            return F.layer_norm(x, (c.hidden_dim,), w, self.p[f"{prefix}.bias"], c.layer_norm_epsilon)
+            return OF.layer_norm(x, w, self.p[f"{prefix}.bias"], c.layer_norm_epsilon)
         return OF.rmsnorm(x, w, c.layer_norm_epsilon, 1.0 if c.layer_norm_type == "gemma" else 0.0)
 
     def _local_heads(self) -> Tuple[int, int]:

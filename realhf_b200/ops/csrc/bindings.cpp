@@ -41,6 +41,10 @@ int rb_adamw(void*, int, const void*, int, void*, void*, int, float*, int64_t, f
 int rb_sumsq(const void*, int, int64_t, float*, cudaStream_t);
 int rb_rmsnorm_fwd(const void*, const void*, const void*, void*, void*, float*, int64_t, int, float, float, int, cudaStream_t);
 int rb_rmsnorm_bwd_num_partials();
+int rb_layernorm_fwd(const void*, const void*, const void*, void*, float*, float*, int64_t, int, float, int, cudaStream_t);
+int rb_layernorm_bwd_num_partials();
+int rb_layernorm_bwd(const void*, const void*, const void*, const float*, const float*, void*, float*, float*, void*, void*, int64_t, int,
+                     int, cudaStream_t);
 int rb_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, void*, int64_t, int, float, int, cudaStream_t);
 int rb_rope_inplace(void*, const float*, const float*, const int*, int64_t, int, int, int64_t, int, int, int, int, cudaStream_t);
 int rb_gated_act_fwd(const void*, void*, int64_t, int, int, int, cudaStream_t);
@@ -175,6 +179,40 @@ std::vector<Tensor> rmsnorm_bwd(const Tensor& x, const Tensor& w, const Tensor& 
   return {dx, dw};
 }
 
+// y, mean, rstd
+std::vector<Tensor> layernorm_fwd(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& b, double eps) {
+  CHECK_IN(x); CHECK_IN(w);
+  const int H = x.size(-1);
+  const int64_t rows = x.numel() / H;
+  TORCH_CHECK(w.numel() == H && w.scalar_type() == x.scalar_type() && (!b.has_value() || (b->numel() == H && b->scalar_type() == x.scalar_type())));
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  auto mean = at::empty({rows}, x.options().dtype(at::kFloat));
+  auto rstd = at::empty({rows}, x.options().dtype(at::kFloat));
+  int rc = rb_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.has_value() ? b->data_ptr() : nullptr, y.data_ptr(), mean.data_ptr<float>(),
+                            rstd.data_ptr<float>(), rows, H, eps, dt_code(x), cur_stream());
+  TORCH_CHECK(rc == 0, "layernorm_fwd: unsupported shape/dtype");
+  return {y, mean, rstd};
+}
+
+// dx, dw, db
+std::vector<Tensor> layernorm_bwd(const Tensor& x, const Tensor& w, const Tensor& dy, const Tensor& mean, const Tensor& rstd) {
+  CHECK_IN(x); CHECK_IN(w); CHECK_IN(dy); CHECK_IN(mean); CHECK_IN(rstd);
+  const int H = x.size(-1);
+  const int64_t rows = x.numel() / H;
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dx = at::empty_like(x);
+  auto dw = at::empty_like(w);
+  auto db = at::empty_like(w);
+  auto partial = at::empty({2, rb_layernorm_bwd_num_partials(), H}, x.options().dtype(at::kFloat));
+  float* p0 = partial.data_ptr<float>();
+  int rc = rb_layernorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(), p0,
+                            p0 + (int64_t)rb_layernorm_bwd_num_partials() * H, dw.data_ptr(), db.data_ptr(), rows, H, dt_code(x),
+                            cur_stream());
+  TORCH_CHECK(rc == 0, "layernorm_bwd: unsupported shape/dtype");
+  return {dx, dw, db};
+}
+
 // ---------------------------------------------------------------- rope / gated act
 void rope_inplace(Tensor x, const Tensor& cos, const Tensor& sin, const Tensor& pos, int64_t n_heads, int64_t hd,
                   int64_t rot_dim, bool interleaved, bool inverse) {
@@ -278,6 +316,8 @@ TORCH_LIBRARY(realhf_b200, m) {
   m.def("sumsq_accum(Tensor g, Tensor(a!) out2) -> ()", &sumsq_accum);
   m.def("rmsnorm_fwd(Tensor x, Tensor? residual, Tensor w, float eps, float w_offset) -> Tensor[]", &rmsnorm_fwd);
   m.def("rmsnorm_bwd(Tensor x, Tensor w, Tensor dy, Tensor rstd, float w_offset) -> Tensor[]", &rmsnorm_bwd);
+  m.def("layernorm_fwd(Tensor x, Tensor w, Tensor? b, float eps) -> Tensor[]", &layernorm_fwd);
+  m.def("layernorm_bwd(Tensor x, Tensor w, Tensor dy, Tensor mean, Tensor rstd) -> Tensor[]", &layernorm_bwd);
   m.def("rope_inplace(Tensor(a!) x, Tensor cos, Tensor sin, Tensor pos, int n_heads, int hd, int rot_dim, bool interleaved, bool inverse) -> ()", &rope_inplace);
   m.def("gated_act_fwd(Tensor gu, int kind) -> Tensor", &gated_act_fwd);
   m.def("gated_act_bwd(Tensor gu, Tensor dout, int kind) -> Tensor", &gated_act_bwd);

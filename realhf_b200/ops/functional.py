@@ -136,6 +136,31 @@ def add_rmsnorm(x, residual, w, eps: float, w_offset: float = 0.0):
     return rmsnorm(res, w, eps, w_offset), res
 
 
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = lib().layernorm_fwd(x.contiguous(), w, b, eps)
+        ctx.save_for_backward(x, w, mean, rstd)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dx, dw, db = lib().layernorm_bwd(x.contiguous(), w, dy.contiguous(), mean, rstd)
+        return dx, dw, (db if ctx.has_bias else None), None
+
+
+def layer_norm(x, w, b, eps: float):
+    """LayerNorm over the last dimension.  `REAL_LAYERNORM=native` selects `csrc/layernorm.cu` on CUDA tensors (written without
+    hardware access, hence opt-in); the default is `F.layer_norm`."""
+    import os
+    if os.environ.get("REAL_LAYERNORM", "torch") == "native" and use_native(x) and x.dtype == w.dtype \
+            and x.dtype in (torch.bfloat16, torch.float16, torch.float32) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
+        return _LayerNorm.apply(x, w, b, eps)
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
 # ------------------------------------------------------------------------------------------------ rope
 
 

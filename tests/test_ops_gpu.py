@@ -226,3 +226,26 @@ def test_segment_copy_ema():
     plan = OF.SegmentPlan([0], [0], [src.numel() * 2], DEV)
     plan.run(src, dst, eta=0.3)
     torch.testing.assert_close(dst.float(), ref.float(), atol=1e-2, rtol=1e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="layernorm.cu has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
+@pytest.mark.parametrize("H,dtype", [(768, torch.bfloat16), (1024, torch.float16), (4096, torch.bfloat16), (1600, torch.float32)])
+def test_layernorm_native_matches_reference(H, dtype, monkeypatch):
+    from realhf_b200.ops import functional as OF
+    monkeypatch.setenv("REAL_LAYERNORM", "native")
+    torch.manual_seed(0)
+    x = (torch.randn(517, H, device="cuda") * 2 + 0.5).to(dtype).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dtype).requires_grad_(True)
+    b = (0.1 * torch.randn(H, device="cuda")).to(dtype).requires_grad_(True)
+    dy = torch.randn(517, H, device="cuda").to(dtype)
+    y = OF.layer_norm(x, w, b, 1e-5)
+    y.backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.layer_norm(xr, (H,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    tol = dict(atol=2e-2, rtol=2e-2) if dtype != torch.float32 else dict(atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(y.float(), yr, **tol)
+    torch.testing.assert_close(x.grad.float(), xr.grad, **tol)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=tol["atol"] * 20, rtol=tol["rtol"])
+    torch.testing.assert_close(b.grad.float(), br.grad, atol=tol["atol"] * 20, rtol=tol["rtol"])
