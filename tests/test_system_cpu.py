@@ -241,7 +241,7 @@ def test_workers_exit_when_the_controller_is_killed_and_lost_status(tmp_path):
     data = str(tmp_path / "sft.jsonl")
     fixtures.write_sft_dataset(data, words, n=64)
     name = f"orphan-{uuid.uuid4().hex[:6]}"
-    env = dict(os.environ, REAL_STATUS_TTL="3")
+    env = dict(os.environ, REAL_STATUS_TTL="5")
     launcher_log = str(tmp_path / "launcher.log")
     with open(launcher_log, "w") as lf:
         p = subprocess.Popen([sys.executable, "-m", "realhf_b200.apps.quickstart", "sft", f"experiment_name={name}", "trial_name=t0",
