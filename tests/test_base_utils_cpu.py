@@ -327,3 +327,13 @@ def test_quickstart_help_lists_every_option(capsys):
     assert e.value.code == 0 and "actor_train.parallel.model_parallel_size" in out and "ppo.gen.max_new_tokens" in out
     with pytest.raises(SystemExit):
         build_experiment(["no-such-experiment"])
+
+
+def test_package_root_exports_the_public_names():
+    import realhf_b200
+    from realhf_b200 import MFCDef, PPOConfig, SequenceSample  # noqa: F401  (the spelling user code uses)
+    for name in realhf_b200.__all__:
+        assert getattr(realhf_b200, name) is not None
+    assert realhf_b200.PPOConfig().ppo.kl_ctl == 0.1 and "PPOConfig" in dir(realhf_b200)
+    with pytest.raises(AttributeError):
+        realhf_b200.NoSuchName
