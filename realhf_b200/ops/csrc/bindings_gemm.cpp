@@ -104,7 +104,27 @@ Tensor gemm_grouped(const Tensor& a, const Tensor& w, const Tensor& offsets, boo
   return c;
 }
 
+extern "C" int rb_gemm_grouped_wgrad(const void* dy, const void* x, void* out, const int* offsets, int G, int Tp, int M, int N,
+                                     int64_t ld_dy, int64_t ld_x, int out_dt, int accumulate, int num_sms, cudaStream_t s);
+
+// Grouped wgrad: out[g] (+)= dy[rows of g]^T @ x[rows of g]; rows sorted by group with every group's block padded (zero rows) to a
+// multiple of 64, `offsets` int32 [G+1] on the device holding the PADDED block starts.  out [G, M, N] fp32 or bf16.
+void gemm_grouped_wgrad(const Tensor& dy, const Tensor& x, Tensor out, const Tensor& offsets, bool accumulate, int64_t num_sms) {
+  TORCH_CHECK(dy.is_cuda() && dy.dim() == 2 && x.dim() == 2 && out.dim() == 3 && dy.scalar_type() == at::kBFloat16 &&
+              x.scalar_type() == at::kBFloat16 && dy.stride(1) == 1 && x.stride(1) == 1 && out.is_contiguous());
+  TORCH_CHECK(out.scalar_type() == at::kFloat || out.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(offsets.scalar_type() == at::kInt && offsets.is_contiguous() && offsets.is_cuda());
+  const int64_t G = out.size(0), M = out.size(1), N = out.size(2), Tp = dy.size(0);
+  TORCH_CHECK(dy.size(1) == M && x.size(1) == N && x.size(0) == Tp && offsets.numel() == G + 1, "gemm_grouped_wgrad: shape mismatch");
+  c10::cuda::CUDAGuard guard(dy.device());
+  int rc = rb_gemm_grouped_wgrad(dy.data_ptr(), x.data_ptr(), out.data_ptr(), offsets.data_ptr<int>(), (int)G, (int)Tp, (int)M, (int)N,
+                                 dy.stride(0), x.stride(0), out.scalar_type() == at::kFloat ? 0 : 1, accumulate ? 1 : 0, (int)num_sms,
+                                 at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gemm_grouped_wgrad failed with code ", rc);
+}
+
 void register_gemm_ops(torch::Library& m) {
+  m.def("gemm_grouped_wgrad(Tensor dy, Tensor x, Tensor(a!) out, Tensor offsets, bool accumulate, int num_sms) -> ()", &gemm_grouped_wgrad);
   m.def("gemm_grouped(Tensor a, Tensor w, Tensor offsets, bool b_mn, int num_sms) -> Tensor", &gemm_grouped);
   m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
   m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);

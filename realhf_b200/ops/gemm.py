@@ -103,6 +103,50 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return _Linear.apply(x, w, bias)
 
 
+def pad_groups(offsets: torch.Tensor, n_rows: int, block: int = 64):
+    """Row map that pads every group's block of a group-sorted [n_rows, *] tensor to a multiple of `block` rows, computed on
+    the device (no host read of the group sizes).  Returns (dest [n_rows] int64: padded position of every source row,
+    offsets_pad [G + 1] int32: padded block starts, n_pad: static upper bound of padded rows, a multiple of `block`)."""
+    G = offsets.numel() - 1
+    off = offsets.long()
+    counts = off[1:] - off[:-1]
+    padded = (counts + block - 1) // block * block
+    off_pad = torch.zeros(G + 1, dtype=torch.long, device=offsets.device)
+    off_pad[1:] = padded.cumsum(0)
+    rows = torch.arange(n_rows, device=offsets.device)
+    g = torch.bucketize(rows, off[1:], right=True).clamp_(max=G - 1)
+    dest = rows + (off_pad[:-1] - off[:-1])[g]
+    n_pad = (n_rows + G * (block - 1) + block - 1) // block * block
+    return dest, off_pad.int(), n_pad
+
+
+def grouped_wgrad_ref(dy, x, offsets, G):
+    """fp32 reference: dW[g] = dy[rows of g]^T @ x[rows of g]."""
+    off = offsets.tolist()
+    return torch.stack([dy[off[g]:off[g + 1]].float().t() @ x[off[g]:off[g + 1]].float() for g in range(G)])
+
+
+def grouped_wgrad(dy: torch.Tensor, x: torch.Tensor, offsets: torch.Tensor, G: int, out: Optional[torch.Tensor] = None,
+                  accumulate: bool = False) -> torch.Tensor:
+    """dW [G, M, N] for group-sorted dy [T, M], x [T, N] in ONE launch (`csrc/gemm_grouped_wgrad.cu`): both tensors are
+    scattered into zero-padded buffers whose group blocks start at multiples of 64 rows, so that no K block of the kernel
+    straddles two experts.  No host synchronisation."""
+    T = dy.shape[0]
+    dest, off_pad, n_pad = pad_groups(offsets, T)
+    dy_p = torch.zeros(n_pad, dy.shape[1], dtype=dy.dtype, device=dy.device).index_copy_(0, dest, dy)
+    x_p = torch.zeros(n_pad, x.shape[1], dtype=x.dtype, device=x.device).index_copy_(0, dest, x)
+    if out is None:
+        out = torch.empty(G, dy.shape[1], x.shape[1], dtype=dy.dtype, device=dy.device)
+        accumulate = False
+    lib().gemm_grouped_wgrad(dy_p, x_p, out, off_pad, accumulate, _sms(dy.device))
+    return out
+
+
+def _grouped_wgrad_enabled() -> bool:
+    import os
+    return os.environ.get("REAL_MOE_GROUPED_WGRAD", "0") == "1"  # kernel written without hardware access: opt-in
+
+
 class _GroupedLinear(torch.autograd.Function):
     """y[rows of group g] = x[rows of group g] @ w[g]^T for rows sorted by group (MoE experts), one kernel launch."""
 
@@ -118,7 +162,9 @@ class _GroupedLinear(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = lib().gemm_grouped(dy, w, offsets, True, _sms(x.device))        # [rows_g, N] x [N, K]
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _grouped_wgrad_enabled():
+            dw = grouped_wgrad(dy, x, offsets, w.shape[0])
+        elif ctx.needs_input_grad[1]:
             # per-group wgrad: the reduction runs over a data-dependent row range, so it stays one GEMM per group
             dw = torch.zeros_like(w)
             off = offsets.tolist()

@@ -10,6 +10,8 @@ echo "== attention forward (tcgen05) numerics"
 timeout 240 python -m pytest tests/test_attention_gpu.py -x -q -k attn_fwd_tcgen05 2>&1 | tail -15
 echo "== attention backward (tcgen05) numerics"
 timeout 240 python -m pytest tests/test_attention_gpu.py -x -q -k attn_bwd_tcgen05 2>&1 | tail -15
+echo "== grouped wgrad (MoE) numerics"
+timeout 180 python -m pytest tests/test_gemm_gpu.py -x -q -k grouped_wgrad_single_launch 2>&1 | tail -8
 echo "== LayerNorm kernel numerics"
 timeout 120 python -m pytest tests/test_ops_gpu.py -x -q -k layernorm_native 2>&1 | tail -8
 echo "== attention forward vs flash-attn (CUDA events)"

@@ -204,3 +204,21 @@ def test_grouped_gemm_moe(counts):
     torch.testing.assert_close(y.float(), yr, atol=0.1, rtol=2e-2)
     torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.05, rtol=3e-2)
     torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.3, rtol=3e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="gemm_grouped_wgrad.cu has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
+@pytest.mark.parametrize("counts,M,N", [([300, 0, 64, 1000, 5, 77], 256, 512), ([4096, 4096], 1024, 384), ([0, 0, 9], 128, 128)])
+def test_grouped_wgrad_single_launch(counts, M, N):
+    from realhf_b200.ops import gemm as G
+    torch.manual_seed(0)
+    T, ng = sum(counts), len(counts)
+    offsets = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device="cuda")
+    dy = torch.randn(T, M, device="cuda", dtype=torch.bfloat16)
+    x = torch.randn(T, N, device="cuda", dtype=torch.bfloat16)
+    ref = G.grouped_wgrad_ref(dy, x, offsets, ng)
+    out = G.grouped_wgrad(dy, x, offsets, ng)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2 * max(counts) ** 0.5, rtol=2e-2)
+    acc = torch.ones(ng, M, N, device="cuda", dtype=torch.float32)
+    G.grouped_wgrad(dy, x, offsets, ng, out=acc, accumulate=True)
+    torch.testing.assert_close(acc, ref + 1.0, atol=2e-2 * max(counts) ** 0.5, rtol=2e-2)

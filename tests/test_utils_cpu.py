@@ -115,3 +115,27 @@ def test_metric_sinks_jsonl_tensorboard_and_failing_sink(tmp_path, monkeypatch):
     acc = EventAccumulator(str(tmp_path / "tensorboard"))
     acc.Reload()
     assert [e.step for e in acc.Scalars("actor_train/loss")] == [1, 2, 3]
+
+
+def test_group_padding_for_the_grouped_wgrad_kernel():
+    """The dispatch-side contract of csrc/gemm_grouped_wgrad.cu: blocks start at multiples of 64, padding rows are zero, and
+    the per-expert products over the PADDED blocks equal the products over the original ragged blocks."""
+    import torch
+    from realhf_b200.ops.gemm import grouped_wgrad_ref, pad_groups
+    torch.manual_seed(0)
+    for counts in ([5, 0, 64, 130, 1], [0, 0, 7], [128, 64], [1] * 9, [0, 0]):
+        G, T = len(counts), sum(counts)
+        offsets = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32)
+        dy, x = torch.randn(T, 16), torch.randn(T, 24)
+        dest, off_pad, n_pad = pad_groups(offsets, T)
+        assert n_pad % 64 == 0 and int(off_pad[-1]) <= n_pad and all(int(o) % 64 == 0 for o in off_pad)
+        assert [int(b - a) for a, b in zip(off_pad[:-1], off_pad[1:])] == [(c + 63) // 64 * 64 for c in counts]
+        assert dest.numel() == T and (T == 0 or dest.unique().numel() == T)
+        dy_p = torch.zeros(n_pad, 16).index_copy_(0, dest, dy)
+        x_p = torch.zeros(n_pad, 24).index_copy_(0, dest, x)
+        for g in range(G):   # rows land inside their own block, in order
+            a, b = int(offsets[g]), int(offsets[g + 1])
+            torch.testing.assert_close(dy_p[int(off_pad[g]): int(off_pad[g]) + (b - a)], dy[a:b])
+            assert float(dy_p[int(off_pad[g]) + (b - a): int(off_pad[g + 1])].abs().sum()) == 0.0
+        got = torch.stack([dy_p[int(off_pad[g]): int(off_pad[g + 1])].t() @ x_p[int(off_pad[g]): int(off_pad[g + 1])] for g in range(G)])
+        torch.testing.assert_close(got, grouped_wgrad_ref(dy, x, offsets, G), atol=1e-4, rtol=1e-4)
