@@ -18,7 +18,7 @@ echo "== attention forward vs flash-attn (CUDA events)"
 timeout 120 python scripts/bench_attn.py --seqs 32 --len 640 2>&1 | tail -4
 timeout 120 python scripts/bench_attn.py --seqs 8 --len 4096 2>&1 | tail -4
 echo "== model-level: one SFT step with both kernels switched on vs the library path"
-REAL_ATTN=tcgen05 REAL_ATTN_BWD=tcgen05 timeout 300 python - <<'PY' 2>&1 | tail -5
+REAL_ATTN=tcgen05 REAL_ATTN_BWD=tcgen05 timeout 300 python - <<'PY' 2>&1 | tail -6
 import os, torch
 from realhf_b200.models import hf_io
 from realhf_b200.models.real_model import ReaLModel
@@ -31,15 +31,18 @@ dev = "cuda" if torch.cuda.is_available() else "cpu"
 ids = torch.randint(2, cfg.vocab_size, (sum(lens),), device=dev)
 cu = torch.tensor([0, 300, 940, 1017], dtype=torch.int32, device=dev)
 grads = {}
-for impl in ("flash", "tcgen05"):
-    os.environ["REAL_ATTN"] = os.environ["REAL_ATTN_BWD"] = impl
+combos = [("flash", "flash"), ("tcgen05", "flash"), ("flash", "tcgen05"), ("tcgen05", "tcgen05")]   # isolates fwd from bwd problems
+for impl in combos:
+    os.environ["REAL_ATTN"], os.environ["REAL_ATTN_BWD"] = impl
     m = ReaLModel(cfg, dtype=torch.bfloat16 if dev == "cuda" else torch.float32, device=dev).instantiate(seed=3)
     out = m(input_ids=ids, cu_seqlens=cu, max_seqlen=640)
     loss = out.logits.float().logsumexp(-1).mean()
     params = [p for p in m.p.values() if p.requires_grad]
     gs = torch.autograd.grad(loss, params, allow_unused=True)
     grads[impl] = (loss.item(), torch.cat([g.float().flatten() for g in gs if g is not None]))
-(l0, g0), (l1, g1) = grads["flash"], grads["tcgen05"]
-print("loss", l0, l1, "grad rel err", ((g0 - g1).norm() / g0.norm()).item())
+l0, g0 = grads[combos[0]]
+for c in combos[1:]:
+    l1, g1 = grads[c]
+    print("fwd/bwd =", c, "loss", l0, l1, "grad rel err", ((g0 - g1).norm() / g0.norm()).item())
 PY
 echo "== done"
