@@ -196,6 +196,8 @@ class PipelineRunner:
         last_global = lambda: self.ctx.global_rank(pipe=self.pp - 1, data=self.ctx.dp_rank, model=self.ctx.tp_rank)
         first_global = lambda: self.ctx.global_rank(pipe=0, data=self.ctx.dp_rank, model=self.ctx.tp_rank)
         sends = []
+        # PyTorch sampling path (CPU tensors) under TP: the ranks of the last stage must draw the same tokens (generation.generate)
+        sample_gen = m.shared_generator(dev) if (dev.type != "cuda" and self.ctx.tp_size > 1 and not g.greedy) else None
         # ---- prefill, micro-batch by micro-batch
         for i, (ids, cu, mx, T) in enumerate(metas):
             B = cu.numel() - 1
@@ -214,7 +216,7 @@ class PipelineRunner:
             unfinished.append(torch.ones(B, dtype=torch.bool, device=dev))
             if self.last:
                 logits = gen._final_logits(m, out.hidden.index_select(0, (cu[1:] - 1).long()))
-                nxt, lp, mb_, unfinished[i] = gen.genstep(logits, g, 0, eos_id, pad_id, unfinished[i])
+                nxt, lp, mb_, unfinished[i] = gen.genstep(logits, g, 0, eos_id, pad_id, unfinished[i], sample_gen)
                 toks[i].append(nxt); lps[i].append(lp); masks[i].append(mb_)
                 if self.pp > 1:
                     sends.append((nxt, dist.isend(nxt, first_global())))
@@ -237,7 +239,7 @@ class PipelineRunner:
                 st.cache_lens += 1
                 if self.last:
                     logits = gen._final_logits(m, h)
-                    nxt, lp, mb_, unfinished[i] = gen.genstep(logits, g, step, eos_id, pad_id, unfinished[i])
+                    nxt, lp, mb_, unfinished[i] = gen.genstep(logits, g, step, eos_id, pad_id, unfinished[i], sample_gen)
                     toks[i].append(nxt); lps[i].append(lp); masks[i].append(mb_)
                     if step + 1 < g.max_new_tokens:
                         sends.append((nxt, dist.isend(nxt, first_global())))
