@@ -56,6 +56,9 @@ class ModelWorker:
     def setup(self):
         cfg = self.cfg
         seeding.set_random_seed(cfg.seed, offset=self.index)
+        from realhf_b200.models import generation
+        # the fused sampler's Philox seed: a function of the experiment seed, identical on every worker (TP ranks must agree)
+        generation.seed_sampling(seeding.derive_seed("sampling"))
         if cfg.device == "cuda":
             torch.cuda.set_device(int(os.environ.get("REAL_LOCAL_GPU", self.index % max(torch.cuda.device_count(), 1))))
             self.device = torch.device("cuda", torch.cuda.current_device())
