@@ -34,6 +34,9 @@ class AsyncIOSequenceBuffer:
     def size(self) -> int:
         return len(self._slots)
 
+    def __contains__(self, sample_id: Hashable) -> bool:
+        return sample_id in self._slots
+
     def n_ready_for(self, rpc: MFCDef) -> int:
         keys = set(rpc.input_keys)
         return sum(1 for s in self._slots.values() if rpc.name not in s.consumed_by and keys.issubset(s.sample.keys))

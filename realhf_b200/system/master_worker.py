@@ -131,6 +131,10 @@ class MasterWorker:
             if meta.meta_sample is None:
                 continue
             for s in meta.meta_sample.unpack():
+                if s.ids[0] in self.buffer:
+                    # the last batch of an epoch was smaller than n_seqs, its samples are still waiting, and the next epoch
+                    # brought the same prompt again: one live instance per id (the worker-side tensors are identical)
+                    continue
                 for k in s.keys:
                     self.data_owner[(s.ids[0], k)] = w
                 samples.append(s)

@@ -295,3 +295,24 @@ def test_workers_exit_when_the_controller_is_killed_and_lost_status(tmp_path):
     old = time.time() - 3600
     os.utime(repo._file(status_key(name, "t1", "model_worker", 0)), (old, old))
     assert ctl.statuses()["model_worker/0"] == "LOST"
+
+
+def test_dataset_size_not_a_multiple_of_the_batch_size_across_epochs(tmp_path):
+    """20 samples, batches of 8, 2 epochs: the 4 left over from the first epoch wait in the buffer while the second epoch's
+    data (the same ids again) is fetched -- the run must neither trip over duplicate ids nor starve."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=20)
+    name = f"odd-{uuid.uuid4().hex[:6]}"
+    exp = build_experiment(["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1", "n_gpus_per_node=1",
+                            "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}",
+                            "dataset.train_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=2",
+                            "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"])
+    main_start(exp, timeout=600)
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
+    steps = [int(l.split("] step ")[1].split(":")[0]) for l in log.splitlines() if "[trainDefault] step" in l]
+    assert steps == list(range(4)), steps   # 20 // 8 = 2 steps per epoch
