@@ -90,6 +90,10 @@ class MasterWorker:
         src_workers = self._dp_heads(self.src_rpc.model_name)
         specs = await self._group_request(src_workers, "spec")
         self.dataset_size = sum(s.data["dataset_size"] for s in specs)
+        if self.dataset_size < self.src_rpc.n_seqs:
+            raise ValueError(f"the dataset has {self.dataset_size} usable samples but `{self.src_rpc.name}` consumes {self.src_rpc.n_seqs} "
+                             f"sequences per step: lower the batch size (dataset.train_bs_n_seqs) or check the length filter "
+                             f"(max_seqlen / max_prompt_len drops longer records)")
         steps_per_epoch = max(1, self.dataset_size // self.src_rpc.n_seqs)
         total_steps = steps_per_epoch * cfg.exp_ctrl.total_train_epochs
         self.ft_spec = FinetuneSpec(cfg.exp_ctrl.total_train_epochs, total_steps, steps_per_epoch)
