@@ -28,6 +28,22 @@ def option_table(cls, prefix=""):
     return rows
 
 
+def _revalidate(obj, path=""):
+    """Overrides are applied with setattr, after the dataclasses validated their defaults: run the generation options'
+    checks again now, so that e.g. `max_new_tokens=6` with the default `min_new_tokens=256` fails here, on the command line,
+    and not inside a worker minutes later."""
+    import dataclasses
+    from realhf_b200.api.model import GenerationHyperparameters
+    if isinstance(obj, GenerationHyperparameters):
+        try:
+            obj.__post_init__()
+        except ValueError as e:
+            raise SystemExit(f"invalid generation options at `{path or 'gen'}`: {e}")
+    elif dataclasses.is_dataclass(obj) and not isinstance(obj, type):
+        for f in dataclasses.fields(obj):
+            _revalidate(getattr(obj, f.name, None), f"{path}.{f.name}" if path else f.name)
+
+
 def build_experiment(argv):
     import realhf_b200.experiments.algos  # noqa: F401  (registers sft / rw / dpo / ppo / gen)
     import realhf_b200.experiments.profile  # noqa: F401  (registers profile)
@@ -44,6 +60,7 @@ def build_experiment(argv):
             print(f"  {opt:<55} {typ:<28} {default}")
         sys.exit(0)
     parse_overrides(cfg, overrides)
+    _revalidate(cfg)
     for n in (cfg.experiment_name, cfg.trial_name):
         if "_" in n:
             raise SystemExit(f"experiment_name / trial_name must not contain `_` (got `{n}`)")

@@ -337,3 +337,12 @@ def test_package_root_exports_the_public_names():
     assert realhf_b200.PPOConfig().ppo.kl_ctl == 0.1 and "PPOConfig" in dir(realhf_b200)
     with pytest.raises(AttributeError):
         realhf_b200.NoSuchName
+
+
+def test_generation_options_are_validated_on_the_command_line():
+    from realhf_b200.apps.quickstart import build_experiment
+    with pytest.raises(SystemExit, match="ppo.gen.*min_new_tokens > max_new_tokens"):
+        build_experiment(["ppo", "experiment_name=e", "trial_name=t", "ppo.gen.max_new_tokens=6"])
+    exp = build_experiment(["ppo", "experiment_name=e", "trial_name=t", "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2",
+                            "ppo.gen.temperature=0.0"])
+    assert exp.ppo.gen.greedy and exp.ppo.gen.temperature == 1.0   # temperature 0 means greedy, as in the dataclass's own check
