@@ -284,11 +284,18 @@ class MasterWorker:
         self.rpc_secs.clear()
         return dt
 
+    def _ckpt_tag(self) -> str:
+        """Name of a checkpoint written after the step that just finished: epoch index of that step, its 1-based position in
+        the epoch, global step count (the reference's convention, master_worker.py:1330-1343 -- the last step of an epoch is
+        `epoch{e}epochstep{steps_per_epoch}`, not `epoch{e+1}epochstep0`)."""
+        if self.epoch_step == 0 and self.step > 0:
+            return f"epoch{self.epoch - 1}epochstep{self.ft_spec.steps_per_epoch}globalstep{self.step}"
+        return f"epoch{self.epoch}epochstep{self.epoch_step}globalstep{self.step}"
+
     async def _save(self):
         for nm in sorted(self.topos, key=str):
             if any(r.model_name == nm and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in self.rpcs):
-                d = os.path.join(constants.run_dirs(self.exp, self.trial)["save"], nm.role,
-                                 f"epoch{self.epoch}epochstep{self.epoch_step}globalstep{self.step}")
+                d = os.path.join(constants.run_dirs(self.exp, self.trial)["save"], nm.role, self._ckpt_tag())
                 await self._group_request(self.workers_of[nm], "save", data=d, model_name=nm)
                 logger.info(f"saved {nm} to {d}")
 

@@ -52,6 +52,8 @@ def test_gpt2_sft_dp2_gloo(tmp_path):
     save_root = os.path.join(os.environ["REAL_FILEROOT"], "checkpoints")
     found = [os.path.join(d, f) for d, _, fs in os.walk(save_root) for f in fs if f == "config.json"]
     assert found, "no checkpoint was written"
+    # 4 steps per epoch, saved every 4 steps: named after the step that just finished (last step of its epoch)
+    assert sorted(os.path.basename(os.path.dirname(f)) for f in found) == ["epoch0epochstep4globalstep4", "epoch1epochstep4globalstep8"]
     import transformers
     transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
 
