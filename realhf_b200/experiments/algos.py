@@ -211,7 +211,8 @@ class PPOConfig(CommonExperimentConfig):
         rw_itf = ModelInterfaceAbstraction("paired_rw", args=dict(enable_save=False, output_scaling=p.reward_output_scaling,
                                                                   output_bias=p.reward_output_bias))
         n = self.dataset.train_bs_n_seqs
-        mask_keys = () if p.gen.force_no_logits_mask else ("packed_logits_mask",)
+        # greedy decoding filters nothing, so generation emits no keep-mask (and nobody must wait for one)
+        mask_keys = () if (p.gen.force_no_logits_mask or p.gen.greedy or p.gen.temperature == 0.0) else ("packed_logits_mask",)
         return {
             "actor_gen": MFCDef(name="actor_gen", n_seqs=n, interface_type=T.GENERATE, interface_impl=actor_itf, model_name="actor",
                                 input_keys=("packed_prompts",),

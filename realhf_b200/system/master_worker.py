@@ -233,6 +233,11 @@ class MasterWorker:
                 continue
             if r.data.get("meta") is not None:
                 m: SequenceSample = r.data["meta"]
+                missing = set(rpc.output_keys) - set(m.keys)
+                if missing:
+                    # the consumers of these keys would wait forever: a hang with idle GPUs is the worst way to learn about it
+                    raise RuntimeError(f"MFC `{rpc.name}` declares the output keys {sorted(rpc.output_keys)} but its interface returned "
+                                       f"{sorted(m.keys)}: missing {sorted(missing)}")
                 items = m.unpack()
                 for it in items:
                     for k in it.keys:

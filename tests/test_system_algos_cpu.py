@@ -199,10 +199,13 @@ def test_two_node_cluster_shape_through_runtime(tmp_path, mode):
             f"allocation_mode={mode}", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
             "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
             "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2"]
+    if mode == "pipe_model":
+        args.append("ppo.gen.greedy=True")   # greedy decoding emits no keep-mask: the graph must not wait for one (it used to hang)
     for role, path in (("actor", ckpt), ("ref", ckpt), ("critic", crit), ("rew", crit)):
         args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
     exp = build_experiment(args)
     sys_cfg = exp.initial_setup()
     assert len(sys_cfg.model_worker) == 4
+    assert any("packed_logits_mask" in r.output_keys for r in sys_cfg.model_rpcs) == (mode != "pipe_model")
     main_start(exp, timeout=900)
     assert "benchmark finished" in _master_log(exp)
