@@ -190,6 +190,12 @@ class ModelWorker:
             es = torch.tensor([], dtype=(src_model or dst_model).dtype).element_size()
             self._realloc_cache[key] = realloc.ReallocExecutor(plan, self.index, es, self.device)
         ex = self._realloc_cache[key]
+        # ZeRO-3 keeps only this rank's slice of the source between calls: gather the full buffer for the transfer (a collective
+        # over the source's DP group -- every source worker runs this hook) and drop it again afterwards
+        src_optim = getattr(src_model.module, "optim", None) if src_model is not None else None
+        zero3_src = src_optim is not None and getattr(src_optim.cfg, "zero_stage", 1) >= 3 and not _real(src_model).instantiated
+        if zero3_src:
+            src_optim.materialize()
         src_flat = _real(src_model).flat_param.data if src_model is not None and _real(src_model).instantiated else None
         dst_flat = None
         # receive-only replicas (replica_id > 0, created by the allocation for another layout) live in IPC-shareable
@@ -208,6 +214,10 @@ class ModelWorker:
             ex.run(src_flat, dst_flat, eta=eta, peer_dst_ptrs=ptrs, notify=True)
         else:
             ex.run(src_flat, dst_flat, eta=eta)
+        if zero3_src:
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()  # the transfer reads the gathered buffer asynchronously
+            src_optim.release()
         # a non-trainable source replica is dropped after handing its weights back
         if spec.get("release_src") and src_model is not None:
             _real(src_model).release_params()

@@ -209,3 +209,29 @@ def test_two_node_cluster_shape_through_runtime(tmp_path, mode):
     assert any("packed_logits_mask" in r.output_keys for r in sys_cfg.model_rpcs) == (mode != "pipe_model")
     main_start(exp, timeout=900)
     assert "benchmark finished" in _master_log(exp)
+
+
+def test_ppo_zero3_training_layout_with_reallocated_generation_layout(tmp_path):
+    """ZeRO-3 keeps 1/dp of the trainable weights between calls; generation / inference run on OTHER layouts of the same
+    models, so every step gathers the shards for the parameter reallocation and releases them again (this used to crash)."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    fixtures.make_checkpoint(crit, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=16)
+    name = f"z3-{uuid.uuid4().hex[:6]}"
+    args = ["ppo", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=2", "allocation_mode=manual",
+            "actor_gen.parallel.model_parallel_size=2", "actor_train.parallel.data_parallel_size=2",
+            "critic_train.parallel.data_parallel_size=2", "critic_inf.parallel.model_parallel_size=2",
+            "rew_inf.parallel.data_parallel_size=2", "ref_inf.parallel.data_parallel_size=2", "actor.zero_stage=3", "critic.zero_stage=3",
+            f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16", "ppo.gen.max_new_tokens=6",
+            "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2", "exp_ctrl.total_train_epochs=1"]
+    for role, path in (("actor", ckpt), ("ref", ckpt), ("critic", crit), ("rew", crit)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=600)
+    log = _master_log(exp)
+    assert log.count("[actor_train] step") == 2
