@@ -154,9 +154,12 @@ class SequenceSample:
         return max(sorted(self.keys), key=lambda k: self.total_len(k))
 
     def get_split_spec(self, k: int, key: Optional[str] = None, min_size: int = 1) -> SequenceSplitSpec:
-        """Token-balanced contiguous split into k parts."""
+        """Token-balanced contiguous split into k parts of at least `min_size` sequences.  `min_size` is a preference (room
+        for micro-batches / pipeline stages downstream): when the batch cannot honour it, it is relaxed to what k equal parts
+        allow -- the engines cope with fewer sequences than micro-batches, an exception here would only kill the run."""
         key = key or self._get_split_key()
         lens = [sum(l) for l in self.seqlens[key]]
+        min_size = max(1, min(min_size, len(lens) // max(k, 1)))
         return SequenceSplitSpec(partitions=datapack.min_abs_diff_partition(lens, k, min_size))
 
     def split_with_spec(self, spec: SequenceSplitSpec) -> List["SequenceSample"]:

@@ -221,3 +221,20 @@ def test_dataset_disk_cache(tmp_path):
     path.write_text(path.read_text() + "\n" + json.dumps({"id": 99, "prompt": "one more"}))
     d3 = data_api.make_dataset(cfg, 1, 0, 1, Tok(), cache_root=str(tmp_path / "cache"))
     assert len(d3) == 9 and Tok.calls > n_calls
+
+
+def test_split_relaxes_an_infeasible_min_size():
+    """`min_size` expresses room for micro-batches downstream; a batch that is too small for it is split as evenly as it
+    can be instead of raising (the engines clamp their micro-batch count to the number of sequences)."""
+    import torch
+    from realhf_b200.api.data import SequenceSample
+    lens = [5, 7, 3, 9, 4, 6, 8, 2]
+    s = SequenceSample.from_default(ids=list(range(8)), seqlens=lens, data=dict(packed_input_ids=torch.arange(sum(lens))))
+    parts = s.split(2, min_size=8)          # 2 parts of >= 8 from 8 items is impossible: falls back to >= 4
+    assert [p.bs for p in parts] == [4, 4] and sum(p.bs for p in parts) == 8
+    parts = s.split(3, min_size=100)
+    assert sorted(p.bs for p in parts) == [2, 3, 3] or all(p.bs >= 2 for p in parts)
+    assert torch.equal(torch.cat([p.data["packed_input_ids"] for p in parts]), s.data["packed_input_ids"])
+    import pytest
+    with pytest.raises(ValueError):
+        s.split(9)                           # more parts than sequences stays an error
