@@ -64,9 +64,9 @@ class SFTInterface(ModelInterface):
         tot = {"nll_sum": torch.zeros((), device=dev), "n_tokens": torch.zeros((), device=dev)}
         for batch in eval_dataloader:
             batch = batch.to_device(dev)
-            st = eng.eval_batch(batch, sft_loss_from_output)
-            tot["nll_sum"] += st["nll_sum"]
-            tot["n_tokens"] += st["n_tokens"]
+            st = eng.eval_batch(batch, sft_loss_from_output)  # statistics exist on the last pipeline stage only
+            tot["nll_sum"] += st.get("nll_sum", 0.0)
+            tot["n_tokens"] += st.get("n_tokens", 0.0)
         g = IF.dp_reduce_stats(tot, _dp_group(model), dev)
         loss = g["nll_sum"] / max(g["n_tokens"], 1.0)
         return dict(loss=loss, ppl=float(torch.tensor(loss).exp()))
@@ -149,7 +149,7 @@ class PairedRewardInterface(ModelInterface):
         for batch in eval_dataloader:
             st = eng.eval_batch(batch.to_device(dev), _paired_rw_loss)
             for k in tot:
-                tot[k] += st[k]
+                tot[k] += st.get(k, 0.0)  # empty on all but the last pipeline stage
         g = IF.dp_reduce_stats(tot, _dp_group(model), dev)
         t = max(g["total"], 1.0)
         return dict(loss=g["loss"] / max(g["n_groups"], 1.0), acc=g["correct"] / t, pos_score=g["pos_score"] / t,

@@ -308,7 +308,13 @@ class MasterWorker:
         for nm in sorted(self.topos, key=str):
             if any(r.model_name == nm and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in self.rpcs):
                 res = await self._group_request(self.workers_of[nm], "evaluate", model_name=nm)
-                logger.info(f"eval {nm}: {[r.data for r in res if r.data][:1]}")
+                # the statistics live on the last pipeline stage (already reduced over DP): report a DP head's reply
+                heads = set(self._dp_heads(nm))
+                stats = [r.data for r in res if r.handler in heads and r.data]
+                logger.info(f"eval {nm}: {stats[:1]}")
+                if stats:
+                    self._write_stats({"rpc": f"eval/{nm.role}", "step": self.step, "epoch": self.epoch, "time": time.time(),
+                                       **{k: v for k, v in stats[0].items() if isinstance(v, (int, float))}})
 
     async def _main(self):
         await self._lazy_init()

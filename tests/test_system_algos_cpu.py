@@ -235,3 +235,28 @@ def test_ppo_zero3_training_layout_with_reallocated_generation_layout(tmp_path):
     main_start(exp, timeout=600)
     log = _master_log(exp)
     assert log.count("[actor_train] step") == 2
+
+
+def test_sft_evaluation_under_pipeline_parallelism_reports_the_last_stage(tmp_path):
+    """pp=2 + periodic evaluation: only the last stage has the loss; the first stage used to crash on the missing statistics
+    and the master used to log the first worker's (empty) reply."""
+    import json
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "llama")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=16)
+    name = f"ppev-{uuid.uuid4().hex[:6]}"
+    exp = build_experiment(["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=2",
+                            "allocation_mode=manual", "allocation.parallel.pipeline_parallel_size=2", "model.type._class=llama",
+                            f"model.path={ckpt}", f"dataset.train_path={data}", f"dataset.valid_path={data}", "dataset.train_bs_n_seqs=8",
+                            "dataset.valid_bs_n_seqs=8", "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=1", "exp_ctrl.eval_freq_steps=1",
+                            "model.optimizer.grad_dtype=fp32", "model.gradient_checkpointing=false"])
+    main_start(exp, timeout=600)
+    stats = [json.loads(l) for l in open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "stats.jsonl"))]
+    evals = [r for r in stats if r["rpc"] == "eval/default"]
+    train = [r for r in stats if r["rpc"] == "trainDefault"]
+    assert len(evals) == 2 and all(3.0 < r["loss"] < 7.0 and r["ppl"] > 20 for r in evals), evals   # ~ln(vocab), not 0.0
+    assert abs(evals[0]["loss"] - train[0]["loss"]) < 0.5
