@@ -90,8 +90,30 @@ class Controller:
             time.sleep(poll)
 
 
+def preflight(exp_cfg) -> None:
+    """Cheap checks before any worker is launched: a typo in a path should cost seconds, not a scheduler round trip plus
+    model loading on every GPU.  Local mode only (with Slurm the paths may exist on the compute nodes alone)."""
+    problems = []
+    for role, m in (getattr(exp_cfg, "models", None) or {}).items():
+        path = getattr(m, "path", "")
+        if path and not os.path.isdir(path):
+            problems.append(f"{role}.path: `{path}` is not a directory")
+        elif path and not os.path.exists(os.path.join(path, "config.json")):
+            problems.append(f"{role}.path: `{path}` has no config.json (not a HuggingFace checkpoint directory)")
+        elif not path and not getattr(m, "init_from_scratch", False):
+            problems.append(f"{role}.path is empty and {role}.init_from_scratch is not set")
+    for ds in list(getattr(exp_cfg, "datasets", None) or []) + list(getattr(exp_cfg, "eval_datasets", None) or []):
+        path = (getattr(ds, "args", None) or {}).get("dataset_path")
+        if path and not os.path.isfile(path):
+            problems.append(f"dataset file `{path}` does not exist")
+    if problems:
+        raise FileNotFoundError("the experiment cannot start:\n  " + "\n  ".join(problems))
+
+
 def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[float] = None, env_vars=None):
     exp, trial = exp_cfg.experiment_name, exp_cfg.trial_name
+    if getattr(exp_cfg, "mode", "local") == "local" and recover_count == 0:
+        preflight(exp_cfg)
     mode = getattr(exp_cfg, "mode", "local")
     recover_mode = getattr(exp_cfg, "recover_mode", "disabled")
     if mode == "local" and recover_mode == "auto":

@@ -346,3 +346,23 @@ def test_generation_options_are_validated_on_the_command_line():
     exp = build_experiment(["ppo", "experiment_name=e", "trial_name=t", "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2",
                             "ppo.gen.temperature=0.0"])
     assert exp.ppo.gen.greedy and exp.ppo.gen.temperature == 1.0   # temperature 0 means greedy, as in the dataclass's own check
+
+
+def test_launcher_preflight_names_every_bad_path(tmp_path, monkeypatch):
+    monkeypatch.setenv("REAL_FILEROOT", str(tmp_path))
+    from realhf_b200.apps.main import main_start, preflight
+    from realhf_b200.apps.quickstart import build_experiment
+    good = tmp_path / "ckpt"
+    good.mkdir()
+    (good / "config.json").write_text("{}")
+    data = tmp_path / "d.jsonl"
+    data.write_text("{}\\n")
+    exp = build_experiment(["dpo", "experiment_name=e", "trial_name=t", "device=cpu", f"actor.path={good}", "ref.path=/no/such/dir",
+                            "dataset.train_path=/no/such/file.jsonl"])
+    with pytest.raises(FileNotFoundError) as e:
+        main_start(exp)          # fails before any process is started
+    msg = str(e.value)
+    assert "ref.path: `/no/such/dir` is not a directory" in msg and "/no/such/file.jsonl" in msg and "actor.path" not in msg
+    exp = build_experiment(["dpo", "experiment_name=e", "trial_name=t", "device=cpu", f"actor.path={good}", f"ref.path={good}",
+                            f"dataset.train_path={data}"])
+    preflight(exp)               # nothing to complain about
