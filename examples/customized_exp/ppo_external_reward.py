@@ -49,3 +49,11 @@ class PPOExternalRewardConfig(PPOConfig):
 
 
 register_quickstart_exp("ppo-external-reward", PPOExternalRewardConfig)
+
+if __name__ == "__main__":
+    import os
+    import sys
+
+    os.environ["REAL_USER_CODE"] = os.path.abspath(__file__)   # workers re-import this file before building anything
+    from realhf_b200.apps.quickstart import main
+    main(sys.argv[1:])

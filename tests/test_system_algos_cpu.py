@@ -129,9 +129,16 @@ def test_sharded_optimizer_variants_save_hf_checkpoint(tmp_path, opt):
     transformers.AutoModelForCausalLM.from_pretrained(os.path.dirname(found[0]))
 
 
-def test_custom_experiment_script_through_runtime(tmp_path):
-    """`python examples/new_algorithms/grpo.py grpo ...`: the user's file registers an interface + experiment, the launcher
-    starts workers that re-import it (REAL_USER_CODE) and the run completes."""
+@pytest.mark.parametrize("script,exp_name,roles", [
+    ("new_algorithms/grpo.py", "grpo", ("actor", "ref", "rew")),
+    ("new_algorithms/reinforce.py", "reinforce", ("actor", "rew")),
+    ("customized_exp/ppo_ref_ema.py", "ppo-ref-ema", ("actor", "ref", "critic", "rew")),
+    ("customized_exp/ppo_external_reward.py", "ppo-external-reward", ("actor", "ref", "critic", "rew")),
+])
+def test_custom_experiment_script_through_runtime(tmp_path, script, exp_name, roles):
+    """`python examples/<script> <experiment> ...`: the user's file registers an interface and / or an experiment, the launcher
+    starts workers that re-import it (REAL_USER_CODE) and the run completes -- group sampling (GRPO), key remaps (ReMax),
+    an EMA parameter-reallocation hook into the reference model, a Python reward function instead of a reward model."""
     import subprocess
     _env(tmp_path)
     ckpt, crit = str(tmp_path / "llama"), str(tmp_path / "critic")
@@ -140,11 +147,17 @@ def test_custom_experiment_script_through_runtime(tmp_path):
     data = str(tmp_path / "prompts.jsonl")
     fixtures.write_prompt_dataset(data, words, n=32)
     name = f"ex-{uuid.uuid4().hex[:6]}"
-    args = [sys.executable, os.path.join(ROOT, "examples", "new_algorithms", "grpo.py"), "grpo", f"experiment_name={name}", "trial_name=t0",
+    args = [sys.executable, os.path.join(ROOT, "examples", script), exp_name, f"experiment_name={name}", "trial_name=t0",
             "device=cpu", "dtype=fp32", "n_gpus_per_node=2", "allocation_mode=heuristic", f"dataset.path={data}", "dataset.train_bs_n_seqs=8",
-            "dataset.max_prompt_len=16", "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2", "actor.type._class=llama",
-            f"actor.path={ckpt}", "ref.type._class=llama", f"ref.path={ckpt}", "rew.type._class=llama", f"rew.path={crit}",
-            "actor.optimizer.grad_dtype=fp32", "actor.gradient_checkpointing=false"]
+            "dataset.max_prompt_len=16", "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=2"]
+    for role in roles:
+        args += [f"{role}.type._class=llama", f"{role}.path={crit if role in ('critic', 'rew') else ckpt}"]
+        if role in ("actor", "critic"):
+            args += [f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    if exp_name.startswith("ppo"):
+        args += ["ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2"]
+    if exp_name == "ppo-ref-ema":
+        args += ["ref_ema_eta=0.5"]
     r = subprocess.run(args, cwd=ROOT, env=dict(os.environ), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
