@@ -88,17 +88,20 @@ def test_ppo_with_realloc_gloo(tmp_path):
 
 
 def test_failure_detection_raises_instead_of_hanging(tmp_path):
-    """A worker that dies during setup (missing dataset) must surface as a JobException from the launcher."""
+    """A worker that dies during setup (unreadable dataset: the launcher's preflight only checks that the file exists) must
+    surface as a JobException from the launcher."""
     _env(tmp_path)
     from realhf_b200.apps.main import main_start
     from realhf_b200.apps.quickstart import build_experiment
     from realhf_b200.scheduler.client import JobException
     ckpt = str(tmp_path / "gpt2")
     fixtures.make_checkpoint(ckpt, "gpt2")
+    bad = tmp_path / "corrupt.jsonl"
+    bad.write_text('{"id": 0, "prompt": "a", "answer": "b"}\n{this is not json\n')
     exp = build_experiment([
         "sft", f"experiment_name=bad-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_nodes=1",
         "n_gpus_per_node=1", "allocation_mode=manual", "model.type._class=gpt2", f"model.path={ckpt}",
-        f"dataset.train_path={tmp_path / 'does-not-exist.jsonl'}", "dataset.train_bs_n_seqs=8", "exp_ctrl.total_train_epochs=1"])
+        f"dataset.train_path={bad}", "dataset.train_bs_n_seqs=8", "exp_ctrl.total_train_epochs=1"])
     with pytest.raises((JobException, TimeoutError)) as ei:
         main_start(exp, timeout=180)
     assert isinstance(ei.value, JobException), "the launcher should notice the failed worker long before the timeout"
