@@ -321,3 +321,51 @@ def test_dataset_size_not_a_multiple_of_the_batch_size_across_epochs(tmp_path):
     log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
     steps = [int(l.split("] step ")[1].split(":")[0]) for l in log.splitlines() if "[trainDefault] step" in l]
     assert steps == list(range(4)), steps   # 20 // 8 = 2 steps per epoch
+
+
+def test_graceful_stop_saves_recover_states_and_resume_continues(tmp_path):
+    """`stop_experiment` on a run launched with recover_mode=save ends it cleanly after the current step and leaves recover
+    states; a `resume` run picks up at the next step (no step repeated, none skipped)."""
+    import threading
+    import time
+    _env(tmp_path)
+    from realhf_b200.apps import main as M
+    from realhf_b200.apps.quickstart import build_experiment
+    ckpt = str(tmp_path / "gpt2")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "gpt2")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=64)
+    name = f"sr-{uuid.uuid4().hex[:6]}"
+
+    def args(mode):
+        return ["sft", f"experiment_name={name}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=1", "allocation_mode=manual",
+                "model.type._class=gpt2", f"model.path={ckpt}", f"dataset.train_path={data}", "dataset.train_bs_n_seqs=4",
+                "dataset.max_seqlen=64", "exp_ctrl.total_train_epochs=30", "model.optimizer.grad_dtype=fp32",
+                "model.gradient_checkpointing=false", f"recover_mode={mode}"]
+    log_path = os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")
+
+    def steps():
+        if not os.path.exists(log_path):
+            return []
+        return [int(l.split("] step ")[1].split(":")[0]) for l in open(log_path).read().splitlines() if "[trainDefault] step" in l]
+    err = []
+
+    def first_run():
+        try:
+            M.main_start(build_experiment(args("save")), timeout=600)
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+    th = threading.Thread(target=first_run, daemon=True)
+    th.start()
+    t0 = time.time()
+    while len(steps()) < 3 and time.time() - t0 < 240:
+        time.sleep(0.2)
+    M.stop_experiment(name, "t0")
+    th.join(timeout=240)
+    assert not th.is_alive() and not err, err
+    s1 = steps()
+    assert 3 <= len(s1) < 30 * 16 and s1 == list(range(len(s1)))
+    assert os.path.exists(os.path.join(os.environ["REAL_FILEROOT"], "recover", name, "t0", "recover_info.pkl"))
+    M.main_start(build_experiment(args("resume") + [f"exp_ctrl.benchmark_steps={s1[-1] + 4}"]), timeout=600)
+    s2 = steps()
+    assert s2[: len(s1) + 3] == list(range(len(s1) + 3)), (s1[-3:], s2[len(s1) - 2: len(s1) + 4])
