@@ -43,6 +43,7 @@ class Controller:
     def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int):
         self.exp, self.trial, self.sched, self.n = exp, trial, sched, n_model_workers
         self._seen = set()
+        self._lost_since = {}
         # liveness lease of the launcher itself: workers exit when it expires (apps/remote.py::_watch_controller)
         name_resolve.add(status_key(exp, trial, "controller", 0), "RUNNING", replace=True, keepalive_ttl=status_ttl())
 
@@ -75,7 +76,14 @@ class Controller:
             if time.monotonic() - last_status > status_poll:
                 # a worker that caught its own exception publishes ERROR before the scheduler sees the process exit
                 last_status = time.monotonic()
-                bad = {k: v for k, v in self.statuses().items() if v in ("ERROR", "LOST")}
+                st = self.statuses()
+                now = time.monotonic()
+                for k, v in st.items():   # LOST must persist for a full extra lease before it counts: a worker that holds the
+                    if v == "LOST":       # GIL through a long host-side step (unpickling a big checkpoint) misses touches too
+                        self._lost_since.setdefault(k, now)
+                    else:
+                        self._lost_since.pop(k, None)
+                bad = {k: v for k, v in st.items() if v == "ERROR" or (v == "LOST" and now - self._lost_since[k] >= status_ttl())}
                 if bad:
                     raise sched_client.JobException(self.sched.run_name, sorted(bad)[0], "localhost", sched_client.JobState.FAILED)
             infos = self.sched.find_all()
