@@ -221,6 +221,11 @@ class TrainBackend(ModelBackend):
         f = os.path.join(load_dir, f"optim_pp{c.pp_rank}_tp{c.tp_rank}_dp{c.dp_rank}.pt")
         if os.path.exists(f):
             eng.optim.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))
+        else:
+            # e.g. this rank's worker was killed outright and could not dump its shard: the weights are restored from the HF
+            # checkpoint, the Adam moments of this shard restart from zero
+            from realhf_b200.base import logging
+            logging.getLogger("engine").warning(f"no optimizer state for this rank in {load_dir}: moments of this shard are reset")
 
 
 register_backend("inference", InferenceBackend)
