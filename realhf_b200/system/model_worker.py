@@ -18,7 +18,7 @@ import torch.distributed as dist
 from realhf_b200.api import data as data_api
 from realhf_b200.api import model as model_api
 from realhf_b200.api import system as system_api
-from realhf_b200.api.config import ModelName, ModelShardID
+from realhf_b200.api.config import ModelInterfaceType, ModelName, ModelShardID
 from realhf_b200.api.data import SequenceSample
 from realhf_b200.base import constants, logging, monitor, name_resolve, seeding
 from realhf_b200.base.topology import ParallelContext
@@ -104,6 +104,10 @@ class ModelWorker:
             self.shard_ids[name] = shard.id
             model_cfg = shard.model
             rdir = self._recover_dir(name)
+            trainable = any(r.model_name == name and r.interface_type == ModelInterfaceType.TRAIN_STEP for r in cfg.model_rpcs)
+            if rdir is None and trainable and shard.should_instantiate and os.environ.get("REAL_RECOVER_RUN", "0") == "1":
+                # e.g. the rank that writes the weights was the one that died: the step counters will resume, the weights cannot
+                logger.warning(f"recover run, but no saved weights for the trainable model {name}: starting it from {shard.model.args.get('model_path')}")
             if rdir is not None and shard.should_instantiate:
                 # recover run: weights come from the states saved at the failure (reference: model_worker.py:308-313)
                 import copy
