@@ -2,12 +2,11 @@
 single-token decode attention over a dense KV cache.
 
 CUDA tensors: decode runs the split-KV sm_100a kernel in `csrc/attn_decode.cu` (with fused RoPE and
-in-place KV append); varlen forward/backward calls the flash-attn library kernel by default (a library
-call on this path, recorded as such in DESIGN.md).  `REAL_ATTN=tcgen05` switches the varlen FORWARD to
-`csrc/attn_fwd_tcgen05.cu` (TMA + tcgen05 + TMEM; head dim 64 / 128, no dropout / sliding window) and
-`REAL_ATTN_BWD=tcgen05` the BACKWARD to `csrc/attn_bwd_tcgen05.cu`; both use the LSE layout of the library, so
-they can be switched independently.  These kernels are compiled and SASS-checked but have not run on hardware
-yet, hence opt-in.
+in-place KV append); varlen forward runs `csrc/attn_fwd_tcgen05.cu` and backward `csrc/attn_bwd_tcgen05.cu`
+(TMA + tcgen05 + TMEM; head dim 64 / 128, validated on B200 against the fp32 reference and the library kernel:
+`profiles/attention_validation.log`).  The flash-attn library kernel is only the fallback for what the own
+kernels do not cover (attention dropout, other head dims) and the A/B arm: `REAL_ATTN=flash` /
+`REAL_ATTN_BWD=flash` select it explicitly; both produce / consume the same LSE layout.
 CPU tensors: plain PyTorch reference (also the numerics oracle for the tests).
 """
 
@@ -24,8 +23,8 @@ from realhf_b200.ops import lib, use_native
 
 
 def attn_impl() -> str:
-    """`flash` (library kernel, default) or `tcgen05` (own forward kernel, experimental)."""
-    return os.environ.get("REAL_ATTN", "flash")
+    """`tcgen05` (own forward kernel, default) or `flash` (library kernel, A/B runs only)."""
+    return os.environ.get("REAL_ATTN", "tcgen05")
 
 
 def _own_fwd_ok(hd: int, dropout_p: float) -> bool:
@@ -34,8 +33,8 @@ def _own_fwd_ok(hd: int, dropout_p: float) -> bool:
 
 def _own_bwd_ok(hd: int, dropout_p: float) -> bool:
     """`REAL_ATTN_BWD=tcgen05`: own backward (`csrc/attn_bwd_tcgen05.cu`), independent of the forward switch (both produce /
-    consume the same LSE layout).  Experimental for the same reason as the forward."""
-    return os.environ.get("REAL_ATTN_BWD", "flash") == "tcgen05" and hd in (64, 128) and dropout_p == 0.0
+    consume the same LSE layout).  Default; `REAL_ATTN_BWD=flash` selects the library kernel."""
+    return os.environ.get("REAL_ATTN_BWD", "tcgen05") == "tcgen05" and hd in (64, 128) and dropout_p == 0.0
 
 
 def varlen_attention_ref(q, k, v, cu_seqlens, scale: float, causal: bool = True, sliding_window: Optional[int] = None):

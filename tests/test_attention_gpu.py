@@ -71,8 +71,6 @@ def test_packed_qkv_attention_forward_backward(heads):
     torch.testing.assert_close(g.float(), x.grad, atol=3e-2, rtol=3e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="tcgen05 varlen attention forward has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
 @pytest.mark.parametrize("hd,nq,nkv,causal", [(128, 8, 8, True), (128, 8, 2, True), (64, 4, 4, True), (128, 4, 4, False)])
 def test_attn_fwd_tcgen05_matches_reference(hd, nq, nkv, causal):
     import math
@@ -101,8 +99,6 @@ def test_attn_fwd_tcgen05_matches_reference(hd, nq, nkv, causal):
         torch.testing.assert_close(lse[:, s:e], torch.logsumexp(att, -1), atol=2e-2, rtol=2e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="tcgen05 varlen attention backward has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
 @pytest.mark.parametrize("hd,nq,nkv,causal", [(128, 8, 8, True), (128, 8, 2, True), (64, 4, 4, True), (128, 4, 4, False)])
 def test_attn_bwd_tcgen05_matches_autograd_of_the_reference(hd, nq, nkv, causal):
     """dq / dk / dv written into the three column ranges of one d(qkv) buffer vs autograd through the fp32 reference."""

@@ -206,8 +206,6 @@ def test_grouped_gemm_moe(counts):
     torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.3, rtol=3e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="gemm_grouped_wgrad.cu has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
 @pytest.mark.parametrize("counts,M,N", [([300, 0, 64, 1000, 5, 77], 256, 512), ([4096, 4096], 1024, 384), ([0, 0, 9], 128, 128)])
 def test_grouped_wgrad_single_launch(counts, M, N):
     from realhf_b200.ops import gemm as G

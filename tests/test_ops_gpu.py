@@ -228,8 +228,6 @@ def test_segment_copy_ema():
     torch.testing.assert_close(dst.float(), ref.float(), atol=1e-2, rtol=1e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("REAL_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="layernorm.cu has not run on hardware yet (REAL_TEST_EXPERIMENTAL=1 enables it)")
 @pytest.mark.parametrize("H,dtype", [(768, torch.bfloat16), (1024, torch.float16), (4096, torch.bfloat16), (1600, torch.float32)])
 def test_layernorm_native_matches_reference(H, dtype, monkeypatch):
     from realhf_b200.ops import functional as OF
