@@ -91,7 +91,8 @@ class ReaLEngine(PipelinableEngine):
         else:
             stats: Dict[str, Any] = collections.defaultdict(float)
             mbs = input_.split(min(n_mbs, input_.bs))
-            for mb in mbs:
+            for j, mb in enumerate(mbs):
+                self.optim.arm(j == len(mbs) - 1)  # last micro-batch: gradient buckets are reduced from inside backward
                 out = self._forward_mb(mb)
                 loss, st = loss_fn(out, mb)
                 self.optim.scale_loss(loss / len(mbs)).backward()

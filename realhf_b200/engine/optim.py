@@ -18,13 +18,15 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Dict, Optional, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from realhf_b200.base.topology import ParallelContext
 from realhf_b200.ops import functional as OF
+from realhf_b200.ops import lib
 
 
 @dataclasses.dataclass
@@ -53,6 +55,8 @@ class OptimizerConfig:
     share_grad_buffer: bool = False  # trainable models on one GPU that never train concurrently share one grad buffer
     zero_stage: int = 1              # 1/2: optimizer state (+ reduced grads) sharded over DP; 3: parameters too, between calls
     offload_param: bool = False      # ZeRO-3 only: park the parameter shard in pinned host memory between calls
+    bucket_numel: int = 1 << 28      # gradient bucket size (elements) of the overlapped reduce-scatter; 0: one bucket
+    comm: str = "auto"               # auto | nvls | nccl: transport of the gradient reduce-scatter / parameter all-gather
 
 
 class LRScheduler:
@@ -93,23 +97,80 @@ class LRScheduler:
 
 _DT = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
-_GRAD_POOL: Dict[Tuple, torch.Tensor] = {}
+_GRAD_POOL: Dict[Tuple, Tuple[torch.Tensor, object]] = {}
 
 
-def _grad_pool_get(numel: int, dtype, device) -> torch.Tensor:
-    """One gradient buffer per (dtype, device), grown to the largest request; every train_batch zeroes it first and
-    consumes it in its own optimizer step, so sequentially-trained models (PPO actor / critic) can alias it."""
-    key = (dtype, str(device))
-    buf = _GRAD_POOL.get(key)
-    if buf is None or buf.numel() < numel:
-        assert buf is None, "grad pool must be sized by its largest user first (create the largest model's optimizer first)"
-        buf = torch.zeros(numel, dtype=dtype, device=device)
-        _GRAD_POOL[key] = buf
-    return buf[:numel]
+def _nvls_usable(ctx: ParallelContext, dev: torch.device, cfg: "OptimizerConfig") -> bool:
+    """The in-switch (NVLS) ZeRO path needs: CUDA, a data-parallel group of 2..8 ranks on one NVSwitch domain, multicast
+    support in the driver, and optimizer state resident on the GPU (`REAL_ZERO_COMM=nccl|nvls` overrides the choice)."""
+    want = os.environ.get("REAL_ZERO_COMM", cfg.comm)
+    if want == "nccl" or dev.type != "cuda" or ctx.dp_size < 2 or ctx.dp_size > 8 or cfg.zero_stage >= 3 or cfg.offload:
+        return False
+    if dist.get_backend(ctx.dp_group) != "nccl":
+        return False
+    from realhf_b200.parallel import symm_mem
+    ok = symm_mem.multicast_supported(dev)
+    flags: List = [None] * ctx.dp_size
+    dist.all_gather_object(flags, (bool(ok), os.uname().nodename), group=ctx.dp_group)
+    ok = all(f[0] for f in flags) and len({f[1] for f in flags}) == 1
+    if want == "nvls" and not ok:
+        raise RuntimeError("REAL_ZERO_COMM=nvls but the data-parallel group has no NVSwitch multicast support")
+    return ok
+
+
+def _grad_pool_get(numel: int, dtype, device, symm_group=None):
+    """One gradient buffer per (dtype, device, group), grown to the largest request; every train_batch zeroes it first and
+    consumes it in its own optimizer step, so sequentially-trained models (PPO actor / critic) can alias it.
+    Returns (tensor, symmetric buffer or None)."""
+    key = (dtype, str(device), id(symm_group) if symm_group is not None else None)
+    ent = _GRAD_POOL.get(key)
+    if ent is None or ent[0].numel() < numel:
+        assert ent is None, "grad pool must be sized by its largest user first (create the largest model's optimizer first)"
+        ent = _alloc_flat(numel, dtype, device, symm_group)
+        _GRAD_POOL[key] = ent
+    return ent[0][:numel], ent[1]
+
+
+def _alloc_flat(numel: int, dtype, device, symm_group=None):
+    """Zeroed flat buffer; with `symm_group` it lives in VMM symmetric memory with an NVSwitch multicast mapping."""
+    if symm_group is None:
+        return torch.zeros(numel, dtype=dtype, device=device), None
+    from realhf_b200.parallel.symm_mem import VmmSymmetricBuffer
+    sb = VmmSymmetricBuffer(numel * torch.tensor([], dtype=dtype).element_size(), group=symm_group, device=device)
+    assert sb.mc_ptr != 0
+    return sb.data(dtype=dtype)[:numel], sb
+
+
+class _GradReady(torch.autograd.Function):
+    """Identity on the activation entering layer `i`; its backward runs once every parameter gradient of layers >= i of this
+    micro-batch has been enqueued, and tells the optimizer so (bucketed reduce-scatter overlapped with the rest of backward)."""
+
+    @staticmethod
+    def forward(ctx, x, cb, layer_idx):
+        ctx.cb, ctx.layer_idx = cb, layer_idx
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.cb(ctx.layer_idx)
+        return g, None, None
 
 
 class FlatAdamW:
-    """AdamW over a ReaLModel's flat parameter buffer, sharded across the data-parallel group."""
+    """AdamW over a ReaLModel's flat parameter buffer, sharded across the data-parallel group (ZeRO-1).
+
+    The flat buffer is cut into equal buckets (multiples of 64*dp elements, ~`bucket_numel`); rank r owns slice r of EVERY
+    bucket.  During the backward pass of the last micro-batch a bucket is reduce-scattered as soon as the layers that write
+    into it have finished (`grad_ready`), overlapped with the remaining backward compute (the reference overlaps through
+    Megatron DDP's `overlap_grad_reduce`, backend/megatron.py:883-909).  Two transports:
+
+      * NVLS (single NVSwitch domain): gradients and parameters live in VMM symmetric memory; the reduce-scatter is ONE kernel
+        per bucket that pulls the in-switch sum of this rank's slice (`multimem.ld_reduce`) fused with the 1/dp average, the
+        cast and the grad-norm statistics; after the global norm is known ONE kernel per bucket runs AdamW on the slice and
+        stores the new weights with `multimem.st`, i.e. the parameter all-gather is the optimizer's own store (csrc/nvls.cu);
+      * NCCL (any topology, also gloo on CPU): asynchronous in-place `reduce_scatter_tensor` per bucket during backward,
+        fused AdamW per slice, in-place `all_gather_into_tensor` per bucket issued as soon as that bucket's update is queued.
+    """
 
     def __init__(self, model, cfg: OptimizerConfig, total_steps: int = 1000):
         self.model, self.cfg = model, cfg
@@ -118,17 +179,48 @@ class FlatAdamW:
         dev, n = model.device, model.flat_numel
         dp = self.ctx.dp_size
         assert n % 64 == 0
-        # pad so that every rank's shard is 64-element aligned
-        self.padded = (n + 64 * dp - 1) // (64 * dp) * (64 * dp)
+        align = 64 * dp  # every rank's slice of every bucket is 64-element aligned
+        self.padded = (n + align - 1) // align * align
         self.shard_n = self.padded // dp
-        self.lo = self.ctx.dp_rank * self.shard_n
-        self.hi = min(n, self.lo + self.shard_n)
         self.grad_dtype = _DT[cfg.grad_dtype]
-        self.flat_grad = _grad_pool_get(self.padded, self.grad_dtype, dev) if cfg.share_grad_buffer else \
-            torch.zeros(self.padded, dtype=self.grad_dtype, device=dev)
-        model.attach_grad_buffer(self.flat_grad[:n])
         self.state_dtype = _DT[cfg.state_dtype]
         pdt = model.dtype
+        self.nvls = _nvls_usable(self.ctx, dev, cfg)
+        # ---- buckets and this rank's slices
+        bsz = self.padded
+        if dp > 1 and cfg.zero_stage < 3 and cfg.bucket_numel > 0:
+            bsz = max(align, cfg.bucket_numel // align * align)
+        self.buckets: List[Tuple[int, int]] = []
+        lo = 0
+        while lo < self.padded:
+            hi = min(self.padded, lo + bsz)
+            if self.padded - hi < bsz // 4:  # no runt bucket at the end
+                hi = self.padded
+            self.buckets.append((lo, hi))
+            lo = hi
+        r = self.ctx.dp_rank
+        self.ranges: List[Tuple[int, int]] = []   # my slice of every bucket (element offsets into the padded flat buffer)
+        self.state_off: List[int] = []            # where that slice starts in m / v / master
+        off = 0
+        for (blo, bhi) in self.buckets:
+            per = (bhi - blo) // dp
+            self.ranges.append((blo + r * per, blo + (r + 1) * per))
+            self.state_off.append(off)
+            off += per
+        assert off == self.shard_n
+        self.lo, self.hi = self.ranges[0][0], min(n, self.ranges[-1][1])  # legacy names (exact with a single bucket)
+        # ---- gradient buffer
+        sg = self.ctx.dp_group if self.nvls else None
+        if cfg.share_grad_buffer:
+            self.flat_grad, self._grad_symm = _grad_pool_get(self.padded, self.grad_dtype, dev, sg)
+        else:
+            self.flat_grad, self._grad_symm = _alloc_flat(self.padded, self.grad_dtype, dev, sg)
+        model.attach_grad_buffer(self.flat_grad[:n])
+        # ---- parameter storage: padded (in-place all-gather of the last bucket) and symmetric on the NVLS path
+        self._param_symm = None
+        self.param_store: Optional[torch.Tensor] = None
+        if dp > 1 and cfg.zero_stage < 3 and (self.nvls or self.padded != n):
+            self._rehome_params()
         self.use_master = cfg.use_master_weights and pdt != torch.float32 and self.state_dtype == torch.float32
         self.offload = cfg.offload and dev.type == "cuda"
         sdev = "cpu" if self.offload else dev
@@ -138,9 +230,11 @@ class FlatAdamW:
         self.master = None
         if self.use_master:
             self.master = torch.zeros(self.shard_n, dtype=torch.float32, device=sdev, **pin)
-            self.master[: self.hi - self.lo].copy_(model.flat_param.data[self.lo: self.hi].float())
-        if dp > 1 and self.padded != n:
-            self._param_padded = torch.zeros(self.padded, dtype=pdt, device=dev)
+            flat = model.flat_param.data
+            for (a, b), so in zip(self.ranges, self.state_off):
+                b = min(b, n)
+                if b > a:
+                    self.master[so: so + b - a].copy_(flat[a:b].float())
         self.step_count = 0
         self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
         self._scale = torch.ones((), dtype=torch.float32, device=dev)
@@ -148,28 +242,109 @@ class FlatAdamW:
         self.loss_scale = 1.0 if pdt != torch.float16 else float(min(cfg.initial_loss_scale, 2 ** 16))
         self._good_steps = 0
         self.last_grad_norm: Optional[torch.Tensor] = None
-        # elements of replicated (non-TP-split) params in my shard: counted once (tp rank 0) in the global norm
-        self._dup_idx = None
+        # elements of replicated (non-TP-split) params in my slices: counted once (tp rank 0) in the global norm
+        self._dup_idx: List[Optional[torch.Tensor]] = [None] * len(self.ranges)
         if self.ctx.tp_size > 1 and self.ctx.tp_rank != 0:
-            idx = []
-            for slot in model.slots.values():
-                if slot.spec.split_dim is None:
-                    a, b = max(slot.offset, self.lo), min(slot.offset + slot.numel, self.hi)
-                    if b > a:
-                        idx.append(torch.arange(a - self.lo, b - self.lo))
-            if idx:
-                self._dup_idx = torch.cat(idx).to(dev)
+            for j, (lo_j, hi_j) in enumerate(self.ranges):
+                idx = []
+                for slot in model.slots.values():
+                    if slot.spec.split_dim is None:
+                        a, b = max(slot.offset, lo_j), min(slot.offset + slot.numel, hi_j)
+                        if b > a:
+                            idx.append(torch.arange(a - lo_j, b - lo_j))
+                if idx:
+                    self._dup_idx[j] = torch.cat(idx).to(dev)
         self._sp_sync = [s for s in model.slots.values() if s.spec.sp_grad_sync] if model.sequence_parallel else []
+        # ---- overlap machinery
+        self._layer_lo: Dict[int, int] = {}
+        for slot in model.slots.values():
+            li = int(slot.spec.name.split(".", 1)[0])
+            self._layer_lo[li] = min(self._layer_lo.get(li, 1 << 62), slot.offset)
+        self._next_bucket = len(self.buckets) - 1   # buckets are reduced from the end of the buffer (head) to the start
+        self._pending: List = []                     # async NCCL works of this step
+        self._comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" and dp > 1 else None
+        self._overlap_ok = dp > 1 and len(self.buckets) > 1 and not self._sp_sync and not model.tied_embedding_params() \
+            and os.environ.get("REAL_ZERO_OVERLAP", "1") == "1"
+        self.n_overlapped = 0  # buckets whose reduce-scatter was issued from inside backward in the last step (diagnostics)
+
+    # ------------------------------------------------------------------ storage
+    def _rehome_params(self):
+        """Move the model's flat parameters into optimizer-owned storage of `padded` elements (VMM symmetric memory with a
+        multicast mapping on the NVLS path): the per-bucket all-gather then runs in place, without staging copies."""
+        m = self.model
+        n = m.flat_numel
+        store, symm = _alloc_flat(self.padded, m.dtype, m.device, self.ctx.dp_group if self.nvls else None)
+        with torch.no_grad():
+            store[:n].copy_(m.flat_param.data)
+        m.attach_flat(store[:n])
+        if m.flat_grad is not None:
+            m.attach_grad_buffer(self.flat_grad[:n])
+        self.param_store, self._param_symm = store, symm
+
+    def _store(self) -> torch.Tensor:
+        """The padded parameter buffer the all-gather works on (the model's own buffer when no padding is needed)."""
+        flat = self.model.flat_param.data
+        if self.param_store is not None and self.param_store.data_ptr() == flat.data_ptr():
+            return self.param_store
+        if self.padded == flat.numel():
+            return flat
+        # somebody re-attached the model to a fresh buffer (recover / realloc into a trainable replica): adopt it again
+        self.nvls_params_lost = True
+        self._rehome_params()
+        return self.param_store
 
     # ------------------------------------------------------------------ step
     def zero_grad(self):
         self.flat_grad.zero_()
+        self._next_bucket = len(self.buckets) - 1
+        self._pending = []
+        self.n_overlapped = 0
+        if self.nvls:
+            self._stats.zero_()
 
     def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
         return loss * self.loss_scale if self.loss_scale != 1.0 else loss
 
-    def _sync_grads(self) -> torch.Tensor:
-        """Returns this rank's gradient shard (averaged over DP)."""
+    def boundary(self, x: torch.Tensor, layer_idx: int) -> torch.Tensor:
+        """Called by the model on the activation entering layer `layer_idx` while `grad_ready` hooks are armed."""
+        return _GradReady.apply(x, self.grad_ready, layer_idx)
+
+    def arm(self, on: bool):
+        """Arm / disarm the in-backward reduce-scatter (armed for the last micro-batch of a train_batch only)."""
+        self.model._grad_boundary = self.boundary if (on and self._overlap_ok and self.model.ctx.pp_size == 1) else None
+
+    def grad_ready(self, layer_idx: int):
+        """All parameter gradients of layers >= layer_idx are final (and enqueued): reduce every bucket that lies entirely
+        at or above the first parameter of that layer."""
+        ready_lo = self._layer_lo.get(layer_idx)
+        if ready_lo is None:
+            return
+        while self._next_bucket >= 0 and self.buckets[self._next_bucket][0] >= ready_lo:
+            self._reduce_bucket(self._next_bucket, overlapped=True)
+            self._next_bucket -= 1
+
+    def _reduce_bucket(self, k: int, overlapped: bool = False):
+        ctx = self.ctx
+        blo, bhi = self.buckets[k]
+        lo, hi = self.ranges[k]
+        self.n_overlapped += int(overlapped)
+        if self.nvls:
+            es = self.flat_grad.element_size()
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream(self.flat_grad.device))
+            with torch.cuda.stream(cs):
+                self._grad_symm.reduce_scatter_(lo * es, (hi - lo) * es, self.grad_dtype, 1.0 / ctx.dp_size, self._stats)
+            return
+        bucket = self.flat_grad[blo:bhi]
+        if self.flat_grad.is_cuda:
+            w = dist.reduce_scatter_tensor(self.flat_grad[lo:hi], bucket, op=dist.ReduceOp.AVG, group=ctx.dp_group, async_op=True)
+            self._pending.append(w)
+        else:  # gloo has no AVG / reduce_scatter_tensor: all-reduce the bucket, keep my slice
+            dist.all_reduce(bucket, group=ctx.dp_group)
+            self.flat_grad[lo:hi].div_(ctx.dp_size)
+
+    def _sync_grads(self):
+        """Finish the gradient reduction: afterwards flat_grad[ranges[k]] holds the DP-averaged gradient of my slices."""
         ctx = self.ctx
         if self._sp_sync and ctx.tp_size > 1:  # norm params see only T/tp tokens under sequence parallelism
             bufs = [self.model.flat_grad[s.offset: s.offset + s.numel] for s in self._sp_sync]
@@ -186,23 +361,29 @@ class FlatAdamW:
                 if g is not None:
                     dist.all_reduce(g, group=ctx.embedding_group)
         if ctx.dp_size == 1:
-            return self.flat_grad[self.lo: self.lo + self.shard_n]
-        shard = torch.empty(self.shard_n, dtype=self.grad_dtype, device=self.flat_grad.device)
-        try:
-            dist.reduce_scatter_tensor(shard, self.flat_grad, op=dist.ReduceOp.AVG, group=ctx.dp_group)
-        except (RuntimeError, ValueError):  # gloo has no AVG / reduce_scatter_tensor: all-reduce then slice
-            dist.all_reduce(self.flat_grad, group=ctx.dp_group)
-            shard = (self.flat_grad[self.lo: self.lo + self.shard_n] / ctx.dp_size).to(self.grad_dtype)
-        return shard
+            return
+        while self._next_bucket >= 0:  # whatever backward did not hand over itself (embedding bucket, pipeline runs, ...)
+            self._reduce_bucket(self._next_bucket)
+            self._next_bucket -= 1
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        if self.nvls:
+            torch.cuda.current_stream(self.flat_grad.device).wait_stream(self._comm_stream)
 
     def step(self, version_steps: Optional[int] = None) -> Dict[str, torch.Tensor]:
         cfg, ctx = self.cfg, self.ctx
-        g = self._sync_grads()
-        # ---- global grad norm + overflow detection, all on device
-        self._stats.zero_()
-        OF.sumsq_accum(g, self._stats)
-        if self._dup_idx is not None:
-            self._stats[0] -= g[self._dup_idx].float().pow(2).sum()
+        self.arm(False)
+        self._sync_grads()
+        n = self.model.flat_numel
+        # ---- global grad norm + overflow detection, all on device (the NVLS reduce-scatter kernels accumulated them already)
+        if not self.nvls:
+            self._stats.zero_()
+            for (lo, hi) in self.ranges:
+                OF.sumsq_accum(self.flat_grad[lo:hi], self._stats)
+        for (lo, hi), dup in zip(self.ranges, self._dup_idx):
+            if dup is not None:
+                self._stats[0] -= self.flat_grad[lo:hi][dup].float().pow(2).sum()
         if ctx.model_group is not None and ctx.topo.world_size() > 1:
             dist.all_reduce(self._stats, group=ctx.model_group)
         inv_ls = 1.0 / self.loss_scale
@@ -212,51 +393,65 @@ class FlatAdamW:
         coef = torch.clamp(clip / (norm + 1e-6), max=1.0) if clip and clip > 0 else torch.ones_like(norm)
         self._scale.copy_(coef * inv_ls)
         self._skip.copy_((self._stats[1:2] > 0).int())
-        # ---- AdamW on my shard
+        # ---- AdamW on my slices + parameter all-gather, bucket by bucket
         self.step_count += 1
         if version_steps is not None:
             self.sched.step_absolute(version_steps)
         lr = self.sched.get_lr()
-        n_my = self.hi - self.lo
-        p_shard = self.model.flat_param.data[self.lo: self.hi]
-        if n_my > 0:
-            if self.offload:
-                self._offloaded_update(p_shard, g[:n_my], lr)
-            else:
-                OF.adamw_step(p_shard, g[:n_my], self.m[:n_my], self.v[:n_my],
-                              self.master[:n_my] if self.master is not None else None, lr, cfg.beta1, cfg.beta2, cfg.eps,
-                              cfg.weight_decay, self.step_count, self._scale, self._skip,
-                              stochastic=(self.state_dtype == torch.bfloat16), seed=self.step_count * 2654435761 % (2 ** 31))
-        # ---- all-gather the updated parameters
-        if ctx.dp_size > 1:
-            flat = self.model.flat_param.data
-            if self.padded == flat.numel():
-                dist.all_gather_into_tensor(flat, flat[self.lo: self.lo + self.shard_n].clone(), group=ctx.dp_group)
-            else:
-                self._param_padded[: flat.numel()].copy_(flat)
-                dist.all_gather_into_tensor(self._param_padded, self._param_padded[self.lo: self.lo + self.shard_n].clone(),
-                                            group=ctx.dp_group)
-                flat.copy_(self._param_padded[: flat.numel()])
+        store = self._store() if ctx.dp_size > 1 and cfg.zero_stage < 3 else self.model.flat_param.data
+        seed = self.step_count * 2654435761 % (2 ** 31)
+        works = []
+        for k, ((blo, bhi), (lo, hi), so) in enumerate(zip(self.buckets, self.ranges, self.state_off)):
+            hi = min(hi, store.numel())  # an unpadded store (ZeRO-3 / dp == 1) ends before the last slice's padding
+            n_my = max(0, hi - lo)
+            g = self.flat_grad[lo:hi]
+            mst = self.master[so: so + n_my] if self.master is not None else None
+            stoch = self.state_dtype == torch.bfloat16
+            if self.nvls:
+                sb = self._param_symm
+                lib().nvls_adam_allgather(sb.data_ptrs, sb.pad_ptrs, sb.mc_ptr, lo * store.element_size(), 0 if store.dtype == torch.float32 else 1,
+                                          g, self.m[so: so + n_my], self.v[so: so + n_my], mst, n_my, lr, cfg.beta1, cfg.beta2, cfg.eps,
+                                          cfg.weight_decay, self.step_count, self._scale, self._skip, stoch, (seed + 7919 * k) % (2 ** 31),
+                                          sb.rank)
+                continue
+            if n_my > 0:
+                if self.offload:
+                    self._offloaded_update(store[lo:hi], g, lr, so)
+                else:
+                    OF.adamw_step(store[lo:hi], g, self.m[so: so + n_my], self.v[so: so + n_my], mst, lr, cfg.beta1, cfg.beta2, cfg.eps,
+                                  cfg.weight_decay, self.step_count, self._scale, self._skip, stochastic=stoch,
+                                  seed=(seed + 7919 * k) % (2 ** 31))
+            if ctx.dp_size > 1 and cfg.zero_stage < 3:
+                if store.is_cuda:  # in place: my slice already sits at its final position; overlaps the next bucket's update
+                    works.append(dist.all_gather_into_tensor(store[blo:bhi], store[lo:hi], group=ctx.dp_group, async_op=True))
+                else:
+                    parts = [torch.empty(n_my, dtype=store.dtype) for _ in range(ctx.dp_size)]
+                    dist.all_gather(parts, store[lo:hi].contiguous(), group=ctx.dp_group)
+                    store[blo:bhi].copy_(torch.cat(parts))
+        for w in works:
+            w.wait()
         if self.model.dtype == torch.float16:
             self._update_loss_scale()
         return {"grad_norm": norm, "lr": torch.tensor(lr), "skipped": self._skip.float()[0]}
 
-    def _offloaded_update(self, p_shard, g, lr, chunk: int = 1 << 26):
-        """Stream pinned-host optimizer state through the GPU in chunks, double-buffered on a side stream."""
+    def _offloaded_update(self, p_shard, g, lr, so: int = 0, chunk: int = 1 << 26):
+        """Stream pinned-host optimizer state through the GPU in chunks, double-buffered on a side stream.
+        `so`: offset of this slice in the state tensors."""
         cfg = self.cfg
         n = p_shard.numel()
         dev = p_shard.device
         if not hasattr(self, "_h2d"):
             self._h2d, self._d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
-        pending = None
         offs = list(range(0, n, chunk))
+        sm, sv = self.m[so: so + n], self.v[so: so + n]
+        smaster = self.master[so: so + n] if self.master is not None else None
 
         def fetch(a):
             b = min(n, a + chunk)
             with torch.cuda.stream(self._h2d):
-                bufs = [t[a:b].to(dev, non_blocking=True) for t in (self.m, self.v)]
-                bufs.append(self.master[a:b].to(dev, non_blocking=True) if self.master is not None else None)
+                bufs = [t[a:b].to(dev, non_blocking=True) for t in (sm, sv)]
+                bufs.append(smaster[a:b].to(dev, non_blocking=True) if smaster is not None else None)
                 ev = torch.cuda.Event()
                 ev.record(self._h2d)
             return a, b, bufs, ev
@@ -273,10 +468,10 @@ class FlatAdamW:
             done.record(main)
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done)
-                self.m[a:b].copy_(m, non_blocking=True)
-                self.v[a:b].copy_(v, non_blocking=True)
+                sm[a:b].copy_(m, non_blocking=True)
+                sv[a:b].copy_(v, non_blocking=True)
                 if ms is not None:
-                    self.master[a:b].copy_(ms, non_blocking=True)
+                    smaster[a:b].copy_(ms, non_blocking=True)
                 for t in (m, v, ms):
                     if t is not None:
                         t.record_stream(self._d2h)
@@ -297,8 +492,7 @@ class FlatAdamW:
     # ------------------------------------------------------------------ ZeRO-3: parameters sharded between calls
     # Between model function calls only this rank's 1/dp slice of the flat parameter buffer stays resident (on the GPU,
     # or in pinned host memory with `offload_param`); `materialize()` all-gathers the full buffer before a call and
-    # `release()` drops it afterwards.  (DeepSpeed gathers per layer inside the forward; gathering per call keeps the
-    # hot path identical to ZeRO-1 and is enough to fit e.g. 7B DPO with an offloaded reference on one GPU's budget.)
+    # `release()` drops it afterwards.  ZeRO-3 uses ONE bucket (ranges[0] is the classic contiguous shard).
     def release(self):
         if self.cfg.zero_stage < 3 or not self.model.instantiated:
             return
@@ -323,7 +517,13 @@ class FlatAdamW:
         src = self._param_shard if self._param_shard is not None else self._param_shard_host
         buf[self.lo: self.hi].copy_(src, non_blocking=True)
         if self.ctx.dp_size > 1:
-            dist.all_gather_into_tensor(buf, buf[self.lo: self.lo + self.shard_n].clone(), group=self.ctx.dp_group)
+            mine = buf[self.lo: self.lo + self.shard_n]
+            if buf.is_cuda:
+                dist.all_gather_into_tensor(buf, mine, group=self.ctx.dp_group)  # in place
+            else:
+                parts = [torch.empty_like(mine) for _ in range(self.ctx.dp_size)]
+                dist.all_gather(parts, mine.contiguous(), group=self.ctx.dp_group)
+                buf.copy_(torch.cat(parts))
         self.model.attach_flat(buf[:n])
         self.model.attach_grad_buffer(self.flat_grad[:n])
         self._param_shard = None
@@ -332,10 +532,11 @@ class FlatAdamW:
     def state_dict(self):
         return {"m": self.m.cpu(), "v": self.v.cpu(), "master": None if self.master is None else self.master.cpu(),
                 "step": self.step_count, "sched": self.sched.state_dict(), "loss_scale": self.loss_scale,
-                "shard": (self.lo, self.hi)}
+                "shard": (self.lo, self.hi), "ranges": list(self.ranges)}
 
     def load_state_dict(self, sd):
-        assert tuple(sd["shard"]) == (self.lo, self.hi), "optimizer shard layout changed"
+        assert [tuple(r) for r in sd.get("ranges", [sd["shard"]])] == [tuple(r) for r in self.ranges] or \
+            (len(self.ranges) == 1 and tuple(sd["shard"]) == (self.lo, self.hi)), "optimizer shard layout changed"
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
         if self.master is not None and sd["master"] is not None:

@@ -457,16 +457,23 @@ class ReaLModel(nn.Module):
         ckpt = self.gradient_checkpointing and torch.is_grad_enabled() and kv_sink is None
         n_keep = self._n_unckpt_blocks(T if T is not None else int(hidden.shape[0])) if ckpt else 0
         first_kept = c.n_layers + 1 - n_keep  # the LAST n_keep blocks keep their activations (any subset would do)
+        # armed by the optimizer for the last micro-batch of a step: marks where the gradients of all later layers are final,
+        # so their buckets are reduce-scattered while the earlier layers are still in backward (engine/optim.py)
+        gb = getattr(self, "_grad_boundary", None) if torch.is_grad_enabled() else None
         for i in self.layers:
             if i == 0:
                 x = self._embed(input_ids, position_ids)
             elif i <= c.n_layers:
+                if gb is not None and x.requires_grad:
+                    x = gb(x, i)
                 if ckpt and i < first_kept:
                     x = self._ckpt_block(i, x, position_ids, cu_seqlens, max_seqlen)
                 else:
                     x = self._block_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
         if not self.is_last_stage:
             return x
+        if gb is not None and x.requires_grad:
+            x = gb(x, c.n_layers + 1)
         if self.sequence_parallel:
             x = TP.gather_from_sp(x, self.ctx, reduce_scatter_bwd=False)
         return ModelOutput(hidden=x, head_weight=self.head_weight(), ctx=self.ctx, is_critic=c.is_critic)

@@ -10,27 +10,10 @@
 // states with stochastic rounding of the bf16 parameter (master-free mode for memory-tight layouts).
 #include <type_traits>
 
-#include "common.cuh"
+#include "adam_math.cuh"
 
 namespace {
-
-RB_DEVICE uint32_t hash32(uint32_t x) {  // lowbias32
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-
-// Round fp32 -> bf16 stochastically using 16 random bits.
-RB_DEVICE __nv_bfloat16 sr_bf16(float x, uint32_t rnd16) {
-  uint32_t u = __float_as_uint(x);
-  if ((u & 0x7f800000u) != 0x7f800000u) u += (rnd16 & 0xffffu);
-  return __ushort_as_bfloat16((unsigned short)(u >> 16));
-}
-
-RB_DEVICE float sqrt_approx(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
+using namespace rbadam;
 
 template <typename TP, typename TG, typename TS, bool kMaster, bool kStochastic>
 __global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p, const TG* __restrict__ g, TS* __restrict__ m,

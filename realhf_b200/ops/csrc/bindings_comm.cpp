@@ -20,6 +20,29 @@ int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, 
                        int a_mn, int b_mn, int in_dt, int out_dt, int accumulate, int bn, int num_sms, const uint32_t* ready_flags,
                        uint32_t ready_epoch, int rows_per_flag, int m_rot_rows, uint32_t* done_counters, cudaStream_t s);
 int rb_spin_wait(const uint32_t* flag, uint32_t target, cudaStream_t s);
+// vmm.cpp
+int rb_vmm_multicast_supported(int dev);
+int64_t rb_vmm_granularity(int dev, int ndev);
+int rb_vmm_alloc(int64_t size, int64_t align, int dev, uint64_t* ptr, uint64_t* handle, int* fd);
+int rb_vmm_import(int fd, int64_t size, int64_t align, int dev, uint64_t* ptr, uint64_t* handle);
+int rb_vmm_free(uint64_t ptr, int64_t size, uint64_t handle);
+int rb_mc_create(int64_t size, int ndev, uint64_t* mc, int* fd);
+int rb_mc_import(int fd, uint64_t* mc);
+int rb_mc_add_device(uint64_t mc, int dev);
+int rb_mc_bind_and_map(uint64_t mc, uint64_t mem_handle, int64_t size, int64_t align, int dev, uint64_t* mc_ptr);
+int rb_mc_unbind(uint64_t mc, int dev, int64_t size);
+int rb_close_fd(int fd);
+// nvls.cu
+int rb_nvls_allreduce(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, const void* in, void* out, int64_t nbytes,
+                      int64_t off_in, int64_t off_out, int rank, int world, int dt, int mode, int max_blocks, cudaStream_t s);
+int rb_nvls_reduce_scatter(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t off, int64_t nbytes, int dt, float scale,
+                           float* stats, int rank, int world, cudaStream_t s);
+int rb_nvls_adam_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t p_off, int p_dt, const void* g, int g_dt,
+                           void* m, void* v, int s_dt, float* master, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                           int step, const float* scale_ptr, const int* skip_ptr, int stochastic, uint32_t seed, int rank, int world,
+                           cudaStream_t s);
+int rb_nvls_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t off, int64_t nbytes, int lead_barrier, int rank,
+                      int world, cudaStream_t s);
 int rb_gemm_fused_tp(int mode, const void* A, const int64_t* peer_a, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                      int64_t ldc, int b_mn, const int64_t* peer_base, const int64_t* peer_counter, int rows_per_rank, int my_rank,
                      int world, int num_sms, cudaStream_t s);
@@ -157,7 +180,128 @@ Tensor symm_open(const Tensor& handle, int64_t nbytes, int64_t device) {
                        at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (c10::DeviceIndex)device));
 }
 
+// ---- VMM symmetric memory + NVSwitch multicast (vmm.cpp).  Handles and pointers cross the binding as integers; the python
+// side (parallel/symm_mem.py) owns the lifetime and ships the file descriptors between processes over unix sockets.
+int64_t vmm_multicast_supported(int64_t device) { return rb_vmm_multicast_supported((int)device); }
+int64_t vmm_granularity(int64_t device, int64_t ndev) { return rb_vmm_granularity((int)device, (int)ndev); }
+
+// -> [ptr, handle, fd]
+std::vector<int64_t> vmm_alloc(int64_t nbytes, int64_t align, int64_t device) {
+  c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+  TORCH_CHECK(cudaFree(nullptr) == cudaSuccess);  // make sure the primary context exists
+  uint64_t ptr = 0, h = 0;
+  int fd = -1;
+  int rc = rb_vmm_alloc(nbytes, align, (int)device, &ptr, &h, &fd);
+  TORCH_CHECK(rc == 0, "vmm_alloc(", nbytes, ") failed: ", rc);
+  TORCH_CHECK(cudaMemset(reinterpret_cast<void*>(ptr), 0, nbytes) == cudaSuccess);
+  TORCH_CHECK(cudaDeviceSynchronize() == cudaSuccess);
+  return {(int64_t)ptr, (int64_t)h, (int64_t)fd};
+}
+
+// -> [ptr, handle]
+std::vector<int64_t> vmm_import(int64_t fd, int64_t nbytes, int64_t align, int64_t device) {
+  c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+  TORCH_CHECK(cudaFree(nullptr) == cudaSuccess);
+  uint64_t ptr = 0, h = 0;
+  int rc = rb_vmm_import((int)fd, nbytes, align, (int)device, &ptr, &h);
+  TORCH_CHECK(rc == 0, "vmm_import failed: ", rc);
+  return {(int64_t)ptr, (int64_t)h};
+}
+
+void vmm_free(int64_t ptr, int64_t nbytes, int64_t handle) { rb_vmm_free((uint64_t)ptr, nbytes, (uint64_t)handle); }
+
+// -> [mc_handle, fd]
+std::vector<int64_t> mc_create(int64_t nbytes, int64_t ndev) {
+  uint64_t mc = 0;
+  int fd = -1;
+  int rc = rb_mc_create(nbytes, (int)ndev, &mc, &fd);
+  TORCH_CHECK(rc == 0, "cuMulticastCreate failed: ", rc);
+  return {(int64_t)mc, (int64_t)fd};
+}
+int64_t mc_import(int64_t fd) {
+  uint64_t mc = 0;
+  TORCH_CHECK(rb_mc_import((int)fd, &mc) == 0, "multicast handle import failed");
+  return (int64_t)mc;
+}
+void mc_add_device(int64_t mc, int64_t device) { TORCH_CHECK(rb_mc_add_device((uint64_t)mc, (int)device) == 0, "cuMulticastAddDevice failed"); }
+int64_t mc_bind_and_map(int64_t mc, int64_t mem_handle, int64_t nbytes, int64_t align, int64_t device) {
+  c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+  uint64_t p = 0;
+  int rc = rb_mc_bind_and_map((uint64_t)mc, (uint64_t)mem_handle, nbytes, align, (int)device, &p);
+  TORCH_CHECK(rc == 0, "multicast bind/map failed: ", rc);
+  return (int64_t)p;
+}
+void mc_unbind(int64_t mc, int64_t device, int64_t nbytes) { rb_mc_unbind((uint64_t)mc, (int)device, nbytes); }
+void close_fd(int64_t fd) { rb_close_fd((int)fd); }
+
+// A tensor view of raw device memory owned elsewhere (the symmetric buffer object keeps the mapping alive).
+Tensor tensor_from_ptr(int64_t ptr, int64_t nbytes, int64_t device) {
+  return at::from_blob(reinterpret_cast<void*>(ptr), {nbytes}, [](void*) {},
+                       at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (c10::DeviceIndex)device));
+}
+
+// ---- NVLS collectives (nvls.cu)
+void nvls_allreduce(const c10::optional<Tensor>& in, const c10::optional<Tensor>& out, int64_t nbytes, std::vector<int64_t> data_ptrs,
+                    std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t off_in, int64_t off_out, int64_t rank, int64_t dt, int64_t mode,
+                    int64_t max_blocks, int64_t device) {
+  c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+  if (in.has_value()) TORCH_CHECK(in->is_contiguous() && (int64_t)in->nbytes() == nbytes);
+  if (out.has_value()) TORCH_CHECK(out->is_contiguous() && (int64_t)out->nbytes() == nbytes);
+  int rc = rb_nvls_allreduce(data_ptrs.data(), pad_ptrs.data(), (uint64_t)mc_ptr, in.has_value() ? in->data_ptr() : nullptr,
+                             out.has_value() ? out->data_ptr() : nullptr, nbytes, off_in, off_out, (int)rank, (int)data_ptrs.size(), (int)dt,
+                             (int)mode, (int)max_blocks, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "nvls_allreduce failed: ", rc);
+}
+
+void nvls_reduce_scatter(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t off, int64_t nbytes, int64_t dt,
+                         double scale, Tensor stats, int64_t rank) {
+  TORCH_CHECK(stats.is_cuda() && stats.scalar_type() == at::kFloat && stats.numel() >= 2);
+  c10::cuda::CUDAGuard g(stats.device());
+  int rc = rb_nvls_reduce_scatter(data_ptrs.data(), pad_ptrs.data(), (uint64_t)mc_ptr, off, nbytes, (int)dt, (float)scale, stats.data_ptr<float>(),
+                                  (int)rank, (int)data_ptrs.size(), at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "nvls_reduce_scatter failed: ", rc);
+}
+
+void nvls_adam_allgather(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t p_off, int64_t p_dt, const Tensor& g,
+                         Tensor m, Tensor v, const c10::optional<Tensor>& master, int64_t n, double lr, double b1, double b2, double eps, double wd,
+                         int64_t step, const c10::optional<Tensor>& scale, const c10::optional<Tensor>& skip, bool stochastic, int64_t seed,
+                         int64_t rank) {
+  TORCH_CHECK(g.is_cuda() && m.is_cuda() && v.is_cuda() && g.numel() >= n && m.numel() >= n && v.numel() >= n);
+  TORCH_CHECK(m.scalar_type() == v.scalar_type());
+  c10::cuda::CUDAGuard gd(g.device());
+  int rc = rb_nvls_adam_allgather(data_ptrs.data(), pad_ptrs.data(), (uint64_t)mc_ptr, p_off, (int)p_dt, g.data_ptr(), dtc(g.scalar_type()),
+                                  m.data_ptr(), v.data_ptr(), dtc(m.scalar_type()), master.has_value() ? master->data_ptr<float>() : nullptr, n,
+                                  (float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (int)step,
+                                  scale.has_value() ? scale->data_ptr<float>() : nullptr, skip.has_value() ? skip->data_ptr<int>() : nullptr,
+                                  stochastic ? 1 : 0, (uint32_t)seed, (int)rank, (int)data_ptrs.size(), at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "nvls_adam_allgather failed: ", rc);
+}
+
+void nvls_allgather(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t off, int64_t nbytes, bool lead_barrier,
+                    int64_t rank, int64_t device) {
+  c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+  int rc = rb_nvls_allgather(data_ptrs.data(), pad_ptrs.data(), (uint64_t)mc_ptr, off, nbytes, lead_barrier ? 1 : 0, (int)rank,
+                             (int)data_ptrs.size(), at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "nvls_allgather failed: ", rc);
+}
+
 void register_comm_ops(torch::Library& m) {
+  m.def("vmm_multicast_supported(int device) -> int", &vmm_multicast_supported);
+  m.def("vmm_granularity(int device, int ndev) -> int", &vmm_granularity);
+  m.def("vmm_alloc(int nbytes, int align, int device) -> int[]", &vmm_alloc);
+  m.def("vmm_import(int fd, int nbytes, int align, int device) -> int[]", &vmm_import);
+  m.def("vmm_free(int ptr, int nbytes, int handle) -> ()", &vmm_free);
+  m.def("mc_create(int nbytes, int ndev) -> int[]", &mc_create);
+  m.def("mc_import(int fd) -> int", &mc_import);
+  m.def("mc_add_device(int mc, int device) -> ()", &mc_add_device);
+  m.def("mc_bind_and_map(int mc, int mem_handle, int nbytes, int align, int device) -> int", &mc_bind_and_map);
+  m.def("mc_unbind(int mc, int device, int nbytes) -> ()", &mc_unbind);
+  m.def("close_fd(int fd) -> ()", &close_fd);
+  m.def("tensor_from_ptr(int ptr, int nbytes, int device) -> Tensor", &tensor_from_ptr);
+  m.def("nvls_allreduce(Tensor? inp, Tensor? out, int nbytes, int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off_in, int off_out, int rank, int dt, int mode, int max_blocks, int device) -> ()", &nvls_allreduce);
+  m.def("nvls_reduce_scatter(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off, int nbytes, int dt, float scale, Tensor(a!) stats, int rank) -> ()", &nvls_reduce_scatter);
+  m.def("nvls_adam_allgather(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int p_off, int p_dt, Tensor g, Tensor(a!) m, Tensor(b!) v, Tensor? master, int n, float lr, float b1, float b2, float eps, float wd, int step, Tensor? scale, Tensor? skip, bool stochastic, int seed, int rank) -> ()", &nvls_adam_allgather);
+  m.def("nvls_allgather(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off, int nbytes, bool lead_barrier, int rank, int device) -> ()", &nvls_allgather);
   m.def("symm_alloc(int nbytes, int device) -> Tensor[]", &symm_alloc);
   m.def("symm_open(Tensor handle, int nbytes, int device) -> Tensor", &symm_open);
   m.def("symm_pad_words() -> int", &symm_pad_words);

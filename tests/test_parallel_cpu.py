@@ -23,7 +23,7 @@ def _batch(bs=8, seed=0, vocab=128):
     return SequenceSample.from_default(seqlens=lens, ids=list(range(bs)), data=dict(packed_input_ids=ids, prompt_mask=pm))
 
 
-def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torch.float32, pg_backend="gloo"):
+def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torch.float32, pg_backend="gloo", opt_extra=None):
     import types
 
     from realhf_b200.api.config import ModelName
@@ -44,7 +44,7 @@ def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torc
     m = ReaLModel(cfg, ctx, dtype=dtype, device=torch.device(device)).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
-                                        grad_dtype="fp32", gradient_clipping=1.0)).initialize(Model(ModelName("m", 0), m, tok, device),
+                                        grad_dtype="fp32", gradient_clipping=1.0, **(opt_extra or {}))).initialize(Model(ModelName("m", 0), m, tok, device),
                                                                                                FinetuneSpec(1, 10, 10))
     full = _batch(8)
     mine = full.split(dp)[ctx.dp_rank] if dp > 1 else full
@@ -58,7 +58,8 @@ def _worker(rank, world, layout, fam, n_steps, n_mbs=1, device="cpu", dtype=torc
                                           data=dict(packed_input_ids=(torch.arange(2, 2 + sum(plens)) % cfg.vocab_size).to(device)))
     outs = model.module.generate(prompts, tok, g, num_micro_batches=1)
     gen_tokens = torch.cat([o.tokens for o in outs]).tolist() if outs is not None else None
-    return dict(losses=losses, gen=gen_tokens, coord=tuple(ctx.coord))
+    opt = model.module.optim
+    return dict(losses=losses, gen=gen_tokens, coord=tuple(ctx.coord), n_buckets=len(opt.buckets), n_overlapped=opt.n_overlapped)
 
 
 def _reference(fam, n_steps, n_mbs=1):
@@ -77,6 +78,24 @@ def test_layout_matches_single_process(layout):
     for r in res:
         for a, b in zip(r["losses"], ref["losses"]):
             assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (layout, r["losses"], ref["losses"])
+    gens = [r["gen"] for r in res if r["gen"] is not None]
+    assert gens and all(g == ref["gen"] for g in gens), (gens, ref["gen"])
+
+
+@pytest.mark.parametrize("cfg", [(2, 1, 1), (2, 2, 1), (4, 1, 1), (2, 1, 2)])
+def test_bucketed_overlapped_reduce_scatter_matches_single_process(cfg):
+    """ZeRO-1 with many small gradient buckets: buckets are reduced from inside the backward pass of the last micro-batch
+    (`FlatAdamW.grad_ready`), every rank owns a slice of every bucket, and the result equals the single-process run."""
+    from realhf_b200.base.testing import run_distributed
+    dp, n_mbs, tp = cfg
+    fam, n_steps = "llama", 3
+    ref = _reference(fam, n_steps, n_mbs=dp * n_mbs)
+    res = run_distributed(_worker, dp * tp, layout=(1, dp, tp, False), fam=fam, n_steps=n_steps, n_mbs=n_mbs, opt_extra=dict(bucket_numel=2048))
+    for r in res:
+        assert r["n_buckets"] >= 4, r
+        assert r["n_overlapped"] >= r["n_buckets"] // 2, r   # everything above the embedding starts inside backward
+        for a, b in zip(r["losses"], ref["losses"]):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (cfg, r["losses"], ref["losses"])
     gens = [r["gen"] for r in res if r["gen"] is not None]
     assert gens and all(g == ref["gen"] for g in gens), (gens, ref["gen"])
 
