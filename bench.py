@@ -121,7 +121,28 @@ def run_reference(args):
     return 0
 
 
-GEN_TP_DEFAULT = {1: 1, 2: 1, 4: 1, 8: 1}  # per-N generation layout (measured)
+def choose_gen_tp(world: int, n_prompts: int, prompt_len: int, new_tokens: int, n_layers: int) -> dict:
+    """Generation layout for this node size, picked by the allocation search's cost model (`search/engine.py::estimate`, the
+    function the `search` / `heuristic` allocation modes use) over every tp x dp factorisation of the node: decode streams
+    1/tp of the weights per GPU per token, pays the layer-boundary all-reduces (fused into the RMSNorm kernels over NVSwitch
+    multicast) and keeps the same KV bytes per GPU.  Returns {tp: predicted seconds} and the arg-min."""
+    from realhf_b200.api.config import ModelInterfaceAbstraction, ModelInterfaceType
+    from realhf_b200.api.dfg import MFCDef
+    from realhf_b200.api.quickstart import ParallelismConfig
+    from realhf_b200.search.engine import HardwareModel, estimate
+    hw = HardwareModel.from_measured()
+    h, f, v = 4096, 11008, 32000
+    shape = dict(h=h, L=n_layers, f=f, v=v, n=n_layers * (4 * h * h + 3 * h * f) + 2 * v * h)
+    rpc = MFCDef("actor_gen", n_prompts, ModelInterfaceType.GENERATE, ModelInterfaceAbstraction("ppo_actor"), "actor",
+                 input_keys=("packed_prompts",), output_keys=("packed_input_ids",))
+    pred = {}
+    for tp in (1, 2, 4, 8):
+        if world % tp or 32 % tp:
+            continue
+        par = ParallelismConfig(data_parallel_size=world // tp, model_parallel_size=tp, pipeline_parallel_size=1)
+        pred[tp] = estimate(rpc, shape, par, hw, prompt_len, new_tokens, 1, True)[0] / 1e6
+    best = min(pred, key=pred.get)
+    return dict(pred_s={k: round(t, 3) for k, t in pred.items()}, best=best)
 
 
 def main():
@@ -136,6 +157,10 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=512)
     ap.add_argument("--gemm", default=os.environ.get("REAL_GEMM", "tcgen05"), choices=["tcgen05", "cublas"])
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--optimizer", default="lean", choices=["lean", "fp32"],
+                    help="lean (default at every N, so the scaling curve compares like with like): bf16 Adam moments + stochastic "
+                         "rounding, no master copy -- what fits four 7B models + optimizer states on ONE GPU; fp32: fp32 master weights + "
+                         "fp32 moments, the reference's Megatron optimizer precision (fits from N >= 2; reported in profiles/)")
     ap.add_argument("--ckpt", default="auto", type=lambda v: {"auto": "auto", "all": True, "none": False}[v],
                     help="activation checkpointing: auto (recompute only what the free HBM requires), all (every block, the reference default), none")
     ap.add_argument("--offload-frozen", default="auto", choices=["auto", "on", "off"],
@@ -196,6 +221,8 @@ def main():
     spec = FinetuneSpec(total_train_epochs=1, total_train_steps=1000, steps_per_epoch=1000)
     lean = dict(lr=1e-5, weight_decay=0.05, state_dtype="bf16", use_master_weights=False, grad_dtype="bf16",
                 share_grad_buffer=True, warmup_steps_proportion=0.0, lr_scheduler_type="constant")
+    if args.optimizer == "fp32":  # the reference's precision: fp32 master weights + fp32 Adam moments (Megatron distributed optimizer)
+        lean.update(state_dtype="fp32", use_master_weights=True)
     models = {}
     for role, critic, train in (("actor", False, True), ("critic", True, True), ("ref", False, False), ("reward", True, False)):
         m = ReaLModel(llama7b(critic), ctx, dtype=torch.bfloat16, device=dev).init_random_fast(seed=11 + len(models))
@@ -247,7 +274,8 @@ def main():
             ex.post_hooks.setdefault(mfc, []).append(lambda m=frozen[role]: m.offload(frozen=True))
             ex.hooks.setdefault(mfc, []).append(lambda: torch.cuda.current_stream(dev).wait_stream(side))
         ex.hooks.setdefault("actor_gen", []).append(lambda: [m.reload(stream=side) for m in frozen.values()])
-    gen_tp = args.gen_tp if args.gen_tp > 0 else GEN_TP_DEFAULT.get(world, 1)
+    gen_choice = choose_gen_tp(world, args.prompts, args.prompt_len, args.new_tokens, args.layers)
+    gen_tp = args.gen_tp if args.gen_tp > 0 else gen_choice["best"]
     if world > 1 and gen_tp > 1:
         # generation on a tp x dp replica of the actor: decode streams 1/tp of the weights per GPU per token; the replica is
         # refreshed from the (dp-replicated) training layout by local segment copies before every generation
@@ -302,6 +330,11 @@ def main():
     clocks = sampler.stop()
     n_launch = launches.total
     unckpt = {r: getattr(getattr(models[r].module, "module", None), "last_unckpt_blocks", 0) for r in ("actor", "critic")}
+    _o = models["actor"].module.optim
+    zero_comm = ("none (dp=1)" if world == 1 else
+                 (f"NVLS: multimem.ld_reduce reduce-scatter fused with avg/cast/grad-norm + AdamW with multimem.st all-gather, "
+                  f"{len(_o.buckets)} buckets, {_o.n_overlapped} reduced inside backward" if _o.nvls else
+                  f"NCCL in-place reduce-scatter / all-gather, {len(_o.buckets)} buckets, {_o.n_overlapped} reduced inside backward"))
     pool = ex.last_pool
     tokens_this_rank = float(sum(pool.flat_seqlens("packed_input_ids")))
     t = torch.tensor([dev_s, wall, tokens_this_rank, float(n_launch)], dtype=torch.float64, device=dev)
@@ -325,11 +358,13 @@ def main():
                        "prompt_len": args.prompt_len, "new_tokens": args.new_tokens, "ppo_minibatches": 4,
                        "parallelism": (f"dp{world} (all 6 MFCs)" if not (world > 1 and gen_tp > 1) else
                                        f"actor_gen tp{gen_tp}xdp{world // gen_tp} (realloc'd replica), other MFCs dp{world}") + ", ZeRO-1 flat AdamW", "tokens_per_step": tokens_per_step,
-                       "optimizer": "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads",
+                       "optimizer": ("AdamW, fp32 master weights + fp32 moments (reference precision), bf16 grads" if args.optimizer == "fp32" else
+                                     "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads"),
+                       "zero_comm": zero_comm, "gen_layout_search": gen_choice,
                        "frozen_model_offload": args.offload_frozen == "on" or (args.offload_frozen == "auto" and world == 1 and args.ckpt == "auto"),
                        "activation_checkpointing": (f"auto: {unckpt} of {args.layers} blocks keep activations (free-HBM budget)" if args.ckpt == "auto"
                                                     else ("every block" if args.ckpt else "none")),
-                       "gemm": args.gemm, "attention": "flash-attn lib (varlen) + own split-KV decode kernel",
+                       "gemm": args.gemm, "attention": "own tcgen05 varlen fwd/bwd + own split-KV decode kernel",
                        "l2": "working set >> L2 (54 GB weights per GPU); fresh inputs every step",
                        "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}},
             "clocks": clocks,

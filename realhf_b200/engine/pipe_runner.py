@@ -124,51 +124,79 @@ class PipelineRunner:
         saved: Dict[int, Tuple[Optional[torch.Tensor], torch.Tensor]] = {}
         sends = []
         n_warm = min(self.pp - self.rank - 1, M)
+        dev, dt = self.m.device, self.m.dtype
 
-        def fwd(i):
+        # Point-to-point plumbing.  In steady state a stage has a send and a receive pending towards the SAME neighbour in
+        # opposite directions (activation out / gradient in, gradient out / activation in); posted as separate isend / irecv
+        # they can deadlock on NCCL once a message exceeds the p2p FIFO (both sides block in their send while the matching
+        # receive is queued behind it).  Each such pair is therefore ONE `batch_isend_irecv` group, which NCCL progresses
+        # concurrently (Megatron's send_forward_recv_backward / send_backward_recv_forward; the reference orders blocking
+        # send / recv per stage parity instead, pipe_runner.py:650-753).
+        def exchange(send_t, send_to, recv_shape, recv_from):
+            ops, buf = [], None
+            if send_t is not None:
+                ops.append(dist.P2POp(dist.isend, send_t, send_to))
+            if recv_shape is not None:
+                buf = torch.empty(recv_shape, dtype=dt, device=dev)
+                ops.append(dist.P2POp(dist.irecv, buf, recv_from))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            return buf
+
+        def compute_fwd(i, hidden):
             ids, cu, mx, T, n_pad = metas[i]
-            hidden = None
-            if not self.first:
-                buf, h = self._irecv(self._hidden_shape(T), self.m.dtype, self.prev)
-                h.wait()
-                hidden = buf.requires_grad_(True)
+            if hidden is not None:
+                hidden = hidden.requires_grad_(True)
             out = self._stage_forward(ids, cu, mx, hidden, n_pad)
             if self.last:
                 loss, st = loss_fn(out, mbs[i])
                 for k, v in st.items():
                     stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / M
                 saved[i] = (hidden, optim.scale_loss(loss / M))
-            else:
-                x = out.contiguous()
-                sends.append((x, dist.isend(x.detach(), self.next)))
-                saved[i] = (hidden, x)
+                return None
+            x = out.contiguous()
+            saved[i] = (hidden, x)
+            return x.detach()
 
-        def bwd(i):
+        def compute_bwd(i, g):
             hidden, out = saved.pop(i)
             if self.last:
                 out.backward()
             else:
-                g, h = self._irecv(out.shape, out.dtype, self.next)
-                h.wait()
                 torch.autograd.backward(out, g)
-            if not self.first:
-                gi = hidden.grad.contiguous()
-                sends.append((gi, dist.isend(gi, self.prev)))
+            return None if self.first else hidden.grad.contiguous()
 
+        hshape = lambda i: self._hidden_shape(metas[i][3])
         f = b = 0
+        # warm-up: forwards only (activation in from prev, activation out to next: one direction per neighbour)
         for _ in range(n_warm):
-            fwd(f)
+            h = exchange(None, None, None if self.first else hshape(f), self.prev)
+            x = compute_fwd(f, h)
+            sends.append((x, dist.isend(x, self.next)))
             f += 1
-        while f < M:  # steady state: one forward, one backward
-            fwd(f)
+        # steady state: one forward, one backward
+        h = None
+        if f < M and not self.first:
+            h = exchange(None, None, hshape(f), self.prev)
+        while f < M:
+            x = compute_fwd(f, h)
             f += 1
-            bwd(b)
+            # activation out + gradient in, same neighbour: one group
+            g = None if self.last else exchange(x, self.next, saved[b][1].shape, self.next)
+            gi = compute_bwd(b, g)
             b += 1
+            # gradient out + next activation in, same neighbour: one group
+            h = exchange(gi, self.prev, hshape(f) if (f < M and not self.first) else None, self.prev)
+        # cool-down: backwards only
         while b < M:
-            bwd(b)
+            g = None if self.last else exchange(None, None, saved[b][1].shape, self.next)
+            gi = compute_bwd(b, g)
             b += 1
-        for _, h in sends:
-            h.wait()
+            if gi is not None:
+                sends.append((gi, dist.isend(gi, self.prev)))
+        for _, hnd in sends:
+            hnd.wait()
         # statistics live on the last stage: share them along the pipe so every stage returns the same dict
         keys = sorted(stats) if self.last else None
         obj = [keys]
@@ -197,7 +225,7 @@ class PipelineRunner:
         first_global = lambda: self.ctx.global_rank(pipe=0, data=self.ctx.dp_rank, model=self.ctx.tp_rank)
         sends = []
         # PyTorch sampling path (CPU tensors) under TP: the ranks of the last stage must draw the same tokens (generation.generate)
-        sample_gen = m.shared_generator(dev) if (dev.type != "cuda" and self.ctx.tp_size > 1 and not g.greedy) else None
+        sample_gen = m.shared_generator(dev) if (self.ctx.tp_size > 1 and not g.greedy and not gen.fused_sampler_ok(dev, m.config.vocab_size)) else None
         # ---- prefill, micro-batch by micro-batch
         for i, (ids, cu, mx, T) in enumerate(metas):
             B = cu.numel() - 1

@@ -59,6 +59,11 @@ def _filter_logits(logits: torch.Tensor, g: GenerationHyperparameters) -> torch.
     return logits
 
 
+def fused_sampler_ok(device, vocab_size: int) -> bool:
+    """The fused sampling kernel stages one fp32 logits row in shared memory (<= 200 KB: vocabularies up to 51200)."""
+    return torch.device(device).type == "cuda" and vocab_size * 4 <= 200 * 1024
+
+
 def genstep(logits: torch.Tensor, g: GenerationHyperparameters, step: int, eos_id: Optional[int], pad_id: int,
             unfinished: torch.Tensor, generator: Optional[torch.Generator] = None, want_mask: bool = True):
     """One sampling step on full-vocab logits [B, V].  Returns (next_tokens, logprob, mask_bits | None, unfinished).
@@ -114,7 +119,25 @@ class DecodeState:
         self.out: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_launches = 0
+        self.graph_sig = None
         self.B, self.S = B, S
+        # in-graph sampling: per-row step counters, liveness flags, device-resident seed and the [B, n_gen] history buffers the
+        # sampling kernel writes at column `step`
+        self.step_rows = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.unfinished = torch.ones(B, dtype=torch.bool, device=dev)
+        self.seed = torch.zeros(1, dtype=torch.long, device=dev)
+        self.tok_hist = self.lp_hist = self.mask_hist = None
+
+    def prepare_hist(self, n_gen: int, V: int, need_mask: bool):
+        dev = self.cache_lens.device
+        if self.tok_hist is None or self.tok_hist.shape[1] != n_gen or (need_mask and self.mask_hist is None):
+            self.tok_hist = torch.zeros(self.B, n_gen, dtype=torch.long, device=dev)
+            self.lp_hist = torch.zeros(self.B, n_gen, dtype=torch.float32, device=dev)
+            self.mask_hist = torch.zeros(self.B, n_gen, (V + 7) // 8, dtype=torch.uint8, device=dev) if need_mask else None
+            self.graph = None  # a captured graph points at the old buffers
+
+    def drop_hist(self):
+        self.tok_hist = self.lp_hist = self.mask_hist = None
 
     def fill_from_prefill(self, kv: List[Tuple[torch.Tensor, torch.Tensor]], cu_seqlens: torch.Tensor, lens: torch.Tensor):
         """Scatter the packed prefill K/V of every block into the dense caches."""
@@ -144,9 +167,10 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     """Generate for a packed batch of prompts on a single pipeline stage (pp == 1)."""
     assert model.is_first_stage and model.is_last_stage, "pipelined generation goes through engine.pipe_runner"
     dev = model.device
-    if generator is None and dev.type != "cuda" and model.ctx.tp_size > 1 and not g.greedy:
+    if generator is None and model.ctx.tp_size > 1 and not g.greedy and not fused_sampler_ok(dev, model.config.vocab_size):
         # every TP rank samples from the same (gathered) distribution and must draw the same token: the PyTorch sampling
-        # path needs a stream shared by the group (the fused CUDA sampler is seeded identically on all ranks already)
+        # path (CPU tensors, and CUDA vocabularies too large for the fused sampler's shared-memory row: Llama-3, Qwen2, Gemma)
+        # needs a stream shared by the group; the fused CUDA sampler is seeded identically on all ranks already
         generator = model.shared_generator(dev)
     cu = cu_seqlens.int()
     B = cu.numel() - 1
@@ -171,11 +195,31 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     toks.append(nxt); lps.append(lp); masks.append(mb)
     # ---- decode loop
     use_graph = g.use_cuda_graph and dev.type == "cuda"
+    V = logits.shape[1]
+    # the fused sampler can run as the tail of the captured step: then a decode step is ONE graph replay and nothing else
+    # (no eager copy of the next token, no cache_lens += 1, no sampling launch, no per-step python bookkeeping)
+    in_graph = use_graph and generator is None and V * 4 <= 200 * 1024 and os.environ.get("REAL_GEN_SAMPLE_IN_GRAPH", "1") == "1"
+    need_mask = mb is not None
 
     def one_step():
         h = model.decode_step(state.input_ids, state.k, state.v, state.cache_lens)
         return _final_logits(model, h)
 
+    sig = (in_graph, g.max_new_tokens, g.min_new_tokens, g.top_k, g.top_p, g.temperature, g.greedy, need_mask, eos_id, pad_id,
+           int(model.flat_param.data_ptr()))
+    if state.graph is not None and state.graph_sig != sig:
+        state.graph = None  # sampling options changed, or the flat parameter buffer moved (realloc / offload reload / ZeRO-3)
+    if in_graph:
+        state.prepare_hist(g.max_new_tokens, V, need_mask)
+        state.tok_hist[:, 0] = nxt
+        state.lp_hist[:, 0] = lp
+        if need_mask:
+            state.mask_hist[:, 0] = mb
+        state.step_rows.fill_(1)
+        state.unfinished.copy_(unfinished)
+        seed = int(_SAMPLE_SEED[0])
+        _SAMPLE_SEED[0] = (seed * 6364136223846793005 + 1442695040888963407) % (1 << 62)
+        state.seed.fill_(seed)
     if use_graph and state.graph is None:
         state.input_ids.copy_(nxt)
         lens_backup = state.cache_lens.clone()
@@ -189,26 +233,47 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         launches.begin_capture()
         with torch.cuda.graph(graph):
             state.out = one_step()
+            if in_graph:
+                from realhf_b200.ops import lib
+                lib().sample_graph(state.out, state.tok_hist, state.lp_hist, state.mask_hist if need_mask else None, state.unfinished,
+                                   state.step_rows, state.input_ids, state.cache_lens, state.seed, g.min_new_tokens if eos_id is not None else 0,
+                                   g.top_k, g.top_p, 1.0 / g.temperature, eos_id if eos_id is not None else -1, g.greedy, pad_id)
         state.graph_launches = launches.end_capture()
         state.graph = graph
+        state.graph_sig = sig
     step = 1
-    while step < g.max_new_tokens:
+    if in_graph:
         state.input_ids.copy_(nxt)
-        if use_graph:
+        while step < g.max_new_tokens:
             state.graph.replay()
             launches.count_replay(state.graph_launches)
-            logits = state.out
-        else:
-            logits = one_step()
-        state.cache_lens += 1
-        nxt, lp, mb, unfinished = genstep(logits, g, step, eos_id, pad_id, unfinished, generator)
-        toks.append(nxt); lps.append(lp); masks.append(mb)
-        step += 1
-        if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(unfinished.any()):
-            break
-    tokens = torch.stack(toks, 1)
-    logprobs = torch.stack(lps, 1)
-    mask_bits = torch.stack(masks, 1) if masks[0] is not None else None
+            step += 1
+            if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(state.unfinished.any()):
+                break
+        take = (lambda t: t) if g.force_cudagraph_recapture else (lambda t: t.clone())  # a kept graph keeps writing these buffers
+        tokens = take(state.tok_hist[:, :step])
+        logprobs = take(state.lp_hist[:, :step])
+        mask_bits = take(state.mask_hist[:, :step]) if need_mask else None
+        if g.force_cudagraph_recapture:
+            state.drop_hist()
+    else:
+        while step < g.max_new_tokens:
+            state.input_ids.copy_(nxt)
+            if use_graph:
+                state.graph.replay()
+                launches.count_replay(state.graph_launches)
+                logits = state.out
+            else:
+                logits = one_step()
+            state.cache_lens += 1
+            nxt, lp, mb, unfinished = genstep(logits, g, step, eos_id, pad_id, unfinished, generator)
+            toks.append(nxt); lps.append(lp); masks.append(mb)
+            step += 1
+            if eos_id is not None and step >= g.min_new_tokens and step % sync_every == 0 and not bool(unfinished.any()):
+                break
+        tokens = torch.stack(toks, 1)
+        logprobs = torch.stack(lps, 1)
+        mask_bits = torch.stack(masks, 1) if masks[0] is not None else None
     n_gen = tokens.shape[1]
     if eos_id is not None:
         is_eos = tokens == eos_id

@@ -517,36 +517,59 @@ class ReaLModel(nn.Module):
         rms = c.layer_norm_type is not None
         w_off = 1.0 if c.layer_norm_type == "gemma" else 0.0
         eps = c.layer_norm_epsilon
-        d = None  # branch output not yet added to the residual stream: every add is fused into the next RMSNorm kernel
+        # Tensor-parallel decode over NVSwitch multicast memory: the row-parallel GEMMs (o, down) write their partial sums into
+        # symmetric memory and the all-reduce happens INSIDE the next residual-add + RMSNorm kernel (`multimem.ld_reduce`), so a
+        # TP layer has exactly the kernels of a single-GPU layer (parallel/fused_tp.py::ar_add_rmsnorm)
+        fused = getattr(self.ctx, "symm", None) if self.ctx.tp_size > 1 else None
+        tp_fused = fused is not None and getattr(fused, "nvls", False) and rms and c.mlp_type == "llama" and not c.use_attn_proj_bias \
+            and self.dtype in (torch.bfloat16, torch.float16)
+        d = None      # branch output not yet added to the residual stream: every add is fused into the next RMSNorm kernel
+        d_sym = None  # same, but still a per-rank partial sum in symmetric memory (tensor-parallel decode)
+
+        def add_norm(x_, wname):
+            """(normalised input, new residual stream) at a layer boundary, consuming the pending branch output."""
+            nonlocal d, d_sym
+            w_ = self.p[wname]
+            if d_sym is not None:
+                h_, x_ = fused.ar_add_rmsnorm(d_sym, x_, w_, eps, w_off)
+            elif rms and d is not None:
+                h_, x_ = OF.add_rmsnorm(d, x_, w_, eps, w_off)
+            else:
+                if d is not None:
+                    x_ = x_ + d
+                h_ = self._norm(x_, wname[: -len(".weight")])
+            d = d_sym = None
+            return h_, x_
+
         for i in self.layers:
             if i == 0:
                 x = self._embed(input_ids, cache_lens)
             elif i <= c.n_layers:
-                if rms and d is not None:
-                    h, x = OF.add_rmsnorm(d, x, self.p[f"{i}.attn.ln.weight"], eps, w_off)
-                else:
-                    if d is not None:
-                        x = x + d
-                    h = self._norm(x, f"{i}.attn.ln")
+                h, x = add_norm(x, f"{i}.attn.ln.weight")
                 qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
                 o = attn_ops.decode_attention(qkv, k_caches[li], v_caches[li], cache_lens, nq, nkv, hd, self._attn_scale(i),
                                               cos, sin, hd, c.rotary_interleaved)
                 li += 1
-                o = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
-                if rms:
-                    h2, x = OF.add_rmsnorm(o, x, self.p[f"{i}.mlp.ln.weight"], eps, w_off)
-                    d = self._mlp(i, x, h2)
+                if tp_fused:
+                    d_sym = fused.gemm_partial(o, self.p[f"{i}.attn.o.weight"])
+                if d_sym is None:
+                    d = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
+                h2, x = add_norm(x, f"{i}.mlp.ln.weight")
+                if tp_fused:
+                    gu = TP.col_linear(h2, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, False)
+                    d_sym = fused.gemm_partial(OF.gated_act(gu, c.activation_function), self.p[f"{i}.mlp.down.weight"])
+                    if d_sym is None:
+                        d = TP.row_linear(OF.gated_act(gu, c.activation_function), self.p[f"{i}.mlp.down.weight"], None, self.ctx, False)
                 else:
-                    x = x + o
-                    d = self._mlp(i, x)
+                    d = self._mlp(i, x, h2)
                 if i == c.n_layers:
-                    if rms:
-                        x, _ = OF.add_rmsnorm(d, x, self.p[f"{i}.ln_f.weight"], eps, w_off)
-                    else:
-                        x = self._norm(x + d, f"{i}.ln_f")
-                    d = None
-        if d is not None:  # a pipeline stage that does not end with ln_f hands on the summed residual stream
+                    x, _ = add_norm(x, f"{i}.ln_f.weight")
+        if d_sym is not None:  # a pipeline stage that does not end with ln_f hands on the summed residual stream
+            x = fused.ar_add_rmsnorm(d_sym, x, None)
+        elif d is not None:
             x = x + d
+        if fused is not None and hasattr(fused, "align_parity"):
+            fused.align_parity()
         return x
 
     def n_local_blocks(self) -> int:

@@ -132,7 +132,43 @@ void attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor
   TORCH_CHECK(rc == 0, "attn_bwd: unsupported configuration (", rc, ")");
 }
 
+extern "C" int rb_sample_graph(const void* logits, int64_t row_stride, int64_t* tok_hist, float* lp_hist, uint8_t* mask_hist,
+                               int64_t mask_bytes, bool* unfinished, int* step_rows, int64_t* input_ids, int* cache_lens, int n_gen,
+                               int min_new_tokens, int B, int V, int top_k, float top_p, float inv_temp, int eos_id, int greedy,
+                               int pad_id, const int64_t* seed_ptr, int dt, cudaStream_t s);
+
+// The sampling step as the tail of a captured decode step: reads the per-row step counter on the device, writes token /
+// log-prob / keep-mask into column `step` of the history buffers and prepares the next replay (input_ids, cache_lens,
+// unfinished, step).  No host-side state changes between replays.
+void sample_graph(const Tensor& logits, Tensor tok_hist, Tensor lp_hist, const c10::optional<Tensor>& mask_hist, Tensor unfinished,
+                  Tensor step_rows, Tensor input_ids, Tensor cache_lens, const Tensor& seed, int64_t min_new_tokens, int64_t top_k,
+                  double top_p, double inv_temp, int64_t eos_id, bool greedy, int64_t pad_id) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  const int64_t B = logits.size(0), V = logits.size(1), n_gen = tok_hist.size(1);
+  TORCH_CHECK(tok_hist.is_contiguous() && tok_hist.scalar_type() == at::kLong && tok_hist.size(0) == B);
+  TORCH_CHECK(lp_hist.is_contiguous() && lp_hist.scalar_type() == at::kFloat && lp_hist.size(0) == B && lp_hist.size(1) == n_gen);
+  TORCH_CHECK(unfinished.scalar_type() == at::kBool && unfinished.numel() == B && step_rows.scalar_type() == at::kInt &&
+              step_rows.numel() == B && input_ids.scalar_type() == at::kLong && input_ids.numel() == B &&
+              cache_lens.scalar_type() == at::kInt && cache_lens.numel() == B && seed.scalar_type() == at::kLong && seed.is_cuda());
+  int64_t mask_bytes = 0;
+  uint8_t* mh = nullptr;
+  if (mask_hist.has_value()) {
+    TORCH_CHECK(mask_hist->is_contiguous() && mask_hist->scalar_type() == at::kByte && mask_hist->dim() == 3 && mask_hist->size(0) == B &&
+                mask_hist->size(1) == n_gen && mask_hist->size(2) == (V + 7) / 8);
+    mask_bytes = mask_hist->size(2);
+    mh = mask_hist->data_ptr<uint8_t>();
+  }
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int dt = logits.scalar_type() == at::kFloat ? 0 : (logits.scalar_type() == at::kBFloat16 ? 1 : (logits.scalar_type() == at::kHalf ? 2 : -1));
+  int rc = rb_sample_graph(logits.data_ptr(), logits.stride(0), tok_hist.data_ptr<int64_t>(), lp_hist.data_ptr<float>(), mh, mask_bytes,
+                           unfinished.data_ptr<bool>(), step_rows.data_ptr<int>(), input_ids.data_ptr<int64_t>(), cache_lens.data_ptr<int>(),
+                           (int)n_gen, (int)min_new_tokens, (int)B, (int)V, (int)top_k, (float)top_p, (float)inv_temp, (int)eos_id,
+                           greedy ? 1 : 0, (int)pad_id, seed.data_ptr<int64_t>(), dt, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "sample_graph: unsupported configuration (", rc, ")");
+}
+
 void register_attn_ops(torch::Library& m) {
+  m.def("sample_graph(Tensor logits, Tensor(a!) tok_hist, Tensor(b!) lp_hist, Tensor(c!)? mask_hist, Tensor(d!) unfinished, Tensor(e!) step_rows, Tensor(f!) input_ids, Tensor(g!) cache_lens, Tensor seed, int min_new_tokens, int top_k, float top_p, float inv_temp, int eos_id, bool greedy, int pad_id) -> ()", &sample_graph);
   m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor(a!) dq, Tensor(b!) dk, Tensor(c!) dv, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> ()", &attn_bwd);
   m.def("attn_fwd(Tensor q, Tensor k, Tensor v, Tensor cu_seqlens, int max_seqlen, float scale, bool causal) -> Tensor[]", &attn_fwd);
   m.def("sample(Tensor logits, Tensor? unfinished, int top_k, float top_p, float inv_temp, int eos_id, bool suppress_eos, bool greedy, int pad_id, int seed, int step, bool want_mask) -> Tensor[]", &sample);

@@ -41,6 +41,8 @@ int rb_nvls_adam_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, ui
                            void* m, void* v, int s_dt, float* master, int64_t n, float lr, float b1, float b2, float eps, float wd,
                            int step, const float* scale_ptr, const int* skip_ptr, int stochastic, uint32_t seed, int rank, int world,
                            cudaStream_t s);
+int rb_nvls_ar_add_rmsnorm(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t off, const void* res_in, const void* w,
+                           void* y, void* res_out, int rows, int H, float eps, float w_offset, int rank, int world, int dt, cudaStream_t s);
 int rb_nvls_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t off, int64_t nbytes, int lead_barrier, int rank,
                       int world, cudaStream_t s);
 int rb_gemm_fused_tp(int mode, const void* A, const int64_t* peer_a, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -277,6 +279,27 @@ void nvls_adam_allgather(std::vector<int64_t> data_ptrs, std::vector<int64_t> pa
   TORCH_CHECK(rc == 0, "nvls_adam_allgather failed: ", rc);
 }
 
+// (h, x_new) = (rmsnorm(sum_ranks(partial) + residual), sum_ranks(partial) + residual); `partial` [rows, H] lives at byte offset `off`
+// of every rank's data region.  Without `w` only the reduced (+ residual) tensor is produced.
+std::vector<Tensor> nvls_ar_add_rmsnorm(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t off, int64_t rows,
+                                        int64_t H, const c10::optional<Tensor>& residual, const c10::optional<Tensor>& w, double eps,
+                                        double w_offset, int64_t rank, const Tensor& like) {
+  c10::cuda::CUDAGuard g(like.device());
+  TORCH_CHECK(like.scalar_type() == at::kBFloat16 || like.scalar_type() == at::kHalf);
+  if (residual.has_value()) TORCH_CHECK(residual->is_contiguous() && residual->numel() == rows * H && residual->scalar_type() == like.scalar_type());
+  if (w.has_value()) TORCH_CHECK(w->is_contiguous() && w->numel() == H && w->scalar_type() == like.scalar_type());
+  auto x_new = at::empty({rows, H}, like.options());
+  Tensor y;
+  if (w.has_value()) y = at::empty({rows, H}, like.options());
+  int rc = rb_nvls_ar_add_rmsnorm(data_ptrs.data(), pad_ptrs.data(), (uint64_t)mc_ptr, off, residual.has_value() ? residual->data_ptr() : nullptr,
+                                  w.has_value() ? w->data_ptr() : nullptr, w.has_value() ? y.data_ptr() : nullptr, x_new.data_ptr(), (int)rows,
+                                  (int)H, (float)eps, (float)w_offset, (int)rank, (int)data_ptrs.size(), dtc(like.scalar_type()),
+                                  at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "nvls_ar_add_rmsnorm failed: ", rc);
+  if (w.has_value()) return {y, x_new};
+  return {x_new};
+}
+
 void nvls_allgather(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t mc_ptr, int64_t off, int64_t nbytes, bool lead_barrier,
                     int64_t rank, int64_t device) {
   c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
@@ -301,6 +324,7 @@ void register_comm_ops(torch::Library& m) {
   m.def("nvls_allreduce(Tensor? inp, Tensor? out, int nbytes, int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off_in, int off_out, int rank, int dt, int mode, int max_blocks, int device) -> ()", &nvls_allreduce);
   m.def("nvls_reduce_scatter(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off, int nbytes, int dt, float scale, Tensor(a!) stats, int rank) -> ()", &nvls_reduce_scatter);
   m.def("nvls_adam_allgather(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int p_off, int p_dt, Tensor g, Tensor(a!) m, Tensor(b!) v, Tensor? master, int n, float lr, float b1, float b2, float eps, float wd, int step, Tensor? scale, Tensor? skip, bool stochastic, int seed, int rank) -> ()", &nvls_adam_allgather);
+  m.def("nvls_ar_add_rmsnorm(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off, int rows, int H, Tensor? residual, Tensor? w, float eps, float w_offset, int rank, Tensor like) -> Tensor[]", &nvls_ar_add_rmsnorm);
   m.def("nvls_allgather(int[] data_ptrs, int[] pad_ptrs, int mc_ptr, int off, int nbytes, bool lead_barrier, int rank, int device) -> ()", &nvls_allgather);
   m.def("symm_alloc(int nbytes, int device) -> Tensor[]", &symm_alloc);
   m.def("symm_open(Tensor handle, int nbytes, int device) -> Tensor", &symm_open);

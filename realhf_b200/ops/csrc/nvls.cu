@@ -194,6 +194,69 @@ __global__ void __launch_bounds__(kThreads) nvls_allgather_kernel(Peers P, const
   block_barrier(P, rank, world);
 }
 
+// ---------------------------------------------------------------------------------------------- AR + residual + RMSNorm
+// The tensor-parallel decode layer boundary in ONE kernel: the row-parallel GEMM (o-proj / down-proj) wrote its partial
+// [B, H] output into symmetric memory at byte offset `off`; this kernel waits for every rank's partial (epoch barrier),
+// pulls the in-switch sum row by row (`multimem.ld_reduce`), adds the residual stream, writes the new residual and the
+// RMS-normalised activations for the next column-parallel GEMM.  Replaces [all-reduce kernel] + [add+RMSNorm kernel]
+// (reference: RowParallelLinear all-reduce, modules.py:1010 + eager _LlamaRMSNorm, modules/mlp.py:425-444).
+// No trailing barrier: callers alternate between two regions (see FusedTP.symm_out).
+template <typename T, int kMaxVec>
+__global__ void __launch_bounds__(kThreads) nvls_ar_add_rmsnorm_kernel(Peers P, const uint8_t* __restrict__ mc, int64_t off,
+                                                                       const T* __restrict__ res_in, const T* __restrict__ w,
+                                                                       T* __restrict__ y, T* __restrict__ res_out, int rows, int H,
+                                                                       float eps, float w_offset, int rank, int world) {
+  __shared__ float red[32];
+  constexpr int V = 8;
+  const int nvec = H / V;
+  rb::pdl_trigger();
+  rb::pdl_wait();  // the producing GEMM of THIS rank is complete; the barrier below covers the peers'
+  block_barrier(P, rank, world);
+  const rb::Pack<T, V>* wr = reinterpret_cast<const rb::Pack<T, V>*>(w);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int4* src = reinterpret_cast<const int4*>(mc + off + (int64_t)row * H * sizeof(T));
+    float vals[kMaxVec][V];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxVec; ++it) {
+      const int i = threadIdx.x + it * kThreads;
+      if (i < nvec) {
+        int4 raw = mm_ld_reduce<T>(src + i);
+        const T* a = reinterpret_cast<const T*>(&raw);
+        if (res_in != nullptr) {
+          rb::Pack<T, V> b = reinterpret_cast<const rb::Pack<T, V>*>(res_in + (int64_t)row * H)[i];
+          rb::Pack<T, V> o;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            o.v[k] = rb::from_f<T>(rb::to_f(a[k]) + rb::to_f(b.v[k]));
+            vals[it][k] = rb::to_f(o.v[k]);
+          }
+          reinterpret_cast<rb::Pack<T, V>*>(res_out + (int64_t)row * H)[i] = o;
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) vals[it][k] = rb::to_f(a[k]);
+          if (res_out != nullptr) reinterpret_cast<int4*>(res_out + (int64_t)row * H)[i] = raw;
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) ss = fmaf(vals[it][k], vals[it][k], ss);
+      }
+    }
+    if (y == nullptr) continue;  // plain all-reduce (+ residual) without a norm
+    ss = rb::block_reduce<false>(ss, red);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+    for (int it = 0; it < kMaxVec; ++it) {
+      const int i = threadIdx.x + it * kThreads;
+      if (i < nvec) {
+        rb::Pack<T, V> ww = wr[i], o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(vals[it][k] * rstd * (rb::to_f(ww.v[k]) + w_offset));
+        reinterpret_cast<rb::Pack<T, V>*>(y + (int64_t)row * H)[i] = o;
+      }
+    }
+  }
+}
+
 Peers make_peers(const int64_t* data_ptrs, const int64_t* pad_ptrs, int world) {
   Peers P;
   for (int i = 0; i < kMaxRanks; ++i) {
@@ -275,6 +338,25 @@ int rb_nvls_adam_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, ui
   }
 #undef RB_CASE
 #undef RB_K
+  return 0;
+}
+
+// y = rmsnorm(allreduce(partial) + res_in) * (w + w_offset); res_out = allreduce(partial) + res_in.  `partial` is the [rows, H]
+// tensor every rank wrote at byte offset `off` of its data region.  y / res_in may be null (plain all-reduce into res_out).
+int rb_nvls_ar_add_rmsnorm(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, int64_t off, const void* res_in, const void* w,
+                           void* y, void* res_out, int rows, int H, float eps, float w_offset, int rank, int world, int dt, cudaStream_t s) {
+  if (world > kMaxRanks || mc == 0 || (off & 15) || H % 8 || H > 8 * kThreads * 4) return -1;
+  if (rows == 0) return 0;
+  Peers P = make_peers(data_ptrs, pad_ptrs, world);
+  const int nb = rows < kMaxBlocks ? rows : kMaxBlocks;
+  const int nvec = H / 8;
+#define RB_GO(T, MV)                                                                                                               \
+  rb::launch_pdl(nvls_ar_add_rmsnorm_kernel<T, MV>, dim3(nb), dim3(kThreads), 0, s, P, (const uint8_t*)mc, off, (const T*)res_in, (const T*)w, \
+                 (T*)y, (T*)res_out, rows, H, eps, w_offset, rank, world)
+#define RB_T(T) { if (nvec <= kThreads) RB_GO(T, 1); else if (nvec <= 2 * kThreads) RB_GO(T, 2); else RB_GO(T, 4); }
+  if (dt == 1) RB_T(__nv_bfloat16) else if (dt == 2) RB_T(__half) else return -2;
+#undef RB_T
+#undef RB_GO
   return 0;
 }
 

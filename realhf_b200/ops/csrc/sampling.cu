@@ -38,6 +38,15 @@ struct SampleParams {
   float inv_temp, top_p;
   uint64_t seed;
   uint32_t step;
+  // ---- in-graph mode (step_rows != nullptr): the kernel is the tail of the captured decode step.  The step index lives on the
+  // device (one counter per row, advanced here), outputs go to column `step` of [B, n_gen] history buffers, and the kernel
+  // also feeds the next replay: next token -> input_ids, cache_lens += 1, unfinished &= (token != eos).
+  int* step_rows;
+  int64_t* input_ids;
+  int* cache_lens;
+  bool* unfinished_rw;
+  int n_gen, min_new_tokens;
+  const int64_t* seed_ptr;   // device-resident seed (a replayed graph must not repeat the random stream of the previous call)
 };
 
 template <typename T>
@@ -51,6 +60,17 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(SampleParams p) {
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* src = reinterpret_cast<const T*>(p.logits) + (int64_t)row * p.row_stride;
   const int V = p.V;
+  const bool in_graph = p.step_rows != nullptr;
+  if (in_graph) {
+    const int st = min(p.step_rows[row], p.n_gen - 1);
+    p.step = (uint32_t)st;
+    if (p.seed_ptr != nullptr) p.seed = (uint64_t)*p.seed_ptr;
+    p.suppress_eos = (p.eos_id >= 0 && st < p.min_new_tokens) ? 1 : 0;
+    p.next_tok += st;                                    // row stride of the history buffers is n_gen (set by the host)
+    p.logprob += st;
+    if (p.mask_bits != nullptr) p.mask_bits += (int64_t)st * (p.mask_stride / p.n_gen);
+    __syncthreads();                                     // everybody has read the counter before thread 0 advances it
+  }
 
   // ---- stage + max
   float mx = -INFINITY;
@@ -220,9 +240,18 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(SampleParams p) {
   }
 
   const bool live = p.unfinished == nullptr || p.unfinished[row];
+  const int64_t out_stride = in_graph ? p.n_gen : 1;
+  __syncthreads();  // all reads of unfinished[row] precede its update
   if (tid == 0) {
-    p.next_tok[row] = live ? chosen : (int64_t)p.pad_id;
-    p.logprob[row] = live ? chosen_lp : 0.f;
+    const int64_t tok = live ? chosen : (int64_t)p.pad_id;
+    p.next_tok[row * out_stride] = tok;
+    p.logprob[row * out_stride] = live ? chosen_lp : 0.f;
+    if (in_graph) {
+      p.input_ids[row] = tok;
+      p.cache_lens[row] += 1;
+      p.step_rows[row] = (int)p.step + 1;
+      if (p.eos_id >= 0) p.unfinished_rw[row] = live && tok != (int64_t)p.eos_id;
+    }
   }
   if (p.mask_bits != nullptr) {
     uint8_t* mrow = p.mask_bits + (int64_t)row * p.mask_stride;
@@ -239,17 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(SampleParams p) {
   }
 }
 
-}  // namespace
-
-extern "C" int rb_sample(const void* logits, int64_t row_stride, int64_t* next_tok, float* logprob, uint8_t* mask_bits,
-                         int64_t mask_stride, const bool* unfinished, int B, int V, int top_k, float top_p, float inv_temp,
-                         int eos_id, int suppress_eos, int greedy, int pad_id, uint64_t seed, uint32_t step, int dt,
-                         cudaStream_t s) {
-  if (B == 0) return 0;
-  const size_t smem = (size_t)V * sizeof(float);
-  if (smem > 200 * 1024) return -1;
-  SampleParams p{logits, row_stride, next_tok, logprob, mask_bits, mask_stride, unfinished, V, top_k, eos_id, suppress_eos, greedy,
-                 pad_id, inv_temp, top_p, seed, step};
+int launch_sample(const SampleParams& p, int B, int dt, cudaStream_t s) {
+  const size_t smem = (size_t)p.V * sizeof(float);
 #define RB_GO(T)                                                                                                  \
   {                                                                                                               \
     static bool cfgd = false;                                                                                     \
@@ -263,3 +283,31 @@ extern "C" int rb_sample(const void* logits, int64_t row_stride, int64_t* next_t
 #undef RB_GO
   return 0;
 }
+
+
+}  // namespace
+
+extern "C" int rb_sample(const void* logits, int64_t row_stride, int64_t* next_tok, float* logprob, uint8_t* mask_bits,
+                         int64_t mask_stride, const bool* unfinished, int B, int V, int top_k, float top_p, float inv_temp,
+                         int eos_id, int suppress_eos, int greedy, int pad_id, uint64_t seed, uint32_t step, int dt,
+                         cudaStream_t s) {
+  if (B == 0) return 0;
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  SampleParams p{logits, row_stride, next_tok, logprob, mask_bits, mask_stride, unfinished, V, top_k, eos_id, suppress_eos, greedy,
+                 pad_id, inv_temp, top_p, seed, step, nullptr, nullptr, nullptr, nullptr, 1, 0, nullptr};
+  return launch_sample(p, B, dt, s);
+}
+
+// In-graph variant: see SampleParams.  tok_hist / lp_hist are [B, n_gen], mask_hist [B, n_gen, mask_bytes] (or null).
+extern "C" int rb_sample_graph(const void* logits, int64_t row_stride, int64_t* tok_hist, float* lp_hist, uint8_t* mask_hist,
+                               int64_t mask_bytes, bool* unfinished, int* step_rows, int64_t* input_ids, int* cache_lens, int n_gen,
+                               int min_new_tokens, int B, int V, int top_k, float top_p, float inv_temp, int eos_id, int greedy,
+                               int pad_id, const int64_t* seed_ptr, int dt, cudaStream_t s) {
+  if (B == 0) return 0;
+  if ((size_t)V * sizeof(float) > 200 * 1024) return -1;
+  SampleParams p{logits, row_stride, tok_hist, lp_hist, mask_hist, mask_bytes * n_gen, unfinished, V, top_k, eos_id, 0, greedy,
+                 pad_id, inv_temp, top_p, 0, 0, step_rows, input_ids, cache_lens, unfinished, n_gen, min_new_tokens, seed_ptr};
+  return launch_sample(p, B, dt, s);
+}
+

@@ -27,7 +27,7 @@ import torch.distributed as dist
 
 from realhf_b200.ops import functional as OF
 from realhf_b200.ops import lib
-from realhf_b200.parallel.symm_mem import SymmetricBuffer
+from realhf_b200.parallel.symm_mem import SymmetricBuffer, VmmSymmetricBuffer, multicast_supported
 
 
 class FusedTP:
@@ -45,7 +45,16 @@ class FusedTP:
         self.stage_off = [2 * inbox, 2 * inbox + stage]
         self.ar_off = 2 * inbox + 2 * stage
         ar_bytes = 64 << 20
-        self.symm = SymmetricBuffer(self.ar_off + ar_bytes, group=self.group, device=self.device)
+        # VMM allocation with an NVSwitch multicast mapping when the platform has one (multimem.ld_reduce all-reduce fused with
+        # the residual add + RMSNorm of the decode path); CUDA-IPC buffer with peer loads otherwise
+        use_mc = os.environ.get("REAL_TP_NVLS", "1") == "1" and multicast_supported(self.device)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(use_mc), group=self.group)
+        if all(flags):
+            self.symm = VmmSymmetricBuffer(self.ar_off + ar_bytes, group=self.group, device=self.device)
+        else:
+            self.symm = SymmetricBuffer(self.ar_off + ar_bytes, group=self.group, device=self.device)
+        self.nvls = getattr(self.symm, "mc_ptr", 0) != 0
         self._rs_calls = 0
         self._ag_calls = 0
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
@@ -182,6 +191,13 @@ class FusedTP:
 
     def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
         n = x.numel() * x.element_size()
+        if self.nvls and x.dtype in (torch.bfloat16, torch.float16) and x.dim() >= 1 and n % 16 == 0 and x.is_contiguous() \
+                and (x.shape[-1] * x.element_size()) % 16 == 0 and x.shape[-1] % 8 == 0:
+            x2 = x.reshape(-1, x.shape[-1])
+            y = self.symm_out(x2.shape[0], x2.shape[1], x.dtype)
+            if y is not None:
+                y.copy_(x2)
+                return self.all_reduce_symm(y).view(x.shape)
         algo = 1 if (self.world == 2 or n <= (512 << 10 if self.world <= 4 else 256 << 10)) else 2
         need = n if algo == 1 else 2 * ((n + 1023) // 1024 * 1024)
         if need > self._ar_bytes or n % 16 != 0 or not x.is_contiguous():
@@ -203,10 +219,45 @@ class FusedTP:
         return self.symm.data()[off: off + nbytes].view(dtype).view(rows, cols)
 
     def all_reduce_symm(self, y_sym: torch.Tensor) -> torch.Tensor:
-        """Sum over ranks of a tensor obtained from `symm_out` (one barrier, no staging copy)."""
+        """Sum over ranks of a tensor obtained from `symm_out` (one barrier, no staging copy).  With a multicast mapping the sum
+        is formed inside the switch (`multimem.ld_reduce`), else by loads from every peer."""
+        if self.nvls and y_sym.dtype in (torch.bfloat16, torch.float16):
+            return self.ar_add_rmsnorm(y_sym, None, None)
         out = torch.empty(y_sym.shape, dtype=y_sym.dtype, device=y_sym.device)
         lib().symm_allreduce(y_sym, out, self.symm.data_ptrs, self.symm.pad_ptrs, self.rank, 3)
         return out
+
+    def gemm_partial(self, x: torch.Tensor, w: torch.Tensor) -> Optional[torch.Tensor]:
+        """This rank's partial product x @ w^T written straight into symmetric memory ([rows, N] view), to be reduced by
+        `ar_add_rmsnorm` / `all_reduce_symm`; None when the shapes do not qualify."""
+        from realhf_b200.ops import gemm as G
+        x2 = x.reshape(-1, x.shape[-1])
+        if not (G.supported(x2, w) and x2.stride(-1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0):
+            return None
+        y_sym = self.symm_out(x2.shape[0], w.shape[0], x.dtype)
+        if y_sym is None:
+            return None
+        G.gemm(x2, w, out=y_sym)
+        return y_sym
+
+    def ar_add_rmsnorm(self, y_sym: torch.Tensor, residual: Optional[torch.Tensor], w: Optional[torch.Tensor], eps: float = 1e-5,
+                       w_offset: float = 0.0):
+        """ONE kernel for the layer boundary of tensor-parallel decode: x_new = sum_ranks(y_sym) + residual,
+        h = rmsnorm(x_new) * (w + w_offset).  Returns (h, x_new), or x_new alone when `w` is None."""
+        assert self.nvls
+        rows, H = y_sym.shape
+        off = y_sym.data_ptr() - self.symm.data_ptrs[self.rank]
+        res = lib().nvls_ar_add_rmsnorm(self.symm.data_ptrs, self.symm.pad_ptrs, self.symm.mc_ptr, off, rows, H, residual, w, eps, w_offset,
+                                        self.rank, y_sym)
+        return (res[0], res[1]) if w is not None else res[0]
+
+    def align_parity(self):
+        """Symmetric output regions alternate per call and a region may only be rewritten two calls later (the barrier of the
+        call in between proves every peer finished reading it).  A CUDA graph replays a fixed region sequence, so a captured
+        step must use an even number of regions: pad with one barrier if it did not."""
+        if self._ar_calls & 1:
+            self.symm.barrier()
+            self._ar_calls += 1
 
     # ------------------------------------------------------------------ autograd-aware entry points used by parallel/tp.py
     def gemm_rs(self, x, w):

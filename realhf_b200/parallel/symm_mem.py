@@ -159,7 +159,7 @@ class VmmSymmetricBuffer(SymmetricBuffer):
         # rank 0 ships two descriptors (memory + multicast object), the others one: pad to a common count
         if want_mc and self.rank != 0:
             my_fds = [fd, fd]
-        fds = _exchange_fds(my_fds, group, tag=f"{id(self) & 0xffff:x}")
+        fds = _exchange_fds(my_fds, group, tag="vmm")  # the socket names carry a fresh token per exchange (broadcast by rank 0)
         ptrs = []
         for r in range(self.world):
             if r == self.rank:
@@ -176,13 +176,11 @@ class VmmSymmetricBuffer(SymmetricBuffer):
             dist.barrier(group=group)  # every device is part of the object before anybody binds memory
             self.mc_ptr = int(L.mc_bind_and_map(mc_handle, handle, self.total, gran, dev))
             self._mc_handle = mc_handle
-        for r in range(self.world):
-            for f in set(fds[r]):
-                if r != self.rank or f in my_fds:
-                    try:
-                        L.close_fd(f)
-                    except Exception:
-                        pass
+        for f in {f for r in range(self.world) for f in fds[r]}:  # imported (or, for my own, delivered): the mappings keep the memory alive
+            try:
+                L.close_fd(f)
+            except Exception:
+                pass
         self.peers = [L.tensor_from_ptr(p, self.total, dev) for p in ptrs]
         self.local = self.peers[self.rank]
         torch.cuda.synchronize(self.device)

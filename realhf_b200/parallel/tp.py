@@ -33,6 +33,10 @@ def _all_reduce(x, ctx, op=dist.ReduceOp.SUM):
     if _tp(ctx) == 1:
         return x
     x = x.contiguous()
+    fused = getattr(ctx, "symm", None)
+    if fused is not None and op == dist.ReduceOp.SUM and x.is_cuda and not torch.is_grad_enabled() \
+            and x.dtype in (torch.bfloat16, torch.float16) and x.numel() * x.element_size() <= (1 << 20):
+        return fused.all_reduce(x)  # decode-sized message: peer-memory / in-switch all-reduce instead of an NCCL launch
     dist.all_reduce(x, op=op, group=ctx.tp_group)
     return x
 

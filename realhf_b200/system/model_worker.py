@@ -67,11 +67,17 @@ class ModelWorker:
         self.stream = WorkerStream(self.exp, self.trial, self.index)
         # global process group over all model workers
         if self.index == 0:
-            from realhf_b200.system.stream import free_port
-            name_resolve.add(_pg_key(self.exp, self.trial), f"tcp://127.0.0.1:{free_port()}", replace=True)
+            from realhf_b200.system.stream import free_port, host_ip
+            name_resolve.add(_pg_key(self.exp, self.trial), f"tcp://{host_ip()}:{free_port()}", replace=True)
         addr = name_resolve.wait(_pg_key(self.exp, self.trial), timeout=300)
         kw = dict(device_id=self.device) if cfg.device == "cuda" else {}
         dist.init_process_group(cfg.backend, init_method=addr, rank=self.index, world_size=self.count, **kw)
+        # peer-memory paths (CUDA IPC / VMM handles: direct-store reallocation, fused TP kernels, NVLS optimizer) need every
+        # participant on ONE host; across nodes the NCCL paths stay in place
+        hosts = [None] * self.count
+        dist.all_gather_object(hosts, os.uname().nodename)
+        self.worker_hosts = hosts
+        self.single_host = len(set(hosts)) == 1
         # every worker builds the groups of EVERY model in the same order (new_group is collective)
         worker_of: Dict[ModelName, List[int]] = {}
         for sid, wi in cfg.msid2mwid.items():
@@ -88,7 +94,7 @@ class ModelWorker:
                 self.ctxs[name] = ctx
         # fused tensor-parallel GEMM + collective kernels over peer memory (one node, GPUs mutually visible); construction is
         # collective over each TP group, so every member decides from the same config / env
-        if cfg.device == "cuda" and os.environ.get("REAL_FUSED_TP", "1") != "0" and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1":
+        if cfg.device == "cuda" and self.single_host and os.environ.get("REAL_FUSED_TP", "1") != "0" and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1":
             for name in sorted(self.ctxs, key=str):
                 ctx = self.ctxs[name]
                 if ctx.tp_size > 1 and getattr(ctx, "symm", None) is None:
@@ -208,7 +214,15 @@ class ModelWorker:
         if dst_model is not None:
             m = _real(dst_model)
             if not m.instantiated:
-                self._alloc_recv_flat(dst_name, m)
+                if getattr(m, "_offloaded", None) is not None:
+                    # the destination was parked in pinned host memory by an OffloadHook: bring its weights back before
+                    # they are overwritten (eta == 1) or mixed into (EMA, eta != 1: a fresh zero buffer would turn
+                    # ref <- eta*actor + (1-eta)*ref into eta*actor)
+                    m.reload()
+                    if self.device.type == "cuda":
+                        torch.cuda.current_stream(self.device).synchronize()
+                else:
+                    self._alloc_recv_flat(dst_name, m)
             dst_flat = m.flat_param.data
         if dst_model is not None:
             self._host_copy_stale.add(dst_name)
@@ -229,7 +243,7 @@ class ModelWorker:
     # ------------------------------------------------------------------ direct (peer-store) reallocation plumbing
     def _direct_realloc_ok(self, dst_name: ModelName) -> bool:
         return (self.device.type == "cuda" and dst_name.replica_id > 0 and os.environ.get("REAL_REALLOC_DIRECT", "1") != "0"
-                and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1")
+                and os.environ.get("REAL_ISOLATE_GPUS", "0") != "1" and getattr(self, "single_host", True))
 
     def _ipc_key(self, name: ModelName, worker: int) -> str:
         return f"{self.exp}/{self.trial}/realloc_ipc/{name}/{worker}"

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import dataclasses
 import pickle
+import os
 import socket
 import time
 import uuid
@@ -33,7 +34,29 @@ def free_port() -> int:
 
 
 def host_ip() -> str:
-    return "127.0.0.1" if True else socket.gethostbyname(socket.gethostname())
+    """Address other workers use to reach this process (ZMQ master endpoint, torch.distributed rendezvous).
+
+    `REAL_HOST_IP` wins.  Local mode (every worker on this host) publishes loopback: container hostnames often do not
+    resolve.  Any other mode (slurm, ...) publishes a routable address of this host, like the reference
+    (`base/network.py` gethostip): the hostname's address, or, when that is loopback / unresolvable, the source address of
+    the default route."""
+    ip = os.environ.get("REAL_HOST_IP")
+    if ip:
+        return ip
+    if os.environ.get("REAL_MODE", "LOCAL").upper() == "LOCAL":
+        return "127.0.0.1"
+    try:
+        ip = socket.gethostbyname(socket.gethostname())
+        if not ip.startswith("127."):
+            return ip
+    except OSError:
+        pass
+    try:  # no packet is sent: connect() on a UDP socket only selects the outgoing interface
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s:
+            s.connect(("10.255.255.255", 1))
+            return s.getsockname()[0]
+    except OSError:
+        return "127.0.0.1"
 
 
 @dataclasses.dataclass

@@ -56,3 +56,56 @@ def test_sample_distribution_and_greedy():
     tok, lp, _ = lib().sample(logits[:8], None, 8, 1.0, 1.0, -1, False, True, 0, 99, 0, False)
     assert (tok == base[0].argmax()).all()
     torch.testing.assert_close(lp, torch.log_softmax(base[0], 0)[tok], atol=1e-3, rtol=1e-3)
+
+
+def _tiny_llama():
+    from realhf_b200.api.model import ReaLModelConfig
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.ops import gemm as G
+    OF.set_gemm_impl(G.linear)
+    cfg = ReaLModelConfig(n_layers=2, n_kv_heads=4, n_q_heads=8, hidden_dim=1024, intermediate_dim=2816, vocab_size=32000, n_positions=2048,
+                          embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, activation_function="silu", scale_attn_by_inverse_layer_idx=False,
+                          use_attention_bias=False, use_attn_proj_bias=False, use_mlp_bias=False, layer_norm_type="rms", mlp_type="llama",
+                          apply_rotary=True)
+    m = ReaLModel(cfg, dtype=torch.bfloat16, device=torch.device(DEV)).init_random_fast(std=0.05)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m.eval()
+
+
+@pytest.mark.parametrize("greedy", [True, False])
+def test_in_graph_sampling_matches_eager_decode_loop(greedy, monkeypatch):
+    """The sampling kernel as the tail of the captured decode step (device-side step counters, history buffers, next-token
+    feed, EOS bookkeeping) must reproduce the eager loop: exactly for greedy decoding; for sampling the log-probs must be those
+    of the sampled tokens under the model (teacher-forced forward) and EOS / padding semantics must hold."""
+    m = _tiny_llama()
+    lens = [5, 17, 9, 30]
+    ids = torch.randint(3, 32000, (sum(lens),), device=DEV)
+    cu = torch.tensor([0, 5, 22, 31, 61], dtype=torch.int32, device=DEV)
+    g = GenerationHyperparameters(max_new_tokens=24, min_new_tokens=6, greedy=greedy, top_k=50, top_p=0.9, temperature=0.8,
+                                  use_cuda_graph=True, force_cudagraph_recapture=True)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("REAL_GEN_SAMPLE_IN_GRAPH", mode)
+        gen.seed_sampling(7)
+        outs[mode], _ = gen.generate(m, ids, cu, g, eos_id=2, pad_id=0)
+    a, b = outs["1"], outs["0"]
+    assert a.tokens.shape == b.tokens.shape == (4, 24)
+    if greedy:
+        assert torch.equal(a.tokens, b.tokens)
+        torch.testing.assert_close(a.logprobs, b.logprobs, atol=1e-3, rtol=1e-3)
+        assert torch.equal(a.gen_lens, b.gen_lens)
+        return
+    # sampling: teacher-forced check of the in-graph path
+    assert a.mask_bits is not None and a.mask_bits.shape == (4, 24, 4000)
+    for i, L in enumerate(lens):
+        n = int(a.gen_lens[i])
+        seq = torch.cat([ids[int(cu[i]): int(cu[i + 1])], a.tokens[i, :n]])
+        out = m(input_ids=seq, cu_seqlens=torch.tensor([0, seq.numel()], dtype=torch.int32, device=DEV), max_seqlen=int(seq.numel()))
+        lg = out.logits.float()[L - 1: L - 1 + n] / 0.8
+        removed = OF.unpack_mask_bits(a.mask_bits[i, :n], 32000)
+        assert not removed[torch.arange(n), a.tokens[i, :n]].any(), "sampled a filtered token"
+        lp_ref = torch.log_softmax(lg.masked_fill(removed, float("-inf")), -1)[torch.arange(n), a.tokens[i, :n]]
+        torch.testing.assert_close(a.logprobs[i, :n], lp_ref, atol=0.08, rtol=0.05)  # bf16 decode vs packed forward
+        assert (a.tokens[i, :min(n, 6) - 1] != 2).all()          # EOS suppressed before min_new_tokens
+        assert (a.tokens[i, n:] == 0).all() and (a.logprobs[i, n:] == 0).all()  # padding after EOS
