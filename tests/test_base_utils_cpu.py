@@ -12,9 +12,14 @@ from realhf_b200.base import name_resolve, timeutil
 from realhf_b200.base.topology import ProcessTopology
 
 
-@pytest.mark.parametrize("kind", ["memory", "nfs"])
+@pytest.mark.parametrize("kind", ["memory", "nfs", "redis"])
 def test_name_resolve_backends(tmp_path, kind):
-    repo = name_resolve.make_repository(kind, **({"record_root": str(tmp_path)} if kind == "nfs" else {}))
+    srv = None
+    if kind == "redis":  # the repository speaks RESP2 itself; the test double is the bundled mini server (with AUTH)
+        srv = name_resolve.MiniRedisServer(password="s3cret").start()
+        repo = name_resolve.make_repository("redis", host=srv.host, port=srv.port, password="s3cret")
+    else:
+        repo = name_resolve.make_repository(kind, **({"record_root": str(tmp_path)} if kind == "nfs" else {}))
     repo.add("exp/t/a", "1")
     with pytest.raises(name_resolve.NameEntryExistsError):
         repo.add("exp/t/a", "2")
@@ -37,6 +42,29 @@ def test_name_resolve_backends(tmp_path, kind):
     repo.clear_subtree("exp/t")
     assert repo.find_subtree("exp/t") == []
     repo.reset()
+    if srv is not None:
+        srv.stop()
+
+
+def test_redis_lease_expires_without_keepalive_and_survives_with_it():
+    """TTL'd keys are leases: the server drops them when the owner stops refreshing (a silently dead worker reads LOST), the
+    keep-alive thread of a live owner keeps them; a second client sees both; wrong passwords are refused."""
+    srv = name_resolve.MiniRedisServer(password="pw").start()
+    owner = name_resolve.make_repository("redis", host=srv.host, port=srv.port, password="pw")
+    owner.KEEPALIVE_POLL = 0.1
+    other = name_resolve.make_repository("redis", host=srv.host, port=srv.port, password="pw")
+    owner.add("lease/kept", "1", keepalive_ttl=1)
+    other._conn.call("SET", "lease/orphan", "1", "EX", 1)  # nobody refreshes this one
+    time.sleep(2.2)
+    assert other.get("lease/kept") == "1"
+    with pytest.raises(name_resolve.NameEntryNotFoundError):
+        other.get("lease/orphan")
+    owner.reset()  # delete_on_exit keys go away with their owner
+    with pytest.raises(name_resolve.NameEntryNotFoundError):
+        other.get("lease/kept")
+    with pytest.raises(RuntimeError):
+        name_resolve.make_repository("redis", host=srv.host, port=srv.port, password="wrong").get("x")
+    srv.stop()
 
 
 def test_watch_names_fires_when_a_key_disappears(tmp_path):
