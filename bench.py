@@ -121,6 +121,112 @@ def run_reference(args):
     return 0
 
 
+def run_master_runtime(args):
+    """`--runtime master`: the SAME PPO config driven through the production runtime -- quickstart config -> launcher
+    (`apps/main.py::main_start`) -> one master worker (asyncio DFG walker, metadata only) + one model worker process per GPU over
+    ZMQ / NCCL, dataset on disk, tokenizer, data transfer between MFCs -- instead of the in-process SPMD executor.  The step time
+    is the master's host clock around one full DFG traversal (what the reference reports as e2e time,
+    system/master_worker.py:1353-1358); warm-up steps are dropped.  Random-init weights (`init_from_scratch`), synthetic prompts
+    padded to `prompt_len`, `min_new_tokens == max_new_tokens` as in the reference's benchmark recipe (docs quickstart.rst:287-297)."""
+    import re
+    import tempfile
+    import uuid
+
+    import torch
+
+    from realhf_b200.api.model import ReaLModelConfig
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    from realhf_b200.models import hf_io
+    n = args.gpus
+    root = tempfile.mkdtemp(prefix="realhf_b200_bench_")
+    os.environ.setdefault("REAL_FILEROOT", os.path.join(root, "fileroot"))
+    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")  # the worker processes import this checkout
+    os.environ["REAL_FAST_INIT"] = "1"  # device-side random init (a host-side draw of 4 x 6.7e9 normals takes minutes)
+    # tokenizer + config-only "checkpoint" directories
+    from tokenizers import Tokenizer, models, pre_tokenizers, trainers
+    from transformers import PreTrainedTokenizerFast
+    import random
+    rng = random.Random(0)
+    words = ["".join(rng.choice("abcdefghijklmnop") for _ in range(rng.randint(2, 6))) for _ in range(400)]
+    tk = Tokenizer(models.WordLevel(unk_token="[UNK]"))
+    tk.pre_tokenizer = pre_tokenizers.Whitespace()
+    tk.train_from_iterator([" ".join(words)], trainers.WordLevelTrainer(vocab_size=1000, special_tokens=["[PAD]", "[EOS]", "[UNK]"]))
+    fast = PreTrainedTokenizerFast(tokenizer_object=tk, pad_token="[PAD]", eos_token="[EOS]", unk_token="[UNK]")
+    dirs = {}
+    for role, critic in (("actor", False), ("critic", True)):
+        d = os.path.join(root, role)
+        os.makedirs(d)
+        cfg = ReaLModelConfig(n_layers=args.layers, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008, vocab_size=32000,
+                              n_positions=4096, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, layer_norm_epsilon=1e-5,
+                              activation_function="silu", scale_attn_by_inverse_layer_idx=False, use_attention_bias=False,
+                              use_attn_proj_bias=False, use_mlp_bias=False, layer_norm_type="rms", mlp_type="llama", apply_rotary=True,
+                              is_critic=critic)
+        if args.tiny:
+            cfg.hidden_dim, cfg.intermediate_dim, cfg.n_q_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab_size = 256, 512, 4, 4, 64, 1024
+        fam = hf_io.family("llama")
+        hf_cfg = fam.config_to_hf(cfg)
+        hf_cfg.architectures = [fam.hf_cls_name]
+        hf_cfg.save_pretrained(d)
+        fast.save_pretrained(d)
+        dirs[role] = d
+    data = os.path.join(root, "prompts.jsonl")
+    total = args.warmup + args.steps
+    with open(data, "w") as f:
+        for i in range(args.prompts * total):
+            f.write(json.dumps(dict(id=i, prompt=" ".join(rng.choice(words) for _ in range(2 * args.prompt_len)))) + "\n")
+    dev = "cpu" if args.tiny and not torch.cuda.is_available() else "cuda"
+    exp_name = f"bench-{uuid.uuid4().hex[:6]}"
+    qs = ["ppo", f"experiment_name={exp_name}", "trial_name=t0", f"device={dev}", f"dtype={'fp32' if dev == 'cpu' else 'bf16'}",
+          f"n_gpus_per_node={n}", "allocation_mode=manual", f"dataset.path={data}", f"dataset.train_bs_n_seqs={args.prompts}",
+          f"dataset.max_prompt_len={args.prompt_len}", "dataset.pad_to_max_length=true",
+          f"ppo.gen.max_new_tokens={args.new_tokens}", f"ppo.gen.min_new_tokens={args.new_tokens}", "ppo.gen.top_p=0.9", "ppo.gen.top_k=1000",
+          "ppo.gen.use_cuda_graph=true", "ppo.gen.force_cudagraph_recapture=true", "ppo.ppo_n_minibatches=4",
+          "exp_ctrl.total_train_epochs=1", f"exp_ctrl.benchmark_steps={total}"]
+    inf_mbs = 2 if (args.prompts // n) * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
+    for role, path in (("actor", dirs["actor"]), ("ref", dirs["actor"]), ("critic", dirs["critic"]), ("rew", dirs["critic"])):
+        qs += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.init_from_scratch=true",
+               f"{role}.gradient_checkpointing={'auto' if dev == 'cuda' else 'false'}"]
+    for role in ("actor", "critic"):
+        qs += [f"{role}.optimizer.state_dtype=bf16", f"{role}.optimizer.use_master_weights=false", f"{role}.optimizer.grad_dtype=bf16",
+               f"{role}.optimizer.share_grad_buffer=true", f"{role}.optimizer.lr_scheduler_type=constant", f"{role}.optimizer.warmup_steps_proportion=0.0"]
+        if dev == "cpu":
+            qs += [f"{role}.optimizer.state_dtype=fp32", f"{role}.optimizer.grad_dtype=fp32"]
+    for mfc in ("actor_gen", "actor_train", "critic_train", "critic_inf", "ref_inf", "rew_inf"):
+        qs += [f"{mfc}.parallel.data_parallel_size={n}"]
+    for mfc in ("critic_inf", "ref_inf", "rew_inf"):
+        qs += [f"{mfc}.n_mbs={inf_mbs}"]
+    exp = build_experiment(qs)
+    t0 = time.perf_counter()
+    main_start(exp, timeout=3600)
+    wall_total = time.perf_counter() - t0
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp_name, "t0", "master_worker-0")).read()
+    steps = [(float(m.group(1)), m.group(2)) for m in re.finditer(r"step \d+ \(epoch[^)]*\) e2e ([0-9.]+)s; (.*)", log)]
+    assert len(steps) >= total, f"master log has {len(steps)} steps, expected {total}:\n{log[-3000:]}"
+    timed = steps[args.warmup: total]
+    secs = sum(t for t, _ in timed)
+    mfc = {}
+    for _, line in timed:
+        for part in line.split(", "):
+            k, v = part.rsplit(" ", 1)
+            mfc[k] = mfc.get(k, 0.0) + float(v.rstrip("s")) * 1e3 / len(timed)
+    tokens_per_step = args.prompts * (args.prompt_len + args.new_tokens)
+    value = tokens_per_step * len(timed) / secs
+    headline = args.layers == 32 and args.prompts == 128 and args.prompt_len == 128 and args.new_tokens == 512 and not args.tiny
+    print(json.dumps({
+        "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": n, "steps": len(timed), "warmup": args.warmup,
+        "ms_per_step": round(secs * 1e3 / len(timed), 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3) if headline else None, "dtype": "bf16" if dev == "cuda" else "fp32",
+        "data": "synthetic prompts (random words, padded to prompt_len), random-init weights",
+        "runtime": "master/worker (quickstart -> launcher -> master worker + one model worker process per GPU, ZMQ control plane)",
+        "timer": "master worker host clock around each DFG traversal (includes dataset fetch, data transfer, all six MFCs, replies)",
+        "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline else " [DEBUG shapes]"),
+                   "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens, "parallelism": f"dp{n} (all 6 MFCs), ZeRO-1 flat AdamW",
+                   "mfc_ms": {k: round(v, 1) for k, v in mfc.items()}, "launch_to_exit_s": round(wall_total, 1)},
+        "impl": "ours"}), flush=True)
+    return 0
+
+
 def choose_gen_tp(world: int, n_prompts: int, prompt_len: int, new_tokens: int, n_layers: int) -> dict:
     """Generation layout for this node size, picked by the allocation search's cost model (`search/engine.py::estimate`, the
     function the `search` / `heuristic` allocation modes use) over every tp x dp factorisation of the node: decode streams
@@ -157,6 +263,10 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=512)
     ap.add_argument("--gemm", default=os.environ.get("REAL_GEMM", "tcgen05"), choices=["tcgen05", "cublas"])
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--runtime", default="spmd", choices=["spmd", "master"],
+                    help="spmd (default): every rank walks the DFG in-process (launched by torchrun for N > 1); master: the production "
+                         "master/worker runtime launched through the quickstart + local scheduler (run WITHOUT torchrun: it spawns its own workers)")
+    ap.add_argument("--tiny", action="store_true", help="debug only: toy model shapes for --runtime master (CPU smoke test of the arm)")
     ap.add_argument("--optimizer", default="lean", choices=["lean", "fp32"],
                     help="lean (default at every N, so the scaling curve compares like with like): bf16 Adam moments + stochastic "
                          "rounding, no master copy -- what fits four 7B models + optimizer states on ONE GPU; fp32: fp32 master weights + "
@@ -171,6 +281,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.runtime == "master":
+        return run_master_runtime(args)
 
     # four 7B models + optimizer state + a 43 GB KV cache leave little slack on one GPU: expandable segments keep the caching
     # allocator from fragmenting (a failed 43 GB request makes it free and re-cudaMalloc its whole cache inside the timed region)

@@ -55,7 +55,7 @@ class ModelTrainEvalConfig:
     backend: str = "train"  # train (aliases: megatron, deepspeed) | inference
     path: str = ""
     lora: Optional[LoRAConfig] = None
-    gradient_checkpointing: bool = True
+    gradient_checkpointing: Union[bool, str] = True   # true | false | auto (recompute only the blocks the free HBM requires)
     enable_fp16: bool = False
     enable_bf16: bool = True
     offload: bool = False

@@ -37,7 +37,11 @@ def make_real_model(name: ModelName, device, model_path: str, is_critic: bool, i
     m.hf_family = hf_model_family
     if instantiate:
         if init_from_scratch or not model_path:
-            m.instantiate(seed=1)
+            import os
+            if os.environ.get("REAL_FAST_INIT", "0") == "1" and m.device.type == "cuda":
+                m.init_random_fast(seed=1)  # benchmarks: device-side draw (NOT layout-invariant like `instantiate`)
+            else:
+                m.instantiate(seed=1)
         else:
             hf_io.load_from_hf(m, hf_model_family, model_path, init_critic_from_actor=init_critic_from_actor)
     if tokenizer is None:

@@ -369,3 +369,21 @@ def test_graceful_stop_saves_recover_states_and_resume_continues(tmp_path):
     M.main_start(build_experiment(args("resume") + [f"exp_ctrl.benchmark_steps={s1[-1] + 4}"]), timeout=600)
     s2 = steps()
     assert s2[: len(s1) + 3] == list(range(len(s1) + 3)), (s1[-3:], s2[len(s1) - 2: len(s1) + 4])
+
+
+def test_bench_master_runtime_arm_tiny(tmp_path):
+    """`bench.py --runtime master` drives the benchmark config through quickstart -> launcher -> master + model workers and
+    prints the bench JSON line (toy shapes on CPU here; the GPU box runs it with the headline shapes)."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, REAL_FILEROOT=str(tmp_path / "fileroot"), REAL_NAME_RESOLVE_ROOT=str(tmp_path / "nr"))
+    p = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--runtime", "master", "--tiny", "--gpus", "2", "--layers", "2",
+                        "--prompts", "8", "--prompt-len", "8", "--new-tokens", "6", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["n_gpus"] == 2 and out["steps"] == 2 and out["value"] > 0
+    assert set(out["config"]["mfc_ms"]) == {"actor_gen", "rew_inf", "ref_inf", "critic_inf", "actor_train", "critic_train"}
