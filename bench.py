@@ -256,7 +256,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torchlib"],
+                    help="ours; reference (the unmodified reference: unavailable offline, see DESIGN.md); torchlib: an on-box A/B arm that is "
+                         "NOT the reference -- this repo's executor with library kernels (cuBLAS GEMMs, flash-attn varlen attention, "
+                         "F.layer_norm, NCCL reduce-scatter / all-gather / all-reduce) in place of the sm_100a kernels")
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers (result is then NOT the headline config)")
     ap.add_argument("--prompts", type=int, default=128)
     ap.add_argument("--prompt-len", type=int, default=128)
@@ -281,6 +284,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torchlib":
+        args.gemm = "cublas"
+        os.environ.update(REAL_ATTN="flash", REAL_ATTN_BWD="flash", REAL_LAYERNORM="torch", REAL_ZERO_COMM="nccl", REAL_TP_NVLS="0",
+                          REAL_ZERO_OVERLAP="0")
     if args.runtime == "master":
         return run_master_runtime(args)
 
@@ -490,7 +497,7 @@ def main():
                        "peak_reserved_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1),
                        "alloc_retries": int(torch.cuda.memory_stats().get("num_alloc_retries", 0)),
                        "allocator": os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "")},
-            "impl": "ours",
+            "impl": "ours" if args.impl == "ours" else "torchlib (cuBLAS + flash-attn + NCCL on this repo's executor; NOT the reference)",
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -67,6 +67,13 @@ class ReaLEngine(PipelinableEngine):
     def config(self):
         return self.module.config
 
+    def _check_ep(self):
+        """The fused expert-parallel exchange sizes its receive buffers for `cap_factor` x the balanced load and reports an
+        overflow through a device flag: read it once per engine call (the only host sync of the MoE path)."""
+        ep = getattr(self.ctx, "_fused_ep", None)
+        if ep is not None:
+            ep.raise_if_overflow()
+
     # ------------------------------------------------------------------ single-stage forward
     def _forward_mb(self, mb: SequenceSample) -> ModelOutput:
         m = self.module
@@ -100,6 +107,7 @@ class ReaLEngine(PipelinableEngine):
                     stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / len(mbs)
         ost = self.optim.step(version_steps)
         self.optim.release()
+        self._check_ep()
         stats = dict(stats)
         stats.update(ost)
         return stats
@@ -139,6 +147,7 @@ class ReaLEngine(PipelinableEngine):
             for mb in input_.split(min(n_mbs, input_.bs)):
                 out = self._forward_mb(mb)
                 outs.append(post_hook(out, mb) if post_hook is not None else out.logits)
+            self._check_ep()
             return aggregate_fn(outs) if len(outs) > 1 else outs[0]
         finally:
             if self.optim is not None:

@@ -9,6 +9,7 @@ ranks and tokens travel by all-to-all (`dispatch -> grouped GEMM -> combine`); t
 
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -139,7 +140,15 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
     if ep and sp:
         from realhf_b200.parallel import ep as EP
         x_sorted = h.index_select(0, tok)
-        y_sorted = EP.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ctx.tp_group)
+        fep = None
+        if h.is_cuda and h.dtype in (torch.bfloat16, torch.float16) and _use_grouped_kernel(x_sorted, w_gu, w_dn) \
+                and os.environ.get("REAL_EP_FUSED", "1") == "1":
+            fep = EP.fused_ep_for(ctx, E, H, h.dtype, h.device)
+        if fep is not None and x_sorted.shape[0] <= fep.max_rows:
+            # device-driven peer-store dispatch / combine around the grouped GEMMs (csrc/ep.cu): no host sync in this layer
+            y_sorted = EP.dispatch_compute_combine_fused(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, fep)
+        else:
+            y_sorted = EP.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ctx.tp_group)
         return torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
     if ep:
         # replicated tokens: keep only the assignments of my experts, all-reduce the partial outputs

@@ -32,6 +32,11 @@ int rb_mc_add_device(uint64_t mc, int dev);
 int rb_mc_bind_and_map(uint64_t mc, uint64_t mem_handle, int64_t size, int64_t align, int dev, uint64_t* mc_ptr);
 int rb_mc_unbind(uint64_t mc, int dev, int64_t size);
 int rb_close_fd(int fd);
+// ep.cu
+int rb_ep_plan(const int64_t* data_ptrs, const int64_t* pad_ptrs, int64_t post_off, const int* counts, int E, int e_local, int rank, int world,
+               int parity, int* send_tab, int* ret_tab, int* per_expert, int* overflow, int cap_rows, cudaStream_t s);
+int rb_ep_move_rows(const int64_t* data_ptrs, const int64_t* pad_ptrs, const int* table, int n_seg, const void* src, int64_t src_pitch,
+                    int64_t dst_off, int64_t dst_pitch, int row_bytes, int dst_cap_rows, int rank, int world, int blocks, cudaStream_t s);
 // nvls.cu
 int rb_nvls_allreduce(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_t mc, const void* in, void* out, int64_t nbytes,
                       int64_t off_in, int64_t off_out, int rank, int world, int dt, int mode, int max_blocks, cudaStream_t s);
@@ -236,10 +241,16 @@ int64_t mc_bind_and_map(int64_t mc, int64_t mem_handle, int64_t nbytes, int64_t 
 void mc_unbind(int64_t mc, int64_t device, int64_t nbytes) { rb_mc_unbind((uint64_t)mc, (int)device, nbytes); }
 void close_fd(int64_t fd) { rb_close_fd((int)fd); }
 
-// A tensor view of raw device memory owned elsewhere (the symmetric buffer object keeps the mapping alive).
+// A tensor view of raw device memory owned elsewhere (the symmetric buffer object keeps the mapping alive).  Built from a
+// hand-made storage: `at::from_blob` asks the driver which device the pointer belongs to and rejects VMM mappings of a PEER's
+// physical memory ("device of data cuda:1") although they are perfectly usable from this device.
 Tensor tensor_from_ptr(int64_t ptr, int64_t nbytes, int64_t device) {
-  return at::from_blob(reinterpret_cast<void*>(ptr), {nbytes}, [](void*) {},
-                       at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (c10::DeviceIndex)device));
+  const at::Device dev(at::kCUDA, (c10::DeviceIndex)device);
+  c10::DataPtr dp(reinterpret_cast<void*>(ptr), reinterpret_cast<void*>(ptr), [](void*) {}, dev);
+  c10::Storage storage(c10::Storage::use_byte_size_t(), (size_t)nbytes, std::move(dp), /*allocator=*/nullptr, /*resizable=*/false);
+  auto t = at::empty({0}, at::TensorOptions().dtype(at::kByte).device(dev));
+  t.set_(storage, 0, {nbytes}, {1});
+  return t;
 }
 
 // ---- NVLS collectives (nvls.cu)
@@ -308,7 +319,39 @@ void nvls_allgather(std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptr
   TORCH_CHECK(rc == 0, "nvls_allgather failed: ", rc);
 }
 
+// ---- expert-parallel token exchange (ep.cu)
+// counts [E] int32 (device) -> [send_tab [E,4], ret_tab [e_local*world,4], per_expert [e_local+1]]; `overflow` is set on the device
+// when more rows than cap_rows would arrive here.
+std::vector<Tensor> ep_plan(const Tensor& counts, std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t post_off, int64_t e_local,
+                            int64_t rank, int64_t parity, Tensor overflow, int64_t cap_rows) {
+  TORCH_CHECK(counts.is_cuda() && counts.scalar_type() == at::kInt && counts.is_contiguous());
+  TORCH_CHECK(overflow.scalar_type() == at::kInt && overflow.is_cuda());
+  const int64_t E = counts.numel(), world = (int64_t)data_ptrs.size();
+  c10::cuda::CUDAGuard g(counts.device());
+  auto opt = counts.options();
+  auto send_tab = at::empty({E, 4}, opt), ret_tab = at::empty({e_local * world, 4}, opt), per_expert = at::empty({e_local + 1}, opt);
+  int rc = rb_ep_plan(data_ptrs.data(), pad_ptrs.data(), post_off, counts.data_ptr<int>(), (int)E, (int)e_local, (int)rank, (int)world, (int)parity,
+                      send_tab.data_ptr<int>(), ret_tab.data_ptr<int>(), per_expert.data_ptr<int>(), overflow.data_ptr<int>(), (int)cap_rows,
+                      at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "ep_plan failed: ", rc);
+  return {send_tab, ret_tab, per_expert};
+}
+
+// Store the row groups of `src` listed in `table` into the peers' buffers at byte offset dst_off (rows of src.size(1) elements).
+void ep_move_rows(const Tensor& src, const Tensor& table, std::vector<int64_t> data_ptrs, std::vector<int64_t> pad_ptrs, int64_t dst_off,
+                  int64_t dst_cap_rows, int64_t rank, int64_t blocks) {
+  TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.stride(1) == 1 && table.scalar_type() == at::kInt && table.is_contiguous());
+  c10::cuda::CUDAGuard g(src.device());
+  const int64_t row_bytes = src.size(1) * src.element_size();
+  int rc = rb_ep_move_rows(data_ptrs.data(), pad_ptrs.data(), table.data_ptr<int>(), (int)table.size(0), src.data_ptr(),
+                           src.stride(0) * src.element_size(), dst_off, row_bytes, (int)row_bytes, (int)dst_cap_rows, (int)rank,
+                           (int)data_ptrs.size(), (int)blocks, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "ep_move_rows failed: ", rc);
+}
+
 void register_comm_ops(torch::Library& m) {
+  m.def("ep_plan(Tensor counts, int[] data_ptrs, int[] pad_ptrs, int post_off, int e_local, int rank, int parity, Tensor(a!) overflow, int cap_rows) -> Tensor[]", &ep_plan);
+  m.def("ep_move_rows(Tensor src, Tensor table, int[] data_ptrs, int[] pad_ptrs, int dst_off, int dst_cap_rows, int rank, int blocks) -> ()", &ep_move_rows);
   m.def("vmm_multicast_supported(int device) -> int", &vmm_multicast_supported);
   m.def("vmm_granularity(int device, int ndev) -> int", &vmm_granularity);
   m.def("vmm_alloc(int nbytes, int align, int device) -> int[]", &vmm_alloc);

@@ -261,3 +261,58 @@ def test_tp_decode_with_in_switch_allreduce_matches_single_gpu(world):
     first_fork = (res[0]["tokens"] != ref["tokens"]).float().argmax(1)
     same = (res[0]["tokens"] == ref["tokens"]).all(1)
     assert (same | (first_fork >= 1)).all()
+
+
+def _ep_worker(rank, world, fused):
+    """Mixtral-style MoE under expert parallelism + sequence parallelism on `world` GPUs: SFT steps with the device-driven
+    peer-store dispatch / combine (csrc/ep.cu) or the NCCL all-to-all path; returns losses and a weight checksum."""
+    import test_parallel_cpu as T
+    os.environ["REAL_EP_FUSED"] = "1" if fused else "0"
+    os.environ["REAL_EP_MAX_ROWS"] = "4096"
+    from realhf_b200.ops import functional as OF
+    from realhf_b200.ops import gemm as G
+    OF.set_gemm_impl(G.linear)
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.ops import launches
+    cfg = hf_io.family("mixtral").make_test_config()
+    cfg.hidden_dim, cfg.intermediate_dim, cfg.n_q_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab_size, cfg.n_layers = 512, 1024, 4, 4, 128, 1024, 2
+    cfg.moe.num_experts, cfg.moe.top_k = 8, 2
+    cfg.moe.expert_parallel = world > 1
+    cfg.moe.aux_loss_coeff = 0.0
+    dev = torch.device("cuda", rank)
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl", sequence_parallel=world > 1) \
+        if world > 1 else ParallelContext.single()
+    m = ReaLModel(cfg, ctx, dtype=torch.bfloat16, device=dev).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-3, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant",
+                                        grad_dtype="fp32")).initialize(Model(ModelName("m", 0), m, tok, dev), FinetuneSpec(1, 10, 10))
+    batch = T._batch(16, vocab=1024)
+    batch.to_device(dev)
+    launches.reset()
+    losses = [float(basic.SFTInterface().train_step(model, batch, n_mbs=1)["loss"]) for _ in range(3)]
+    return dict(losses=losses, ep_ops={k: v for k, v in launches.by_op.items() if k.startswith("ep_")})
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_expert_parallel_matches_all_to_all_and_single_gpu(world):
+    _need(world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from realhf_b200.base.testing import run_distributed
+    ref = run_distributed(_ep_worker, 1, backend="nccl", fused=False)[0]
+    a2a = run_distributed(_ep_worker, world, backend="nccl", fused=False)
+    fus = run_distributed(_ep_worker, world, backend="nccl", fused=True)
+    assert fus[0]["ep_ops"].get("ep_plan", 0) > 0 and fus[0]["ep_ops"].get("ep_move_rows", 0) > 0, fus[0]["ep_ops"]
+    assert not a2a[0]["ep_ops"]
+    for r in fus + a2a:
+        for x, y in zip(r["losses"], ref["losses"]):
+            assert abs(x - y) < 5e-2 * max(1.0, abs(y)), (r["losses"], ref["losses"])
+    for x, y in zip(fus[0]["losses"], a2a[0]["losses"]):
+        assert abs(x - y) < 2e-2 * max(1.0, abs(y)), (fus[0]["losses"], a2a[0]["losses"])
