@@ -348,33 +348,33 @@ class ReaLModel(nn.Module):
         keep = torch.empty_like(x).bernoulli_(1.0 - p, generator=self.shared_generator(x.device))
         return x * keep * (1.0 / (1.0 - p))
 
-    def _ckpt_block(self, i, x, position_ids, cu_seqlens, max_seqlen):
+    def _ckpt_block(self, i, x, d, position_ids, cu_seqlens, max_seqlen):
         """Activation checkpointing of one block.  torch's checkpoint replays the GLOBAL generators; the TP-shared generator
         is ours to replay: the recomputation must see the state the first pass saw, and must not disturb the live state."""
         uses_shared = self.training and self.ctx.tp_size > 1 and not self.sequence_parallel and self.config.resid_pdrop > 0
         if not uses_shared:
-            return checkpoint(self._block_packed, i, x, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
+            return checkpoint(self._block_packed, i, x, d, position_ids, cu_seqlens, max_seqlen, use_reentrant=False)
         g = self.shared_generator(x.device)
         at_forward = g.get_state()
         calls = [0]
 
-        def run(x_):
+        def run(x_, d_):
             calls[0] += 1
             if calls[0] == 1:
-                return self._block_packed(i, x_, position_ids, cu_seqlens, max_seqlen)
+                return self._block_packed(i, x_, d_, position_ids, cu_seqlens, max_seqlen)
             live = g.get_state()
             g.set_state(at_forward)
             try:
-                return self._block_packed(i, x_, position_ids, cu_seqlens, max_seqlen)
+                return self._block_packed(i, x_, d_, position_ids, cu_seqlens, max_seqlen)
             finally:
                 g.set_state(live)
-        return checkpoint(run, x, use_reentrant=False)
+        return checkpoint(run, x, d, use_reentrant=False)
 
-    def _attention_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink: Optional[list]):
+    def _attention_packed(self, i: int, h, position_ids, cu_seqlens, max_seqlen, kv_sink: Optional[list]):
+        """Attention branch of block i on the already-normalised input h."""
         c = self.config
         nq, nkv = self._local_heads()
         hd = c.head_dim
-        h = self._norm(x, f"{i}.attn.ln")
         qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, self.sequence_parallel)
         if c.apply_rotary:
             cos, sin = self.rope_tables(max_seqlen)
@@ -407,12 +407,28 @@ class ReaLModel(nn.Module):
             o = TP.row_linear(a, self.p[f"{i}.mlp.proj.weight"], self._w(f"{i}.mlp.proj.bias"), self.ctx, sp)
         return self._dropout(o, c.resid_pdrop)
 
-    def _block_packed(self, i: int, x, position_ids, cu_seqlens, max_seqlen, kv_sink=None):
-        x = x + self._attention_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
-        x = x + self._mlp(i, x)
+    def _add_norm(self, x, d, prefix: str):
+        """(normalised activations, residual stream) at a layer boundary.  `d` is the previous branch's output that has not been
+        added to the residual stream yet: for RMSNorm models the add is fused into the norm kernel (forward AND backward,
+        `OF.add_rmsnorm`), which removes every eager residual add / gradient-accumulation add from a training step."""
+        c = self.config
+        if d is None:
+            return self._norm(x, prefix), x
+        if c.layer_norm_type is not None:
+            return OF.add_rmsnorm(d, x, self.p[f"{prefix}.weight"], c.layer_norm_epsilon, 1.0 if c.layer_norm_type == "gemma" else 0.0)
+        x = x + d
+        return self._norm(x, prefix), x
+
+    def _block_packed(self, i: int, x, d, position_ids, cu_seqlens, max_seqlen, kv_sink=None):
+        """One transformer block on the packed batch.  Takes and returns (residual stream, pending branch output)."""
+        h, x = self._add_norm(x, d, f"{i}.attn.ln")
+        o = self._attention_packed(i, h, position_ids, cu_seqlens, max_seqlen, kv_sink)
+        h2, x = self._add_norm(x, o, f"{i}.mlp.ln")
+        d = self._mlp(i, x, h2)
         if i == self.config.n_layers:
-            x = self._norm(x, f"{i}.ln_f")
-        return x
+            x, _ = self._add_norm(x, d, f"{i}.ln_f")
+            d = None
+        return x, d
 
     def head_weight(self) -> Optional[torch.Tensor]:
         c = self.config
@@ -460,6 +476,7 @@ class ReaLModel(nn.Module):
         # armed by the optimizer for the last micro-batch of a step: marks where the gradients of all later layers are final,
         # so their buckets are reduce-scattered while the earlier layers are still in backward (engine/optim.py)
         gb = getattr(self, "_grad_boundary", None) if torch.is_grad_enabled() else None
+        d = None  # branch output not yet folded into the residual stream (see _add_norm)
         for i in self.layers:
             if i == 0:
                 x = self._embed(input_ids, position_ids)
@@ -467,9 +484,11 @@ class ReaLModel(nn.Module):
                 if gb is not None and x.requires_grad:
                     x = gb(x, i)
                 if ckpt and i < first_kept:
-                    x = self._ckpt_block(i, x, position_ids, cu_seqlens, max_seqlen)
+                    x, d = self._ckpt_block(i, x, d, position_ids, cu_seqlens, max_seqlen)
                 else:
-                    x = self._block_packed(i, x, position_ids, cu_seqlens, max_seqlen, kv_sink)
+                    x, d = self._block_packed(i, x, d, position_ids, cu_seqlens, max_seqlen, kv_sink)
+        if d is not None:  # a pipeline stage that does not end with the final norm hands on the summed stream
+            x = x + d
         if not self.is_last_stage:
             return x
         if gb is not None and x.requires_grad:

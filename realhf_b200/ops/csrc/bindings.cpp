@@ -45,7 +45,7 @@ int rb_layernorm_fwd(const void*, const void*, const void*, void*, float*, float
 int rb_layernorm_bwd_num_partials();
 int rb_layernorm_bwd(const void*, const void*, const void*, const float*, const float*, void*, float*, float*, void*, void*, int64_t, int,
                      int, cudaStream_t);
-int rb_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, void*, int64_t, int, float, int, cudaStream_t);
+int rb_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, void*, int64_t, int, float, int, const void*, cudaStream_t);
 int rb_rope_inplace(void*, const float*, const float*, const int*, int64_t, int, int, int64_t, int, int, int, int, cudaStream_t);
 int rb_gated_act_fwd(const void*, void*, int64_t, int, int, int, cudaStream_t);
 int rb_gated_act_bwd(const void*, const void*, void*, int64_t, int, int, int, cudaStream_t);
@@ -165,8 +165,10 @@ std::vector<Tensor> rmsnorm_fwd(const Tensor& x, const c10::optional<Tensor>& re
   return {y, rstd};
 }
 
-std::vector<Tensor> rmsnorm_bwd(const Tensor& x, const Tensor& w, const Tensor& dy, const Tensor& rstd, double w_offset) {
+std::vector<Tensor> rmsnorm_bwd(const Tensor& x, const Tensor& w, const Tensor& dy, const Tensor& rstd, double w_offset,
+                                const c10::optional<Tensor>& dres) {
   CHECK_IN(x); CHECK_IN(w); CHECK_IN(dy); CHECK_IN(rstd);
+  if (dres.has_value()) { CHECK_IN((*dres)); TORCH_CHECK(dres->numel() == x.numel() && dres->scalar_type() == x.scalar_type()); }
   const int H = x.size(-1);
   const int64_t rows = x.numel() / H;
   c10::cuda::CUDAGuard guard(x.device());
@@ -174,7 +176,8 @@ std::vector<Tensor> rmsnorm_bwd(const Tensor& x, const Tensor& w, const Tensor& 
   auto dw = at::empty_like(w);
   auto partial = at::empty({rb_rmsnorm_bwd_num_partials(), H}, x.options().dtype(at::kFloat));
   int rc = rb_rmsnorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
-                          partial.data_ptr<float>(), dw.data_ptr(), rows, H, w_offset, dt_code(x), cur_stream());
+                          partial.data_ptr<float>(), dw.data_ptr(), rows, H, w_offset, dt_code(x),
+                          dres.has_value() ? dres->data_ptr() : nullptr, cur_stream());
   TORCH_CHECK(rc == 0, "rmsnorm_bwd: unsupported shape/dtype");
   return {dx, dw};
 }
@@ -315,7 +318,7 @@ TORCH_LIBRARY(realhf_b200, m) {
   m.def("adamw_step(Tensor(a!) p, Tensor g, Tensor(b!) m, Tensor(c!) v, Tensor? master, float lr, float b1, float b2, float eps, float wd, int step, Tensor? scale, Tensor? skip, bool stochastic, int seed) -> ()", &adamw_step);
   m.def("sumsq_accum(Tensor g, Tensor(a!) out2) -> ()", &sumsq_accum);
   m.def("rmsnorm_fwd(Tensor x, Tensor? residual, Tensor w, float eps, float w_offset) -> Tensor[]", &rmsnorm_fwd);
-  m.def("rmsnorm_bwd(Tensor x, Tensor w, Tensor dy, Tensor rstd, float w_offset) -> Tensor[]", &rmsnorm_bwd);
+  m.def("rmsnorm_bwd(Tensor x, Tensor w, Tensor dy, Tensor rstd, float w_offset, Tensor? dres) -> Tensor[]", &rmsnorm_bwd);
   m.def("layernorm_fwd(Tensor x, Tensor w, Tensor? b, float eps) -> Tensor[]", &layernorm_fwd);
   m.def("layernorm_bwd(Tensor x, Tensor w, Tensor dy, Tensor mean, Tensor rstd) -> Tensor[]", &layernorm_bwd);
   m.def("rope_inplace(Tensor(a!) x, Tensor cos, Tensor sin, Tensor pos, int n_heads, int hd, int rot_dim, bool interleaved, bool inverse) -> ()", &rope_inplace);

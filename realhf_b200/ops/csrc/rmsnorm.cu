@@ -70,7 +70,8 @@ template <typename T, int kMaxVec>
 __global__ void __launch_bounds__(2 * kThreads) rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                                const T* __restrict__ dy, const float* __restrict__ rstd,
                                                                T* __restrict__ dx, float* __restrict__ dw_partial,
-                                                               int64_t T_rows, int H, float w_offset) {
+                                                               int64_t T_rows, int H, float w_offset,
+                                                               const T* __restrict__ dres) {
   __shared__ float red[32];
   constexpr int V = 8;
   const int nvec = H / V;
@@ -113,8 +114,14 @@ __global__ void __launch_bounds__(2 * kThreads) rmsnorm_bwd_kernel(const T* __re
       const int i = threadIdx.x + it * 2 * kThreads;
       if (i < nvec) {
         rb::Pack<T, V> o;
+        if (dres != nullptr) {  // fused residual add in training: the gradient arriving on the residual stream joins here
+          rb::Pack<T, V> e = reinterpret_cast<const rb::Pack<T, V>*>(dres + row * H)[i];
 #pragma unroll
-        for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(rs * (g[it][k] - xh[it][k] * dot));
+          for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(rs * (g[it][k] - xh[it][k] * dot) + rb::to_f(e.v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(rs * (g[it][k] - xh[it][k] * dot));
+        }
         reinterpret_cast<rb::Pack<T, V>*>(dx + row * H)[i] = o;
       }
     }
@@ -164,13 +171,13 @@ int rb_rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* y, vo
 int rb_rmsnorm_bwd_num_partials() { return rb::kNumSMs * 4; }
 
 int rb_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx, float* dw_partial,
-                   void* dw, int64_t rows, int H, float w_offset, int dt, cudaStream_t s) {
+                   void* dw, int64_t rows, int H, float w_offset, int dt, const void* dres, cudaStream_t s) {
   if (rows == 0) return 0;
   if (H % 8 != 0 || H > kThreads * 8 * 8) return -1;
   const int grid = (int)(rows < rb::kNumSMs * 4 ? rows : rb::kNumSMs * 4);
 #define RB_L2(T, NV)                                                                                               \
   rmsnorm_bwd_kernel<T, NV><<<grid, 2 * kThreads, 0, s>>>((const T*)x, (const T*)w, (const T*)dy, rstd, (T*)dx,        \
-                                                          dw_partial, rows, H, w_offset);
+                                                          dw_partial, rows, H, w_offset, (const T*)dres);
 #define RB_L(T)                                                            \
   { const int nv = RB_CEIL_DIV(H, 2 * kThreads * 8);                        \
     if (nv <= 1) { RB_L2(T, 1) } else if (nv <= 2) { RB_L2(T, 2) } else { RB_L2(T, 4) }                            \

@@ -115,8 +115,30 @@ class _RMSNorm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, rstd = ctx.saved_tensors
-        dx, dw = lib().rmsnorm_bwd(x.contiguous(), w, dy.contiguous(), rstd, ctx.w_offset)
+        dx, dw = lib().rmsnorm_bwd(x.contiguous(), w, dy.contiguous(), rstd, ctx.w_offset, None)
         return dx, dw, None, None
+
+
+class _AddRMSNorm(torch.autograd.Function):
+    """(h, x_new) = (rmsnorm(x + d), x + d) in one kernel, with a one-kernel backward: the gradient of the normalised branch
+    and the gradient arriving on the residual stream are summed inside the RMSNorm backward kernel.  Replaces, per residual
+    connection of a training step, one eager add in the forward pass and the autograd accumulation add in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, d, x, w, eps, w_offset):
+        y, rstd, res = lib().rmsnorm_fwd(d.contiguous(), x.contiguous(), w, eps, w_offset)
+        ctx.save_for_backward(res, w, rstd)
+        ctx.w_offset = w_offset
+        ctx.mark_non_differentiable(rstd)
+        return y, res
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        res, w, rstd = ctx.saved_tensors
+        if dy is None:  # the normalised output was not used
+            return dres, dres, None, None, None
+        dsum, dw = lib().rmsnorm_bwd(res, w, dy.contiguous(), rstd, ctx.w_offset, dres.contiguous() if dres is not None else None)
+        return dsum, dsum, dw, None, None
 
 
 def rmsnorm(x, w, eps: float, w_offset: float = 0.0):
@@ -128,10 +150,13 @@ def rmsnorm(x, w, eps: float, w_offset: float = 0.0):
 
 
 def add_rmsnorm(x, residual, w, eps: float, w_offset: float = 0.0):
-    """(residual + x) -> new residual, and its RMSNorm; inference-only fused path (no autograd)."""
-    if use_native(x) and not torch.is_grad_enabled() and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
-        y, _, res = lib().rmsnorm_fwd(x.contiguous(), residual.contiguous(), w, eps, w_offset)
-        return y, res
+    """(residual + x) -> new residual, and its RMSNorm: one kernel forward, one kernel backward."""
+    if use_native(x) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192 and x.dtype in (torch.bfloat16, torch.float16, torch.float32) \
+            and x.dtype == residual.dtype == w.dtype:
+        if not torch.is_grad_enabled():
+            y, _, res = lib().rmsnorm_fwd(x.contiguous(), residual.contiguous(), w, eps, w_offset)
+            return y, res
+        return _AddRMSNorm.apply(x, residual, w, eps, w_offset)
     res = x + residual
     return rmsnorm(res, w, eps, w_offset), res
 

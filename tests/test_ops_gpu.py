@@ -86,6 +86,38 @@ def test_add_rmsnorm_gemma_offset():
     torch.testing.assert_close(y.float(), yr.float(), atol=2e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("w_off", [0.0, 1.0])
+def test_add_rmsnorm_training_forward_and_fused_backward(dtype, w_off):
+    """(h, x_new) = (rmsnorm(x + d), x + d) with autograd: both outputs are used downstream (the norm feeds the block, the sum
+    continues as the residual stream), so the backward kernel must add the residual-stream gradient to the norm gradient."""
+    torch.manual_seed(0)
+    H = 4096
+    d = torch.randn(257, H, device=DEV, dtype=dtype, requires_grad=True)
+    x = torch.randn(257, H, device=DEV, dtype=dtype, requires_grad=True)
+    w = (torch.randn(H, device=DEV) * 0.1 + (0.0 if w_off else 1.0)).to(dtype).requires_grad_(True)
+    h, xn = OF.add_rmsnorm(d, x, w, 1e-5, w_off)
+    gh, gx = torch.randn_like(h), torch.randn_like(xn)
+    torch.autograd.backward([h, xn], [gh, gx])
+    dr, xr, wr = (t.detach().float().requires_grad_(True) for t in (d, x, w))
+    s = (dr + xr) if dtype == torch.float32 else (dr + xr).to(dtype).float() + 0 * (dr + xr)  # the stream is stored in `dtype`
+    sr = dr + xr
+    hr = sr * torch.rsqrt(sr.pow(2).mean(-1, keepdim=True) + 1e-5) * (wr + w_off)
+    torch.autograd.backward([hr, sr], [gh.float(), gx.float()])
+    tol = dict(atol=3e-2, rtol=3e-2) if dtype != torch.float32 else dict(atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(h.float(), hr, **tol)
+    torch.testing.assert_close(xn.float(), sr, **tol)
+    torch.testing.assert_close(d.grad.float(), dr.grad, **tol)
+    torch.testing.assert_close(x.grad.float(), xr.grad, **tol)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.4 if dtype != torch.float32 else 2e-3, rtol=3e-2)
+    # only the residual output used (e.g. a stage boundary): gradient passes straight through
+    d2, x2 = d.detach().clone().requires_grad_(True), x.detach().clone().requires_grad_(True)
+    _, xn2 = OF.add_rmsnorm(d2, x2, w.detach().requires_grad_(True), 1e-5, w_off)
+    xn2.backward(gx)
+    torch.testing.assert_close(d2.grad, gx)
+    torch.testing.assert_close(x2.grad, gx)
+
+
 @pytest.mark.parametrize("interleaved", [False, True])
 def test_rope_inplace_and_grad(interleaved):
     torch.manual_seed(0)
