@@ -395,8 +395,12 @@ class ReaLModel(nn.Module):
             h = self._norm(x, f"{i}.mlp.ln")
         sp = self.sequence_parallel
         if c.mlp_type == "llama":
-            gu = TP.col_linear(h, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, sp)
-            a = OF.gated_act(gu, c.activation_function)
+            if not sp:  # gated activation fused into the gate|up GEMM epilogue (the SP path fuses the all-gather instead)
+                hh = TP.copy_to_tp(h, self.ctx) if self.ctx.tp_size > 1 else h
+                a = OF.gated_linear(hh, self.p[f"{i}.mlp.gate_up.weight"], c.activation_function)
+            else:
+                gu = TP.col_linear(h, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, sp)
+                a = OF.gated_act(gu, c.activation_function)
             o = TP.row_linear(a, self.p[f"{i}.mlp.down.weight"], None, self.ctx, sp)
         elif c.mlp_type == "moe":
             from realhf_b200.models import moe

@@ -123,7 +123,29 @@ void gemm_grouped_wgrad(const Tensor& dy, const Tensor& x, Tensor out, const Ten
   TORCH_CHECK(rc == 0, "rb_gemm_grouped_wgrad failed with code ", rc);
 }
 
+extern "C" int rb_gemm_2cta_glu(const void* A, const void* B, void* act, void* raw, int M, int F, int K, int64_t lda, int64_t ldb, int64_t ld_act,
+                                int64_t ld_raw, int in_dt, int act_kind, int num_sms, cudaStream_t s);
+
+// act = glu(x @ [gate; up]^T): the gated activation runs in the GEMM epilogue (CTA-pair kernel); with `want_raw` the raw
+// gate | up projections [M, 2F] are written too (the backward pass needs them).  Returns [act] or [act, raw].
+std::vector<Tensor> gemm_glu(const Tensor& x, const Tensor& w, int64_t act_kind, bool want_raw, int64_t num_sms) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.stride(1) == 1 && w.stride(1) == 1 && w.size(0) % 2 == 0 && w.size(1) == x.size(1));
+  TORCH_CHECK(x.scalar_type() == w.scalar_type() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kHalf));
+  const int64_t M = x.size(0), K = x.size(1), F = w.size(0) / 2;
+  c10::cuda::CUDAGuard g(x.device());
+  auto act = at::empty({M, F}, x.options());
+  Tensor raw;
+  if (want_raw) raw = at::empty({M, 2 * F}, x.options());
+  int rc = rb_gemm_2cta_glu(x.data_ptr(), w.data_ptr(), act.data_ptr(), want_raw ? raw.data_ptr() : nullptr, (int)M, (int)F, (int)K, x.stride(0),
+                            w.stride(0), F, 2 * F, x.scalar_type() == at::kBFloat16 ? 1 : 2, (int)act_kind, (int)num_sms,
+                            at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "gemm_glu failed: ", rc);
+  if (want_raw) return {act, raw};
+  return {act};
+}
+
 void register_gemm_ops(torch::Library& m) {
+  m.def("gemm_glu(Tensor x, Tensor w, int act_kind, bool want_raw, int num_sms) -> Tensor[]", &gemm_glu);
   m.def("gemm_grouped_wgrad(Tensor dy, Tensor x, Tensor(a!) out, Tensor offsets, bool accumulate, int num_sms) -> ()", &gemm_grouped_wgrad);
   m.def("gemm_grouped(Tensor a, Tensor w, Tensor offsets, bool b_mn, int num_sms) -> Tensor", &gemm_grouped);
   m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);

@@ -84,7 +84,17 @@ RB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   return v;
 }
 
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+RB_DEVICE float glu_act_fwd(float g, int kind) {
+  if (kind == 0) return g / (1.f + __expf(-g));
+  const float u = 0.7978845608028654f * (g + 0.044715f * g * g * g);
+  return 0.5f * g * (1.f + tanhf(u));
+}
+
+// kGlu: gated-linear-unit epilogue (SwiGLU / GeGLU fused into the gate|up projection).  The pair's B tile is made of
+// 128 GATE rows (loaded by CTA 0) and the 128 matching UP rows (loaded by CTA 1) of the fused [gate; up] weight -- two TMA boxes
+// at different row coordinates, no change to the parameter layout -- so accumulator columns [0,128) and [128,256) of every row
+// hold gate_j and up_j for the same 128 output features and the epilogue writes act(gate) * up directly.
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, bool kGlu = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                 const __grid_constant__ CUtensorMap tma_b, Params p) {
   using C = Cfg2<BN>;
@@ -103,7 +113,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int tiles_m = RB_CEIL_DIV(p.M, 2 * BM), tiles_n = RB_CEIL_DIV(p.N, BN);
+  constexpr int kTileN = kGlu ? BN / 2 : BN;  // output columns per pair tile
+  const int tiles_m = RB_CEIL_DIV(p.M, 2 * BM), tiles_n = RB_CEIL_DIV(p.N, kTileN);
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = RB_CEIL_DIV(p.K, BK);
 
@@ -137,9 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         int m0, n0;
-        tile_coords2(tile, tiles_m, tiles_n, BN, p.m_rot, m0, n0);
+        tile_coords2(tile, tiles_m, tiles_n, kTileN, p.m_rot, m0, n0);
         m0 += (int)rank * BM;          // my 128 rows of A (and of the output)
-        n0 += (int)rank * (BN / 2);    // my half of the B tile
+        if constexpr (kGlu) n0 += (int)rank * p.glu_F;  // CTA 0: gate rows of these features, CTA 1: the matching up rows
+        else n0 += (int)rank * (BN / 2);                // my half of the B tile
         if (p.ready_flags != nullptr && m0 < p.M) {  // A rows of this tile may still be in flight from a peer
           const uint32_t* f = p.ready_flags + m0 / p.rows_per_flag;
           while ((int32_t)(ld_acquire_gpu_u32(f) - p.ready_epoch) < 0) {}
@@ -208,11 +220,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
     const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m0, n0;
-      tile_coords2(tile, tiles_m, tiles_n, BN, p.m_rot, m0, n0);
+      tile_coords2(tile, tiles_m, tiles_n, kTileN, p.m_rot, m0, n0);
       ptx::mbar_wait(ptx::smem_u32(&tmem_full[as]), aphase);
       ptx::tc_fence_after();
       const int row = m0 + (int)rank * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      if constexpr (kGlu) {
+        OutT* raw = reinterpret_cast<OutT*>(p.glu_raw);
+        const bool raw_vec = raw != nullptr && (p.ld_raw % 8 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) && (p.glu_F % 8 == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 2 / 32; ++c) {
+          uint32_t rg[32], ru[32];
+          ptx::tc_ld_32x32(taddr + c * 32, rg);
+          ptx::tc_ld_32x32(taddr + BN / 2 + c * 32, ru);
+          ptx::tc_wait_ld();
+          const int col = n0 + c * 32;
+          const int n_valid = min(32, p.N - col);
+          if (row < p.M && n_valid > 0) {
+            float g[32], u[32], v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              g[i] = __uint_as_float(rg[i]);
+              u[i] = __uint_as_float(ru[i]);
+              // the unfused path rounds gate / up to the activation dtype before the nonlinearity: do the same, so that the saved
+              // raw projections (backward) and the activation are consistent
+              const float gr = rb::to_f(rb::from_f<OutT>(g[i])), ur = rb::to_f(rb::from_f<OutT>(u[i]));
+              v[i] = glu_act_fwd(gr, p.glu_act) * ur;
+            }
+            store_chunk<OutT>(Cp + (int64_t)row * p.ldc + col, v, n_valid, vec_ok);
+            if (raw != nullptr) {
+              store_chunk<OutT>(raw + (int64_t)row * p.ld_raw + col, g, n_valid, raw_vec);
+              store_chunk<OutT>(raw + (int64_t)row * p.ld_raw + p.glu_F + col, u, n_valid, raw_vec);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -236,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
           store_chunk<OutT>(dst, v, n_valid, vec_ok);
         }
       }
+      }
       if (p.done_counters != nullptr) {
         __threadfence();
         __syncwarp();
@@ -258,15 +301,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_2cta_kernel(const __grid_con
   }
 }
 
-template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt>
+template <int BN, bool kAMN, bool kBMN, typename OutT, int kFmt, bool kGlu = false>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int num_sms, cudaStream_t s) {
-  auto kern = gemm_2cta_kernel<BN, kAMN, kBMN, OutT, kFmt>;
+  auto kern = gemm_2cta_kernel<BN, kAMN, kBMN, OutT, kFmt, kGlu>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes) != cudaSuccess) return -2;
     configured = true;
   }
-  const int tiles = RB_CEIL_DIV(p.M, 2 * BM) * RB_CEIL_DIV(p.N, BN);
+  const int tiles = RB_CEIL_DIV(p.M, 2 * BM) * RB_CEIL_DIV(p.N, kGlu ? BN / 2 : BN);
   const int pairs = num_sms / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
@@ -334,7 +377,7 @@ int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, 
                    : make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)(bn / 2)));
   if (!ok) return -13;
   Params p{C, bias, ldc, M, N, K, accumulate, ready_flags, ready_epoch, rows_per_flag > 0 ? rows_per_flag : 1,
-           (m_rot_rows / (2 * BM)) % RB_CEIL_DIV(M, 2 * BM), done_counters};
+           (m_rot_rows / (2 * BM)) % RB_CEIL_DIV(M, 2 * BM), done_counters, 0, 0, nullptr, 0};
 #define RB_GO2(OutT, FMT)                                                                     \
   return bn == 256 ? dispatch_major2<256, OutT, FMT>(a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s) \
                    : dispatch_major2<128, OutT, FMT>(a_mn != 0, b_mn != 0, ta, tb, p, num_sms, s)
@@ -347,6 +390,24 @@ int rb_gemm_2cta_gated(const void* A, const void* B, void* C, const void* bias, 
   }
 #undef RB_GO2
   return -14;
+}
+
+// act[M, F] = glu(A[M,K] x [gate; up][2F, K]^T) with the activation in the epilogue; raw (optional) [M, 2F] receives gate | up.
+// in_dt: 1 bf16, 2 fp16 (outputs use the same dtype).  act_kind: 0 silu, 1 gelu-tanh.
+int rb_gemm_2cta_glu(const void* A, const void* B, void* act, void* raw, int M, int F, int K, int64_t lda, int64_t ldb, int64_t ld_act,
+                     int64_t ld_raw, int in_dt, int act_kind, int num_sms, cudaStream_t s) {
+  if (M <= 0 || F <= 0 || K <= 0) return 0;
+  if (in_dt != 1 && in_dt != 2) return -10;
+  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
+  if (num_sms <= 0) num_sms = rb::kNumSMs;
+  CUtensorMap ta, tb;
+  const int bf = in_dt == 1;
+  bool ok = make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)BM);
+  ok = ok && make_tmap(&tb, B, bf, (uint64_t)(2 * F), (uint64_t)K, (uint64_t)ldb, BK, 128);
+  if (!ok) return -13;
+  Params p{act, nullptr, ld_act, M, F, K, 0, nullptr, 0, 1, 0, nullptr, F, act_kind, raw, ld_raw};
+  if (in_dt == 1) return launch2<256, false, false, __nv_bfloat16, 1, true>(ta, tb, p, num_sms, s);
+  return launch2<256, false, false, __half, 0, true>(ta, tb, p, num_sms, s);
 }
 
 }  // extern "C"

@@ -28,6 +28,12 @@ struct Params {
   // optional completion counters (GEMM -> reduce-scatter): every epilogue warp bumps done[row / rows_per_flag] once its 32
   // rows x BN columns of a tile are stored, so a copy stream can ship finished row-blocks while later tiles still compute
   uint32_t* done_counters;
+  // optional gated-linear-unit epilogue (2-CTA kernel): B is the fused [gate; up] weight with glu_F rows each, N = glu_F output
+  // columns act(gate) * up are written to C, and (when glu_raw != nullptr) the raw gate | up projections to glu_raw [M, 2 glu_F]
+  int glu_F;
+  int glu_act;       // 0 silu, 1 gelu (tanh approximation)
+  void* glu_raw;
+  int64_t ld_raw;
 };
 
 template <typename T> RB_DEVICE void store_chunk(T* dst, const float* v, int n_valid, bool vec_ok);

@@ -54,6 +54,10 @@ RB_DEVICE void mm_st(void* mc, const int4& v) {
 
 template <typename T> struct VecOf { static constexpr int N = 16 / sizeof(T); };
 
+// bulk (ZeRO) kernels: 64 blocks x 1024 threads x 4 vectors in flight = 4 MB outstanding per GPU, enough to cover the NVLink
+// round trip of multimem loads at full link rate; the epoch barrier only uses the first `world` threads of a block
+constexpr int kBwThreads = 1024;
+
 // ---------------------------------------------------------------------------------------------- all-reduce
 // Input: `nvec` 16-byte vectors at byte offset off_in of every rank's data region (staged from `in` first when given).
 // kTwoShot = false: out[i] = switch-sum(i) for all i; no trailing barrier — callers alternate between two regions.
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) nvls_allreduce_kernel(Peers P, uint8
 // The leading barrier makes every rank's backward writes of this bucket visible; a barrier before the gradients are
 // overwritten again is the caller's (the all-gather kernel's trailing barrier provides it).
 template <typename TG>
-__global__ void __launch_bounds__(kThreads) nvls_rs_sumsq_kernel(Peers P, uint8_t* __restrict__ mc, int64_t off, int64_t nvec, float scale,
+__global__ void __launch_bounds__(kBwThreads) nvls_rs_sumsq_kernel(Peers P, uint8_t* __restrict__ mc, int64_t off, int64_t nvec, float scale,
                                                                  float* __restrict__ stats, int rank, int world) {
   __shared__ float red[32];
   block_barrier(P, rank, world);
@@ -185,11 +189,20 @@ __global__ void __launch_bounds__(kThreads) nvls_adam_ag_kernel(Peers P, const T
 }
 
 // Broadcast `nvec` vectors of this rank's shard (local pointer `src`) to the same offset of every replica.
-__global__ void __launch_bounds__(kThreads) nvls_allgather_kernel(Peers P, const int4* __restrict__ src, int4* __restrict__ dst_mc,
+__global__ void __launch_bounds__(kBwThreads) nvls_allgather_kernel(Peers P, const int4* __restrict__ src, int4* __restrict__ dst_mc,
                                                                   int64_t nvec, int lead_barrier, int rank, int world) {
   if (lead_barrier) block_barrier(P, rank, world);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) mm_st(dst_mc + i, rb::ld_stream(src + i));
+  constexpr int U = 4;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < nvec; base += stride * U) {
+    int4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (base + u * stride < nvec) r[u] = rb::ld_stream(src + base + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (base + u * stride < nvec) mm_st(dst_mc + base + u * stride, r[u]);
+  }
   __threadfence_system();
   block_barrier(P, rank, world);
 }
@@ -299,8 +312,8 @@ int rb_nvls_reduce_scatter(const int64_t* data_ptrs, const int64_t* pad_ptrs, ui
   if (nbytes == 0) return 0;
   Peers P = make_peers(data_ptrs, pad_ptrs, world);
   const int64_t nvec = nbytes / 16;
-  if (dt == 0) nvls_rs_sumsq_kernel<float><<<kMaxBlocks, kThreads, 0, s>>>(P, (uint8_t*)mc, off, nvec, scale, stats, rank, world);
-  else if (dt == 1) nvls_rs_sumsq_kernel<__nv_bfloat16><<<kMaxBlocks, kThreads, 0, s>>>(P, (uint8_t*)mc, off, nvec, scale, stats, rank, world);
+  if (dt == 0) nvls_rs_sumsq_kernel<float><<<kMaxBlocks, kBwThreads, 0, s>>>(P, (uint8_t*)mc, off, nvec, scale, stats, rank, world);
+  else if (dt == 1) nvls_rs_sumsq_kernel<__nv_bfloat16><<<kMaxBlocks, kBwThreads, 0, s>>>(P, (uint8_t*)mc, off, nvec, scale, stats, rank, world);
   else return -2;
   return 0;
 }
@@ -364,7 +377,7 @@ int rb_nvls_allgather(const int64_t* data_ptrs, const int64_t* pad_ptrs, uint64_
                       int world, cudaStream_t s) {
   if (world > kMaxRanks || (nbytes & 15) || (off & 15) || mc == 0) return -1;
   Peers P = make_peers(data_ptrs, pad_ptrs, world);
-  nvls_allgather_kernel<<<kMaxBlocks, kThreads, 0, s>>>(P, (const int4*)(P.data[rank] + off), (int4*)(reinterpret_cast<uint8_t*>(mc) + off),
+  nvls_allgather_kernel<<<kMaxBlocks, kBwThreads, 0, s>>>(P, (const int4*)(P.data[rank] + off), (int4*)(reinterpret_cast<uint8_t*>(mc) + off),
                                                         nbytes / 16, lead_barrier, rank, world);
   return 0;
 }

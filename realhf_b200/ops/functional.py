@@ -288,6 +288,16 @@ def gated_act(gu, kind: str = "silu"):
     return gated_act_ref(gu, kind)
 
 
+def gated_linear(x, w_gate_up, kind: str = "silu"):
+    """act(x @ Wg^T) * (x @ Wu^T) with the fused [Wg; Wu] weight.  CUDA tensors with the tcgen05 GEMM enabled run the
+    projection and the gated activation as ONE kernel (activation in the epilogue); everything else composes the two ops."""
+    if use_native(x) and x.dtype in (torch.bfloat16, torch.float16) and kind in _ACT_KIND and gemm_impl() is not None:
+        from realhf_b200.ops import gemm as G
+        if gemm_impl() is G.linear and G.gated_linear_supported(x, w_gate_up):
+            return G.gated_linear(x, w_gate_up, _ACT_KIND[kind])
+    return gated_act(linear(x, w_gate_up), kind)
+
+
 # ------------------------------------------------------------------------------------------------ logprob
 
 

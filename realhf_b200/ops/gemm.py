@@ -77,24 +77,66 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x2, w = ctx.saved_tensors
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        if dy2.stride(-1) != 1 or dy2.stride(0) % 8 != 0 or dy2.data_ptr() % 16 != 0:
-            dy2 = dy2.contiguous()
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, w, b_mn=True).view(ctx.x_shape)            # [T,N] x [N,K] -> [T,K]
-        if ctx.needs_input_grad[1]:
-            main_grad = getattr(w, "main_grad", None)
-            if main_grad is None and getattr(w, "_grad_in_flat_buffer", False) and w.grad is not None and w.grad.dtype == dy2.dtype:
-                main_grad = w.grad                                      # same-dtype flat gradient buffer: no temp dW + add
-            if main_grad is not None:                                   # accumulate straight into the flat grad bucket
-                gemm(dy2, x2, out=main_grad.view(w.shape), a_mn=True, b_mn=True, accumulate=True)
-                dw = None
-            else:
-                dw = gemm(dy2, x2, a_mn=True, b_mn=True)               # [T,N]^T x [T,K] -> [N,K]
+        dx, dw = _linear_backward(x2, w, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_shape)
+        db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(0)
+            db = dy.reshape(-1, dy.shape[-1]).sum(0)
         return dx, dw, db
+
+
+def _linear_backward(x2, w, dy, need_dx: bool, need_dw: bool, x_shape):
+    """dgrad and wgrad of y = x2 @ w^T on the tcgen05 kernel (no transposed copies); the weight gradient accumulates straight
+    into the flat gradient buffer when the parameter lives in one (returns dw = None then)."""
+    dy2 = dy.reshape(-1, dy.shape[-1])
+    if dy2.stride(-1) != 1 or dy2.stride(0) % 8 != 0 or dy2.data_ptr() % 16 != 0:
+        dy2 = dy2.contiguous()
+    dx = dw = None
+    if need_dx:
+        dx = gemm(dy2, w, b_mn=True).view(x_shape)                     # [T,N] x [N,K] -> [T,K]
+    if need_dw:
+        main_grad = getattr(w, "main_grad", None)
+        if main_grad is None and getattr(w, "_grad_in_flat_buffer", False) and w.grad is not None and w.grad.dtype == dy2.dtype:
+            main_grad = w.grad                                          # same-dtype flat gradient buffer: no temp dW + add
+        if main_grad is not None:                                       # accumulate straight into the flat grad bucket
+            gemm(dy2, x2, out=main_grad.view(w.shape), a_mn=True, b_mn=True, accumulate=True)
+        else:
+            dw = gemm(dy2, x2, a_mn=True, b_mn=True)                   # [T,N]^T x [T,K] -> [N,K]
+    return dx, dw
+
+
+class _GatedLinear(torch.autograd.Function):
+    """act(x @ Wg^T) * (x @ Wu^T) for the fused [Wg; Wu] weight with the gated activation in the GEMM epilogue
+    (`csrc/gemm_2cta.cu`, kGlu): the [T, 2F] projection is not re-read by a separate activation kernel; it is written once
+    only when a backward pass will need it."""
+
+    @staticmethod
+    def forward(ctx, x, w, kind: int):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        need_raw = any(ctx.needs_input_grad[:2])
+        res = lib().gemm_glu(x2, w, kind, need_raw, _sms(x.device))
+        if need_raw:
+            ctx.save_for_backward(x2, w, res[1])
+        ctx.kind, ctx.x_shape = kind, x.shape
+        return res[0].view(*x.shape[:-1], w.shape[0] // 2)
+
+    @staticmethod
+    def backward(ctx, dact):
+        x2, w, gu = ctx.saved_tensors
+        dgu = lib().gated_act_bwd(gu, dact.reshape(-1, dact.shape[-1]).contiguous(), ctx.kind)
+        dx, dw = _linear_backward(x2, w, dgu, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_shape)
+        return dx, dw, None
+
+
+def gated_linear_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
+    n_rows = x.numel() // max(1, x.shape[-1])
+    return (supported(x, w) and n_rows > 128 and w.shape[0] % 16 == 0 and (w.shape[0] // 2) % 8 == 0 and w.is_contiguous()
+            and os.environ.get("REAL_GEMM_GLU", "1") == "1")
+
+
+def gated_linear(x: torch.Tensor, w: torch.Tensor, kind: int) -> torch.Tensor:
+    return _GatedLinear.apply(x, w, kind)
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:

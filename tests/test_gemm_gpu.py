@@ -220,3 +220,33 @@ def test_grouped_wgrad_single_launch(counts, M, N):
     acc = torch.ones(ng, M, N, device="cuda", dtype=torch.float32)
     G.grouped_wgrad(dy, x, offsets, ng, out=acc, accumulate=True)
     torch.testing.assert_close(acc, ref + 1.0, atol=2e-2 * max(counts) ** 0.5, rtol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(300, 1024, 512), (4096, 4096, 11008), (129, 512, 136)])
+@pytest.mark.parametrize("kind", ["silu", "gelu_pytorch_tanh"])
+def test_gated_linear_fused_epilogue_matches_reference(shape, kind):
+    """SwiGLU / GeGLU in the epilogue of the CTA-pair GEMM (gate rows from CTA 0, up rows from CTA 1 of the fused weight):
+    forward equals gated_act(x @ W^T), backward (through the saved raw projections) equals autograd of the fp32 reference."""
+    from realhf_b200.ops import functional as OF
+    from realhf_b200.ops import gemm as G
+    OF.set_gemm_impl(G.linear)
+    M, K, F_ = shape
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(2 * F_, K, device="cuda") * (1.0 / K ** 0.5)).to(torch.bfloat16).requires_grad_(True)
+    assert G.gated_linear_supported(x, w)
+    a = OF.gated_linear(x, w, kind)
+    da = torch.randn_like(a)
+    a.backward(da)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    gu = (xr @ wr.t()).to(torch.bfloat16).float() + 0 * (xr @ wr.t())  # the projection is rounded to bf16 before the activation
+    gur = xr @ wr.t()
+    ar = OF.gated_act_ref(gur, kind)
+    ar.backward(da.float())
+    torch.testing.assert_close(a.float(), ar, atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=6e-2, rtol=6e-2)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.25 if M > 1000 else 8e-2, rtol=6e-2)
+    # inference: no raw projection is written
+    with torch.no_grad():
+        a2 = OF.gated_linear(x.detach(), w.detach(), kind)
+    torch.testing.assert_close(a2, a.detach())
