@@ -175,76 +175,100 @@ def _count_gpus() -> int:
 
 
 class SlurmSchedulerClient(SchedulerClient):
-    """Builds one sbatch script per worker type with `srun --multi-prog` (reference: scheduler/slurm/utils.py:357-471).
-    Submission needs a Slurm cluster; command construction is unit-testable offline."""
+    """Slurm mode (reference: scheduler/slurm/client.py + utils.py).  `submit_array` only records a launch; `commit()` (called by
+    `wait()` or explicitly) queries the free resources of the partition, places the job steps of ALL worker types together
+    (`scheduler.slurm.allocate_resources`: GPU workers packed in rank order, so the ranks of a TP / DP group share an NVSwitch
+    domain), writes one hostfile + multi-prog file + sbatch script per worker type and submits them.  Every Slurm command goes
+    through `run`, so the whole flow is tested offline with canned command output."""
 
     def __init__(self, expr_name, trial_name, partition: Optional[str] = None, container_image: Optional[str] = None,
-                 container_mounts: Optional[str] = None):
+                 container_mounts: Optional[str] = None, run=None):
         super().__init__(expr_name, trial_name)
         from realhf_b200.base import cluster
+        from realhf_b200.scheduler import slurm
         cs = cluster.spec()  # partition / images / mounts default to the cluster spec ($CLUSTER_SPEC_PATH)
         self.partition = partition or cs.partition or "dev"
         self.image, self.cpu_image = container_image or cs.gpu_image, container_image or cs.cpu_image
-        self.mounts = container_mounts or cs.default_mount or "/:/host"
-        self._job_ids: Dict[str, str] = {}
+        self.mounts = container_mounts or cs.default_mount or None
+        self.gpu_type = os.environ.get("REAL_SLURM_GPU_TYPE") or None  # e.g. "b200": only request typed GPUs when asked to
+        self._run = run or slurm.run_cmd
+        self._pending: List = []
+        self._launched: Dict[str, object] = {}
 
-    def build_script(self, worker_type: str, cmd: str, count: int, cpu: int = 4, gpu: int = 0, mem: int = 10000,
-                     nodelist: Optional[str] = None, exclude: Optional[str] = None, time_limit: Optional[str] = None,
-                     env_vars: Optional[Dict[str, str]] = None, gpus_per_node: Optional[int] = None,
-                     container_image: Optional[str] = None) -> str:
-        if gpus_per_node is None:
+    def submit_array(self, worker_type, cmd, count, cpu: int = 4, gpu: int = 0, mem: int = 10000, nodelist: Optional[str] = None,
+                     exclude: Optional[str] = None, time_limit: Optional[str] = None, env_vars: Optional[Dict[str, str]] = None,
+                     container_image: Optional[str] = None, wprocs_per_jobstep: int = 1, begin: Optional[str] = None,
+                     deadline: Optional[str] = None, **_ignored):
+        from realhf_b200.scheduler import slurm
+        n_prev = sum(1 for i in self._pending + list(self._launched.values()) if i.worker_type == worker_type)
+        offset = sum(i.wprocs_in_job for i in self._pending + list(self._launched.values()) if i.worker_type == worker_type)
+        info = slurm.SlurmLaunchInfo(
+            run_name=self.run_name, worker_type=worker_type, cmd=cmd, wprocs_in_job=count, wprocs_per_jobstep=wprocs_per_jobstep,
+            worker_submission_index=n_prev, wproc_offset=offset,
+            resource=slurm.SlurmResource(cpu=cpu, mem=mem, gpu=gpu, gpu_type=self.gpu_type if gpu else None), partition=self.partition,
+            nodelist=nodelist, exclude=exclude, container_image=container_image or (self.image if gpu else self.cpu_image),
+            container_mounts=self.mounts, env_vars=dict(env_vars or {}), time_limit=time_limit, begin=begin, deadline=deadline,
+            log_dir=constants.run_dirs(self.expr_name, self.trial_name)["log"])
+        self._pending.append(info)
+
+    def build_script(self, worker_type: str, cmd: str, count: int, **kw) -> str:
+        """The sbatch script `submit_array` + `commit` would produce for one worker type placed on its own (for inspection)."""
+        from realhf_b200.scheduler import slurm
+        saved, self._pending = self._pending, []
+        try:
+            self.submit_array(worker_type, cmd, count, **kw)
+            info = self._pending[0]
+        finally:
+            self._pending = saved
+        try:
+            nodes = slurm.query_nodes(self.partition, self._run)
+        except (OSError, subprocess.CalledProcessError):
+            # no Slurm on this machine (dry run / tests): an idle partition shaped by the cluster spec
             from realhf_b200.base import cluster
-            gpus_per_node = cluster.spec().n_gpus_per_node
-        log_dir = constants.run_dirs(self.expr_name, self.trial_name)["log"]
-        n_nodes = max(1, (count * max(gpu, 0) + gpus_per_node - 1) // gpus_per_node) if gpu else 1
-        lines = ["#!/bin/bash", f"#SBATCH --job-name={self.run_name}:{worker_type}", f"#SBATCH --partition={self.partition}",
-                 f"#SBATCH --ntasks={count}", f"#SBATCH --nodes={n_nodes}", f"#SBATCH --cpus-per-task={cpu}", f"#SBATCH --mem-per-cpu={max(1, mem // max(cpu, 1))}M",
-                 f"#SBATCH --output={log_dir}/{worker_type}-%t.out", "#SBATCH --open-mode=append"]
-        if gpu:
-            lines.append(f"#SBATCH --gpus-per-task={gpu}")
-        if nodelist:
-            lines.append(f"#SBATCH --nodelist={nodelist}")
-        if exclude:
-            lines.append(f"#SBATCH --exclude={exclude}")
-        if time_limit:
-            lines.append(f"#SBATCH --time={time_limit}")
-        for k, v in (env_vars or {}).items():
-            lines.append(f"export {k}={shlex.quote(str(v))}")
-        multiprog = os.path.join(log_dir, f"{worker_type}.multiprog")
-        with open(multiprog, "w") as f:
-            for i in range(count):
-                f.write(f"{i} " + cmd.format(jobstep_id=i, n_jobsteps=count, worker_submission_index=0, wprocs_per_jobstep=1,
-                                             wprocs_in_job=count, wproc_offset=0) + "\n")
-        image = container_image or (self.image if gpu else self.cpu_image)
-        container = f"--container-image={image} --container-mounts={self.mounts} " if image else ""
-        lines.append(f"srun {container}--multi-prog {multiprog}")
-        return "\n".join(lines) + "\n"
+            cs = cluster.spec()
+            per = max(1, cs.n_gpus_per_node)
+            names = slurm.parse_nodelist(info.nodelist) or cs.node_names(list(range(1, 2 + (count * max(1, info.resource.gpu)) // per)))
+            nodes = {n: slurm.SlurmResource(cpu=1 << 20, mem=1 << 40, gpu=per, gpu_type=info.resource.gpu_type) for n in names}
+        slurm.allocate_resources([info], nodes)
+        info.commit()  # the script refers to its hostfile / multi-prog file
+        return info.sbatch_script()
 
-    def submit_array(self, worker_type, cmd, count, **kw):
-        allowed = ("cpu", "gpu", "mem", "nodelist", "exclude", "time_limit", "env_vars", "gpus_per_node", "container_image")
-        script = self.build_script(worker_type, cmd, count, **{k: v for k, v in kw.items() if k in allowed and v is not None})
-        path = os.path.join(constants.run_dirs(self.expr_name, self.trial_name)["log"], f"{worker_type}.sbatch")
-        with open(path, "w") as f:
-            f.write(script)
-        out = subprocess.run(["sbatch", "--parsable", path], capture_output=True, text=True, check=True).stdout.strip()
-        self._job_ids[worker_type] = out.split(";")[0]
-
-    def _state(self, job_id: str) -> JobState:
-        out = subprocess.run(["squeue", "-h", "-j", job_id, "-o", "%T"], capture_output=True, text=True).stdout.strip()
-        m = {"PENDING": JobState.PENDING, "RUNNING": JobState.RUNNING, "COMPLETED": JobState.COMPLETED, "FAILED": JobState.FAILED,
-             "CANCELLED": JobState.CANCELLED, "": JobState.COMPLETED}
-        return m.get(out.split("\n")[0], JobState.FAILED)
+    def commit(self):
+        from realhf_b200.scheduler import slurm
+        if not self._pending:
+            return
+        slurm.allocate_resources(self._pending, slurm.query_nodes(self.partition, self._run))
+        for info in self._pending:
+            path = info.commit()
+            out = self._run(["sbatch", "--parsable", path]).strip()
+            info.job_id = out.split(";")[0]
+            key = info.worker_type if info.worker_submission_index == 0 else f"{info.worker_type}:{info.worker_submission_index}"
+            self._launched[key] = info
+            logger.info(f"submitted {info.slurm_name} as slurm job {info.job_id} on {sorted(set(info.hosts))}")
+        self._pending = []
 
     def find_all(self, job_name_regex=".*"):
-        return [JobInfo(k, self._state(v)) for k, v in self._job_ids.items()]
+        import re
+
+        from realhf_b200.scheduler import slurm
+        self.commit()
+        ids = [i.job_id for i in self._launched.values()]
+        st = slurm.job_states(ids, self._run)
+        m = {"PENDING": JobState.PENDING, "RUNNING": JobState.RUNNING, "COMPLETED": JobState.COMPLETED, "FAILED": JobState.FAILED,
+             "CANCELLED": JobState.CANCELLED}
+        return [JobInfo(k, m[st[i.job_id][0]], host=st[i.job_id][2] or None) for k, i in self._launched.items() if re.fullmatch(job_name_regex, k)]
+
+    def find(self, job_name: str):
+        return next(iter(self.find_all(job_name)), None)
 
     def wait(self, timeout=None, poll=10, **kw):
+        self.commit()
         t0 = time.monotonic()
         while True:
             infos = self.find_all()
-            if any(i.state in (JobState.FAILED, JobState.CANCELLED) for i in infos):
-                bad = next(i for i in infos if i.state in (JobState.FAILED, JobState.CANCELLED))
-                raise JobException(self.run_name, bad.name, "slurm", bad.state)
+            bad = next((i for i in infos if i.state in (JobState.FAILED, JobState.CANCELLED)), None)
+            if bad is not None:
+                raise JobException(self.run_name, bad.name, bad.host or "slurm", bad.state)
             if all(i.state == JobState.COMPLETED for i in infos):
                 return
             if timeout is not None and time.monotonic() - t0 > timeout:
@@ -253,12 +277,16 @@ class SlurmSchedulerClient(SchedulerClient):
 
     def stop_all(self, signal_=None):
         sig = ["-s", "INT"] if signal_ == signal.SIGINT else []
-        if self._job_ids:
-            for jid in self._job_ids.values():
-                subprocess.run(["scancel"] + sig + [jid])
+        self._pending = []
+        if self._launched:
+            for info in self._launched.values():
+                self._run(["scancel"] + sig + [info.job_id])
         else:  # a fresh client (`apps.main stop` from another shell): address the trial's jobs by name
             for wt in ("master_worker", "model_worker"):
-                subprocess.run(["scancel"] + sig + ["--name", f"{self.run_name}:{wt}"])
+                try:
+                    self._run(["scancel"] + sig + ["--name", f"{self.run_name}:{wt}"])
+                except Exception:
+                    pass
 
 
 def make(mode: str, expr_name: str, trial_name: str, **kw) -> SchedulerClient:
@@ -267,5 +295,7 @@ def make(mode: str, expr_name: str, trial_name: str, **kw) -> SchedulerClient:
     if mode == "slurm":
         return SlurmSchedulerClient(expr_name, trial_name, **kw)
     if mode == "ray":
-        raise NotImplementedError("ray is not available in this image; use `local` or `slurm`")
+        # Not supported, by design: the reference's Ray mode only replaces process launching (controller.py:398-575); this
+        # framework launches one process per GPU through the local / slurm clients and its own control plane (docs/distributed.md)
+        raise NotImplementedError("mode=ray is not supported: use `local` (one node) or `slurm` (multi-node); see docs/distributed.md")
     raise NotImplementedError(mode)
