@@ -19,7 +19,29 @@ logger = logging.getLogger("main", "system")
 
 
 def _command(exp: str, trial: str, cmd: str):
+    """Deliver `pause` / `resume` / `exit` to the master worker: through the control key it polls between steps (works from any
+    machine that sees the name store), and through its RPC endpoint when that is reachable (immediate acknowledgement)."""
     name_resolve.add(control_key(exp, trial, "master_worker", 0), cmd, replace=True)
+    try:
+        from realhf_b200.system.worker_control import WorkerControlPanel
+        panel = WorkerControlPanel(exp, trial, timeout=2.0)
+        panel.connect(["master_worker/0"], timeout=0.5)
+        ack = panel.request("master_worker/0", cmd)
+        panel.close()
+        return ack
+    except Exception:  # no endpoint published (yet) / not reachable from here: the control key does the job
+        return None
+
+
+def worker_panel_status(exp: str, trial: str):
+    """{worker: {status, uptime_s, served, progress}} through the workers' RPC endpoints (`apps.main status --rpc`)."""
+    from realhf_b200.system.worker_control import WorkerControlPanel
+    panel = WorkerControlPanel(exp, trial, timeout=5.0)
+    names = panel.connect(timeout=1.0)
+    st = panel.group_request("status")
+    pr = panel.group_request("progress")
+    panel.close()
+    return {n: dict(st[n] if isinstance(st[n], dict) else dict(status="LOST"), progress=pr[n] if isinstance(pr[n], dict) else None) for n in names}
 
 
 def pause_experiment(exp: str, trial: str):
@@ -194,6 +216,7 @@ def main(argv=None):
             sp.add_argument("--mode", default="local", choices=["local", "slurm"])
         if name == "status":
             sp.add_argument("--n_model_workers", "-n", type=int, default=None)
+            sp.add_argument("--rpc", action="store_true", help="also query every worker's control endpoint (live progress, memory)")
     sp = sub.add_parser("find_config")
     sp.add_argument("--regex", "-r", required=True)
     sub.add_parser("profile_layers", add_help=False)
@@ -221,6 +244,11 @@ def main(argv=None):
                 out[k.split("/status/", 1)[1]] = "LOST"
         for k in sorted(out):
             print(f"{k}: {out[k]}")
+        if getattr(args, "rpc", False):
+            live = worker_panel_status(exp, trial)
+            for k in sorted(live):
+                print(f"{k} [rpc]: {live[k]}")
+            out = dict(out, rpc=live)
         return out
     if args.cmd == "pause":
         return pause_experiment(exp, trial)

@@ -392,16 +392,33 @@ class MasterWorker:
                 return name_resolve.get(ckey)
             except name_resolve.NameEntryNotFoundError:
                 return None
+        ctl = self._control_server()
+        paused = lambda c_: c_ == "pause" or ctl.paused.is_set()  # the control key, or a `pause` request on the RPC panel
         c = cmd()
-        if c == "pause":
+        if paused(c) and not ctl.exit_requested.is_set():
+            from realhf_b200.system.worker_control import WorkerServerStatus
             name_resolve.add(skey, "PAUSED", replace=True, keepalive_ttl=status_ttl())
+            ctl.set_status(WorkerServerStatus.PAUSED)
             logger.info(f"paused by the controller at step {self.step}")
-            while c == "pause":
+            while paused(c) and not ctl.exit_requested.is_set():
                 await asyncio.sleep(0.2)
                 c = cmd()
             name_resolve.add(skey, "RUNNING", replace=True, keepalive_ttl=status_ttl())
+            ctl.set_status(WorkerServerStatus.RUNNING)
             logger.info("resumed")
-        return c != "exit"
+        return c != "exit" and not ctl.exit_requested.is_set()
+
+    def _control_server(self):
+        """Request / response control endpoint of this worker (`system/worker_control.py`), created on first use."""
+        ctl = getattr(self, "_ctl", None)
+        if ctl is None:
+            from realhf_b200.system.worker_control import WorkerServer, WorkerServerStatus
+            ctl = self._ctl = WorkerServer(self.exp, self.trial, "master_worker/0")
+            ctl.set_status(WorkerServerStatus.RUNNING)
+            ctl.register_handler("progress", lambda: dict(step=self.step, epoch=self.epoch, epoch_step=self.epoch_step,
+                                                          total_steps=self.ft_spec.total_train_steps if self.ft_spec else None,
+                                                          rpc_secs=dict(self.rpc_secs)))
+        return ctl
 
     def _write_stats(self, rec: Dict):
         """Per-step statistics -> stats.jsonl (+ TensorBoard / wandb when enabled), see `system/metrics.py`."""

@@ -447,10 +447,22 @@ class ModelWorker:
     # ------------------------------------------------------------------ main loop
     def run(self):
         self.setup()
+        from realhf_b200.system.worker_control import WorkerServer, WorkerServerStatus
+        # request / response control endpoint (ping / status / progress / exit), served on its own thread so that it answers
+        # while an MFC is running
+        self.ctl = WorkerServer(self.exp, self.trial, f"model_worker/{self.index}")
+        self.ctl.set_status(WorkerServerStatus.RUNNING)
+        self.ctl.register_handler("progress", lambda: dict(current=getattr(self, "_current_handle", None),
+                                                           n_handled=getattr(self, "_n_handled", 0), memory=self._memory_stats()))
         while not self._exiting:
+            if self.ctl.exit_requested.is_set():
+                logger.info("exit requested through the control panel")
+                break
             req = self.stream.poll(timeout_ms=50)
             if req is None:
                 continue
+            self._current_handle = req.handle_name
+            self._n_handled = getattr(self, "_n_handled", 0) + 1
             if req.handle_name == "exit":
                 self.stream.reply(req, None)
                 break
