@@ -251,29 +251,60 @@ class PipelineRunner:
             else:
                 x = out.contiguous()
                 sends.append((x, dist.isend(x, self.next)))
-        # ---- decode steps
+        # ---- decode steps.  Each stage captures ONE CUDA graph per micro-batch (the KV-cache addresses differ per micro-batch):
+        # its blocks' decode step, the cache-length bump and, on the last stage, the LM head; a token round of a stage is then
+        # [receive into a static buffer] -> graph replay -> [sample / send] (reference: pipe_runner.py:422-445, one graph per
+        # micro-batch for the same reason)
+        use_graph = g.use_cuda_graph and dev.type == "cuda"
+
+        def stage_step(st):
+            h = m.decode_step(st.input_ids if self.first else None, st.k, st.v, st.cache_lens, hidden=None if self.first else st.hidden_in)
+            out = gen._final_logits(m, h) if self.last else h
+            st.cache_lens += 1
+            return out
+
+        if use_graph and g.max_new_tokens > 1:
+            from realhf_b200.ops import launches
+            for st in states:
+                lens_backup = st.cache_lens.clone()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    stage_step(st)  # warm-up outside capture (allocations, lazy inits); its KV write is overwritten by the real step
+                torch.cuda.current_stream(dev).wait_stream(side)
+                st.cache_lens.copy_(lens_backup)
+                st.graph = torch.cuda.CUDAGraph()
+                launches.begin_capture()
+                with torch.cuda.graph(st.graph):
+                    st.out = stage_step(st)
+                st.graph_launches = launches.end_capture()
+        last_send = [None] * M  # the static output buffer of a micro-batch may only be rewritten once its previous send completed
         for step in range(1, g.max_new_tokens):
             for i in range(M):
                 st = states[i]
                 B = st.B
                 if self.first:
-                    nxt = torch.empty(B, dtype=torch.long, device=dev)
-                    dist.recv(nxt, last_global())
-                    h = m.decode_step(nxt, st.k, st.v, st.cache_lens)
+                    dist.recv(st.input_ids, last_global())
                 else:
-                    hid = torch.empty(B, H, dtype=m.dtype, device=dev)
-                    dist.recv(hid, self.prev)
-                    h = m.decode_step(None, st.k, st.v, st.cache_lens, hidden=hid)
-                st.cache_lens += 1
+                    dist.recv(st.hidden_in, self.prev)
+                if use_graph:
+                    if last_send[i] is not None:
+                        last_send[i].wait()
+                    st.graph.replay()
+                    launches.count_replay(st.graph_launches)
+                    out = st.out
+                else:
+                    out = stage_step(st)
                 if self.last:
-                    logits = gen._final_logits(m, h)
-                    nxt, lp, mb_, unfinished[i] = gen.genstep(logits, g, step, eos_id, pad_id, unfinished[i], sample_gen)
+                    nxt, lp, mb_, unfinished[i] = gen.genstep(out, g, step, eos_id, pad_id, unfinished[i], sample_gen)
                     toks[i].append(nxt); lps[i].append(lp); masks[i].append(mb_)
                     if step + 1 < g.max_new_tokens:
                         sends.append((nxt, dist.isend(nxt, first_global())))
                 else:
-                    x = h.contiguous()
-                    sends.append((x, dist.isend(x, self.next)))
+                    x = out if use_graph else out.contiguous()
+                    hnd = dist.isend(x, self.next)
+                    last_send[i] = hnd
+                    sends.append((x, hnd))
             if len(sends) > 4 * M:
                 for _, hnd in sends[: -2 * M]:
                     hnd.wait()
