@@ -91,7 +91,7 @@ class ReaLEngine(PipelinableEngine):
                     num_micro_batches: Optional[int] = None) -> Dict[str, Any]:
         assert self.optim is not None, "train_batch needs the `train` backend"
         n_mbs = num_micro_batches or 1
-        self.optim.materialize()
+        self.optim.begin_call(train=True)
         self.optim.zero_grad()
         if self._pipe is not None:
             stats = self._pipe.train_batch(input_, loss_fn, n_mbs)
@@ -106,7 +106,7 @@ class ReaLEngine(PipelinableEngine):
                 for k, v in st.items():
                     stats[k] = stats[k] + (v.detach() if torch.is_tensor(v) else v) / len(mbs)
         ost = self.optim.step(version_steps)
-        self.optim.release()
+        self.optim.end_call()
         self._check_ep()
         stats = dict(stats)
         stats.update(ost)
@@ -116,7 +116,7 @@ class ReaLEngine(PipelinableEngine):
     def eval_batch(self, input_: SequenceSample, loss_fn: Callable, num_micro_batches: Optional[int] = None):
         n_mbs = num_micro_batches or 1
         if self.optim is not None:
-            self.optim.materialize()
+            self.optim.begin_call()
         try:
             if self._pipe is not None:
                 return self._pipe.eval_batch(input_, loss_fn, n_mbs)
@@ -129,7 +129,7 @@ class ReaLEngine(PipelinableEngine):
             return dict(stats)
         finally:
             if self.optim is not None:
-                self.optim.release()
+                self.optim.end_call()
 
     @torch.no_grad()
     def forward(self, input_: SequenceSample, num_micro_batches: Optional[int] = None,
@@ -139,7 +139,7 @@ class ReaLEngine(PipelinableEngine):
         before aggregation so full logits never pile up (reference: backend/inference.py:96-124)."""
         n_mbs = num_micro_batches or 1
         if self.optim is not None:
-            self.optim.materialize()
+            self.optim.begin_call()
         try:
             if self._pipe is not None:
                 return self._pipe.forward(input_, n_mbs, post_hook, aggregate_fn)
@@ -151,7 +151,7 @@ class ReaLEngine(PipelinableEngine):
             return aggregate_fn(outs) if len(outs) > 1 else outs[0]
         finally:
             if self.optim is not None:
-                self.optim.release()
+                self.optim.end_call()
 
     @torch.no_grad()
     def generate(self, input_: SequenceSample, tokenizer, gconfig: GenerationHyperparameters = None,

@@ -209,13 +209,23 @@ class FlatAdamW:
             off += per
         assert off == self.shard_n
         self.lo, self.hi = self.ranges[0][0], min(n, self.ranges[-1][1])  # legacy names (exact with a single bucket)
-        # ---- gradient buffer
-        sg = self.ctx.dp_group if self.nvls else None
-        if cfg.share_grad_buffer:
-            self.flat_grad, self._grad_symm = _grad_pool_get(self.padded, self.grad_dtype, dev, sg)
+        # ---- per-layer ZeRO-3: parameters / gradients / states exist only as per-layer shards (engine/zero3.py)
+        self.z3 = None
+        if cfg.zero_stage >= 3 and model.ctx.pp_size == 1 and os.environ.get("REAL_ZERO3_GRANULARITY", "layer") == "layer" \
+                and model.config.resid_pdrop == 0 and model.config.attn_pdrop == 0 and model.config.embd_pdrop == 0 \
+                and not model.sequence_parallel:
+            from realhf_b200.engine.zero3 import Zero3Layers
+            self.flat_grad, self._grad_symm = None, None
+            self.z3 = Zero3Layers(self)
+            self.shard_n = self.z3.shard_n
         else:
-            self.flat_grad, self._grad_symm = _alloc_flat(self.padded, self.grad_dtype, dev, sg)
-        model.attach_grad_buffer(self.flat_grad[:n])
+            # ---- gradient buffer
+            sg = self.ctx.dp_group if self.nvls else None
+            if cfg.share_grad_buffer:
+                self.flat_grad, self._grad_symm = _grad_pool_get(self.padded, self.grad_dtype, dev, sg)
+            else:
+                self.flat_grad, self._grad_symm = _alloc_flat(self.padded, self.grad_dtype, dev, sg)
+            model.attach_grad_buffer(self.flat_grad[:n])
         # ---- parameter storage: padded (in-place all-gather of the last bucket) and symmetric on the NVLS path
         self._param_symm = None
         self.param_store: Optional[torch.Tensor] = None
@@ -230,11 +240,14 @@ class FlatAdamW:
         self.master = None
         if self.use_master:
             self.master = torch.zeros(self.shard_n, dtype=torch.float32, device=sdev, **pin)
-            flat = model.flat_param.data
-            for (a, b), so in zip(self.ranges, self.state_off):
-                b = min(b, n)
-                if b > a:
-                    self.master[so: so + b - a].copy_(flat[a:b].float())
+            if self.z3 is not None:
+                self.master.copy_(self.z3.pshard.float())
+            else:
+                flat = model.flat_param.data
+                for (a, b), so in zip(self.ranges, self.state_off):
+                    b = min(b, n)
+                    if b > a:
+                        self.master[so: so + b - a].copy_(flat[a:b].float())
         self.step_count = 0
         self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
         self._scale = torch.ones((), dtype=torch.float32, device=dev)
@@ -295,6 +308,9 @@ class FlatAdamW:
 
     # ------------------------------------------------------------------ step
     def zero_grad(self):
+        if self.z3 is not None:
+            self.z3.zero_grad()
+            return
         self.flat_grad.zero_()
         self._next_bucket = len(self.buckets) - 1
         self._pending = []
@@ -311,7 +327,7 @@ class FlatAdamW:
 
     def arm(self, on: bool):
         """Arm / disarm the in-backward reduce-scatter (armed for the last micro-batch of a train_batch only)."""
-        self.model._grad_boundary = self.boundary if (on and self._overlap_ok and self.model.ctx.pp_size == 1) else None
+        self.model._grad_boundary = self.boundary if (on and self._overlap_ok and self.model.ctx.pp_size == 1 and self.z3 is None) else None
 
     def grad_ready(self, layer_idx: int):
         """All parameter gradients of layers >= layer_idx are final (and enqueued): reduce every bucket that lies entirely
@@ -371,7 +387,33 @@ class FlatAdamW:
         if self.nvls:
             torch.cuda.current_stream(self.flat_grad.device).wait_stream(self._comm_stream)
 
+    def _step_zero3(self, version_steps: Optional[int]) -> Dict[str, torch.Tensor]:
+        cfg, ctx = self.cfg, self.ctx
+        z = self.z3
+        z.finish_grads()
+        self._stats.zero_()
+        z.grad_sumsq(self._stats)
+        if ctx.model_group is not None and ctx.topo.world_size() > 1:
+            dist.all_reduce(self._stats, group=ctx.model_group)
+        inv_ls = 1.0 / self.loss_scale
+        norm = self._stats[0].sqrt() * inv_ls
+        self.last_grad_norm = norm
+        clip = cfg.gradient_clipping
+        coef = torch.clamp(clip / (norm + 1e-6), max=1.0) if clip and clip > 0 else torch.ones_like(norm)
+        self._scale.copy_(coef * inv_ls)
+        self._skip.copy_((self._stats[1:2] > 0).int())
+        self.step_count += 1
+        if version_steps is not None:
+            self.sched.step_absolute(version_steps)
+        lr = self.sched.get_lr()
+        z.step(lr)  # the updated shard IS the parameter store: the next gather picks the new values up, no all-gather here
+        if self.model.dtype == torch.float16:
+            self._update_loss_scale()
+        return {"grad_norm": norm, "lr": torch.tensor(lr), "skipped": self._skip.float()[0]}
+
     def step(self, version_steps: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        if self.z3 is not None:
+            return self._step_zero3(version_steps)
         cfg, ctx = self.cfg, self.ctx
         self.arm(False)
         self._sync_grads()
@@ -493,7 +535,29 @@ class FlatAdamW:
     # Between model function calls only this rank's 1/dp slice of the flat parameter buffer stays resident (on the GPU,
     # or in pinned host memory with `offload_param`); `materialize()` all-gathers the full buffer before a call and
     # `release()` drops it afterwards.  ZeRO-3 uses ONE bucket (ranges[0] is the classic contiguous shard).
+    def begin_call(self, train: bool = False):
+        """Start of an engine call on a ZeRO-3 model: per-layer streaming when available, whole-model gather otherwise."""
+        if self.z3 is not None:
+            if self.model.instantiated:   # somebody materialised the full buffer (generation / save): drop it first
+                self.release()
+            self.z3.begin_call(train)
+        else:
+            self.materialize()
+
+    def end_call(self):
+        if self.z3 is not None:
+            self.z3.end_call()
+        else:
+            self.release()
+
     def release(self):
+        if self.z3 is not None:
+            if self.model.instantiated:
+                if getattr(self, "_full_dirty", False):  # the full buffer was written (checkpoint load, realloc into this model)
+                    self.z3.absorb_full(self.model.flat_param.data)
+                    self._full_dirty = False
+                self.model.detach_params()
+            return
         if self.cfg.zero_stage < 3 or not self.model.instantiated:
             return
         flat = self.model.flat_param.data
@@ -510,6 +574,11 @@ class FlatAdamW:
         self.model.release_params()
 
     def materialize(self):
+        if self.z3 is not None:
+            if not self.model.instantiated:
+                self.z3.end_call()
+                self.model.attach_flat(self.z3.materialize_full())
+            return
         if self.cfg.zero_stage < 3 or self.model.instantiated:
             return
         n = self.model.flat_numel

@@ -142,7 +142,20 @@ class ReaLModel(nn.Module):
 
     @property
     def instantiated(self) -> bool:
-        return self.flat_param is not None
+        return self.flat_param is not None and not getattr(self, "_params_detached", False)
+
+    def detach_params(self):
+        """Drop the flat buffer but KEEP the parameter objects (per-layer ZeRO-3 re-points their `.data` at gathered scratch
+        buffers layer by layer; hooks and requires_grad flags live on the objects)."""
+        if self.flat_param is None:
+            return
+        empty = torch.empty(0, dtype=self.dtype, device=self.device)
+        self.flat_param.data = empty
+        for v in self.p.values():
+            v.data = empty
+            v.grad = None
+        self.flat_grad = None
+        self._params_detached = True
 
     def instantiate(self, init: str = "random", std: float = 0.02, seed: Optional[int] = None) -> "ReaLModel":
         """Allocate the flat buffer and carve parameter views.  init: random | empty."""
@@ -184,6 +197,7 @@ class ReaLModel(nn.Module):
     def attach_flat(self, flat: torch.Tensor):
         """(Re)point every parameter view at `flat` (used by instantiate, realloc and offload reload)."""
         assert flat.numel() == self.flat_numel, (flat.numel(), self.flat_numel)
+        self._params_detached = False
         if self.flat_param is None:
             self.flat_param = nn.Parameter(flat, requires_grad=False)
         else:
@@ -487,7 +501,11 @@ class ReaLModel(nn.Module):
             elif i <= c.n_layers:
                 if gb is not None and x.requires_grad:
                     x = gb(x, i)
-                if ckpt and i < first_kept:
+                z3 = getattr(self, "_zero3", None)
+                if z3 is not None and z3.streaming:
+                    # per-layer ZeRO-3: gather this block's parameters, run it without keeping activations, release (engine/zero3.py)
+                    x, d = z3.run_block(i, lambda x_, d_, i=i: self._block_packed(i, x_, d_, position_ids, cu_seqlens, max_seqlen), x, d)
+                elif ckpt and i < first_kept:
                     x, d = self._ckpt_block(i, x, d, position_ids, cu_seqlens, max_seqlen)
                 else:
                     x, d = self._block_packed(i, x, d, position_ids, cu_seqlens, max_seqlen, kv_sink)

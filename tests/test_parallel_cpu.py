@@ -146,11 +146,12 @@ def test_moe_tp_and_expert_parallel_match_single_process(cfg):
             assert abs(a - b) < 3e-3 * max(1.0, abs(b)), (cfg, r, ref)
 
 
-def _zero3_worker(rank, world, zero_stage):
+def _zero3_worker(rank, world, zero_stage, n_mbs=1, grad_dtype="fp32"):
     import types
 
     from realhf_b200.api.config import ModelName
-    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.api.data import SequenceSample
+    from realhf_b200.api.model import FinetuneSpec, GenerationHyperparameters, Model
     from realhf_b200.base.topology import ParallelContext, ProcessTopology
     from realhf_b200.engine.engine import TrainBackend
     from realhf_b200.interfaces import basic
@@ -159,22 +160,42 @@ def _zero3_worker(rank, world, zero_stage):
     cfg = hf_io.family("llama").make_test_config()
     ctx = ParallelContext.build(ProcessTopology(1, world, 1), list(range(world)), rank, backend="gloo")
     m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    n_params = m.flat_numel
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
-    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant", grad_dtype="fp32"),
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant", grad_dtype=grad_dtype),
                          zero_stage=zero_stage).initialize(Model(ModelName("m", 0), m, tok, "cpu"), FinetuneSpec(1, 10, 10))
     resident = model.module.module.instantiated
-    mine = _batch(8).split(world)[rank]
-    losses = [basic.SFTInterface().train_step(model, mine, n_mbs=1)["loss"] for _ in range(3)]
-    return dict(losses=losses, resident_between_calls=resident and model.module.module.instantiated)
+    mine = _batch(12).split(world)[rank]
+    losses = [basic.SFTInterface().train_step(model, mine, n_mbs=n_mbs)["loss"] for _ in range(3)]
+    opt = model.module.optim
+    z3 = opt.z3
+    # generation needs every parameter at once: the optimizer materialises the full buffer, the next call drops it again
+    g = GenerationHyperparameters(max_new_tokens=4, min_new_tokens=4, greedy=True)
+    prompts = SequenceSample.from_default(seqlens=[4, 6], ids=[0, 1], data=dict(packed_input_ids=(torch.arange(2, 12) % cfg.vocab_size)))
+    gen_tokens = torch.cat([o.tokens for o in model.module.generate(prompts, tok, g, num_micro_batches=1)]).tolist()
+    logits = model.module.forward(prompts, num_micro_batches=1).float()
+    return dict(losses=losses, resident_between_calls=resident and model.module.module.instantiated, gen=gen_tokens,
+                logit_sum=float(logits.sum()), per_layer=z3 is not None, n_gathers=0 if z3 is None else z3.n_gathers,
+                shard_elems=opt.m.numel(), n_params=n_params, full_grad_buffer=opt.flat_grad is not None)
 
 
-def test_zero3_matches_zero1_and_releases_params():
+@pytest.mark.parametrize("cfg", [(2, 1), (3, 2)])
+def test_zero3_matches_zero1_and_releases_params(cfg):
+    """ZeRO-3 with per-layer gather / release (engine/zero3.py): same losses, generations and logits as ZeRO-1, parameters never
+    resident between calls, no full-size gradient buffer, optimizer state ~1/dp of the model; dp=3 exercises uneven slices and
+    n_mbs=2 the accumulation of reduce-scattered gradients over micro-batches."""
     from realhf_b200.base.testing import run_distributed
-    z1 = run_distributed(_zero3_worker, 2, zero_stage=1)
-    z3 = run_distributed(_zero3_worker, 2, zero_stage=3)
+    world, n_mbs = cfg
+    z1 = run_distributed(_zero3_worker, world, zero_stage=1, n_mbs=n_mbs)
+    z3 = run_distributed(_zero3_worker, world, zero_stage=3, n_mbs=n_mbs)
     assert z1[0]["resident_between_calls"] and not z3[0]["resident_between_calls"]
-    for a, b in zip(z1[0]["losses"], z3[0]["losses"]):
-        assert abs(a - b) < 1e-5
+    assert all(r["per_layer"] and r["n_gathers"] > 20 and not r["full_grad_buffer"] for r in z3)
+    assert z3[0]["shard_elems"] <= z3[0]["n_params"] // world + 64 * 16
+    for r1, r3 in zip(z1, z3):
+        for a, b in zip(r1["losses"], r3["losses"]):
+            assert abs(a - b) < 1e-5
+        assert r1["gen"] == r3["gen"]
+        assert abs(r1["logit_sum"] - r3["logit_sum"]) < 1e-3 * max(1.0, abs(r1["logit_sum"]))
 
 
 def _dropout_worker(rank, world, ckpt):
