@@ -61,6 +61,19 @@ def test_profile_experiment_cpu(tmp_path):
     assert json.load(open(out))[0]["bs"] == 2
 
 
+def test_profile_experiment_sweeps_layouts_in_one_launch(tmp_path):
+    """`layouts=[...]` sweeps parallel layouts inside one launch: multi-device layouts run in their own process group (gloo here),
+    a point's time is the maximum over its ranks, `bs` is the global batch."""
+    from realhf_b200.apps.quickstart import build_experiment
+    out = tmp_path / "prof.json"
+    cfg = build_experiment(["profile", "device=cpu", "interface=sft", "batch_sizes=[4]", "seqlens=[12]", "handles=[train_step]", "repeats=1",
+                            "layouts=[d1m1p1,d2m1p1,d1m2p1]", f"output_file={out}"])
+    rows = cfg.run_local()
+    assert [r["layout"] for r in rows] == ["d1m1p1", "d2m1p1", "d1m2p1"]
+    assert all(r["secs"] > 0 and r["bs"] == 4 and r["handle"] == "train_step" for r in rows)
+    assert len(json.load(open(out))) == 3
+
+
 def test_kernel_trace_categorisation():
     ev = [dict(cat="kernel", name="ncclDevKernel_AllReduce_Sum_bf16", dur=10.0), dict(cat="kernel", name="gemm_2cta_kernel<256>", dur=30.0),
           dict(cat="gpu_memcpy", name="Memcpy DtoD", dur=5.0), dict(cat="cpu_op", name="aten::add", dur=99.0)]
