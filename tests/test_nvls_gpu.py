@@ -201,9 +201,10 @@ def test_zero1_nvls_matches_nccl_and_single_gpu(world, state):
     assert abs(nvls[0]["grad_norm"] - nccl[0]["grad_norm"]) < 0.05 * max(1.0, nccl[0]["grad_norm"])
 
 
-def _tp_gen_worker(rank, world, nvls, n_new=16):
-    """Greedy CUDA-graph generation of a tp=world LLaMA whose row-parallel GEMMs write partial sums into symmetric memory and
-    whose all-reduce lives inside the residual-add + RMSNorm kernel (multimem.ld_reduce)."""
+def _tp_gen_worker(rank, world, nvls, n_new=16, force_tokens=None):
+    """CUDA-graph generation of a tp=world LLaMA whose row-parallel GEMMs write partial sums into symmetric memory and whose
+    all-reduce lives inside the residual-add + RMSNorm kernel (multimem.ld_reduce).  Returns tokens + log-probs; with
+    `force_tokens` (single GPU) the log-probs of THOSE continuations from one packed forward pass (teacher forcing)."""
     from realhf_b200.api.model import GenerationHyperparameters, ReaLModelConfig
     from realhf_b200.base.topology import ParallelContext, ProcessTopology
     from realhf_b200.models import generation as gen
@@ -232,6 +233,23 @@ def _tp_gen_worker(rank, world, nvls, n_new=16):
     g0 = torch.Generator().manual_seed(11)
     ids = torch.randint(3, 32000, (sum(lens),), generator=g0).to(dev)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    if force_tokens is not None:
+        # teacher forcing: log p(token_t | prompt, tokens_<t) for the given continuations, from the packed training-style forward
+        ft = force_tokens.to(dev)
+        seqs, new_lens = [], []
+        for i, L in enumerate(lens):
+            seqs.append(torch.cat([ids[int(cu[i]): int(cu[i + 1])], ft[i]]))
+            new_lens.append(L + ft.shape[1])
+        packed = torch.cat(seqs)
+        cu2 = torch.tensor([0] + list(torch.tensor(new_lens).cumsum(0)), dtype=torch.int32, device=dev)
+        with torch.no_grad():
+            out = m(input_ids=packed, cu_seqlens=cu2, max_seqlen=max(new_lens))
+            lg = torch.log_softmax(out.logits.float(), -1)
+        lps = []
+        for i, L in enumerate(lens):
+            rows = torch.arange(L - 1, L - 1 + ft.shape[1], device=dev) + int(cu2[i])
+            lps.append(lg[rows, ft[i]])
+        return dict(logprobs=torch.stack(lps).cpu())
     g = GenerationHyperparameters(max_new_tokens=n_new, min_new_tokens=n_new, greedy=True, use_cuda_graph=True, force_cudagraph_recapture=True)
     launches.reset()
     out, _ = gen.generate(m, ids, cu, g, eos_id=2, pad_id=0)
@@ -248,19 +266,15 @@ def test_tp_decode_with_in_switch_allreduce_matches_single_gpu(world):
     from realhf_b200.parallel.symm_mem import multicast_supported
     if not multicast_supported(torch.device("cuda", 0)):
         pytest.skip("no multicast support")
-    ref = run_distributed(_tp_gen_worker, 1, backend="nccl", nvls=False)[0]
     res = run_distributed(_tp_gen_worker, world, backend="nccl", nvls=True)
     assert all(r["nvls"] for r in res), "FusedTP did not get a multicast mapping"
+    assert res[0]["ops"].get("nvls_ar_add_rmsnorm", 0) > 0, res[0]["ops"]
     for r in res:
         assert torch.equal(r["tokens"], res[0]["tokens"]), "TP ranks disagree on the generated tokens"
-    # bf16 partial sums are rounded differently under TP: greedy tokens may fork late in a sequence, log-probs of the first
-    # token (same prefix by construction) must agree closely
-    agree = (res[0]["tokens"] == ref["tokens"]).float().mean().item()
-    assert agree >= 0.8, agree
-    torch.testing.assert_close(res[0]["logprobs"][:, 0], ref["logprobs"][:, 0], atol=0.05, rtol=0.05)
-    first_fork = (res[0]["tokens"] != ref["tokens"]).float().argmax(1)
-    same = (res[0]["tokens"] == ref["tokens"]).all(1)
-    assert (same | (first_fork >= 1)).all()
+    # a random-init model has nearly flat logits, so greedy tokens fork on rounding noise: check the tensor-parallel decode by
+    # teacher forcing instead -- the single-GPU model must assign (almost) the same log-probs to the TP run's own tokens
+    ref = run_distributed(_tp_gen_worker, 1, backend="nccl", nvls=False, force_tokens=res[0]["tokens"])[0]
+    torch.testing.assert_close(res[0]["logprobs"], ref["logprobs"], atol=0.08, rtol=0.05)
 
 
 def _ep_worker(rank, world, fused):
