@@ -14,19 +14,31 @@ from realhf_b200.ops import gemm as G
 
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-ctx = int(sys.argv[3]) if len(sys.argv) > 3 else 384
+ctx_len = int(sys.argv[3]) if len(sys.argv) > 3 else 384
 OF.set_gemm_impl(G.linear)
-dev = torch.device("cuda")
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+ctx = None
+if world > 1:  # tensor-parallel decode (launch with torchrun): B is the batch of the whole TP group
+    import torch.distributed as dist
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    torch.cuda.set_device(rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl")
+    from realhf_b200.parallel.fused_tp import FusedTP
+    ctx.symm = FusedTP(ctx, max_tokens=256, max_features=4096, device=torch.device("cuda", rank))
+dev = torch.device("cuda", rank)
 cfg = ReaLModelConfig(n_layers=layers, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008, vocab_size=32000,
                       n_positions=4096, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, activation_function="silu",
                       scale_attn_by_inverse_layer_idx=False, use_attention_bias=False, use_attn_proj_bias=False, use_mlp_bias=False,
                       layer_norm_type="rms", mlp_type="llama", apply_rotary=True)
-m = ReaLModel(cfg, dtype=torch.bfloat16, device=dev).init_random_fast()
+m = ReaLModel(cfg, ctx, dtype=torch.bfloat16, device=dev).init_random_fast()
 for p in m.parameters():
     p.requires_grad_(False)
 m.eval()
 st = gen.DecodeState(m, B, 640)
-st.cache_lens.fill_(ctx)
+st.cache_lens.fill_(ctx_len)
 st.input_ids.fill_(5)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -65,6 +77,10 @@ for e in evs:
     prev_end = max(prev_end, e.time_range.end)
 total = prev_end - t0
 busy = sum(r["dur_us"] for r in rows)
-print(json.dumps(dict(layers=layers, B=B, ctx=ctx, total_us=round(total, 1), sum_kernel_us=round(busy, 1), n_kernels=len(rows))))
-for r in rows:
-    print(json.dumps(r))
+if rank == 0:
+    print(json.dumps(dict(layers=layers, B=B, ctx=ctx_len, tp=world, total_us=round(total, 1), sum_kernel_us=round(busy, 1), n_kernels=len(rows))))
+    for r in rows:
+        print(json.dumps(r))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
