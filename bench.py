@@ -269,6 +269,8 @@ def main():
     ap.add_argument("--runtime", default="spmd", choices=["spmd", "master"],
                     help="spmd (default): every rank walks the DFG in-process (launched by torchrun for N > 1); master: the production "
                          "master/worker runtime launched through the quickstart + local scheduler (run WITHOUT torchrun: it spawns its own workers)")
+    ap.add_argument("--profile-mfc", default="", help="debug only: comma-separated MFC names to wrap in torch.profiler during the LAST timed step; "
+                                                     "prints kernel-time totals and the top kernels per MFC to stderr (the run's numbers are then not a bench value)")
     ap.add_argument("--tiny", action="store_true", help="debug only: toy model shapes for --runtime master (CPU smoke test of the arm)")
     ap.add_argument("--optimizer", default="lean", choices=["lean", "fp32"],
                     help="lean (default at every N, so the scaling curve compares like with like): bf16 Adam moments + stochastic "
@@ -425,6 +427,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    prof_state = {}
+    if args.profile_mfc and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        def _start(name):
+            if prof_state.get("armed"):
+                torch.cuda.synchronize()
+                prof_state[name] = (profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]), time.perf_counter())
+                prof_state[name][0].__enter__()
+
+        def _stop(name):
+            if name in prof_state and prof_state.get("armed"):
+                torch.cuda.synchronize()
+                pr, t0 = prof_state.pop(name)
+                wall = time.perf_counter() - t0
+                pr.__exit__(None, None, None)
+                rows = []
+                for e in pr.key_averages():
+                    t = getattr(e, "self_device_time_total", 0) or 0
+                    if t > 0:
+                        rows.append((t, e.count, e.key))
+                rows.sort(reverse=True)
+                tot = sum(r[0] for r in rows)
+                cpu_top = sorted(((e.self_cpu_time_total, e.count, e.key) for e in pr.key_averages()), reverse=True)[:12]
+                print(f"[profile {name}] wall {wall * 1e3:.1f} ms, sum of kernel time {tot / 1e3:.1f} ms, {sum(r[1] for r in rows)} launches", file=sys.stderr)
+                for t, c, k in rows[:18]:
+                    print(f"    {t / 1e3:9.2f} ms  x{c:<5d} {k[:110]}", file=sys.stderr)
+                print("    -- host side (self CPU time):", file=sys.stderr)
+                for t, c, k in cpu_top:
+                    print(f"    {t / 1e3:9.2f} ms  x{c:<5d} {k[:110]}", file=sys.stderr)
+        for name in args.profile_mfc.split(","):
+            ex.hooks.setdefault(name, []).append(lambda n=name: _start(n))
+            ex.post_hooks.setdefault(name, []).append(lambda n=name: _stop(n))
     for i in range(args.warmup):
         rec, st_a, st_c = one_step(i)
         if args.verbose and rank == 0:
@@ -439,6 +474,7 @@ def main():
     mfc_ms = {}
     n_tokens_total = 0.0
     for i in range(args.steps):
+        prof_state["armed"] = bool(args.profile_mfc) and i == args.steps - 1
         rec, st_a, st_c = one_step(args.warmup + i)
         for k, v in rec.items():
             mfc_ms[k] = mfc_ms.get(k, 0.0) + v.device_ms / args.steps

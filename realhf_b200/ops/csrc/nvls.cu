@@ -226,45 +226,64 @@ __global__ void __launch_bounds__(kThreads) nvls_ar_add_rmsnorm_kernel(Peers P, 
   rb::pdl_wait();  // the producing GEMM of THIS rank is complete; the barrier below covers the peers'
   block_barrier(P, rank, world);
   const rb::Pack<T, V>* wr = reinterpret_cast<const rb::Pack<T, V>*>(w);
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int4* src = reinterpret_cast<const int4*>(mc + off + (int64_t)row * H * sizeof(T));
-    float vals[kMaxVec][V];
-    float ss = 0.f;
+  // two rows per iteration: both rows' multimem loads are issued before either is consumed (a block of the decode path owns
+  // rows / 64 <= 2 rows, so the whole kernel is ONE NVLink round trip after the barrier)
+  constexpr int R = 2;
+  for (int row0 = blockIdx.x; row0 < rows; row0 += R * gridDim.x) {
+    int4 raw[R][kMaxVec];
 #pragma unroll
-    for (int it = 0; it < kMaxVec; ++it) {
-      const int i = threadIdx.x + it * kThreads;
-      if (i < nvec) {
-        int4 raw = mm_ld_reduce<T>(src + i);
-        const T* a = reinterpret_cast<const T*>(&raw);
-        if (res_in != nullptr) {
-          rb::Pack<T, V> b = reinterpret_cast<const rb::Pack<T, V>*>(res_in + (int64_t)row * H)[i];
-          rb::Pack<T, V> o;
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * gridDim.x;
+      if (row < rows) {
+        const int4* src = reinterpret_cast<const int4*>(mc + off + (int64_t)row * H * sizeof(T));
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            o.v[k] = rb::from_f<T>(rb::to_f(a[k]) + rb::to_f(b.v[k]));
-            vals[it][k] = rb::to_f(o.v[k]);
-          }
-          reinterpret_cast<rb::Pack<T, V>*>(res_out + (int64_t)row * H)[i] = o;
-        } else {
-#pragma unroll
-          for (int k = 0; k < V; ++k) vals[it][k] = rb::to_f(a[k]);
-          if (res_out != nullptr) reinterpret_cast<int4*>(res_out + (int64_t)row * H)[i] = raw;
+        for (int it = 0; it < kMaxVec; ++it) {
+          const int i = threadIdx.x + it * kThreads;
+          if (i < nvec) raw[r][it] = mm_ld_reduce<T>(src + i);
         }
-#pragma unroll
-        for (int k = 0; k < V; ++k) ss = fmaf(vals[it][k], vals[it][k], ss);
       }
     }
-    if (y == nullptr) continue;  // plain all-reduce (+ residual) without a norm
-    ss = rb::block_reduce<false>(ss, red);
-    const float rstd = rsqrtf(ss / (float)H + eps);
 #pragma unroll
-    for (int it = 0; it < kMaxVec; ++it) {
-      const int i = threadIdx.x + it * kThreads;
-      if (i < nvec) {
-        rb::Pack<T, V> ww = wr[i], o;
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * gridDim.x;
+      if (row >= rows) break;
+      float vals[kMaxVec][V];
+      float ss = 0.f;
 #pragma unroll
-        for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(vals[it][k] * rstd * (rb::to_f(ww.v[k]) + w_offset));
-        reinterpret_cast<rb::Pack<T, V>*>(y + (int64_t)row * H)[i] = o;
+      for (int it = 0; it < kMaxVec; ++it) {
+        const int i = threadIdx.x + it * kThreads;
+        if (i < nvec) {
+          const T* a = reinterpret_cast<const T*>(&raw[r][it]);
+          if (res_in != nullptr) {
+            rb::Pack<T, V> bb = reinterpret_cast<const rb::Pack<T, V>*>(res_in + (int64_t)row * H)[i];
+            rb::Pack<T, V> o;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              o.v[k] = rb::from_f<T>(rb::to_f(a[k]) + rb::to_f(bb.v[k]));
+              vals[it][k] = rb::to_f(o.v[k]);
+            }
+            reinterpret_cast<rb::Pack<T, V>*>(res_out + (int64_t)row * H)[i] = o;
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) vals[it][k] = rb::to_f(a[k]);
+            if (res_out != nullptr) reinterpret_cast<int4*>(res_out + (int64_t)row * H)[i] = raw[r][it];
+          }
+#pragma unroll
+          for (int k = 0; k < V; ++k) ss = fmaf(vals[it][k], vals[it][k], ss);
+        }
+      }
+      if (y == nullptr) continue;  // plain all-reduce (+ residual) without a norm
+      ss = rb::block_reduce<false>(ss, red);
+      const float rstd = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+      for (int it = 0; it < kMaxVec; ++it) {
+        const int i = threadIdx.x + it * kThreads;
+        if (i < nvec) {
+          rb::Pack<T, V> ww = wr[i], o;
+#pragma unroll
+          for (int k = 0; k < V; ++k) o.v[k] = rb::from_f<T>(vals[it][k] * rstd * (rb::to_f(ww.v[k]) + w_offset));
+          reinterpret_cast<rb::Pack<T, V>*>(y + (int64_t)row * H)[i] = o;
+        }
       }
     }
   }
