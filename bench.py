@@ -463,7 +463,9 @@ def main():
     for i in range(args.warmup):
         rec, st_a, st_c = one_step(i)
         if args.verbose and rank == 0:
-            print(f"[warmup {i}] " + " ".join(f"{k}={v.device_ms:.0f}ms" for k, v in rec.items()), file=sys.stderr, flush=True)
+            from realhf_b200.models import generation as _gen
+            print(f"[warmup {i}] " + " ".join(f"{k}={v.device_ms:.0f}ms" for k, v in rec.items())
+                  + (f" gen_phases={_gen.LAST_TIMING}" if _gen.LAST_TIMING else ""), file=sys.stderr, flush=True)
     sampler = ClockSampler(world) if local_rank == 0 else _NoSampler()
     barrier()
     sampler.start()
@@ -494,9 +496,17 @@ def main():
     tokens_this_rank = float(sum(pool.flat_seqlens("packed_input_ids")))
     t = torch.tensor([dev_s, wall, tokens_this_rank, float(n_launch)], dtype=torch.float64, device=dev)
     tmax = t.clone()
+    # per-MFC device time: rank 0's own clock, plus min / max over ranks (collective-free MFCs such as DP generation finish at
+    # different times on different GPUs; the skew is absorbed by the first collective of the next training MFC)
+    names = sorted(mfc_ms)
+    mv = torch.tensor([mfc_ms[k] for k in names], dtype=torch.float64, device=dev)
+    mv_max, mv_min = mv.clone(), mv.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mv_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mv_min, op=dist.ReduceOp.MIN)
+    mfc_minmax = {k: [round(float(a), 1), round(float(b), 1)] for k, a, b in zip(names, mv_min, mv_max)}
     dev_s, wall = float(tmax[0]), float(tmax[1])
     tokens_per_step = float(t[2]) if world > 1 else tokens_this_rank
     value = tokens_per_step * args.steps / dev_s
@@ -521,7 +531,7 @@ def main():
                                                     else ("every block" if args.ckpt else "none")),
                        "gemm": args.gemm, "attention": "own tcgen05 varlen fwd/bwd + own split-KV decode kernel",
                        "l2": "working set >> L2 (54 GB weights per GPU); fresh inputs every step",
-                       "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}},
+                       "mfc_ms": {k: round(v, 1) for k, v in mfc_ms.items()}, "mfc_ms_min_max_over_ranks": mfc_minmax},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": result_host.numel() * 4 * world,

@@ -27,6 +27,7 @@ from realhf_b200.parallel import tp as TP
 
 
 _SAMPLE_SEED = [0x5DEECE66D]
+LAST_TIMING: dict = {}   # REAL_GEN_TIMING=1: device ms of the phases of the last `generate` call (prefill / capture / decode loop)
 
 
 def seed_sampling(seed: int):
@@ -180,6 +181,15 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     was_training = model.training
     model.eval()
     sp_saved, model.sequence_parallel = model.sequence_parallel, False  # token-sharded activations make no sense for decode
+    timing = os.environ.get("REAL_GEN_TIMING", "0") == "1" and dev.type == "cuda"
+    marks = []
+
+    def mark(name):
+        if timing:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+    mark("start")
     # ---- prefill
     kv: List[Tuple[torch.Tensor, torch.Tensor]] = []
     out = model(input_ids=input_ids, cu_seqlens=cu, max_seqlen=max_prompt, kv_sink=kv)
@@ -220,6 +230,7 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         seed = int(_SAMPLE_SEED[0])
         _SAMPLE_SEED[0] = (seed * 6364136223846793005 + 1442695040888963407) % (1 << 62)
         state.seed.fill_(seed)
+    mark("prefill")
     if use_graph and state.graph is None:
         state.input_ids.copy_(nxt)
         lens_backup = state.cache_lens.clone()
@@ -241,6 +252,7 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         state.graph_launches = launches.end_capture()
         state.graph = graph
         state.graph_sig = sig
+    mark("capture")
     step = 1
     if in_graph:
         state.input_ids.copy_(nxt)
@@ -274,6 +286,12 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         tokens = torch.stack(toks, 1)
         logprobs = torch.stack(lps, 1)
         mask_bits = torch.stack(masks, 1) if masks[0] is not None else None
+    mark("decode")
+    if timing:
+        torch.cuda.synchronize(dev)
+        LAST_TIMING.clear()
+        LAST_TIMING.update({f"{b[0]}_ms": round(a[1].elapsed_time(b[1]), 2) for a, b in zip(marks[:-1], marks[1:])})
+        LAST_TIMING.update(steps=step, B=B, ms_per_decode_step=round(marks[-2][1].elapsed_time(marks[-1][1]) / max(step - 1, 1), 4))
     n_gen = tokens.shape[1]
     if eos_id is not None:
         is_eos = tokens == eos_id

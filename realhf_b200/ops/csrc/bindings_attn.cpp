@@ -28,15 +28,15 @@ Tensor decode_attention(const Tensor& qkv, Tensor k_cache, Tensor v_cache, const
   const int S = k_cache.size(1);
   c10::cuda::CUDAGuard guard(qkv.device());
   auto out = at::empty({B, nq * hd}, qkv.options());
-  // Split the KV range of a (sequence, kv head) over several CTAs when there are too few of them to keep enough loads in flight:
-  // a 128-thread CTA holds ~8 KB of cache reads in flight, full HBM rate needs ~45 KB per SM, i.e. ~6 resident CTAs per SM
-  // (`REAL_DECODE_CTAS_PER_SM` overrides; the extra reduce kernel costs a launch, so single-split stays when it is close).
-  static const int target = [] { const char* e = getenv("REAL_DECODE_CTAS_PER_SM"); return e ? atoi(e) : 6; }();
+  // Split the KV range of a (sequence, kv head) over several CTAs only when there are fewer than two CTAs per SM.  Measured on
+  // B200 at B=16 x 32 heads (512 CTAs, ctx 384): forcing 2-3 splits made the 4-layer decode step 4% SLOWER (565 -> 588 us;
+  // the reduce kernel's launch + the partial round trip cost more than the extra loads in flight buy), so the threshold stays
+  // low; `REAL_DECODE_CTAS_PER_SM` overrides it for experiments.
+  static const int target = [] { const char* e = getenv("REAL_DECODE_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
   int splits = 1;
   const int64_t ctas = (int64_t)B * nkv;
-  if (ctas * 4 < (int64_t)target * 148 * 3 && S >= 256) {
+  if (ctas < (int64_t)target * 148 && S >= 512) {
     splits = (int)std::min<int64_t>(16, ((int64_t)target * 148 + ctas - 1) / ctas);
-    while (splits > 1 && S / splits < 64) --splits;
   }
   Tensor pa, pm;
   if (splits > 1) {
