@@ -133,16 +133,18 @@ def run_master_runtime(args):
     import uuid
 
     import torch
-
+    n = args.gpus
+    root = tempfile.mkdtemp(prefix="realhf_b200_bench_")
+    # BEFORE the package is imported: `base.constants` resolves the log / checkpoint roots from the environment at import time,
+    # and the worker processes (which inherit the environment) must resolve the same paths as this launcher
+    os.environ.setdefault("REAL_FILEROOT", os.path.join(root, "fileroot"))
+    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")  # the worker processes import this checkout
+    os.environ["REAL_FAST_INIT"] = "1"  # device-side random init (a host-side draw of 4 x 6.7e9 normals takes minutes)
+    assert "realhf_b200.base.constants" not in sys.modules, "run_master_runtime must set REAL_FILEROOT before realhf_b200 is imported"
     from realhf_b200.api.model import ReaLModelConfig
     from realhf_b200.apps.main import main_start
     from realhf_b200.apps.quickstart import build_experiment
     from realhf_b200.models import hf_io
-    n = args.gpus
-    root = tempfile.mkdtemp(prefix="realhf_b200_bench_")
-    os.environ.setdefault("REAL_FILEROOT", os.path.join(root, "fileroot"))
-    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")  # the worker processes import this checkout
-    os.environ["REAL_FAST_INIT"] = "1"  # device-side random init (a host-side draw of 4 x 6.7e9 normals takes minutes)
     # tokenizer + config-only "checkpoint" directories
     from tokenizers import Tokenizer, models, pre_tokenizers, trainers
     from transformers import PreTrainedTokenizerFast
@@ -356,8 +358,12 @@ def main():
     assert per_rank * world == args.prompts
     gen_mbs = 1  # one decode pass over all local sequences: weights are streamed once per token (KV cache 43 GB at N=1)
     inf_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
+    # On one GPU the 43 GB KV cache must be freed before training, so the decode graph is re-captured every step (~0.15-0.3 s per
+    # generate call: profiles/bench_n1_r2_gen_phases.log).  From 2 GPUs on the cache (<= 21.5 GB per GPU) stays resident together with
+    # the captured graph, like the reference's default (`force_cudagraph_recapture=False`).
+    recapture = world == 1
     gcfg = dict(max_new_tokens=args.new_tokens, min_new_tokens=args.new_tokens, greedy=False, top_p=0.9, top_k=1000,
-                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=True)  # recapture: KV cache is freed before training
+                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=recapture)
     ppo_kw = dict(n_minibatches=4, kl_ctl=0.1, discount=1.0, gae_lambda=1.0, eps_clip=0.2, value_eps_clip=0.2,
                   max_reward_clip=20.0, adaptive_kl_ctl=False, value_norm=True)
     A = lambda t, **a: ModelInterfaceAbstraction(t, a)
@@ -526,6 +532,7 @@ def main():
                        "optimizer": ("AdamW, fp32 master weights + fp32 moments (reference precision), bf16 grads" if args.optimizer == "fp32" else
                                      "AdamW, bf16 moments + stochastic rounding (no fp32 master), bf16 grads"),
                        "zero_comm": zero_comm, "gen_layout_search": gen_choice,
+                       "decode_graph": "re-captured every step (KV cache freed before training)" if recapture else "captured once, KV cache resident",
                        "frozen_model_offload": args.offload_frozen == "on" or (args.offload_frozen == "auto" and world == 1 and args.ckpt == "auto"),
                        "activation_checkpointing": (f"auto: {unckpt} of {args.layers} blocks keep activations (free-HBM budget)" if args.ckpt == "auto"
                                                     else ("every block" if args.ckpt else "none")),

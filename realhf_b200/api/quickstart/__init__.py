@@ -63,6 +63,7 @@ class ModelTrainEvalConfig:
     optimizer: Optional[OptimizerConfig] = dataclasses.field(default_factory=OptimizerConfig)
     init_from_scratch: bool = False
     init_critic_from_actor: bool = False
+    expert_parallel: bool = False   # MoE models: partition whole experts over the tensor-parallel group (parallel/ep.py)
 
 
 # ------------------------------------------------------------------------------------------- datasets

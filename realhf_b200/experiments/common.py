@@ -210,7 +210,8 @@ class CommonExperimentConfig(Experiment):
             trainable = any(b.rpc.role == a.rpc.role and b.rpc.interface_type == ModelInterfaceType.TRAIN_STEP for b in rpc_allocs)
             model = ModelAbstraction("real_model", args=dict(
                 model_path=mcfg.path, is_critic=mcfg.type.is_critic, init_from_scratch=mcfg.init_from_scratch,
-                init_critic_from_actor=mcfg.init_critic_from_actor, dtype=self.dtype, hf_model_family=mcfg.type._class))
+                init_critic_from_actor=mcfg.init_critic_from_actor, dtype=self.dtype, hf_model_family=mcfg.type._class,
+                expert_parallel=getattr(mcfg, "expert_parallel", False)))
             if trainable:
                 backend = ModelBackendAbstraction("train", args=dict(optimizer=dataclasses.asdict(mcfg.optimizer),
                                                                       zero_stage=mcfg.zero_stage, offload_optimizer=mcfg.offload))

@@ -20,7 +20,7 @@ _DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32, Non
 
 def make_real_model(name: ModelName, device, model_path: str, is_critic: bool, init_from_scratch: bool = False,
                     init_critic_from_actor: bool = False, dtype: Optional[str] = None, hf_model_family: str = "llama",
-                    config: Optional[model_api.ReaLModelConfig] = None, tokenizer=None) -> model_api.Model:
+                    config: Optional[model_api.ReaLModelConfig] = None, tokenizer=None, expert_parallel: bool = False) -> model_api.Model:
     scope = constants.current_scope() or {}
     ctx: ParallelContext = scope.get("ctx") or ParallelContext.single()
     instantiate = scope.get("instantiate", True)
@@ -33,6 +33,8 @@ def make_real_model(name: ModelName, device, model_path: str, is_critic: bool, i
             config.is_critic = is_critic
             if is_critic:
                 config.tied_embedding = False
+    if expert_parallel and getattr(config, "moe", None) is not None and config.mlp_type == "moe":
+        config.moe.expert_parallel = True
     m = ReaLModel(config, ctx, dtype=tdtype, device=device)
     m.hf_family = hf_model_family
     if instantiate:
