@@ -359,9 +359,11 @@ def main():
     gen_mbs = 1  # one decode pass over all local sequences: weights are streamed once per token (KV cache 43 GB at N=1)
     inf_mbs = 2 if per_rank * (args.prompt_len + args.new_tokens) > 48 * 1024 else 1
     # On one GPU the 43 GB KV cache must be freed before training, so the decode graph is re-captured every step (~0.15-0.3 s per
-    # generate call: profiles/bench_n1_r2_gen_phases.log).  From 2 GPUs on the cache (<= 21.5 GB per GPU) stays resident together with
-    # the captured graph, like the reference's default (`force_cudagraph_recapture=False`).
-    recapture = world == 1
+    # generate call: profiles/bench_n1_r2_gen_phases.log); at N=2 keeping the 21.5 GB cache resident costs 7 un-recomputed blocks of
+    # the activation budget and loses more in training than it gains in generation (measured 9.9 k vs 10.1 k tokens/s).  From 4 GPUs
+    # on the cache (<= 10.7 GB per GPU) stays resident together with the captured graph, like the reference's default
+    # (`force_cudagraph_recapture=False`).
+    recapture = world <= 2
     gcfg = dict(max_new_tokens=args.new_tokens, min_new_tokens=args.new_tokens, greedy=False, top_p=0.9, top_k=1000,
                 temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=recapture)
     ppo_kw = dict(n_minibatches=4, kl_ctl=0.1, discount=1.0, gae_lambda=1.0, eps_clip=0.2, value_eps_clip=0.2,

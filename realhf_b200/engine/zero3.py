@@ -287,8 +287,12 @@ class Zero3Layers:
 
     # ---------------------------------------------------------------- optimizer step over the shard space
     def step(self, lr: float) -> None:
+        """AdamW on this rank's shard of every layer.  Parameter shard and optimizer state may each live on the GPU or in pinned
+        host memory (`offload_param` / optimizer `offload`): host-resident pieces are streamed through the GPU, the update
+        itself always runs in the fused kernel."""
         o, cfg = self.optim, self.optim.cfg
-        dev_p = self.pshard if self.pshard.is_cuda or not self.model.device.type == "cuda" else None
+        dev = self.model.device
+        p_on_host = dev.type == "cuda" and not self.pshard.is_cuda
         for li in self.layers:
             a, b = self._my_range(li)
             n_my = b - a
@@ -296,20 +300,20 @@ class Zero3Layers:
                 continue
             so = self.off[li]
             g = self.gshard[so: so + n_my]
-            mst = o.master[so: so + n_my] if o.master is not None else None
-            if dev_p is not None:
-                p = self.pshard[so: so + n_my]
+            p = self.pshard[so: so + n_my]
+            if p_on_host:
+                p = p.to(dev, non_blocking=True)
+            if o.offload:   # m / v / master in pinned host memory: chunked, double-buffered (FlatAdamW._offloaded_update)
+                o._offloaded_update(p, g, lr, so)
+            else:
+                mst = o.master[so: so + n_my] if o.master is not None else None
                 OF.adamw_step(p, g, o.m[so: so + n_my], o.v[so: so + n_my], mst, lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.weight_decay,
                               o.step_count, o._scale, o._skip, stochastic=(o.state_dtype == torch.bfloat16),
                               seed=(o.step_count * 2654435761 + 7919 * li) % (2 ** 31))
-            else:  # parameter shard parked in pinned host memory: update a device copy, write it back
-                p = self.pshard[so: so + n_my].to(self.model.device, non_blocking=True)
-                OF.adamw_step(p, g, o.m[so: so + n_my], o.v[so: so + n_my], mst, lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.weight_decay,
-                              o.step_count, o._scale, o._skip, stochastic=(o.state_dtype == torch.bfloat16),
-                              seed=(o.step_count * 2654435761 + 7919 * li) % (2 ** 31))
+            if p_on_host:
                 self.pshard[so: so + n_my].copy_(p, non_blocking=True)
-        if self.model.device.type == "cuda" and not self.pshard.is_cuda:
-            torch.cuda.current_stream(self.model.device).synchronize()
+        if p_on_host:
+            torch.cuda.current_stream(dev).synchronize()
 
     def grad_sumsq(self, stats: torch.Tensor):
         for li in self.layers:

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def _run(zero_stage, offload_param, steps=3):
+def _run(zero_stage, offload_param, steps=3, offload_optimizer=False):
     from realhf_b200.api.config import ModelName
     from realhf_b200.api.data import SequenceSample
     from realhf_b200.api.model import FinetuneSpec, Model, ReaLModelConfig
@@ -29,7 +29,7 @@ def _run(zero_stage, offload_param, steps=3):
     m = ReaLModel(cfg, dtype=torch.bfloat16, device=dev).instantiate(seed=3, std=0.03)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
     model = TrainBackend(optimizer=dict(lr=2e-4, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant", grad_dtype="fp32",
-                                        gradient_clipping=1.0), zero_stage=zero_stage, offload_param=offload_param).initialize(
+                                        gradient_clipping=1.0), zero_stage=zero_stage, offload_param=offload_param, offload_optimizer=offload_optimizer).initialize(
         Model(ModelName("m", 0), m, tok, dev), FinetuneSpec(1, 10, 10))
     g = torch.Generator().manual_seed(0)
     lens = [200, 333, 64, 512, 90, 41]
@@ -42,9 +42,10 @@ def _run(zero_stage, offload_param, steps=3):
     return dict(losses=losses, z3=opt.z3, peak=torch.cuda.max_memory_allocated(), grad_norm=float(opt.last_grad_norm))
 
 
-def test_per_layer_zero3_with_param_offload_tracks_resident_training():
+@pytest.mark.parametrize("offload_optimizer", [False, True])
+def test_per_layer_zero3_with_param_offload_tracks_resident_training(offload_optimizer):
     ref = _run(1, False)
-    z = _run(3, True)
+    z = _run(3, True, offload_optimizer=offload_optimizer)
     assert z["z3"] is not None and z["z3"].n_gathers > 0 and not z["z3"].pshard.is_cuda and z["z3"].pshard.is_pinned()
     for a, b in zip(ref["losses"], z["losses"]):
         assert abs(a - b) < 3e-2 * max(1.0, abs(b)), (ref["losses"], z["losses"])
