@@ -85,6 +85,12 @@ def _apply_capacity(probs, idx, n_experts: int, mcfg):
     return probs * keep.view(T, k).to(probs.dtype)
 
 
+def _count_experts(flat_e: torch.Tensor, n_experts: int) -> torch.Tensor:
+    """Assignments per expert without a host sync (`torch.bincount` reads its input's maximum back to size the output, which also
+    makes it illegal inside CUDA-graph capture)."""
+    return torch.zeros(n_experts, dtype=torch.long, device=flat_e.device).scatter_add_(0, flat_e, torch.ones_like(flat_e))
+
+
 def grouped_mlp_device(x_sorted: torch.Tensor, counts_dev: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor, act: str):
     """Expert MLP over tokens sorted by expert with the counts left on the DEVICE: two grouped tcgen05 GEMM launches and the
     gated activation, no `tokens_per_expert.cpu()` (reference: moe/experts.py:186) and no per-expert Python loop."""
@@ -150,6 +156,24 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
         else:
             y_sorted = EP.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ctx.tp_group)
         return torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
+    if ep and _use_grouped_kernel(h, w_gu, w_dn):
+        # replicated tokens, sync-free (CUDA-graph capturable: the decode path): every rank sorts ALL assignments, the grouped GEMM
+        # is pointed at the row range of MY experts through device-side offsets (rows of other experts are never touched), the
+        # foreign rows are masked out and the partial outputs are all-reduced
+        e_local = E // ctx.tp_size
+        lo = ctx.tp_rank * e_local
+        e_sorted = flat_e[order]
+        offs = torch.zeros(E + 1, dtype=torch.int32, device=h.device)
+        offs[1:] = _count_experts(flat_e, E).cumsum(0)
+        from realhf_b200.ops import gemm as G
+        x_sorted = h.index_select(0, tok)
+        my_offs = offs[lo: lo + e_local + 1].contiguous()
+        hid = G.grouped_linear(x_sorted, w_gu, my_offs)
+        y_sorted = G.grouped_linear(OF.gated_act(hid, c.activation_function), w_dn, my_offs)
+        mine = ((e_sorted >= lo) & (e_sorted < lo + e_local)).unsqueeze(-1)
+        contrib = torch.where(mine, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1), torch.zeros((), dtype=y_sorted.dtype, device=h.device))
+        out = torch.zeros(T, H, dtype=h.dtype, device=h.device).index_add_(0, tok, contrib.to(h.dtype))
+        return TP.reduce_from_tp(out, ctx)
     if ep:
         # replicated tokens: keep only the assignments of my experts, all-reduce the partial outputs
         e_local = E // ctx.tp_size
@@ -165,7 +189,7 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
         return TP.reduce_from_tp(out, ctx)
     x_sorted = h.index_select(0, tok)
     if _use_grouped_kernel(x_sorted, w_gu, w_dn):
-        y_sorted = grouped_mlp_device(x_sorted, torch.bincount(flat_e, minlength=E), w_gu, w_dn, c.activation_function)
+        y_sorted = grouped_mlp_device(x_sorted, _count_experts(flat_e, E), w_gu, w_dn, c.activation_function)
     else:
         counts = torch.bincount(flat_e, minlength=E).tolist()
         y_sorted = grouped_mlp(x_sorted, counts, w_gu, w_dn, c.activation_function)

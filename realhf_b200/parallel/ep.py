@@ -190,5 +190,6 @@ def fused_ep_for(ctx, n_experts: int, hidden: int, dtype, device) -> "FusedEP | 
 
 
 def dispatch_compute_combine_fused(x_sorted, expert_sorted, n_experts, w_gate_up, w_down, act, ep: FusedEP):
-    counts = torch.bincount(expert_sorted, minlength=n_experts).int()
+    from realhf_b200.models.moe import _count_experts
+    counts = _count_experts(expert_sorted, n_experts).int()
     return _FusedEPExperts.apply(x_sorted.contiguous(), counts, w_gate_up, w_down, act, ep)

@@ -87,3 +87,31 @@ def test_train_step_bf16_params_fp32_main_grad():
     itf = basic.SFTInterface()
     losses = [itf.train_step(model, batch, n_mbs=n)["loss"] for n in (1, 2, 4, 1)]
     assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+
+
+def test_moe_decode_is_cuda_graph_capturable():
+    """The MoE decode step must not sync the host (expert counts via scatter_add, device-side offsets for the grouped GEMM): greedy
+    generation with the CUDA graph equals generation without it."""
+    from realhf_b200.api.model import GenerationHyperparameters
+    from realhf_b200.models import generation as gen
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.ops import functional as OF
+    from realhf_b200.ops import gemm as G
+    OF.set_gemm_impl(G.linear)
+    cfg = hf_io.family("mixtral").make_test_config()
+    cfg.hidden_dim, cfg.intermediate_dim, cfg.n_q_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab_size, cfg.n_layers = 512, 1024, 4, 4, 128, 1024, 2
+    cfg.moe.num_experts, cfg.moe.top_k = 8, 2
+    m = ReaLModel(cfg, dtype=torch.bfloat16, device=torch.device("cuda")).instantiate(seed=3, std=0.05)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    m.eval()
+    lens = [7, 19, 4, 11]
+    ids = torch.randint(3, 1024, (sum(lens),), device="cuda")
+    cu = torch.tensor([0, 7, 26, 30, 41], dtype=torch.int32, device="cuda")
+    outs = []
+    for graph in (True, False):
+        g = GenerationHyperparameters(max_new_tokens=10, min_new_tokens=10, greedy=True, use_cuda_graph=graph, force_cudagraph_recapture=True)
+        o, _ = gen.generate(m, ids, cu, g, eos_id=2, pad_id=0)
+        outs.append(o.tokens)
+    assert torch.equal(outs[0], outs[1])
