@@ -14,6 +14,11 @@ extern "C" int rb_gemm_streamk(const void* A, const void* B, void* C, const void
                                int64_t ldb, int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
                                cudaStream_t s);
 
+extern "C" int rb_gemm_streamk_fp8(const void* A, const void* B, void* C, const void* bias, const float* scale_a, const float* scale_b,
+                                   int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int out_dt, int bn, int split, int num_sms,
+                                   void* ws, void* flags, cudaStream_t s);
+extern "C" int rb_quant_rows_e4m3(const void* x, void* q, float* scale, int M, int K, int64_t ld_x, int64_t ld_q, int dt, cudaStream_t s);
+
 extern "C" int rb_gemm_grouped(const void* A, const void* B, void* C, const int* group_offsets, int G, int M, int N, int K, int64_t lda,
                                int64_t ldb, int64_t ldc, int b_mn, int num_sms, cudaStream_t s);
 
@@ -87,6 +92,55 @@ Tensor gemm_streamk(const Tensor& a, const Tensor& b, const c10::optional<Tensor
   return c;
 }
 
+// Row-wise e4m3 quantisation: x [M, K] (bf16 / fp16 / fp32, inner stride 1) -> (q uint8 [M, K], scale fp32 [M]), x ~ q * scale.
+// `q_out` / `scale_out`: optional preallocated destinations (the decode loop reuses them inside a CUDA graph).
+std::vector<Tensor> quant_rows_e4m3(const Tensor& x, const c10::optional<Tensor>& q_out, const c10::optional<Tensor>& scale_out) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1, "quant_rows_e4m3: x must be a CUDA matrix with unit inner stride");
+  const int64_t M = x.size(0), K = x.size(1);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor q = q_out.has_value() ? *q_out : at::empty({M, K}, x.options().dtype(at::kByte));
+  Tensor sc = scale_out.has_value() ? *scale_out : at::empty({M}, x.options().dtype(at::kFloat));
+  TORCH_CHECK(q.scalar_type() == at::kByte && q.dim() == 2 && q.size(0) == M && q.size(1) == K && q.stride(1) == 1 &&
+              sc.scalar_type() == at::kFloat && sc.numel() >= M && sc.is_contiguous(), "quant_rows_e4m3: bad destinations");
+  if (M == 0) return {q, sc};
+  int rc = rb_quant_rows_e4m3(x.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), (int)M, (int)K, x.stride(0), q.stride(0), dtc(x.scalar_type()),
+                              at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_quant_rows_e4m3 failed with code ", rc, " (K % 8 == 0, K <= 16384, 16-byte aligned rows)");
+  return {q, sc};
+}
+
+// W8A8 decode GEMM (M <= 128): y[m, n] = (sum_k a8[m, k] * b8[n, k]) * sa[m] * sb[n] (+ bias); a8 / b8 hold e4m3 bytes.
+Tensor gemm_streamk_fp8(const Tensor& a, const Tensor& b, const Tensor& sa, const Tensor& sb, const c10::optional<Tensor>& out,
+                        const c10::optional<Tensor>& bias, const Tensor& ws, const Tensor& flags, at::ScalarType out_dtype, int64_t bn,
+                        int64_t split, int64_t num_sms) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  TORCH_CHECK(a.scalar_type() == at::kByte && b.scalar_type() == at::kByte && a.size(1) == b.size(1), "gemm_streamk_fp8: operands are e4m3 bytes");
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(M <= 128, "gemm_streamk_fp8: M <= 128");
+  TORCH_CHECK(sa.scalar_type() == at::kFloat && sb.scalar_type() == at::kFloat && sa.numel() >= M && sb.numel() == N && sa.is_contiguous() &&
+              sb.is_contiguous(), "gemm_streamk_fp8: scales are fp32 [M] / [N]");
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.numel() >= 2 * num_sms * 128 * 256 && flags.numel() >= 8192 && flags.element_size() == 4);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor c;
+  if (out.has_value()) {
+    c = *out;
+    TORCH_CHECK(c.dim() == 2 && c.size(0) == M && c.size(1) == N && c.stride(1) == 1, "gemm_streamk_fp8: bad out shape");
+  } else {
+    c = at::empty({M, N}, a.options().dtype(out_dtype));
+  }
+  const void* bp = nullptr;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->scalar_type() == c.scalar_type() && bias->numel() == N && bias->is_contiguous());
+    bp = bias->data_ptr();
+  }
+  if (M == 0 || N == 0) return c;
+  int rc = rb_gemm_streamk_fp8(a.data_ptr(), b.data_ptr(), c.data_ptr(), bp, sa.data_ptr<float>(), sb.data_ptr<float>(), (int)M, (int)N, (int)K,
+                               a.stride(0), b.stride(0), c.stride(0), dtc(c.scalar_type()), (int)bn, (int)split, (int)num_sms, ws.data_ptr(),
+                               flags.data_ptr(), at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gemm_streamk_fp8 failed with code ", rc);
+  return c;
+}
+
 // Grouped GEMM over row groups (MoE experts): a [M, K] sorted by group, offsets int32 [G+1] on the device,
 // w [G, N, K] (b_mn = false: y = a_g @ w_g^T) or [G, K, N] (b_mn = true: y = a_g @ w_g).  One launch, no host sync.
 Tensor gemm_grouped(const Tensor& a, const Tensor& w, const Tensor& offsets, bool b_mn, int64_t num_sms) {
@@ -148,6 +202,8 @@ void register_gemm_ops(torch::Library& m) {
   m.def("gemm_glu(Tensor x, Tensor w, int act_kind, bool want_raw, int num_sms) -> Tensor[]", &gemm_glu);
   m.def("gemm_grouped_wgrad(Tensor dy, Tensor x, Tensor(a!) out, Tensor offsets, bool accumulate, int num_sms) -> ()", &gemm_grouped_wgrad);
   m.def("gemm_grouped(Tensor a, Tensor w, Tensor offsets, bool b_mn, int num_sms) -> Tensor", &gemm_grouped);
+  m.def("quant_rows_e4m3(Tensor x, Tensor? q_out, Tensor? scale_out) -> Tensor[]", &quant_rows_e4m3);
+  m.def("gemm_streamk_fp8(Tensor a, Tensor b, Tensor sa, Tensor sb, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType out_dtype, int bn, int split, int num_sms) -> Tensor", &gemm_streamk_fp8);
   m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);
   m.def("gemm(Tensor a, Tensor b, Tensor? out, Tensor? bias, bool a_mn, bool b_mn, bool accumulate, ScalarType? out_dtype, int bn, int num_sms, int mc) -> Tensor", &gemm);
 }

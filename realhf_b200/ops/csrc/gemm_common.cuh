@@ -99,4 +99,21 @@ bool make_tmap(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint
 }
 
 
+// 2-D row-major tensor of BYTES [rows, cols] (fp8 operands), 128B swizzle: a box row is 128 elements = one swizzle row.
+bool make_tmap_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  static thread_local bool ctx_ready = false;
+  if (!ctx_ready) { cudaFree(nullptr); ctx_ready = true; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[rb_gemm] cuTensorMapEncodeTiled(u8) failed: %d rows=%llu cols=%llu ld=%llu\n", (int)r,
+                                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace

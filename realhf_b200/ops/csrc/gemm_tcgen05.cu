@@ -303,6 +303,10 @@ struct StreamKParams {
   int a_box_rows;
   int bn, stages;
   long long* dbg;    // optional [gridDim.x][8] globaltimer stamps (profiling builds of the benchmark only)
+  // fp8 (e4m3) operands: out[m, n] = acc[m, n] * scale_a[m] * scale_b[n] (per-token activation scale, per-output-channel weight
+  // scale); nullptr for 16-bit operands
+  const float* scale_a;
+  const float* scale_b;
 };
 
 RB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -313,6 +317,8 @@ RB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
 RB_DEVICE long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 RB_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// kFmt: 0 fp16, 1 bf16, 2 fp8 e4m3 (W8A8 generation path: same byte geometry -- a k-block is one 128-byte swizzle row, i.e.
+// 128 fp8 elements instead of 64 bf16 -- `tcgen05.mma.kind::f8f6f4`, per-row x per-column scales in the epilogue)
 template <typename OutT, int kFmt>
 __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                    const __grid_constant__ CUtensorMap tma_b, Params p,
@@ -339,7 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
 
   __shared__ int slot_of[160];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = RB_CEIL_DIV(p.K, BK);
+  constexpr int KBE = kFmt == 2 ? 2 * BK : BK;  // elements per k-block (128 bytes either way)
+  const int num_kb = RB_CEIL_DIV(p.K, KBE);
   const int64_t units = (int64_t)RB_CEIL_DIV(p.N, BN) * num_kb;
   const int G = gridDim.x, g = blockIdx.x;
   const int u_begin = (int)(units * g / G), u_end = (int)(units * (g + 1) / G);
@@ -382,13 +389,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
         const int tile = u / num_kb, kb = u - tile * num_kb;
         const uint32_t fb = ptx::smem_u32(&full_bar[i]);
         ptx::mbar_arrive_expect_tx(fb, stage_tx);
-        ptx::tma_load_2d(ptx::smem_u32(smem_b + i * b_bytes), &tma_b, fb, kb * BK, tile * BN);
+        ptx::tma_load_2d(ptx::smem_u32(smem_b + i * b_bytes), &tma_b, fb, kb * KBE, tile * BN);
       }
       rb::pdl_wait();
       for (int i = 0; i < n_pre; ++i) {
         const int u = u_begin + i;
         const int kb = u - (u / num_kb) * num_kb;
-        ptx::tma_load_2d(ptx::smem_u32(smem_a + i * kABytes), &tma_a, ptx::smem_u32(&full_bar[i]), kb * BK, 0);
+        ptx::tma_load_2d(ptx::smem_u32(smem_a + i * kABytes), &tma_a, ptx::smem_u32(&full_bar[i]), kb * KBE, 0);
       }
       int stage = n_pre == n_stages ? 0 : n_pre;
       uint32_t phase = n_pre == n_stages ? 1 : 0;
@@ -397,14 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
         ptx::mbar_arrive_expect_tx(fb, stage_tx);
-        ptx::tma_load_2d(ptx::smem_u32(smem_a + stage * kABytes), &tma_a, fb, kb * BK, 0);
-        ptx::tma_load_2d(ptx::smem_u32(smem_b + stage * b_bytes), &tma_b, fb, kb * BK, tile * BN);
+        ptx::tma_load_2d(ptx::smem_u32(smem_a + stage * kABytes), &tma_a, fb, kb * KBE, 0);
+        ptx::tma_load_2d(ptx::smem_u32(smem_b + stage * b_bytes), &tma_b, fb, kb * KBE, tile * BN);
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(kFmt, BM, BN, 0, 0);
+      const uint32_t idesc = kFmt == 2 ? ptx::make_idesc_f8(0, 0, BM, BN) : ptx::make_idesc_f16(kFmt, BM, BN, 0, 0);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       int u = u_begin;
@@ -420,9 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
           const uint32_t sa = ptx::smem_u32(smem_a + stage * kABytes);
           const uint32_t sb = ptx::smem_u32(smem_b + stage * b_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            ptx::tc_mma_f16(d_tmem, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024),
-                            idesc, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < BK / 16; ++k) {  // 4 instructions of 32 bytes of K each: 16 bf16 or 32 fp8 elements
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), db = ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            if constexpr (kFmt == 2) ptx::tc_mma_f8(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+            else ptx::tc_mma_f16(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
           }
           ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -477,6 +485,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if constexpr (kFmt == 2) {
+          const float sa = sk.scale_a[row];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] *= sa * sk.scale_b[col + i];
+        }
         if (bias != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (i < n_valid) v[i] += rb::to_f(bias[col + i]);
@@ -554,6 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_streamk_kernel(const __grid_
           const int orow = off[q] % BM, col = n0 + (off[q] / BM) * 4;
           float v[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
           const int nv = min(4, p.N - col);
+          if constexpr (kFmt == 2) {
+            const float sa = sk.scale_a[orow];
+            for (int i = 0; i < nv; ++i) v[i] *= sa * sk.scale_b[col + i];
+          }
           if (bias != nullptr) {
             for (int i = 0; i < nv; ++i) v[i] += rb::to_f(bias[col + i]);
           }
@@ -733,15 +750,19 @@ int rb_gemm_tcgen05(const void* A, const void* B, void* C, const void* bias, int
 // bn = 0 / split = 0: pick the tile width (multiple of 16) and the K split from a byte-ingest cost model:
 //   t = max(weight bytes / HBM, bytes per CTA / ~70 GB/s per-SM TMA ingest) + fix-up(split > 1),
 // over the layouts with tiles_n * split <= #SMs (tile-aligned split: one fix-up round per CTA).
-int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
-                    int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
-                    cudaStream_t s) {
+// in_dt: 1 bf16, 2 fp16, 3 fp8 e4m3 (then scale_a [M] / scale_b [N] fp32 are required; lda / ldb count bytes = elements)
+static int streamk_impl(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                        int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
+                        const float* scale_a, const float* scale_b, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (M > BM || (in_dt != 1 && in_dt != 2)) return -30;
-  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
+  if (M > BM || (in_dt != 1 && in_dt != 2 && in_dt != 3)) return -30;
+  const int esz = in_dt == 3 ? 1 : 2, ld_align = 16 / esz;
+  if ((lda % ld_align) || (ldb % ld_align) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -11;
+  if (in_dt == 3 && (scale_a == nullptr || scale_b == nullptr)) return -34;
   if (num_sms <= 0) num_sms = rb::kNumSMs;
   if (num_sms > 160) num_sms = 160;
-  const int num_kb = RB_CEIL_DIV(K, BK);
+  const int kbe = 128 / esz;  // elements per 128-byte k-block
+  const int num_kb = RB_CEIL_DIV(K, kbe);
   const int box_rows = ((M + 7) / 8) * 8;
   if (bn == 0) {
     double best = 1e30;
@@ -754,7 +775,7 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
         const double waves = (double)RB_CEIL_DIV(tiles * sp, num_sms);
         const double cta_bytes = (double)(box_rows + cand) * 128.0 * RB_CEIL_DIV(num_kb, sp) * waves;
         double t = cta_bytes / 70e3;                              // us
-        const double hbm = (double)N * K * 2.0 / 6.5e6;           // us
+        const double hbm = (double)N * K * esz / 6.5e6;           // us
         if (t < hbm) t = hbm;
         const double kb_floor = 0.33 * RB_CEIL_DIV(num_kb, sp) * waves;  // measured per-k-block pipeline floor
         if (t < kb_floor) t = kb_floor;
@@ -785,12 +806,19 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
   if (stages * b_bytes < BM * BK * 2) return -33;
   CUtensorMap ta, tb;
   const int bf = in_dt == 1;
-  bool ok = make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)box_rows) &&
-            make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn);
+  bool ok = in_dt == 3 ? make_tmap_u8(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, (uint32_t)box_rows) &&
+                             make_tmap_u8(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, (uint32_t)bn)
+                       : make_tmap(&ta, A, bf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, (uint32_t)box_rows) &&
+                             make_tmap(&tb, B, bf, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, (uint32_t)bn);
   if (!ok) return -13;
   Params p{C, bias, ldc, M, N, K, 0};
   StreamKParams sk{reinterpret_cast<float*>(ws), reinterpret_cast<uint32_t*>(flags), box_rows, bn, stages,
-                   reinterpret_cast<long long*>(dbg)};
+                   reinterpret_cast<long long*>(dbg), scale_a, scale_b};
+  if (in_dt == 3) {
+    if (out_dt == 1) return launch_streamk<__nv_bfloat16, 2>(ta, tb, p, sk, grid, s);
+    if (out_dt == 0) return launch_streamk<float, 2>(ta, tb, p, sk, grid, s);
+    return -14;
+  }
   if (in_dt == 1) {
     if (out_dt == 1) return launch_streamk<__nv_bfloat16, 1>(ta, tb, p, sk, grid, s);
     if (out_dt == 0) return launch_streamk<float, 1>(ta, tb, p, sk, grid, s);
@@ -799,6 +827,20 @@ int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int
     if (out_dt == 0) return launch_streamk<float, 0>(ta, tb, p, sk, grid, s);
   }
   return -14;
+}
+
+int rb_gemm_streamk(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int in_dt, int out_dt, int bn, int split, int num_sms, void* ws, void* flags, void* dbg,
+                    cudaStream_t s) {
+  if (in_dt == 3) return -30;
+  return streamk_impl(A, B, C, bias, M, N, K, lda, ldb, ldc, in_dt, out_dt, bn, split, num_sms, ws, flags, dbg, nullptr, nullptr, s);
+}
+
+// W8A8 decode GEMM: A [M, K] / B [N, K] e4m3 bytes, C[m, n] = (sum_k A B) * scale_a[m] * scale_b[n] (+ bias), out bf16 / fp32.
+int rb_gemm_streamk_fp8(const void* A, const void* B, void* C, const void* bias, const float* scale_a, const float* scale_b, int M,
+                        int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int out_dt, int bn, int split, int num_sms, void* ws,
+                        void* flags, cudaStream_t s) {
+  return streamk_impl(A, B, C, bias, M, N, K, lda, ldb, ldc, 3, out_dt, bn, split, num_sms, ws, flags, nullptr, scale_a, scale_b, s);
 }
 
 // Grouped GEMM (MoE experts) in ONE launch: rows [off[g], off[g+1]) of A are multiplied by group g's weight.
