@@ -29,6 +29,9 @@ class GenerationHyperparameters:
     use_cuda_graph: bool = False
     force_cudagraph_recapture: bool = True
     force_no_logits_mask: bool = False
+    # B200 addition (no reference counterpart): decode with e4m3 weights / activations on the fp8 tensor cores.  Sampled
+    # tokens and the returned log-probs are those of the quantised policy (see docs/generation_fp8.md).
+    fp8_weights: bool = False
 
     def __post_init__(self):
         if self.temperature == 0.0:

@@ -155,6 +155,9 @@ class DecodeState:
 
 def _final_logits(model: ReaLModel, hidden: torch.Tensor) -> torch.Tensor:
     """[B, H] -> full-vocab fp32-able logits on every TP rank."""
+    f8 = model._fp8.get("head") if model._fp8_active and model._fp8 else None
+    if f8 is not None and hidden.shape[0] <= 128:
+        return f8(hidden)
     lg = OF.linear(hidden, model.head_weight())
     if model.ctx.tp_size > 1:
         lg = TP._gather_last_dim(lg, model.ctx)
@@ -205,6 +208,10 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
     toks.append(nxt); lps.append(lp); masks.append(mb)
     # ---- decode loop
     use_graph = g.use_cuda_graph and dev.type == "cuda"
+    # opt-in W8A8 decode (ops/fp8.py): the prefill above ran in bf16; from here on block linears and the head read e4m3 copies
+    use_fp8 = (g.fp8_weights or os.environ.get("REAL_GEN_FP8", "0") == "1") and B <= 128 and model.fp8_decode_supported()
+    if use_fp8:
+        model.enable_fp8_decode()
     V = logits.shape[1]
     # the fused sampler can run as the tail of the captured step: then a decode step is ONE graph replay and nothing else
     # (no eager copy of the next token, no cache_lens += 1, no sampling launch, no per-step python bookkeeping)
@@ -216,7 +223,7 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         return _final_logits(model, h)
 
     sig = (in_graph, g.max_new_tokens, g.min_new_tokens, g.top_k, g.top_p, g.temperature, g.greedy, need_mask, eos_id, pad_id,
-           int(model.flat_param.data_ptr()))
+           int(model.flat_param.data_ptr()), use_fp8)
     if state.graph is not None and state.graph_sig != sig:
         state.graph = None  # sampling options changed, or the flat parameter buffer moved (realloc / offload reload / ZeRO-3)
     if in_graph:
@@ -287,6 +294,8 @@ def generate(model: ReaLModel, input_ids: torch.Tensor, cu_seqlens: torch.Tensor
         logprobs = torch.stack(lps, 1)
         mask_bits = torch.stack(masks, 1) if masks[0] is not None else None
     mark("decode")
+    if use_fp8:  # a graph kept for the next call holds pointers into the e4m3 buffers: then they stay (re-quantised in place)
+        model.disable_fp8_decode(free=not (use_graph and state.graph is not None and not g.force_cudagraph_recapture))
     if timing:
         torch.cuda.synchronize(dev)
         LAST_TIMING.clear()

@@ -457,6 +457,46 @@ class ReaLModel(nn.Module):
             return self.p.get("0.wte.weight")
         return None
 
+    # ---- W8A8 decode (ops/fp8.py): e4m3 copies of the local linear weights, used by `decode_step` / the LM head while set
+    _fp8 = None
+    _fp8_active = False  # the copies may outlive a call (kept CUDA graph) but are only READ between enable and disable
+
+    def fp8_decode_supported(self) -> bool:
+        c = self.config
+        return bool(self.device.type == "cuda" and self.ctx.tp_size == 1 and c.mlp_type == "llama"
+                    and self.dtype in (torch.bfloat16, torch.float16) and self.instantiated)
+
+    def enable_fp8_decode(self) -> int:
+        """Quantise (or, when the buffers exist already, re-quantise in place) every local block linear and the LM head.
+        Returns the bytes held by the e4m3 copies.  ~4 ms for a 7B model: done at the start of every generation call."""
+        from realhf_b200.ops import fp8
+        names = []
+        for i in self.layers:
+            if 1 <= i <= self.config.n_layers:
+                names += [f"{i}.attn.qkv.weight", f"{i}.attn.o.weight", f"{i}.mlp.gate_up.weight", f"{i}.mlp.down.weight"]
+        ws = {n: self.p[n] for n in names if n in self.p}
+        if self.is_last_stage and self.head_weight() is not None:
+            ws["head"] = self.head_weight()
+        old = self._fp8 or {}
+        new = {}
+        for n, w in ws.items():
+            if not fp8.supported(w):
+                continue
+            f = old.get(n)
+            if f is not None and (f.N, f.K) == tuple(w.shape) and f.qw.device == w.device:
+                f.requantize(w)
+            else:
+                f = fp8.Fp8Linear(w)
+            new[n] = f
+        self._fp8 = new
+        self._fp8_active = True
+        return sum(f.nbytes() for f in new.values())
+
+    def disable_fp8_decode(self, free: bool = True):
+        self._fp8_active = False
+        if free:
+            self._fp8 = None
+
     def tied_embedding_params(self) -> List[torch.Tensor]:
         """Parameters whose gradients must be summed over the embedding group (tied embeddings with pp > 1)."""
         c = self.config
@@ -566,6 +606,12 @@ class ReaLModel(nn.Module):
             and self.dtype in (torch.bfloat16, torch.float16)
         d = None      # branch output not yet added to the residual stream: every add is fused into the next RMSNorm kernel
         d_sym = None  # same, but still a per-rank partial sum in symmetric memory (tensor-parallel decode)
+        # W8A8 decode: e4m3 weights + per-token e4m3 activations on tcgen05 kind::f8f6f4 (`enable_fp8_decode`, <= 128 rows)
+        fp8 = self._fp8 if (self._fp8_active and self._fp8 and self.ctx.tp_size == 1) else None
+
+        def q8(h_, wname, bname=None):
+            f = fp8.get(wname) if fp8 is not None and h_.shape[0] <= 128 else None
+            return None if f is None else f(h_, self._w(bname) if bname else None)
 
         def add_norm(x_, wname):
             """(normalised input, new residual stream) at a layer boundary, consuming the pending branch output."""
@@ -587,16 +633,23 @@ class ReaLModel(nn.Module):
                 x = self._embed(input_ids, cache_lens)
             elif i <= c.n_layers:
                 h, x = add_norm(x, f"{i}.attn.ln.weight")
-                qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
+                qkv = q8(h, f"{i}.attn.qkv.weight", f"{i}.attn.qkv.bias")
+                if qkv is None:
+                    qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
                 o = attn_ops.decode_attention(qkv, k_caches[li], v_caches[li], cache_lens, nq, nkv, hd, self._attn_scale(i),
                                               cos, sin, hd, c.rotary_interleaved)
                 li += 1
                 if tp_fused:
                     d_sym = fused.gemm_partial(o, self.p[f"{i}.attn.o.weight"])
                 if d_sym is None:
-                    d = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
+                    d = q8(o, f"{i}.attn.o.weight", f"{i}.attn.o.bias")
+                    if d is None:
+                        d = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
                 h2, x = add_norm(x, f"{i}.mlp.ln.weight")
-                if tp_fused:
+                gu8 = q8(h2, f"{i}.mlp.gate_up.weight") if fp8 is not None and f"{i}.mlp.down.weight" in fp8 else None
+                if gu8 is not None:
+                    d = q8(OF.gated_act(gu8, c.activation_function), f"{i}.mlp.down.weight")
+                elif tp_fused:
                     gu = TP.col_linear(h2, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, False)
                     d_sym = fused.gemm_partial(OF.gated_act(gu, c.activation_function), self.p[f"{i}.mlp.down.weight"])
                     if d_sym is None:

@@ -1,0 +1,104 @@
+"""W8A8 (e4m3) linear layers for generation.
+
+The decode step of a 7B model at <= 128 sequences per GPU reads every weight once per token: its floor is weight bytes /
+HBM bandwidth.  Storing the weights as e4m3 with one fp32 scale per output channel halves that floor; activations are
+quantised per token on the fly (`csrc/quant.cu`) and the product runs on `tcgen05.mma.kind::f8f6f4` in the same stream-K
+kernel as the bf16 path (`csrc/gemm_tcgen05.cu`, `kFmt == 2`), both scales applied in the epilogue:
+
+    y[m, n] = (sum_k qx[m, k] * qw[n, k]) * sx[m] * sw[n]
+
+The reference generates in the training dtype only (`realhf/impl/model/nn/real_llm_generate.py`); this path is opt-in
+(`GenerationHyperparameters.fp8_weights` / `REAL_GEN_FP8=1`) because sampled tokens and their log-probs drift from the
+bf16 policy by the quantisation error (tests bound it).  Training and all inference MFCs stay bf16.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from realhf_b200.ops import lib
+from realhf_b200.ops.gemm import _sms, streamk_workspace
+
+E4M3_MAX = 448.0
+
+
+def quantize_rows(x: torch.Tensor, q_out: Optional[torch.Tensor] = None, scale_out: Optional[torch.Tensor] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [M, K] -> (q uint8 [M, K] holding e4m3 bytes, scale fp32 [M]) with x ~= q * scale[:, None]."""
+    q, s = lib().quant_rows_e4m3(x, q_out, scale_out)
+    return q, s
+
+
+def quantize_rows_ref(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Plain PyTorch version of `quantize_rows` (tests, CPU)."""
+    xf = x.float()
+    amax = xf.abs().amax(dim=1)
+    s = torch.where(amax > 0, amax / E4M3_MAX, torch.ones_like(amax))
+    q = (xf / s[:, None]).clamp_(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8), s
+
+
+def dequantize(q: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    return q.view(torch.float8_e4m3fn).float() * s[:, None]
+
+
+def gemm_fp8(qx: torch.Tensor, sx: torch.Tensor, qw: torch.Tensor, sw: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None, bn: int = 0, split: int = 0) -> torch.Tensor:
+    ws, flags = streamk_workspace(qx.device)
+    return lib().gemm_streamk_fp8(qx, qw, sx, sw, out, bias, ws, flags, out_dtype, bn, split, _sms(qx.device))
+
+
+class Fp8Linear:
+    """One quantised weight matrix [N, K] (+ optional bias).  `__call__(x)` quantises x per row and multiplies."""
+
+    __slots__ = ("qw", "sw", "bias", "N", "K")
+
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        assert w.dim() == 2
+        self.N, self.K = w.shape
+        self.qw, self.sw = quantize_weight(w)
+        self.bias = bias
+
+    def requantize(self, w: torch.Tensor):
+        """Refresh the e4m3 copy in place after the weight changed (same buffers: a kept CUDA graph stays valid)."""
+        assert tuple(w.shape) == (self.N, self.K)
+        quantize_weight(w, out=(self.qw, self.sw))
+
+    def __call__(self, x: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.K)
+        if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+            x2 = x2.contiguous()
+        qx, sx = quantize_rows(x2)
+        y = gemm_fp8(qx, sx, self.qw, self.sw, self.bias if bias is None else bias, out_dtype=x.dtype)
+        return y.view(*lead, self.N)
+
+    def nbytes(self) -> int:
+        return self.qw.numel() + 4 * self.sw.numel()
+
+
+def quantize_weight(w: torch.Tensor, chunk_rows: int = 8192, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-output-channel e4m3 copy of a weight [N, K], quantised in row chunks (bounded transient memory)."""
+    N, K = w.shape
+    if out is not None:
+        q, s = out
+    else:
+        q = torch.empty(N, K, dtype=torch.uint8, device=w.device)
+        s = torch.empty(N, dtype=torch.float32, device=w.device)
+    for lo in range(0, N, chunk_rows):
+        hi = min(N, lo + chunk_rows)
+        quantize_rows(w[lo:hi], q[lo:hi], s[lo:hi])
+    return q, s
+
+
+def supported(w: torch.Tensor, max_rows: int = 128) -> bool:
+    """Shapes the fp8 stream-K kernel takes: K a multiple of 16 and <= 16384 (row quantiser), N >= 256."""
+    return bool(w.is_cuda and w.dim() == 2 and w.shape[1] % 16 == 0 and w.shape[1] <= 16384 and w.shape[0] >= 256
+                and w.dtype in (torch.bfloat16, torch.float16))
+
+
+def quantize_named(weights: Dict[str, torch.Tensor]) -> Dict[str, "Fp8Linear"]:
+    return {k: Fp8Linear(w) for k, w in weights.items() if supported(w)}

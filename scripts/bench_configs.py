@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=512)
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--gen-graph", choices=["true", "false"], default="true", help="decode loop inside a CUDA graph")
     args = ap.parse_args()
 
     root = tempfile.mkdtemp(prefix="realhf_b200_cfgbench_")
@@ -118,7 +119,7 @@ def main():
                                  "dataset.pad_to_max_length=true", f"ppo.gen.max_new_tokens={args.new_tokens}",
                                  f"ppo.gen.min_new_tokens={args.new_tokens}", "ppo.gen.top_p=0.9", "ppo.gen.top_k=1000",
                                  # MoE decode is not graph-capturable yet: the expert bucketing (bincount / nonzero) syncs the host
-                                 f"ppo.gen.use_cuda_graph={'false' if args.config == 'mixtral-ep' else 'true'}",
+                                 f"ppo.gen.use_cuda_graph={args.gen_graph}",
                                  "ppo.gen.force_cudagraph_recapture=true", "ppo.ppo_n_minibatches=4"]
         for role, path, train in (("actor", dirs["actor"], True), ("ref", dirs["actor"], False), ("critic", dirs["critic"], True),
                                   ("rew", dirs["critic"], False)):

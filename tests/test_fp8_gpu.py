@@ -1,0 +1,118 @@
+"""W8A8 generation path: row quantiser and the e4m3 stream-K GEMM against fp32 PyTorch references."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K,dtype", [(16, 4096, torch.bfloat16), (128, 11008, torch.bfloat16), (3, 256, torch.float16), (5, 16384, torch.float32)])
+def test_quantize_rows_matches_reference(M, K, dtype):
+    from realhf_b200.ops import fp8
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device="cuda") * torch.logspace(-2, 1, M, device="cuda")[:, None]).to(dtype)
+    x[0, :] = 0  # all-zero row: scale 1, bytes 0
+    q, s = fp8.quantize_rows(x)
+    qr, sr = fp8.quantize_rows_ref(x)
+    torch.testing.assert_close(s, sr, rtol=1e-6, atol=0)
+    assert (q == qr).float().mean().item() > 0.995  # x * (1/s) vs x / s may round differently on ties
+    d, dr = fp8.dequantize(q, s), fp8.dequantize(qr, sr)
+    assert ((d - dr).abs() <= 0.126 * dr.abs() + 1e-12).all()   # never more than one e4m3 step apart
+    assert ((d - x.float()).abs() <= 0.0626 * x.float().abs() + s[:, None] * 2 ** -9 + 1e-12).all()  # half-ulp rounding (+ subnormals)
+    assert (q[0] == 0).all() and s[0].item() == 1.0
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 4096, 4096), (1, 12288, 4096), (128, 4096, 11008), (16, 32000, 4096), (7, 22016, 4096), (33, 4096, 4112),
+                                   (16, 512, 256)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_gemm_fp8_against_fp32_reference(M, N, K, bias):
+    from realhf_b200.ops import fp8
+    torch.manual_seed(1)
+    x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", dtype=torch.bfloat16) if bias else None
+    qx, sx = fp8.quantize_rows(x)
+    qw, sw = fp8.quantize_weight(w)
+    y = fp8.gemm_fp8(qx, sx, qw, sw, b)
+    ref = fp8.dequantize(qx, sx) @ fp8.dequantize(qw, sw).t()   # the same quantised operands, fp32 math
+    if bias:
+        ref = ref + b.float()
+    scale = ref.abs().max().item()
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * scale + 1e-6   # bf16 output rounding; accumulation is fp32
+    # and the quantisation error itself against the unquantised product stays at the e4m3 level
+    full = x.float() @ w.float().t() + (b.float() if bias else 0)
+    rel = (y.float() - full).norm() / full.norm()
+    assert rel.item() < 0.05
+    y32 = fp8.gemm_fp8(qx, sx, qw, sw, None if b is None else b.float(), out_dtype=torch.float32)
+    assert (y32 - ref).abs().max().item() <= 1e-4 * scale + 1e-6
+
+
+def test_gemm_fp8_forced_splits_and_tiles():
+    from realhf_b200.ops import fp8
+    torch.manual_seed(2)
+    M, N, K = 24, 4096, 4096
+    x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+    qx, sx = fp8.quantize_rows(x)
+    qw, sw = fp8.quantize_weight(w)
+    ref = fp8.dequantize(qx, sx) @ fp8.dequantize(qw, sw).t()
+    for bn, split in ((32, 1), (64, 2), (128, 4), (256, 9), (48, 0)):
+        y = fp8.gemm_fp8(qx, sx, qw, sw, out_dtype=torch.float32, bn=bn, split=split)
+        assert (y - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), (bn, split)
+
+
+def test_fp8_linear_module_and_graph_capture():
+    from realhf_b200.ops import fp8
+    torch.manual_seed(3)
+    w = (torch.randn(11008, 4096, device="cuda") * 0.02).to(torch.bfloat16)
+    lin = fp8.Fp8Linear(w)
+    x = torch.randn(2, 8, 4096, device="cuda", dtype=torch.bfloat16)
+    y = lin(x)
+    assert y.shape == (2, 8, 11008)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        yg = lin(x)
+    g.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(yg, y)
+    full = torch.nn.functional.linear(x.float(), w.float())
+    assert ((y.float() - full).norm() / full.norm()).item() < 0.05
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_generation_with_fp8_decode_tracks_the_bf16_policy(graph, monkeypatch):
+    """Opt-in W8A8 decode: the e4m3 GEMM must actually run for every block linear and the head of every decode step, the
+    log-probs returned must stay close to those of the bf16 policy for the same tokens (teacher-forced packed forward), and
+    the quantised copies must be gone after the call."""
+    from realhf_b200.api.model import GenerationHyperparameters
+    from realhf_b200.models import generation as gen
+    from realhf_b200.ops import fp8
+    from tests.test_sampling_gpu import _tiny_llama
+    m = _tiny_llama()
+    calls = [0]
+    real = fp8.gemm_fp8
+
+    def counting(*a, **k):
+        calls[0] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(fp8, "gemm_fp8", counting)
+    lens = [5, 17, 9, 30]
+    ids = torch.randint(3, 32000, (sum(lens),), device="cuda")
+    cu = torch.tensor([0, 5, 22, 31, 61], dtype=torch.int32, device="cuda")
+    g = GenerationHyperparameters(max_new_tokens=16, min_new_tokens=16, greedy=True, use_cuda_graph=graph, fp8_weights=True)
+    out, _ = gen.generate(m, ids, cu, g, eos_id=None, pad_id=0)
+    n_lin = 2 * 4 + 1
+    assert calls[0] == (n_lin * 2 if graph else n_lin * 15), calls[0]   # graph: warm-up + capture; eager: every step after the first
+    assert m._fp8 is None and not m._fp8_active
+    diffs = []
+    for i, L in enumerate(lens):
+        seq = torch.cat([ids[int(cu[i]): int(cu[i + 1])], out.tokens[i]])
+        o = m(input_ids=seq, cu_seqlens=torch.tensor([0, seq.numel()], dtype=torch.int32, device="cuda"), max_seqlen=int(seq.numel()))
+        lp_ref = torch.log_softmax(o.logits.float()[L - 1: L - 1 + 16], -1)[torch.arange(16), out.tokens[i]]
+        diffs.append((out.logprobs[i] - lp_ref).abs())
+    d = torch.stack(diffs)
+    assert d.mean().item() < 0.05 and d.max().item() < 0.5, (d.mean().item(), d.max().item())
+    # the same call without the flag is the plain bf16 path
+    calls[0] = 0
+    g2 = GenerationHyperparameters(max_new_tokens=4, min_new_tokens=4, greedy=True, use_cuda_graph=graph)
+    gen.generate(m, ids, cu, g2, eos_id=None, pad_id=0)
+    assert calls[0] == 0
