@@ -180,7 +180,11 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
         # give workers the chance to dump recover states (they listen for SIGINT), then stop everything
         sched.stop_all(signal.SIGINT if recover_mode in ("auto", "save") else signal.SIGTERM)
         if isinstance(sched, sched_client.LocalSchedulerClient):
-            for info_name in ("master_worker/0", "model_worker/0"):
+            names = ["master_worker/0", "model_worker/0"]
+            failed = getattr(e, "worker_type", None)  # the worker that failed first tells the story: print it first
+            if failed:
+                names = [failed] + [n for n in names if n != failed]
+            for info_name in names:
                 tail = sched.log_tail(info_name)
                 if tail:
                     logger.error(f"---- tail of {info_name} ----\n{tail}")

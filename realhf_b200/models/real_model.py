@@ -613,6 +613,20 @@ class ReaLModel(nn.Module):
             f = fp8.get(wname) if fp8 is not None and h_.shape[0] <= 128 else None
             return None if f is None else f(h_, self._w(bname) if bname else None)
 
+        def norm_q8(x_, ln_name, wname, bname=None):
+            """Layer boundary whose only consumer is an fp8 GEMM: residual add + RMSNorm + e4m3 quantisation in one kernel,
+            then the GEMM.  Returns (GEMM output, new residual stream) or None (then the unfused path runs)."""
+            nonlocal d
+            f = fp8.get(wname) if fp8 is not None and rms and x_.shape[0] <= 128 and d_sym is None else None
+            if f is None:
+                return None
+            from realhf_b200.ops import fp8 as F8
+            r = F8.add_rmsnorm_quant(d, x_, self.p[ln_name], eps, w_off)
+            if r is None:
+                return None
+            d = None
+            return f.gemm_q(r[0], r[1], self._w(bname) if bname else None, out_dtype=x_.dtype), r[2]
+
         def add_norm(x_, wname):
             """(normalised input, new residual stream) at a layer boundary, consuming the pending branch output."""
             nonlocal d, d_sym
@@ -632,9 +646,11 @@ class ReaLModel(nn.Module):
             if i == 0:
                 x = self._embed(input_ids, cache_lens)
             elif i <= c.n_layers:
-                h, x = add_norm(x, f"{i}.attn.ln.weight")
-                qkv = q8(h, f"{i}.attn.qkv.weight", f"{i}.attn.qkv.bias")
-                if qkv is None:
+                fq = norm_q8(x, f"{i}.attn.ln.weight", f"{i}.attn.qkv.weight", f"{i}.attn.qkv.bias")
+                if fq is not None:
+                    qkv, x = fq
+                else:
+                    h, x = add_norm(x, f"{i}.attn.ln.weight")
                     qkv = TP.col_linear(h, self.p[f"{i}.attn.qkv.weight"], self._w(f"{i}.attn.qkv.bias"), self.ctx, False)
                 o = attn_ops.decode_attention(qkv, k_caches[li], v_caches[li], cache_lens, nq, nkv, hd, self._attn_scale(i),
                                               cos, sin, hd, c.rotary_interleaved)
@@ -645,16 +661,23 @@ class ReaLModel(nn.Module):
                     d = q8(o, f"{i}.attn.o.weight", f"{i}.attn.o.bias")
                     if d is None:
                         d = TP.row_linear(o, self.p[f"{i}.attn.o.weight"], self._w(f"{i}.attn.o.bias"), self.ctx, False)
-                h2, x = add_norm(x, f"{i}.mlp.ln.weight")
-                gu8 = q8(h2, f"{i}.mlp.gate_up.weight") if fp8 is not None and f"{i}.mlp.down.weight" in fp8 else None
-                if gu8 is not None:
-                    d = q8(OF.gated_act(gu8, c.activation_function), f"{i}.mlp.down.weight")
+                fq = norm_q8(x, f"{i}.mlp.ln.weight", f"{i}.mlp.gate_up.weight") if fp8 is not None and f"{i}.mlp.down.weight" in fp8 else None
+                if fq is not None:  # W8A8 MLP: norm+quant -> gate|up GEMM -> act+quant -> down GEMM
+                    from realhf_b200.ops import fp8 as F8
+                    gu8, x = fq
+                    aq = F8.gated_act_quant(gu8, c.activation_function)
+                    if aq is not None:
+                        d = fp8[f"{i}.mlp.down.weight"].gemm_q(aq[0], aq[1], out_dtype=gu8.dtype)
+                    else:
+                        d = q8(OF.gated_act(gu8, c.activation_function), f"{i}.mlp.down.weight")
                 elif tp_fused:
+                    h2, x = add_norm(x, f"{i}.mlp.ln.weight")
                     gu = TP.col_linear(h2, self.p[f"{i}.mlp.gate_up.weight"], None, self.ctx, False)
                     d_sym = fused.gemm_partial(OF.gated_act(gu, c.activation_function), self.p[f"{i}.mlp.down.weight"])
                     if d_sym is None:
                         d = TP.row_linear(OF.gated_act(gu, c.activation_function), self.p[f"{i}.mlp.down.weight"], None, self.ctx, False)
                 else:
+                    h2, x = add_norm(x, f"{i}.mlp.ln.weight")
                     d = self._mlp(i, x, h2)
                 if i == c.n_layers:
                     x, _ = add_norm(x, f"{i}.ln_f.weight")

@@ -18,6 +18,10 @@ extern "C" int rb_gemm_streamk_fp8(const void* A, const void* B, void* C, const 
                                    int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int out_dt, int bn, int split, int num_sms,
                                    void* ws, void* flags, cudaStream_t s);
 extern "C" int rb_quant_rows_e4m3(const void* x, void* q, float* scale, int M, int K, int64_t ld_x, int64_t ld_q, int dt, cudaStream_t s);
+extern "C" int rb_gated_act_quant_e4m3(const void* gu, void* q, float* scale, int M, int F, int64_t ld_x, int64_t ld_q, int act, int dt,
+                                       cudaStream_t s);
+extern "C" int rb_add_rmsnorm_quant_e4m3(const void* x, const void* res_in, const void* w, void* res_out, void* q, float* scale, int64_t rows,
+                                         int H, int64_t ld_q, float eps, float w_offset, int dt, cudaStream_t s);
 
 extern "C" int rb_gemm_grouped(const void* A, const void* B, void* C, const int* group_offsets, int G, int M, int N, int K, int64_t lda,
                                int64_t ldb, int64_t ldc, int b_mn, int num_sms, cudaStream_t s);
@@ -106,6 +110,43 @@ std::vector<Tensor> quant_rows_e4m3(const Tensor& x, const c10::optional<Tensor>
   int rc = rb_quant_rows_e4m3(x.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), (int)M, (int)K, x.stride(0), q.stride(0), dtc(x.scalar_type()),
                               at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, "rb_quant_rows_e4m3 failed with code ", rc, " (K % 8 == 0, K <= 16384, 16-byte aligned rows)");
+  return {q, sc};
+}
+
+// gu [M, 2F] = [gate | up] -> (e4m3 bytes [M, F] of act(gate) * up, scale [M]); act_kind: 0 silu, 1 gelu(tanh)
+std::vector<Tensor> gated_act_quant_e4m3(const Tensor& gu, int64_t act_kind) {
+  TORCH_CHECK(gu.is_cuda() && gu.dim() == 2 && gu.stride(1) == 1 && gu.size(1) % 2 == 0, "gated_act_quant_e4m3: gu is [M, 2F]");
+  const int64_t M = gu.size(0), F = gu.size(1) / 2;
+  c10::cuda::CUDAGuard guard(gu.device());
+  Tensor q = at::empty({M, F}, gu.options().dtype(at::kByte));
+  Tensor sc = at::empty({M}, gu.options().dtype(at::kFloat));
+  if (M == 0) return {q, sc};
+  int rc = rb_gated_act_quant_e4m3(gu.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), (int)M, (int)F, gu.stride(0), q.stride(0), (int)act_kind,
+                                   dtc(gu.scalar_type()), at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "rb_gated_act_quant_e4m3 failed with code ", rc);
+  return {q, sc};
+}
+
+// (x [+ residual]) -> [q, scale] of rmsnorm(x + residual) * (w + w_offset), and the new residual stream when `residual` is given
+std::vector<Tensor> add_rmsnorm_quant_e4m3(const Tensor& x, const c10::optional<Tensor>& residual, const Tensor& w, double eps, double w_offset) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && w.is_contiguous() && w.scalar_type() == x.scalar_type() && w.numel() == x.size(-1));
+  const int64_t H = x.size(-1), rows = x.numel() / H;
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor q = at::empty({rows, H}, x.options().dtype(at::kByte));
+  Tensor sc = at::empty({rows}, x.options().dtype(at::kFloat));
+  const void* rin = nullptr;
+  Tensor rout;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == x.sizes() && residual->scalar_type() == x.scalar_type());
+    rin = residual->data_ptr();
+    rout = at::empty_like(x);
+  }
+  if (rows > 0) {
+    int rc = rb_add_rmsnorm_quant_e4m3(x.data_ptr(), rin, w.data_ptr(), rin ? rout.data_ptr() : nullptr, q.data_ptr(), sc.data_ptr<float>(), rows,
+                                       (int)H, q.stride(0), (float)eps, (float)w_offset, dtc(x.scalar_type()), at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == 0, "rb_add_rmsnorm_quant_e4m3 failed with code ", rc);
+  }
+  if (residual.has_value()) return {q, sc, rout};
   return {q, sc};
 }
 
@@ -202,6 +243,8 @@ void register_gemm_ops(torch::Library& m) {
   m.def("gemm_glu(Tensor x, Tensor w, int act_kind, bool want_raw, int num_sms) -> Tensor[]", &gemm_glu);
   m.def("gemm_grouped_wgrad(Tensor dy, Tensor x, Tensor(a!) out, Tensor offsets, bool accumulate, int num_sms) -> ()", &gemm_grouped_wgrad);
   m.def("gemm_grouped(Tensor a, Tensor w, Tensor offsets, bool b_mn, int num_sms) -> Tensor", &gemm_grouped);
+  m.def("gated_act_quant_e4m3(Tensor gu, int act_kind) -> Tensor[]", &gated_act_quant_e4m3);
+  m.def("add_rmsnorm_quant_e4m3(Tensor x, Tensor? residual, Tensor w, float eps, float w_offset) -> Tensor[]", &add_rmsnorm_quant_e4m3);
   m.def("quant_rows_e4m3(Tensor x, Tensor? q_out, Tensor? scale_out) -> Tensor[]", &quant_rows_e4m3);
   m.def("gemm_streamk_fp8(Tensor a, Tensor b, Tensor sa, Tensor sb, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType out_dtype, int bn, int split, int num_sms) -> Tensor", &gemm_streamk_fp8);
   m.def("gemm_streamk(Tensor a, Tensor b, Tensor? out, Tensor? bias, Tensor ws, Tensor flags, ScalarType? out_dtype, int bn, int split, int num_sms, Tensor? dbg) -> Tensor", &gemm_streamk);

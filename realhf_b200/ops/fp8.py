@@ -75,6 +75,10 @@ class Fp8Linear:
         y = gemm_fp8(qx, sx, self.qw, self.sw, self.bias if bias is None else bias, out_dtype=x.dtype)
         return y.view(*lead, self.N)
 
+    def gemm_q(self, qx: torch.Tensor, sx: torch.Tensor, bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """Input already quantised by a fused producer (`add_rmsnorm_quant`, `gated_act_quant`)."""
+        return gemm_fp8(qx, sx, self.qw, self.sw, self.bias if bias is None else bias, out_dtype=out_dtype)
+
     def nbytes(self) -> int:
         return self.qw.numel() + 4 * self.sw.numel()
 
@@ -92,6 +96,30 @@ def quantize_weight(w: torch.Tensor, chunk_rows: int = 8192, out: Optional[Tuple
         hi = min(N, lo + chunk_rows)
         quantize_rows(w[lo:hi], q[lo:hi], s[lo:hi])
     return q, s
+
+
+def gated_act_quant(gu: torch.Tensor, kind: str) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """[M, 2F] = [gate | up] -> e4m3(act(gate) * up) in one kernel; None when the shape / activation has no fused kernel."""
+    from realhf_b200.ops.functional import _ACT_KIND
+    k = _ACT_KIND.get(kind)
+    F = gu.shape[-1] // 2
+    if k is None or gu.dim() != 2 or F % 8 or F > 16384 or gu.stride(-1) != 1 or gu.stride(0) % 8 or gu.dtype not in (torch.bfloat16, torch.float16):
+        return None
+    q, s = lib().gated_act_quant_e4m3(gu, k)
+    return q, s
+
+
+def add_rmsnorm_quant(d: Optional[torch.Tensor], x: torch.Tensor, w: torch.Tensor, eps: float, w_offset: float = 0.0):
+    """Residual add + RMSNorm + e4m3 quantisation of the normalised rows in one kernel.
+    Returns (q, scale, new residual stream) or None when the shape has no fused kernel (H % 8, H > 8192, dtype)."""
+    H = x.shape[-1]
+    if H % 8 or H > 8192 or x.dtype not in (torch.bfloat16, torch.float16) or not x.is_contiguous() or (d is not None and not d.is_contiguous()):
+        return None
+    if d is None:
+        q, s = lib().add_rmsnorm_quant_e4m3(x, None, w, eps, w_offset)
+        return q, s, x
+    q, s, r = lib().add_rmsnorm_quant_e4m3(d, x, w, eps, w_offset)
+    return q, s, r
 
 
 def supported(w: torch.Tensor, max_rows: int = 128) -> bool:

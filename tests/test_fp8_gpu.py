@@ -116,3 +116,36 @@ def test_generation_with_fp8_decode_tracks_the_bf16_policy(graph, monkeypatch):
     g2 = GenerationHyperparameters(max_new_tokens=4, min_new_tokens=4, greedy=True, use_cuda_graph=graph)
     gen.generate(m, ids, cu, g2, eos_id=None, pad_id=0)
     assert calls[0] == 0
+
+
+@pytest.mark.parametrize("M,H", [(16, 4096), (3, 1024), (128, 8192), (5, 264)])
+@pytest.mark.parametrize("residual", [False, True])
+def test_add_rmsnorm_quant_equals_unfused_kernels(M, H, residual):
+    """The fused producer rounds to bf16 before quantising: bytes, scales and the new residual stream are those of
+    `add_rmsnorm` followed by `quantize_rows`."""
+    from realhf_b200.ops import fp8
+    from realhf_b200.ops import functional as OF
+    torch.manual_seed(4)
+    x = torch.randn(M, H, device="cuda", dtype=torch.bfloat16)
+    d = torch.randn(M, H, device="cuda", dtype=torch.bfloat16) if residual else None
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(torch.bfloat16)
+    q, s, r = fp8.add_rmsnorm_quant(d, x, w, 1e-5, 0.0)
+    if residual:
+        h_ref, r_ref = OF.add_rmsnorm(d, x, w, 1e-5, 0.0)
+        assert torch.equal(r, r_ref)
+    else:
+        h_ref = OF.rmsnorm(x, w, 1e-5)
+        assert r is x
+    q_ref, s_ref = fp8.quantize_rows(h_ref)
+    assert torch.equal(s, s_ref) and torch.equal(q, q_ref)
+
+
+@pytest.mark.parametrize("M,F,kind", [(16, 11008, "silu"), (1, 2816, "silu"), (128, 14336, "silu"), (7, 512, "gelu_pytorch_tanh")])
+def test_gated_act_quant_equals_unfused_kernels(M, F, kind):
+    from realhf_b200.ops import fp8
+    from realhf_b200.ops import functional as OF
+    torch.manual_seed(5)
+    gu = torch.randn(M, 2 * F, device="cuda", dtype=torch.bfloat16)
+    q, s = fp8.gated_act_quant(gu, kind)
+    q_ref, s_ref = fp8.quantize_rows(OF.gated_act(gu, kind))
+    assert torch.equal(s, s_ref) and torch.equal(q, q_ref)
