@@ -285,6 +285,9 @@ def main():
                          "(auto: on for a single GPU with --ckpt auto, where the freed HBM buys un-recomputed blocks)")
     ap.add_argument("--gen-tp", type=int, default=int(os.environ.get("REAL_BENCH_GEN_TP", "0")),
                     help="tensor-parallel degree of the generation replica (0: default for this N; 1: generate on the dp layout)")
+    ap.add_argument("--gen-fp8", action="store_true",
+                    help="NOT the headline precision: decode with e4m3 weights / activations (GenerationHyperparameters.fp8_weights); "
+                         "the JSON line is labelled and carries no vs_baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -365,7 +368,7 @@ def main():
     # (`force_cudagraph_recapture=False`).
     recapture = world <= 2
     gcfg = dict(max_new_tokens=args.new_tokens, min_new_tokens=args.new_tokens, greedy=False, top_p=0.9, top_k=1000,
-                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=recapture)
+                temperature=1.0, use_cuda_graph=True, force_cudagraph_recapture=recapture, fp8_weights=args.gen_fp8)
     ppo_kw = dict(n_minibatches=4, kl_ctl=0.1, discount=1.0, gae_lambda=1.0, eps_clip=0.2, value_eps_clip=0.2,
                   max_reward_clip=20.0, adaptive_kl_ctl=False, value_norm=True)
     A = lambda t, **a: ModelInterfaceAbstraction(t, a)
@@ -519,14 +522,15 @@ def main():
     tokens_per_step = float(t[2]) if world > 1 else tokens_this_rank
     value = tokens_per_step * args.steps / dev_s
     e2e = tokens_per_step * args.steps / wall
-    headline = args.layers == 32 and args.prompts == 128 and args.prompt_len == 128 and args.new_tokens == 512
+    headline = args.layers == 32 and args.prompts == 128 and args.prompt_len == 128 and args.new_tokens == 512 and not args.gen_fp8
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_s * 1e3 / args.steps, 1), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3) if headline else None, "dtype": "bf16",
+            "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3) if headline else None,
+            "dtype": "bf16" if not args.gen_fp8 else "bf16 (training, inference, prefill) + e4m3 W8A8 decode [NOT the headline precision]",
             "data": "synthetic prompts (uniform random token ids), random-init weights",
-            "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline else f" [DEBUG layers={args.layers}]"),
+            "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline or args.gen_fp8 else f" [DEBUG layers={args.layers}]"),
                        "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens,
                        "prompt_len": args.prompt_len, "new_tokens": args.new_tokens, "ppo_minibatches": 4,
                        "parallelism": (f"dp{world} (all 6 MFCs)" if not (world > 1 and gen_tp > 1) else

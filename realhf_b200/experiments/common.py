@@ -204,8 +204,12 @@ class CommonExperimentConfig(Experiment):
                 continue
             handled.add(a.rpc.model_name)
             mcfg = self.models[a.rpc.role]
+            # MFCs with the same mesh and (tp, pp, dp) share one replica whatever their SP flag (SP does not change where weights
+            # live): the replica runs token-sharded when ANY of them asks for it -- typically the training call; generation
+            # switches SP off for its own duration (models/generation.py), inference works either way
+            use_sp = any(b.parallel.use_sequence_parallel for b in rpc_allocs if b.rpc.model_name == a.rpc.model_name)
             topo = PipeModelDataParallelTopology(a.parallel.pipeline_parallel_size, a.parallel.model_parallel_size,
-                                                 a.parallel.data_parallel_size, sequence_parallel=a.parallel.use_sequence_parallel,
+                                                 a.parallel.data_parallel_size, sequence_parallel=use_sp and a.parallel.model_parallel_size > 1,
                                                  gradient_checkpointing=mcfg.gradient_checkpointing, max_prompt_len=self.max_prompt_len)
             trainable = any(b.rpc.role == a.rpc.role and b.rpc.interface_type == ModelInterfaceType.TRAIN_STEP for b in rpc_allocs)
             model = ModelAbstraction("real_model", args=dict(

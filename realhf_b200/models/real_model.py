@@ -185,6 +185,8 @@ class ReaLModel(nn.Module):
         self.attach_flat(flat)
         g = torch.Generator(device=self.device)
         g.manual_seed(seed + 1000 * self.ctx.tp_rank + 77 * self.ctx.pp_rank)
+        g_rep = torch.Generator(device=self.device)  # TP-replicated tensors (MoE router, position embeddings, biases of row-
+        g_rep.manual_seed(seed + 77 * self.ctx.pp_rank + 13)  # parallel layers, critic head) must be EQUAL on the ranks of a TP group
         with torch.no_grad():
             flat.normal_(0.0, std, generator=g)
             for name, slot in self.slots.items():
@@ -192,6 +194,8 @@ class ReaLModel(nn.Module):
                     self.p[name].fill_(1.0)
                 elif slot.spec.init == "zeros":
                     self.p[name].zero_()
+                elif self.ctx.tp_size > 1 and slot.spec.split_dim is None:
+                    self.p[name].normal_(0.0, std, generator=g_rep)
         return self
 
     def attach_flat(self, flat: torch.Tensor):

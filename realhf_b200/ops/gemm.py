@@ -148,7 +148,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 def pad_groups(offsets: torch.Tensor, n_rows: int, block: int = 64):
     """Row map that pads every group's block of a group-sorted [n_rows, *] tensor to a multiple of `block` rows, computed on
     the device (no host read of the group sizes).  Returns (dest [n_rows] int64: padded position of every source row,
-    offsets_pad [G + 1] int32: padded block starts, n_pad: static upper bound of padded rows, a multiple of `block`)."""
+    offsets_pad [G + 1] int32: padded block starts, n_pad: static upper bound of padded rows, a multiple of `block`).
+    Rows outside [offsets[0], offsets[G]) belong to no group (an expert-parallel rank that only owns a sub-range of the sorted
+    rows; the unused tail of a receive buffer): their `dest` is n_pad, one row past the padded tensor -- callers allocate
+    n_pad + 1 rows and hand the first n_pad to the kernel, so stale data never lands in a group's zero padding."""
     G = offsets.numel() - 1
     off = offsets.long()
     counts = off[1:] - off[:-1]
@@ -157,8 +160,9 @@ def pad_groups(offsets: torch.Tensor, n_rows: int, block: int = 64):
     off_pad[1:] = padded.cumsum(0)
     rows = torch.arange(n_rows, device=offsets.device)
     g = torch.bucketize(rows, off[1:], right=True).clamp_(max=G - 1)
-    dest = rows + (off_pad[:-1] - off[:-1])[g]
     n_pad = (n_rows + G * (block - 1) + block - 1) // block * block
+    dest = rows + (off_pad[:-1] - off[:-1])[g]
+    dest = torch.where((rows >= off[0]) & (rows < off[G]), dest, torch.full_like(dest, n_pad))
     return dest, off_pad.int(), n_pad
 
 
@@ -175,8 +179,9 @@ def grouped_wgrad(dy: torch.Tensor, x: torch.Tensor, offsets: torch.Tensor, G: i
     straddles two experts.  No host synchronisation."""
     T = dy.shape[0]
     dest, off_pad, n_pad = pad_groups(offsets, T)
-    dy_p = torch.zeros(n_pad, dy.shape[1], dtype=dy.dtype, device=dy.device).index_copy_(0, dest, dy)
-    x_p = torch.zeros(n_pad, x.shape[1], dtype=x.dtype, device=x.device).index_copy_(0, dest, x)
+    # one spare row at the end swallows the rows that belong to no group (see pad_groups)
+    dy_p = torch.zeros(n_pad + 1, dy.shape[1], dtype=dy.dtype, device=dy.device).index_copy_(0, dest, dy)[:n_pad]
+    x_p = torch.zeros(n_pad + 1, x.shape[1], dtype=x.dtype, device=x.device).index_copy_(0, dest, x)[:n_pad]
     if out is None:
         out = torch.empty(G, dy.shape[1], x.shape[1], dtype=dy.dtype, device=dy.device)
         accumulate = False

@@ -59,7 +59,18 @@ def time_step(B, fp8):
     return ms, logits
 
 
+try:
+    hbm_gbs = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    hbm_gbs = 6576.4
+c = cfg
+blk = c.hidden_dim * (c.n_q_heads + 2 * c.n_kv_heads) * c.head_dim + c.n_q_heads * c.head_dim * c.hidden_dim + 3 * c.hidden_dim * c.intermediate_dim
+w_elems = layers * blk + c.vocab_size * c.hidden_dim          # every linear weight is read once per step
+scale_bytes = 4 * (layers * ((c.n_q_heads + 2 * c.n_kv_heads) * c.head_dim + 2 * c.hidden_dim + 2 * c.intermediate_dim) + c.vocab_size)
+
 for B in Bs:
+    kv_bytes = layers * B * ctx_len * 2 * c.n_kv_heads * c.head_dim * 2      # bf16 K and V of the context
+    bytes16, bytes8 = 2 * w_elems + kv_bytes, w_elems + scale_bytes + kv_bytes
     t16, l16 = time_step(B, False)
     t8, l8 = time_step(B, True)
     p16, p8 = torch.log_softmax(l16, -1), torch.log_softmax(l8, -1)
@@ -67,4 +78,7 @@ for B in Bs:
     drift = (p16.gather(1, tok[:, None]) - p8.gather(1, tok[:, None])).abs().mean().item()
     print(json.dumps(dict(layers=layers, B=B, ctx=ctx_len, bf16_ms_per_step=round(t16, 4), fp8_ms_per_step=round(t8, 4),
                           speedup=round(t16 / t8, 3), us_per_layer_bf16=round(1e3 * t16 / layers, 1), us_per_layer_fp8=round(1e3 * t8 / layers, 1),
+                          bytes_per_step_bf16=bytes16, bytes_per_step_fp8=bytes8, bytes_ratio=round(bytes16 / bytes8, 3),
+                          roofline_frac_bf16=round(bytes16 / (t16 * 1e-3) / (hbm_gbs * 1e9), 3),
+                          roofline_frac_fp8=round(bytes8 / (t8 * 1e-3) / (hbm_gbs * 1e9), 3), hbm_gbs=hbm_gbs,
                           argmax_agree=round((l8.argmax(-1) == tok).float().mean().item(), 3), mean_abs_logprob_drift=round(drift, 4))))

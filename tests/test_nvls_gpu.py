@@ -277,7 +277,7 @@ def test_tp_decode_with_in_switch_allreduce_matches_single_gpu(world):
     torch.testing.assert_close(res[0]["logprobs"], ref["logprobs"], atol=0.08, rtol=0.05)
 
 
-def _ep_worker(rank, world, fused):
+def _ep_worker(rank, world, fused, sp=True):
     """Mixtral-style MoE under expert parallelism + sequence parallelism on `world` GPUs: SFT steps with the device-driven
     peer-store dispatch / combine (csrc/ep.cu) or the NCCL all-to-all path; returns losses and a weight checksum."""
     import test_parallel_cpu as T
@@ -302,7 +302,7 @@ def _ep_worker(rank, world, fused):
     cfg.moe.expert_parallel = world > 1
     cfg.moe.aux_loss_coeff = 0.0
     dev = torch.device("cuda", rank)
-    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl", sequence_parallel=world > 1) \
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl", sequence_parallel=world > 1 and sp) \
         if world > 1 else ParallelContext.single()
     m = ReaLModel(cfg, ctx, dtype=torch.bfloat16, device=dev).instantiate(seed=7)
     tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
@@ -330,3 +330,62 @@ def test_fused_expert_parallel_matches_all_to_all_and_single_gpu(world):
             assert abs(x - y) < 5e-2 * max(1.0, abs(y)), (r["losses"], ref["losses"])
     for x, y in zip(fus[0]["losses"], a2a[0]["losses"]):
         assert abs(x - y) < 2e-2 * max(1.0, abs(y)), (fus[0]["losses"], a2a[0]["losses"])
+
+
+def _ep_replicated_worker(rank, world, graph):
+    """Expert parallelism WITHOUT sequence parallelism (the layout of generation and of inference MFCs): tokens are replicated,
+    every rank runs its experts through device-side offsets (no host sync -> CUDA-graph capturable) and the partial outputs are
+    all-reduced.  Returns the logits of a packed forward and a short greedy generation."""
+    from realhf_b200.ops import functional as OF
+    from realhf_b200.ops import gemm as G
+    OF.set_gemm_impl(G.linear)
+    from realhf_b200.api.model import GenerationHyperparameters
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.models import generation as gen
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    cfg = hf_io.family("mixtral").make_test_config()
+    cfg.hidden_dim, cfg.intermediate_dim, cfg.n_q_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab_size, cfg.n_layers = 512, 1024, 4, 4, 128, 1024, 2
+    cfg.moe.num_experts, cfg.moe.top_k = 8, 2
+    cfg.moe.expert_parallel = world > 1
+    dev = torch.device("cuda", rank)
+    ctx = ParallelContext.build(ProcessTopology(1, 1, world), list(range(world)), rank, backend="nccl") if world > 1 else ParallelContext.single()
+    m = ReaLModel(cfg, ctx, dtype=torch.bfloat16, device=dev).instantiate(seed=11).eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    g0 = torch.Generator().manual_seed(3)
+    lens = [9, 30, 17, 5]
+    ids = torch.randint(3, 1024, (sum(lens),), generator=g0).to(dev)
+    cu = torch.tensor([0, 9, 39, 56, 61], dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        logits = m(input_ids=ids, cu_seqlens=cu, max_seqlen=30).logits.float().cpu()
+    g = GenerationHyperparameters(max_new_tokens=8, min_new_tokens=8, greedy=True, use_cuda_graph=graph)
+    out, _ = gen.generate(m, ids, cu, g, eos_id=None, pad_id=0)
+    return dict(logits=logits, tokens=out.tokens.cpu(), logprobs=out.logprobs.float().cpu())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_expert_parallel_with_replicated_tokens_matches_single_gpu(graph):
+    _need(2)
+    from realhf_b200.base.testing import run_distributed
+    ref = run_distributed(_ep_replicated_worker, 1, backend="nccl", graph=graph)[0]
+    eps = run_distributed(_ep_replicated_worker, 2, backend="nccl", graph=graph)
+    for r in eps:
+        assert torch.isfinite(r["logits"]).all()
+        torch.testing.assert_close(r["logits"], ref["logits"], atol=0.06, rtol=0.05)
+        torch.testing.assert_close(r["logprobs"], eps[0]["logprobs"], atol=1e-3, rtol=1e-3)   # ranks agree with each other
+        assert torch.equal(r["tokens"], eps[0]["tokens"])
+
+
+def test_expert_parallel_training_without_sequence_parallel_matches_single_gpu():
+    """EP on a TP group that does not shard tokens (a model whose generation and training share one tp layout): the grouped
+    GEMMs and the grouped wgrad get the offsets of the rank's experts INSIDE the globally sorted rows (offsets[0] > 0 on
+    every rank but the first)."""
+    _need(2)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from realhf_b200.base.testing import run_distributed
+    ref = run_distributed(_ep_worker, 1, backend="nccl", fused=False)[0]
+    rep = run_distributed(_ep_worker, 2, backend="nccl", fused=False, sp=False)
+    for r in rep:
+        for x, y in zip(r["losses"], ref["losses"]):
+            assert abs(x - y) < 5e-2 * max(1.0, abs(y)), (r["losses"], ref["losses"])

@@ -152,3 +152,26 @@ def test_group_padding_for_the_grouped_wgrad_kernel():
             assert float(dy_p[int(off_pad[g]) + (b - a): int(off_pad[g + 1])].abs().sum()) == 0.0
         got = torch.stack([dy_p[int(off_pad[g]): int(off_pad[g + 1])].t() @ x_p[int(off_pad[g]): int(off_pad[g + 1])] for g in range(G)])
         torch.testing.assert_close(got, grouped_wgrad_ref(dy, x, offsets, G), atol=1e-4, rtol=1e-4)
+
+
+def test_group_padding_drops_rows_that_belong_to_no_group():
+    """An expert-parallel rank hands the grouped wgrad the offsets of ITS experts inside the globally sorted rows (offsets[0] > 0,
+    rows of foreign experts before and after), and a receive buffer has an unused tail: those rows must land in the spare row
+    past the padded tensor, never inside a group's zero padding."""
+    import torch
+    from realhf_b200.ops.gemm import grouped_wgrad_ref, pad_groups
+    torch.manual_seed(1)
+    T = 300
+    offsets = torch.tensor([37, 37 + 70, 37 + 70, 37 + 70 + 5], dtype=torch.int32)   # 3 groups inside rows [37, 112)
+    dy, x = torch.randn(T, 8), torch.randn(T, 12)
+    dest, off_pad, n_pad = pad_groups(offsets, T)
+    outside = torch.cat([torch.arange(0, 37), torch.arange(112, T)])
+    assert (dest[outside] == n_pad).all() and int(dest.min()) >= 0
+    inside = dest[37:112]
+    assert inside.unique().numel() == 75 and int(inside.max()) < int(off_pad[-1])
+    dy_p = torch.zeros(n_pad + 1, 8).index_copy_(0, dest, dy)[:n_pad]
+    x_p = torch.zeros(n_pad + 1, 12).index_copy_(0, dest, x)[:n_pad]
+    got = torch.stack([dy_p[int(off_pad[g]): int(off_pad[g + 1])].t() @ x_p[int(off_pad[g]): int(off_pad[g + 1])] for g in range(3)])
+    off = offsets.tolist()
+    ref = torch.stack([dy[off[g]:off[g + 1]].t() @ x[off[g]:off[g + 1]] for g in range(3)])
+    torch.testing.assert_close(got, ref, atol=1e-4, rtol=1e-4)
