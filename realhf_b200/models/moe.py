@@ -156,10 +156,13 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
         else:
             y_sorted = EP.dispatch_compute_combine(x_sorted, flat_e[order], E, w_gu, w_dn, c.activation_function, ctx.tp_group)
         return torch.zeros(T, H, dtype=y_sorted.dtype, device=h.device).index_add_(0, tok, y_sorted * w_sorted.to(y_sorted.dtype).unsqueeze(-1))
-    if ep and _use_grouped_kernel(h, w_gu, w_dn):
+    if ep and not torch.is_grad_enabled() and _use_grouped_kernel(h, w_gu, w_dn):
         # replicated tokens, sync-free (CUDA-graph capturable: the decode path): every rank sorts ALL assignments, the grouped GEMM
         # is pointed at the row range of MY experts through device-side offsets (rows of other experts are never touched), the
-        # foreign rows are masked out and the partial outputs are all-reduced
+        # foreign rows are masked out and the partial outputs are all-reduced.  Inference only: the untouched rows hold
+        # uninitialised memory, which `torch.where` discards in the forward pass but which would leak into the gradients
+        # (0 * NaN in the routing-weight gradient, garbage dgrad rows scattered back into dh); training without SP takes the
+        # compacting path below
         e_local = E // ctx.tp_size
         lo = ctx.tp_rank * e_local
         e_sorted = flat_e[order]
