@@ -115,8 +115,11 @@ class _NoSampler:
 
 def run_reference(args):
     """The unmodified reference cannot run in this image: see DESIGN.md ("Reference arm")."""
-    why = ("reference installs into baseline/_ref only with --no-deps --ignore-requires-python (needs python<3.12) and its "
-           "PPO path imports megatron-core 0.6, deepspeed 0.14, hydra-core and colorlog, none of which exist in this offline image")
+    why = ("reference installs into baseline/_ref only with --no-deps --ignore-requires-python; unmodified it cannot be imported on "
+           "this image's Python 3.12: realhf/api/core/config.py declares a dataclass instance as a field default, which dataclasses "
+           "reject since 3.11 (ValueError: mutable default ... use default_factory) -- every entry point imports that module; beyond "
+           "it the PPO path needs megatron-core 0.6, deepspeed 0.14 and hydra-core, none of which exist offline "
+           "(python baseline/probe_reference.py prints the evidence)")
     print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
