@@ -30,7 +30,10 @@ m.eval()
 def time_step(B, fp8):
     st = gen.DecodeState(m, B, 640)
     st.cache_lens.fill_(ctx_len)
-    st.input_ids.fill_(5)
+    st.input_ids.copy_(torch.arange(B, device=dev) % 1000 + 5)
+    gk = torch.Generator(device=dev).manual_seed(11)   # the same synthetic context for both precisions
+    for t in list(st.k) + list(st.v):
+        t.normal_(0.0, 0.5, generator=gk)
     if fp8:
         m.enable_fp8_decode()
 

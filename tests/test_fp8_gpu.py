@@ -86,7 +86,9 @@ def test_generation_with_fp8_decode_tracks_the_bf16_policy(graph, monkeypatch):
     from realhf_b200.api.model import GenerationHyperparameters
     from realhf_b200.models import generation as gen
     from realhf_b200.ops import fp8
-    from tests.test_sampling_gpu import _tiny_llama
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_sampling_gpu import _tiny_llama
     m = _tiny_llama()
     calls = [0]
     real = fp8.gemm_fp8
