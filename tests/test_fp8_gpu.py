@@ -112,7 +112,10 @@ def test_generation_with_fp8_decode_tracks_the_bf16_policy(graph, monkeypatch):
         lp_ref = torch.log_softmax(o.logits.float()[L - 1: L - 1 + 16], -1)[torch.arange(16), out.tokens[i]]
         diffs.append((out.logprobs[i] - lp_ref).abs())
     d = torch.stack(diffs)
-    assert d.mean().item() < 0.05 and d.max().item() < 0.5, (d.mean().item(), d.max().item())
+    # e4m3 carries 3 mantissa bits: ~4% rms error per operand, ~5% of the output rms per GEMM, and a random-init network has no
+    # logit margins to absorb it -- measured on B200 for this model: mean 0.22, max 0.66 nats.  A wiring mistake (wrong weight,
+    # wrong scale, missing bias) shows up as several nats; the exact check of the path is the next test.
+    assert d.mean().item() < 0.6 and d.max().item() < 2.5, (d.mean().item(), d.max().item())
     # the same call without the flag is the plain bf16 path
     calls[0] = 0
     g2 = GenerationHyperparameters(max_new_tokens=4, min_new_tokens=4, greedy=True, use_cuda_graph=graph)
@@ -151,3 +154,70 @@ def test_gated_act_quant_equals_unfused_kernels(M, F, kind):
     q, s = fp8.gated_act_quant(gu, kind)
     q_ref, s_ref = fp8.quantize_rows(OF.gated_act(gu, kind))
     assert torch.equal(s, s_ref) and torch.equal(q, q_ref)
+
+
+def test_fp8_decode_step_equals_pytorch_emulation_of_the_quantised_layer(monkeypatch):
+    """One decode step of the W8A8 path (fused quantising producers + e4m3 tcgen05 GEMMs, as wired in `ReaLModel.decode_step` and
+    the LM head) against the SAME step with every fp8 piece replaced by plain PyTorch on the same quantisation rule (unfused norm /
+    activation kernels, `quantize_rows_ref`, fp32 matmul of the dequantised operands)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_sampling_gpu import _tiny_llama
+    from realhf_b200.models import generation as gen
+    from realhf_b200.ops import fp8
+    from realhf_b200.ops import functional as OF
+    m = _tiny_llama()
+    B = 4
+    st = gen.DecodeState(m, B, 64)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in list(st.k) + list(st.v):
+        t.normal_(0.0, 0.5, generator=g)
+    ids = torch.tensor([5, 17, 300, 31999], device="cuda")
+
+    def step():
+        st.cache_lens.fill_(20)
+        with torch.no_grad():
+            return gen._final_logits(m, m.decode_step(ids, st.k, st.v, st.cache_lens)).float()
+
+    bf16 = step()
+    m.enable_fp8_decode()
+    calls = [0]
+    real_gemm = fp8.gemm_fp8
+
+    def counting(*a, **k):
+        calls[0] += 1
+        return real_gemm(*a, **k)
+    monkeypatch.setattr(fp8, "gemm_fp8", counting)
+    kern = step()
+    assert calls[0] == 2 * 4 + 1
+
+    def gemm_ref(qx, sx, qw, sw, bias=None, out_dtype=torch.bfloat16, out=None, bn=0, split=0):
+        y = fp8.dequantize(qx, sx[: qx.shape[0]]) @ fp8.dequantize(qw, sw).t()
+        if bias is not None:
+            y = y + bias.float()
+        return y.to(out_dtype)
+
+    def addnorm_ref(d, x, w, eps, w_offset=0.0):
+        if d is None:
+            h, r = OF.rmsnorm(x, w, eps, w_offset), x
+        else:
+            h, r = OF.add_rmsnorm(d, x, w, eps, w_offset)
+        q, s = fp8.quantize_rows_ref(h)
+        return q, s, r
+
+    def gated_ref(gu, kind):
+        return fp8.quantize_rows_ref(OF.gated_act(gu, kind))
+
+    monkeypatch.setattr(fp8, "gemm_fp8", gemm_ref)
+    monkeypatch.setattr(fp8, "add_rmsnorm_quant", addnorm_ref)
+    monkeypatch.setattr(fp8, "gated_act_quant", gated_ref)
+    monkeypatch.setattr(fp8, "quantize_rows", lambda x, q_out=None, scale_out=None: fp8.quantize_rows_ref(x))
+    emu = step()
+    m.disable_fp8_decode()
+    rel = ((kern - emu).norm() / emu.norm()).item()
+    assert rel < 0.02, rel                               # the kernels ARE the emulated computation (rounding ties aside)
+    rel16 = ((kern - bf16).norm() / bf16.norm()).item()
+    assert 0.005 < rel16 < 0.3, rel16                    # ... which differs from bf16 by the quantisation noise, and only by that
+    lp_k, lp_e = torch.log_softmax(kern, -1), torch.log_softmax(emu, -1)
+    tok = emu.argmax(-1)
+    assert (lp_k.gather(1, tok[:, None]) - lp_e.gather(1, tok[:, None])).abs().max().item() < 0.05
