@@ -24,12 +24,18 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kMaxVec = 8;  // 8-element vectors per thread held in registers: K <= 256 * 8 * 8 = 16384
 
-RB_DEVICE uint2 cvt8_e4m3(const float* v, float inv) {
+// IEEE division (not a multiplication by an approximate reciprocal, and immune to --use_fast_math): x / s is exact surprisingly
+// often -- x and the row maximum are both bf16 values, s = amax / 448 -- and exact ties must round the way every other
+// implementation of the same rule rounds them (round-to-nearest-even on the exact quotient), or 3% of the elements of such a row
+// land one e4m3 step away from the PyTorch reference
+RB_DEVICE uint2 cvt8_e4m3(const float* v, float s) {
   uint32_t w[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * h] * inv, v[4 * h + 1] * inv), __NV_SATFINITE, __NV_E4M3);
-    const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * h + 2] * inv, v[4 * h + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+    const __nv_fp8x2_storage_t lo =
+        __nv_cvt_float2_to_fp8x2(make_float2(__fdiv_rn(v[4 * h], s), __fdiv_rn(v[4 * h + 1], s)), __NV_SATFINITE, __NV_E4M3);
+    const __nv_fp8x2_storage_t hi =
+        __nv_cvt_float2_to_fp8x2(make_float2(__fdiv_rn(v[4 * h + 2], s), __fdiv_rn(v[4 * h + 3], s)), __NV_SATFINITE, __NV_E4M3);
     w[h] = (uint32_t)lo | ((uint32_t)hi << 16);
   }
   return make_uint2(w[0], w[1]);
@@ -53,13 +59,12 @@ RB_DEVICE void quant_tail(float (&vals)[NV][8], int nvec, uint8_t* qr, float* sc
     }
   }
   amax = rb::block_reduce<true>(amax, red);
-  const float s = amax > 0.f ? amax * (1.f / 448.f) : 1.f;
-  const float inv = 1.f / s;
+  const float s = amax > 0.f ? __fdiv_rn(amax, 448.f) : 1.f;
   if (threadIdx.x == 0) scale[row] = s;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int i = threadIdx.x + j * kThreads;
-    if (i < nvec) *reinterpret_cast<uint2*>(qr + (int64_t)i * 8) = cvt8_e4m3(vals[j], inv);
+    if (i < nvec) *reinterpret_cast<uint2*>(qr + (int64_t)i * 8) = cvt8_e4m3(vals[j], s);
   }
 }
 

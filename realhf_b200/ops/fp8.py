@@ -35,7 +35,9 @@ def quantize_rows_ref(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Plain PyTorch version of `quantize_rows` (tests, CPU)."""
     xf = x.float()
     amax = xf.abs().amax(dim=1)
-    s = torch.where(amax > 0, amax / E4M3_MAX, torch.ones_like(amax))
+    # tensor / tensor: a true IEEE division like the kernel's `__fdiv_rn` (tensor / python-scalar multiplies by a rounded reciprocal,
+    # which lands 1 ulp away about half of the time and then moves exact rounding ties of x / s)
+    s = torch.where(amax > 0, amax / torch.full_like(amax, E4M3_MAX), torch.ones_like(amax))
     q = (xf / s[:, None]).clamp_(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
     return q.view(torch.uint8), s
 

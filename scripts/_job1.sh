@@ -1,3 +1,3 @@
 set -u
 mkdir -p gpurun_out
-echo "== fp8 tests"; timeout 110 python -m pytest tests/test_fp8_gpu.py -q --tb=short -k "generation or emulation" 2>&1 | grep -v "W921\|NCCL version" | tail -25 | cut -c1-500
+timeout 100 python scripts/diag_fp8_decode.py 2>&1 | grep "^{" | tee gpurun_out/diag_fp8_decode.jsonl | cut -c1-300

@@ -156,10 +156,14 @@ def test_gated_act_quant_equals_unfused_kernels(M, F, kind):
     assert torch.equal(s, s_ref) and torch.equal(q, q_ref)
 
 
-def test_fp8_decode_step_equals_pytorch_emulation_of_the_quantised_layer(monkeypatch):
-    """One decode step of the W8A8 path (fused quantising producers + e4m3 tcgen05 GEMMs, as wired in `ReaLModel.decode_step` and
-    the LM head) against the SAME step with every fp8 piece replaced by plain PyTorch on the same quantisation rule (unfused norm /
-    activation kernels, `quantize_rows_ref`, fp32 matmul of the dequantised operands)."""
+def test_fp8_decode_step_against_pytorch_emulation_call_by_call(monkeypatch):
+    """One decode step of the W8A8 path as wired in `ReaLModel.decode_step` + the LM head, checked call by call IN SITU: every
+    quantiser call against the PyTorch rule on the tensor it actually consumed, every e4m3 GEMM against fp32 math on the operands
+    it actually received; then the whole step against an emulation in which every fp8 piece is replaced by PyTorch.
+    End-to-end the two are NOT bit-close and cannot be: a 1-ulp bf16 difference in an activation flips its e4m3 code with a
+    probability of a few percent, so rounding-level differences grow to a few percent of the logits within two layers of a
+    random network (measured on B200: 3.9%, `profiles/fp8_decode_in_situ_check.jsonl`), while both sit at the same distance from
+    the bf16 logits (16.2% / 16.2%) -- which is the property asserted."""
     import os, sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from test_sampling_gpu import _tiny_llama
@@ -181,43 +185,67 @@ def test_fp8_decode_step_equals_pytorch_emulation_of_the_quantised_layer(monkeyp
 
     bf16 = step()
     m.enable_fp8_decode()
-    calls = [0]
-    real_gemm = fp8.gemm_fp8
+    real = dict(gemm=fp8.gemm_fp8, addnorm=fp8.add_rmsnorm_quant, gated=fp8.gated_act_quant, qrows=fp8.quantize_rows)
+    log = []
 
-    def counting(*a, **k):
-        calls[0] += 1
-        return real_gemm(*a, **k)
-    monkeypatch.setattr(fp8, "gemm_fp8", counting)
+    def gemm(qx, sx, qw, sw, bias=None, out_dtype=torch.bfloat16, out=None, bn=0, split=0):
+        y = real["gemm"](qx, sx, qw, sw, bias, out_dtype, out, bn, split)
+        ref = fp8.dequantize(qx, sx[: qx.shape[0]]) @ fp8.dequantize(qw, sw).t()
+        log.append(("gemm", ((y.float() - ref).norm() / ref.norm()).item()))
+        return y
+
+    def cmp_q(q, s, h):
+        qr, sr = fp8.quantize_rows_ref(h)
+        log.append(("quant", (q == qr).float().mean().item(), float(((s - sr).abs() / sr).max())))
+
+    def addnorm(d, x, w, eps, w_offset=0.0):
+        r = real["addnorm"](d, x, w, eps, w_offset)
+        h = OF.rmsnorm(x, w, eps, w_offset) if d is None else OF.add_rmsnorm(d, x, w, eps, w_offset)[0]
+        cmp_q(r[0], r[1], h)
+        return r
+
+    def gated(gu, kind):
+        r = real["gated"](gu, kind)
+        cmp_q(r[0], r[1], OF.gated_act(gu, kind))
+        return r
+
+    def qrows(x, q_out=None, scale_out=None):
+        r = real["qrows"](x, q_out, scale_out)
+        cmp_q(r[0], r[1], x)
+        return r
+
+    monkeypatch.setattr(fp8, "gemm_fp8", gemm)
+    monkeypatch.setattr(fp8, "add_rmsnorm_quant", addnorm)
+    monkeypatch.setattr(fp8, "gated_act_quant", gated)
+    monkeypatch.setattr(fp8, "quantize_rows", qrows)
     kern = step()
-    assert calls[0] == 2 * 4 + 1
+    gemms = [l for l in log if l[0] == "gemm"]
+    quants = [l for l in log if l[0] == "quant"]
+    assert len(gemms) == 2 * 4 + 1 and len(quants) == 2 * 4 + 1, (len(gemms), len(quants))  # 4 linears per block + the head, one quantiser each
+    assert max(l[1] for l in gemms) < 0.004, gemms           # bf16 output rounding of an exact fp32 accumulation
+    assert min(l[1] for l in quants) > 0.97 and max(l[2] for l in quants) < 1e-6, quants  # ties / 1-ulp scales aside, the same bytes
 
     def gemm_ref(qx, sx, qw, sw, bias=None, out_dtype=torch.bfloat16, out=None, bn=0, split=0):
-        y = fp8.dequantize(qx, sx[: qx.shape[0]]) @ fp8.dequantize(qw, sw).t()
-        if bias is not None:
-            y = y + bias.float()
-        return y.to(out_dtype)
+        return (fp8.dequantize(qx, sx[: qx.shape[0]]) @ fp8.dequantize(qw, sw).t()).to(out_dtype)
 
     def addnorm_ref(d, x, w, eps, w_offset=0.0):
-        if d is None:
-            h, r = OF.rmsnorm(x, w, eps, w_offset), x
-        else:
-            h, r = OF.add_rmsnorm(d, x, w, eps, w_offset)
+        h, r = (OF.rmsnorm(x, w, eps, w_offset), x) if d is None else OF.add_rmsnorm(d, x, w, eps, w_offset)
         q, s = fp8.quantize_rows_ref(h)
         return q, s, r
 
-    def gated_ref(gu, kind):
-        return fp8.quantize_rows_ref(OF.gated_act(gu, kind))
-
     monkeypatch.setattr(fp8, "gemm_fp8", gemm_ref)
     monkeypatch.setattr(fp8, "add_rmsnorm_quant", addnorm_ref)
-    monkeypatch.setattr(fp8, "gated_act_quant", gated_ref)
+    monkeypatch.setattr(fp8, "gated_act_quant", lambda gu, kind: fp8.quantize_rows_ref(OF.gated_act(gu, kind)))
     monkeypatch.setattr(fp8, "quantize_rows", lambda x, q_out=None, scale_out=None: fp8.quantize_rows_ref(x))
     emu = step()
+    monkeypatch.setattr(fp8, "gemm_fp8", real["gemm"])
+    monkeypatch.setattr(fp8, "add_rmsnorm_quant", real["addnorm"])
+    monkeypatch.setattr(fp8, "gated_act_quant", real["gated"])
+    monkeypatch.setattr(fp8, "quantize_rows", real["qrows"])
+    kern2 = step()
     m.disable_fp8_decode()
-    rel = ((kern - emu).norm() / emu.norm()).item()
-    assert rel < 0.02, rel                               # the kernels ARE the emulated computation (rounding ties aside)
-    rel16 = ((kern - bf16).norm() / bf16.norm()).item()
-    assert 0.005 < rel16 < 0.3, rel16                    # ... which differs from bf16 by the quantisation noise, and only by that
-    lp_k, lp_e = torch.log_softmax(kern, -1), torch.log_softmax(emu, -1)
-    tok = emu.argmax(-1)
-    assert (lp_k.gather(1, tok[:, None]) - lp_e.gather(1, tok[:, None])).abs().max().item() < 0.05
+    assert torch.equal(kern, kern2)                                         # deterministic
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert rel(kern, emu) < 0.15, rel(kern, emu)
+    k16, e16 = rel(kern, bf16), rel(emu, bf16)
+    assert 0.02 < k16 < 0.5 and abs(k16 - e16) < 0.05, (k16, e16)           # same quantisation noise, nothing else
