@@ -173,3 +173,34 @@ def test_ppo_hyperparameter_variants(variant):
         d.update_(basic.PairedRewardInterface().inference(rew, d))
         sa, sc = a.train_step(actor, d, n_mbs=2), c.train_step(critic, d, n_mbs=2)
         assert all(x == x for x in list(sa.values()) + list(sc.values()) if isinstance(x, float)), (sa, sc)
+
+
+def test_fp8_generation_flag_is_a_noop_where_the_path_is_unsupported():
+    """`fp8_weights=True` on a device / layout without the W8A8 kernels (CPU here; TP > 1, MoE) must generate exactly what the
+    default path generates and leave no quantised copies behind."""
+    import torch
+    from realhf_b200.api.model import GenerationHyperparameters
+    from realhf_b200.base.topology import ParallelContext
+    from realhf_b200.models import generation as gen
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    from realhf_b200.ops import fp8
+    cfg = hf_io.family("llama").make_test_config()
+    m = ReaLModel(cfg, ParallelContext.single(), dtype=torch.float32, device=torch.device("cpu")).instantiate(seed=3).eval()
+    assert not m.fp8_decode_supported()
+    ids = torch.randint(3, cfg.vocab_size, (12,))
+    cu = torch.tensor([0, 5, 12], dtype=torch.int32)
+    outs = []
+    for flag in (False, True):
+        g = GenerationHyperparameters(max_new_tokens=6, min_new_tokens=6, greedy=True, fp8_weights=flag)
+        out, _ = gen.generate(m, ids, cu, g, eos_id=None, pad_id=0)
+        outs.append(out)
+        assert m._fp8 is None and not m._fp8_active
+    assert torch.equal(outs[0].tokens, outs[1].tokens)
+    torch.testing.assert_close(outs[0].logprobs, outs[1].logprobs)
+    # the PyTorch quantisation rule itself: per-row scale, saturation, all-zero rows
+    x = torch.tensor([[0.0, 0.0, 0.0, 0.0], [1.0, -448.0, 1000.0, 0.5]])
+    q, s = fp8.quantize_rows_ref(x)
+    assert s[0].item() == 1.0 and (q[0] == 0).all()
+    d = fp8.dequantize(q, s)
+    assert d[1, 2].item() == 1000.0 and abs(d[1, 1].item() + 448.0) < 448.0 * 0.07
