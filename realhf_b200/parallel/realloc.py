@@ -99,6 +99,34 @@ def _intersect_general(src_iv, dst_iv):
     return out
 
 
+def _uncovered(segs, covered: List[Tuple[int, int]]):
+    """Parts of `segs` ((src_off, dst_off, len), shard-local) whose destination range is not in `covered` yet; `covered`
+    (sorted, disjoint destination ranges) is extended.  KV heads replicated over the source TP group (n_kv < tp) are held by
+    several source ranks: the destination must receive each element exactly ONCE -- a second copy is harmless for a plain
+    overwrite but applies an EMA merge (eta < 1) twice."""
+    out = []
+    for so, do, ln in segs:
+        pieces = [(do, do + ln)]
+        for c0, c1 in covered:
+            nxt = []
+            for p0, p1 in pieces:
+                if c1 <= p0 or c0 >= p1:
+                    nxt.append((p0, p1))
+                else:
+                    if p0 < c0:
+                        nxt.append((p0, c0))
+                    if c1 < p1:
+                        nxt.append((c1, p1))
+            pieces = nxt
+            if not pieces:
+                break
+        for p0, p1 in pieces:
+            out.append((so + (p0 - do), p0, p1 - p0))
+            covered.append((p0, p1))
+        covered.sort()
+    return out
+
+
 def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Sequence[int], dst_topo: ProcessTopology,
                 dst_workers: Sequence[int]) -> ReallocPlan:
     """`*_workers[r]` = worker (GPU) index of layout-local rank r.  Critic / actor pairs must share the architecture."""
@@ -127,6 +155,7 @@ def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Se
                     else:
                         sslot = src_layouts[spp][name]
                     d_iv = sharding.shard_intervals(spec, cfg, dtp, d_tp)
+                    covered: List[Tuple[int, int]] = []
                     # source TP ranks that hold any of it
                     for stp in range(s_tp):
                         s_iv = sharding.shard_intervals(spec, cfg, stp, s_tp)
@@ -137,7 +166,7 @@ def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Se
                                 continue  # replicated tensor: one source copy is enough
                             segs = [(0, 0, dslot.numel)]
                         else:
-                            segs = _intersect_general(s_iv, d_iv)
+                            segs = _uncovered(_intersect_general(s_iv, d_iv), covered)
                         if not segs:
                             continue
                         # pick the source DP replica: same GPU if possible, else spread by destination dp rank
