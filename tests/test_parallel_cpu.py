@@ -68,7 +68,8 @@ def _reference(fam, n_steps, n_mbs=1):
     return run_distributed(_worker, 1, layout=(1, 1, 1, False), fam=fam, n_steps=n_steps, n_mbs=n_mbs)[0]
 
 
-@pytest.mark.parametrize("layout", [(1, 1, 2, False), (1, 1, 2, True), (2, 1, 1, False), (1, 2, 1, False), (2, 1, 2, True), (2, 2, 1, False)])
+@pytest.mark.parametrize("layout", [(1, 1, 2, False), (1, 1, 2, True), (2, 1, 1, False), (1, 2, 1, False), (2, 1, 2, True), (2, 2, 1, False),
+                                    (2, 2, 2, True), (1, 1, 4, True), (4, 1, 1, False), (1, 2, 2, False)])
 def test_layout_matches_single_process(layout):
     from realhf_b200.base.testing import run_distributed
     fam, n_steps = "llama", 3
