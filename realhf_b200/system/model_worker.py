@@ -303,6 +303,29 @@ class ModelWorker:
         else:
             raise NotImplementedError(h)
 
+    # ------------------------------------------------------------------ dataset prefetch
+    def _load_batch(self):
+        """(next batch, whether the iterator wrapped into a new epoch to produce it).  Runs on the prefetch thread."""
+        try:
+            return next(self.data_iter), False
+        except StopIteration:
+            self.data_iter = iter(self.dataloader)
+            return next(self.data_iter), True
+
+    def _take_batch(self):
+        """The batch for this `fetch`, and the start of the next one's load (tokenisation / collation on a side thread while
+        the MFCs of this step run) -- the reference prefetches from the dataset at every poll (model_worker.py:401-416).
+        The iterator is only ever touched by one thread at a time: the pending load is awaited before anything else."""
+        import concurrent.futures
+        if getattr(self, "_prefetch_pool", None) is None:
+            self._prefetch_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="dataset-prefetch")
+            self._prefetched = None
+        fut, self._prefetched = self._prefetched, None
+        out = fut.result() if fut is not None else self._load_batch()
+        if os.environ.get("REAL_DATASET_PREFETCH", "1") == "1":
+            self._prefetched = self._prefetch_pool.submit(self._load_batch)
+        return out
+
     def _handle_core(self, req: Payload) -> Any:
         h = req.handle_name
         if h == "empty":
@@ -310,14 +333,10 @@ class ModelWorker:
         if h == "spec":
             return dict(dataset_size=self.dataset_size, steps_per_epoch=len(self.dataloader))
         if h == "fetch":
-            try:
-                batch = next(self.data_iter)
-                final = False
-            except StopIteration:
+            batch, wrapped = self._take_batch()
+            final = False
+            if wrapped:
                 self.epoch += 1
-                self.data_iter = iter(self.dataloader)
-                batch = next(self.data_iter)
-                final = False
             ignore = set(req.data.get("ignore_ids", [])) if isinstance(req.data, dict) else set()
             items = [x for x in batch.unpack() if x.ids[0] not in ignore]
             for it in items:
