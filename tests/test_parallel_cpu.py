@@ -248,3 +248,41 @@ def test_replicated_dropout_and_sampling_agree_across_tp_ranks(ckpt):
     if ckpt:   # recomputation replays the same masks: identical training trajectory with and without checkpointing
         c, _ = run_distributed(_dropout_worker, 2, ckpt=False)
         assert c["losses"] == pytest.approx(a["losses"], rel=1e-5)
+
+
+def _zero3_layout_worker(rank, world, layout, zero_stage):
+    import types
+
+    from realhf_b200.api.config import ModelName
+    from realhf_b200.api.model import FinetuneSpec, Model
+    from realhf_b200.base.topology import ParallelContext, ProcessTopology
+    from realhf_b200.engine.engine import TrainBackend
+    from realhf_b200.interfaces import basic
+    from realhf_b200.models import hf_io
+    from realhf_b200.models.real_model import ReaLModel
+    pp, dp, tp, sp = layout
+    cfg = hf_io.family("llama").make_test_config()
+    cfg.n_layers = 4
+    ctx = ParallelContext.build(ProcessTopology(pp, dp, tp), list(range(world)), rank, backend="gloo", sequence_parallel=sp)
+    m = ReaLModel(cfg, ctx, dtype=torch.float32).instantiate(seed=7)
+    tok = types.SimpleNamespace(eos_token_id=1, pad_token_id=0)
+    model = TrainBackend(optimizer=dict(lr=1e-2, weight_decay=0.0, warmup_steps_proportion=0.0, lr_scheduler_type="constant", grad_dtype="fp32"),
+                         zero_stage=zero_stage).initialize(Model(ModelName("m", 0), m, tok, "cpu"), FinetuneSpec(1, 10, 10))
+    full = _batch(8)
+    mine = full.split(dp)[ctx.dp_rank] if dp > 1 else full
+    losses = [basic.SFTInterface().train_step(model, mine, n_mbs=2 if pp > 1 else 1)["loss"] for _ in range(3)]
+    return dict(losses=losses, resident=model.module.module.instantiated)
+
+
+@pytest.mark.parametrize("layout", [(1, 2, 2, False), (1, 2, 2, True), (2, 2, 1, False)])
+def test_zero3_composes_with_tensor_sequence_and_pipeline_parallelism(layout):
+    """The parameter shards of ZeRO-3 are cut over the DATA-parallel group of each (pp, tp) coordinate: the same losses as ZeRO-1
+    under dp2 x tp2 (with and without sequence parallelism) and dp2 x pp2, and no resident parameters between calls."""
+    from realhf_b200.base.testing import run_distributed
+    world = layout[0] * layout[1] * layout[2]
+    z1 = run_distributed(_zero3_layout_worker, world, layout=layout, zero_stage=1)
+    z3 = run_distributed(_zero3_layout_worker, world, layout=layout, zero_stage=3)
+    for a, b in zip(z1, z3):
+        assert a["resident"] and not b["resident"]
+        for x, y in zip(a["losses"], b["losses"]):
+            assert abs(x - y) < 1e-4, (layout, a["losses"], b["losses"])
