@@ -467,8 +467,10 @@ class ReaLModel(nn.Module):
 
     def fp8_decode_supported(self) -> bool:
         c = self.config
-        return bool(self.device.type == "cuda" and self.ctx.tp_size == 1 and c.mlp_type == "llama"
-                    and self.dtype in (torch.bfloat16, torch.float16) and self.instantiated)
+        from realhf_b200.ops import fp8
+        on_dev = self.device.type == "cuda" and self.dtype in (torch.bfloat16, torch.float16)
+        return bool((on_dev or (self.device.type != "cuda" and fp8.emulate())) and self.ctx.tp_size == 1 and c.mlp_type == "llama"
+                    and self.instantiated)
 
     def enable_fp8_decode(self) -> int:
         """Quantise (or, when the buffers exist already, re-quantise in place) every local block linear and the LM head.

@@ -24,9 +24,24 @@ from realhf_b200.ops.gemm import _sms, streamk_workspace
 E4M3_MAX = 448.0
 
 
+def emulate() -> bool:
+    """`REAL_FP8_EMULATE=1`: tensors that are not on a CUDA device take the PyTorch implementation of every piece (same
+    quantisation rule, fp32 matmul of the dequantised operands).  Lets the CPU suite run the whole W8A8 decode path -- which
+    weights are quantised, where biases and norm offsets enter -- for every model family."""
+    import os
+    return os.environ.get("REAL_FP8_EMULATE", "0") == "1"
+
+
 def quantize_rows(x: torch.Tensor, q_out: Optional[torch.Tensor] = None, scale_out: Optional[torch.Tensor] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
     """x [M, K] -> (q uint8 [M, K] holding e4m3 bytes, scale fp32 [M]) with x ~= q * scale[:, None]."""
+    if not x.is_cuda:
+        q, s = quantize_rows_ref(x)
+        if q_out is not None:
+            q_out.copy_(q)
+            scale_out.copy_(s)
+            return q_out, scale_out
+        return q, s
     q, s = lib().quant_rows_e4m3(x, q_out, scale_out)
     return q, s
 
@@ -48,6 +63,11 @@ def dequantize(q: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
 
 def gemm_fp8(qx: torch.Tensor, sx: torch.Tensor, qw: torch.Tensor, sw: torch.Tensor, bias: Optional[torch.Tensor] = None,
              out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None, bn: int = 0, split: int = 0) -> torch.Tensor:
+    if not qx.is_cuda:
+        y = dequantize(qx, sx[: qx.shape[0]]) @ dequantize(qw, sw).t()
+        if bias is not None:
+            y = y + bias.float()
+        return y.to(out_dtype)
     ws, flags = streamk_workspace(qx.device)
     return lib().gemm_streamk_fp8(qx, qw, sx, sw, out, bias, ws, flags, out_dtype, bn, split, _sms(qx.device))
 
@@ -105,6 +125,9 @@ def gated_act_quant(gu: torch.Tensor, kind: str) -> Optional[Tuple[torch.Tensor,
     from realhf_b200.ops.functional import _ACT_KIND
     k = _ACT_KIND.get(kind)
     F = gu.shape[-1] // 2
+    if not gu.is_cuda:
+        from realhf_b200.ops.functional import gated_act
+        return quantize_rows_ref(gated_act(gu, kind))
     if k is None or gu.dim() != 2 or F % 8 or F > 16384 or gu.stride(-1) != 1 or gu.stride(0) % 8 or gu.dtype not in (torch.bfloat16, torch.float16):
         return None
     q, s = lib().gated_act_quant_e4m3(gu, k)
@@ -115,6 +138,11 @@ def add_rmsnorm_quant(d: Optional[torch.Tensor], x: torch.Tensor, w: torch.Tenso
     """Residual add + RMSNorm + e4m3 quantisation of the normalised rows in one kernel.
     Returns (q, scale, new residual stream) or None when the shape has no fused kernel (H % 8, H > 8192, dtype)."""
     H = x.shape[-1]
+    if not x.is_cuda:
+        from realhf_b200.ops.functional import add_rmsnorm, rmsnorm
+        h, r = (rmsnorm(x, w, eps, w_offset), x) if d is None else add_rmsnorm(d, x, w, eps, w_offset)
+        q, s = quantize_rows_ref(h)
+        return q, s, r
     if H % 8 or H > 8192 or x.dtype not in (torch.bfloat16, torch.float16) or not x.is_contiguous() or (d is not None and not d.is_contiguous()):
         return None
     if d is None:
@@ -126,7 +154,9 @@ def add_rmsnorm_quant(d: Optional[torch.Tensor], x: torch.Tensor, w: torch.Tenso
 
 def supported(w: torch.Tensor, max_rows: int = 128) -> bool:
     """Shapes the fp8 stream-K kernel takes: K a multiple of 16 and <= 16384 (row quantiser), N >= 256."""
-    return bool(w.is_cuda and w.dim() == 2 and w.shape[1] % 16 == 0 and w.shape[1] <= 16384 and w.shape[0] >= 256
+    if not w.is_cuda:
+        return bool(emulate() and w.dim() == 2)
+    return bool(w.dim() == 2 and w.shape[1] % 16 == 0 and w.shape[1] <= 16384 and w.shape[0] >= 256
                 and w.dtype in (torch.bfloat16, torch.float16))
 
 
