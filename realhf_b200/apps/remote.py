@@ -51,11 +51,8 @@ def main_worker(args):
     import realhf_b200.models.factory  # noqa: F401
     user_code = os.environ.get("REAL_USER_CODE")
     if user_code:  # custom experiments / interfaces registered by the user's script
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("real_user_code", user_code)
-        mod = importlib.util.module_from_spec(spec)
-        sys.modules[spec.name] = mod  # dataclasses / pickling resolve classes through sys.modules[cls.__module__]
-        spec.loader.exec_module(mod)
+        from realhf_b200.base.importing import import_usercode
+        import_usercode(user_code, "real_user_code")
     with open(config_path(args.experiment_name, args.trial_name), "rb") as f:
         cfg = pickle.load(f)
     key = status_key(args.experiment_name, args.trial_name, args.worker_type, args.jobstep_id)

@@ -31,16 +31,7 @@ def _mb_inputs(mb: SequenceSample, device, key: str = MAIN_KEY):
     return mb.data[key], cu.to(device, non_blocking=True), max(lens)
 
 
-def pad_for_sp(ids: torch.Tensor, cu: torch.Tensor, max_seqlen: int, tp: int):
-    """Sequence parallelism needs T % tp == 0: append one fake sequence of pad tokens (reference:
-    nn/real_llm_api.py:392-433).  Returns (ids, cu, max_seqlen, n_pad)."""
-    T = ids.shape[0]
-    pad = (-T) % tp
-    if pad == 0:
-        return ids, cu, max_seqlen, 0
-    ids = torch.cat([ids, ids.new_zeros(pad)])
-    cu = torch.cat([cu, (cu[-1:] + pad)])
-    return ids, cu, max(max_seqlen, pad), pad
+from realhf_b200.utils.padding import pad_sequence_parallel_input as pad_for_sp  # noqa: E402  (reference: nn/real_llm_api.py:392-433)
 
 
 class ReaLEngine(PipelinableEngine):

@@ -55,11 +55,8 @@ def _weight_map(path: str) -> Dict[str, str]:
     raise FileNotFoundError(f"no HF weights under {path}")
 
 
-def _read_file(fn: str) -> Dict[str, torch.Tensor]:
-    if fn.endswith(".safetensors"):
-        from safetensors.torch import load_file
-        return load_file(fn)
-    return torch.load(fn, map_location="cpu", weights_only=True)
+from realhf_b200.base.saveload_utils import load_weight_file as _read_file  # noqa: E402
+from realhf_b200.base.saveload_utils import split_state_dict_into_shards as _split_into_files  # noqa: E402
 
 
 def load_hf_state_dict(path: str, names: Optional[List[str]] = None) -> Dict[str, torch.Tensor]:
@@ -137,20 +134,6 @@ def gather_full_state_dict(model: ReaLModel) -> Optional[Dict[str, torch.Tensor]
         if ctx.tp_rank == 0:
             out[name] = sharding.merge_shards(slot.spec, model.config, [p.cpu() for p in parts])
     return out if ctx.tp_rank == 0 else None
-
-
-def _split_into_files(sd: Dict[str, torch.Tensor], max_bytes: int) -> List[Dict[str, torch.Tensor]]:
-    files, cur, size = [], {}, 0
-    for k in sorted(sd):
-        n = sd[k].numel() * sd[k].element_size()
-        if cur and size + n > max_bytes:
-            files.append(cur)
-            cur, size = {}, 0
-        cur[k] = sd[k]
-        size += n
-    if cur:
-        files.append(cur)
-    return files
 
 
 def save_to_hf(model: ReaLModel, family_name: str, save_dir: str, tokenizer=None, max_shard_bytes: Optional[int] = None):

@@ -167,11 +167,8 @@ class LocalSchedulerClient(SchedulerClient):
 
 
 def _count_gpus() -> int:
-    try:
-        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=10).stdout
-        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
-    except Exception:
-        return 0
+    from realhf_b200.base.gpu_utils import gpu_count
+    return gpu_count()
 
 
 class SlurmSchedulerClient(SchedulerClient):

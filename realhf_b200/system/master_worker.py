@@ -16,6 +16,7 @@ from typing import Dict, Hashable, List, Tuple
 
 import numpy as np
 
+from realhf_b200.base.asyncio_utils import gather_or_raise
 from realhf_b200.api import system as system_api
 from realhf_b200.api.config import ModelInterfaceType, ModelName
 from realhf_b200.api.data import DataBatchMeta, SequenceSample
@@ -266,7 +267,8 @@ class MasterWorker:
             if attempts > 2 * self.ft_spec.steps_per_epoch + 2:
                 raise RuntimeError(f"dataset cannot supply {self.src_rpc.n_seqs} fresh sequences "
                                    f"({self.buffer.n_ready_for(self.src_rpc)} ready after {attempts} fetches)")
-        results = await asyncio.gather(*[self._run_rpc_once(r) for r in self.rpcs])
+        # one coroutine per MFC; the first failure cancels the others (they would wait for its outputs forever)
+        results = await gather_or_raise([self._run_rpc_once(r) for r in self.rpcs])
         done = self.buffer.pop_fully_consumed()
         if done:
             for k in [k for k in self.data_owner if k[0] in set(done)]:

@@ -27,36 +27,8 @@ def master_addr_key(exp: str, trial: str) -> str:
     return f"{exp}/{trial}/stream/master_addr"
 
 
-def free_port() -> int:
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
-
-
-def host_ip() -> str:
-    """Address other workers use to reach this process (ZMQ master endpoint, torch.distributed rendezvous).
-
-    `REAL_HOST_IP` wins.  Local mode (every worker on this host) publishes loopback: container hostnames often do not
-    resolve.  Any other mode (slurm, ...) publishes a routable address of this host, like the reference
-    (`base/network.py` gethostip): the hostname's address, or, when that is loopback / unresolvable, the source address of
-    the default route."""
-    ip = os.environ.get("REAL_HOST_IP")
-    if ip:
-        return ip
-    if os.environ.get("REAL_MODE", "LOCAL").upper() == "LOCAL":
-        return "127.0.0.1"
-    try:
-        ip = socket.gethostbyname(socket.gethostname())
-        if not ip.startswith("127."):
-            return ip
-    except OSError:
-        pass
-    try:  # no packet is sent: connect() on a UDP socket only selects the outgoing interface
-        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s:
-            s.connect(("10.255.255.255", 1))
-            return s.getsockname()[0]
-    except OSError:
-        return "127.0.0.1"
+from realhf_b200.base.network import find_free_port as free_port  # noqa: E402,F401  (kept under the names the workers import)
+from realhf_b200.base.network import gethostip as host_ip  # noqa: E402,F401
 
 
 @dataclasses.dataclass

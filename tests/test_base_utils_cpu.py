@@ -394,3 +394,151 @@ def test_launcher_preflight_names_every_bad_path(tmp_path, monkeypatch):
     exp = build_experiment(["dpo", "experiment_name=e", "trial_name=t", "device=cpu", f"actor.path={good}", f"ref.path={good}",
                             f"dataset.train_path={data}"])
     preflight(exp)               # nothing to complain about
+
+
+def test_network_and_importing_helpers(tmp_path, monkeypatch):
+    import socket
+    import sys
+
+    from realhf_b200.base import importing, network
+    p = network.find_free_port()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", p))           # still free
+    monkeypatch.setenv("REAL_HOST_IP", "10.1.2.3")
+    assert network.gethostip() == "10.1.2.3"
+    monkeypatch.delenv("REAL_HOST_IP")
+    monkeypatch.setenv("REAL_MODE", "LOCAL")
+    assert network.gethostip() == "127.0.0.1"
+    monkeypatch.setenv("REAL_MODE", "SLURM")
+    socket.inet_aton(network.gethostip())  # some valid IPv4 address, whatever this container resolves to
+    code = tmp_path / "my_exp.py"
+    code.write_text("import dataclasses\n@dataclasses.dataclass\nclass C:\n    x: int = 3\nVALUE = C().x + 1\n")
+    mod = importing.import_usercode(str(code), "my_user_code")
+    assert mod.VALUE == 4 and sys.modules["my_user_code"] is mod
+    import pickle
+    assert pickle.loads(pickle.dumps(mod.C(5))).x == 5          # classes resolve through sys.modules
+    bad = tmp_path / "broken.py"
+    bad.write_text("raise RuntimeError('boom')\n")
+    with pytest.raises(RuntimeError):
+        importing.import_usercode(str(bad), "broken_user_code")
+    assert "broken_user_code" not in sys.modules
+    with pytest.raises(FileNotFoundError):
+        importing.import_usercode(str(tmp_path / "missing.py"))
+    names = importing.import_package_modules("realhf_b200.utils")
+    assert "realhf_b200.utils.padding" in names and all(not n.rsplit(".", 1)[1].startswith("_") for n in names)
+
+
+def test_security_read_key_and_saveload_helpers(tmp_path, monkeypatch):
+    import torch
+
+    from realhf_b200.base import saveload_utils, security
+    (tmp_path / "keys" / "wandb").mkdir(parents=True)
+    (tmp_path / "keys" / "wandb" / "default").write_text("  secret-token\n")
+    monkeypatch.setenv("REAL_KEY_ROOT", str(tmp_path / "keys"))
+    assert security.read_key("wandb") == "secret-token"
+    sd = {f"w{i}": torch.zeros(100, dtype=torch.float32) for i in range(5)}            # 400 bytes each
+    shards = saveload_utils.split_state_dict_into_shards(sd, max_bytes=900)
+    assert [sorted(s) for s in shards] == [["w0", "w1"], ["w2", "w3"], ["w4"]]
+    assert len(saveload_utils.split_state_dict_into_shards({"big": torch.zeros(1000)}, max_bytes=10)) == 1
+    src, dst = tmp_path / "src", tmp_path / "dst"
+    src.mkdir()
+    for fn in ("config.json", "tokenizer.json", "tokenizer_config.json", "generation_config.json", "vocab.txt", "modeling_custom.py"):
+        (src / fn).write_text("{}")
+    for fn in ("model-00001-of-00002.safetensors", "pytorch_model.bin", "model.safetensors.index.json", "optimizer.pt"):
+        (src / fn).write_text("x")
+    copied = saveload_utils.copy_hf_configs(str(src), str(dst))
+    assert sorted(copied) == sorted(["config.json", "tokenizer.json", "tokenizer_config.json", "generation_config.json", "vocab.txt",
+                                     "modeling_custom.py"])
+    from safetensors.torch import save_file
+    save_file({"a": torch.arange(4.0)}, str(tmp_path / "f.safetensors"))
+    torch.save({"b": torch.ones(2)}, str(tmp_path / "f.bin"))
+    assert saveload_utils.load_weight_file(str(tmp_path / "f.safetensors"))["a"].tolist() == [0, 1, 2, 3]
+    assert saveload_utils.load_safetensor(str(tmp_path / "f.bin"))["b"].tolist() == [1, 1]
+
+
+def test_gpu_utils_local_index_by_host_rendezvous(monkeypatch):
+    """Workers of one host find their local GPU id as their position among the workers that published the same host name."""
+    import threading
+    import uuid
+
+    from realhf_b200.base import gpu_utils, name_resolve
+    name_resolve.reconfigure("memory")
+    exp, trial = "gpuid-" + uuid.uuid4().hex[:6], "t"
+    hosts = ["nodeA", "nodeA", "nodeB", "nodeA", "nodeB", "nodeB"]
+    out = [None] * len(hosts)
+
+    def run(i):
+        out[i] = gpu_utils.local_gpu_index(exp, trial, "model_worker", i, len(hosts), host=hosts[i], n_gpus=8, timeout=20)
+    ts = [threading.Thread(target=run, args=(i,)) for i in reversed(range(len(hosts)))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert out == [0, 1, 0, 2, 1, 2]
+    with pytest.raises(RuntimeError):
+        gpu_utils.local_gpu_index(exp, trial, "model_worker", 3, len(hosts), host="nodeA", n_gpus=2, timeout=5)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,5,6")
+    assert gpu_utils.gpu_count() == 3
+    monkeypatch.setenv("REAL_LOCAL_GPU", "2")
+    monkeypatch.setenv("REAL_ISOLATE_GPUS", "1")
+    assert gpu_utils.isolate_cuda_device(exp, trial, "model_worker", 0, 1) == 0
+    import os
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "6" and os.environ["REAL_LOCAL_GPU"] == "0"
+
+
+def test_asyncio_gather_or_raise_cancels_the_survivors():
+    import asyncio
+
+    from realhf_b200.base import asyncio_utils
+    state = {"cancelled": 0, "finished": 0}
+
+    async def sleeper(t):
+        try:
+            await asyncio.sleep(t)
+            state["finished"] += 1
+            return t
+        except asyncio.CancelledError:
+            state["cancelled"] += 1
+            raise
+
+    async def failing():
+        await asyncio.sleep(0.05)
+        raise ValueError("mfc failed")
+
+    assert asyncio.run(asyncio_utils.gather_or_raise([sleeper(0.01), sleeper(0.02)])) == [0.01, 0.02]
+    with pytest.raises(ValueError):
+        asyncio.run(asyncio_utils.gather_or_raise([sleeper(5), failing(), sleeper(5)]))
+    assert state["cancelled"] == 2 and state["finished"] == 2
+
+
+def test_padding_roundtrips():
+    import torch
+
+    from realhf_b200.utils import padding
+    torch.manual_seed(0)
+    B, S, H = 4, 7, 3
+    lens = torch.tensor([7, 2, 5, 1])
+    x = torch.randn(B, S, H, requires_grad=True)
+    # right padding
+    mask = torch.arange(S)[None] < lens[:, None]
+    packed, idx, cu, mx = padding.unpad_input(x, mask)
+    assert packed.shape == (15, H) and cu.tolist() == [0, 7, 9, 14, 15] and mx == 7 and cu.dtype == torch.int32
+    back = padding.pad_input(packed, idx, B, S)
+    assert torch.equal(back, x * mask[..., None])
+    back.sum().backward()
+    assert torch.equal(x.grad, mask[..., None].expand_as(x).float())      # gradients reach exactly the real tokens
+    # left padding and a hole in the middle keep token order
+    lmask = torch.arange(S)[None] >= (S - lens)[:, None]
+    lmask[0, 3] = False
+    p2, idx2, cu2, _ = padding.unpad_input(x.detach(), lmask)
+    assert cu2.tolist() == [0, 6, 8, 13, 14] and torch.equal(p2[:3], x.detach()[0, :3]) and torch.equal(p2[3:6], x.detach()[0, 4:])
+    # packed <-> padded by lengths
+    pk, cu3 = padding.pack_padded(x.detach(), lens)
+    assert torch.equal(pk, packed.detach()) and cu3.tolist() == cu.tolist()
+    right = padding.pad_packed(pk, cu3)
+    left = padding.pad_packed(pk, cu3, seqlen=9, left=True, value=-1.0)
+    assert torch.equal(right, x.detach() * mask[..., None]) and left.shape == (B, 9, H)
+    assert torch.equal(left[1, -2:], x.detach()[1, :2]) and (left[1, :-2] == -1).all()
+    # sequence-parallel padding of the packed token axis
+    ids = torch.arange(15)
+    ids2, cu4, mx4, n_pad = padding.pad_sequence_parallel_input(ids, cu, 7, tp=4, pad_id=0)
+    assert ids2.numel() == 16 and n_pad == 1 and cu4.tolist() == [0, 7, 9, 14, 15, 16] and mx4 == 7
+    assert padding.pad_sequence_parallel_input(ids2, cu4, 7, tp=4)[3] == 0
