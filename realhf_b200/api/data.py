@@ -376,7 +376,19 @@ def make_dataloader(cfg: Union[str, config_api.DataLoaderAbstraction], dataset) 
 def load_hf_tokenizer(path: str, fast: bool = True, padding_side: Optional[str] = None):
     import transformers
     kw = {"padding_side": padding_side} if padding_side else {}
-    tok = transformers.AutoTokenizer.from_pretrained(path, use_fast=fast, trust_remote_code=True, **kw)
+    tok = None
+    if fast and os.path.isfile(os.path.join(path, "tokenizer.json")):
+        # a generic `tokenizers`-backed tokenizer (no model-specific python class): construct the class AutoTokenizer would pick,
+        # without AutoTokenizer's detour through the model config classes (their first import costs a worker ~6 s)
+        try:
+            with open(os.path.join(path, "tokenizer_config.json")) as f:
+                cls_name = json.load(f).get("tokenizer_class")
+        except (OSError, ValueError):
+            cls_name = None
+        if cls_name in (None, "PreTrainedTokenizerFast", "TokenizersBackend"):
+            tok = transformers.PreTrainedTokenizerFast.from_pretrained(path, **kw)
+    if tok is None:
+        tok = transformers.AutoTokenizer.from_pretrained(path, use_fast=fast, trust_remote_code=True, **kw)
     if tok.pad_token_id is None:
         tok.pad_token_id = tok.eos_token_id
     return tok

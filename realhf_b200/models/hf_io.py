@@ -36,7 +36,37 @@ def load_hf_config(path: str):
     return transformers.AutoConfig.from_pretrained(path, trust_remote_code=True)
 
 
+def _config_from_saved_json(fn: str, family_name: str, is_critic: bool) -> Optional[ReaLModelConfig]:
+    """The `ReaLModelConfig` this framework wrote next to `config.json` when it saved the checkpoint, if it describes the same
+    family and head type as requested; None otherwise (older files, foreign keys, critic-from-actor initialisation)."""
+    import dataclasses
+
+    from realhf_b200.api.model import ReaLMoEConfig
+    try:
+        with open(fn) as f:
+            d = json.load(f)
+        if d.pop("_family", None) != family_name or bool(d.get("is_critic", False)) != bool(is_critic):
+            return None
+        names = {f.name for f in dataclasses.fields(ReaLModelConfig)}
+        if set(d) - names:
+            return None
+        if isinstance(d.get("moe"), dict):
+            d["moe"] = ReaLMoEConfig(**d["moe"])
+        return ReaLModelConfig(**d)
+    except (OSError, ValueError, TypeError):
+        return None
+
+
 def config_from_hf_path(family_name: str, path: str, is_critic: bool = False) -> ReaLModelConfig:
+    """Model config of a checkpoint directory.  Checkpoints written by this framework carry `real_model_config.json` (the exact
+    config that produced the weights): reading it avoids instantiating the HuggingFace config class, whose first import costs
+    every worker process several seconds (`transformers` pulls `torch._dynamo` in).  `REAL_TRUST_SAVED_MODEL_CONFIG=0` always goes
+    through `config.json`; so do foreign checkpoints and a critic initialised from an actor checkpoint."""
+    fast = os.path.join(path, "real_model_config.json")
+    if os.environ.get("REAL_TRUST_SAVED_MODEL_CONFIG", "1") == "1" and os.path.exists(fast):
+        cfg = _config_from_saved_json(fast, family_name, is_critic)
+        if cfg is not None:
+            return cfg
     return family(family_name).config_from_hf(load_hf_config(path), is_critic)
 
 
@@ -178,7 +208,7 @@ def save_to_hf(model: ReaLModel, family_name: str, save_dir: str, tokenizer=None
         hf_cfg.save_pretrained(save_dir)
         with open(os.path.join(save_dir, "real_model_config.json"), "w") as f:
             import dataclasses
-            json.dump(dataclasses.asdict(cfg), f, indent=1)
+            json.dump(dict(dataclasses.asdict(cfg), _family=family_name), f, indent=1)
         if tokenizer is not None:
             tokenizer.save_pretrained(save_dir)
     if dist.is_initialized() and ctx.model_group is not None:

@@ -84,3 +84,45 @@ def test_greedy_generation_matches_hf_generate(fam):
         agree += int((out.tokens[i, : ref.numel()] == ref).sum())
         total += ref.numel()
     assert agree == total, (agree, total)
+
+
+@pytest.mark.parametrize("fam", ["llama", "gpt2", "qwen2", "gemma", "mistral", "mixtral"])
+@pytest.mark.parametrize("critic", [False, True])
+def test_saved_model_config_fast_path_equals_the_hf_config_path(fam, critic, tmp_path, monkeypatch):
+    """Checkpoints written by this framework carry `real_model_config.json`; workers read it instead of instantiating the HF config
+    class.  It must give exactly the config the HF route gives, fall back for a critic initialised from an actor checkpoint and for
+    foreign / older files, and the generic fast-tokenizer route must return the class and ids AutoTokenizer returns."""
+    import dataclasses
+    import json
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fixtures
+    from realhf_b200.api import data as data_api
+    from realhf_b200.models import hf_io
+    d = str(tmp_path / "ckpt")
+    cfg, tok, words = fixtures.make_checkpoint(d, fam, is_critic=critic)
+    calls = []
+    real = hf_io.load_hf_config
+    monkeypatch.setattr(hf_io, "load_hf_config", lambda p: (calls.append(p), real(p))[1])
+    fast = hf_io.config_from_hf_path(fam, d, is_critic=critic)
+    assert not calls, "the saved config was not used"
+    monkeypatch.setenv("REAL_TRUST_SAVED_MODEL_CONFIG", "0")
+    slow = hf_io.config_from_hf_path(fam, d, is_critic=critic)
+    assert len(calls) == 1
+    assert dataclasses.asdict(fast) == dataclasses.asdict(slow) == dataclasses.asdict(cfg)
+    monkeypatch.setenv("REAL_TRUST_SAVED_MODEL_CONFIG", "1")
+    if not critic:   # critic initialised from an actor checkpoint: head type differs from the saved one -> HF route
+        c2 = hf_io.config_from_hf_path(fam, d, is_critic=True)
+        assert len(calls) == 2 and c2.is_critic
+    fn = os.path.join(d, "real_model_config.json")
+    saved = json.load(open(fn))
+    json.dump({k: v for k, v in saved.items() if k != "_family"}, open(fn, "w"))       # a file written before the family tag existed
+    hf_io.config_from_hf_path(fam, d, is_critic=critic)
+    assert len(calls) == (3 if not critic else 2)
+    t1 = data_api.load_hf_tokenizer(d)
+    import transformers
+    t2 = transformers.AutoTokenizer.from_pretrained(d)
+    text = " ".join(words[:7])
+    assert type(t1) is type(t2) and t1(text).input_ids == t2(text).input_ids and t1.pad_token_id == t2.pad_token_id
