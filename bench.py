@@ -120,7 +120,8 @@ def run_reference(args):
            "reject since 3.11 (ValueError: mutable default ... use default_factory) -- every entry point imports that module; beyond "
            "it the PPO path needs megatron-core 0.6, deepspeed 0.14 and hydra-core, none of which exist offline "
            "(python baseline/probe_reference.py prints the evidence)")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if os.environ.get("RANK", "0") == "0":  # launched like the other arm (torchrun for N > 1): one line, from rank 0
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 
