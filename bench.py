@@ -38,9 +38,12 @@ BASELINE_TOKENS_PER_S = 128 * 640 / (574.312 / 39)  # reference quickstart log: 
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons of the node's GPUs during the timed region.
 
-    One sampler per node (local rank 0) through NVML in-process (`nvidia_ml_py`), one sample every 3 s: driver queries
-    contend with CUDA-graph launches -- sampling every 0.5 s made the generation MFC 10-25% slower inside the timed region
-    than in the (unsampled) warm-up steps.  Falls back to one `nvidia-smi` query per period when NVML is unavailable."""
+    One sampler per node (local rank 0) through NVML in-process (`nvidia_ml_py`), ONE GPU per tick (round robin), one tick every
+    3 s: driver queries contend with CUDA-graph launches -- sampling one GPU every 0.5 s made its generation MFC 10-25% slower
+    inside the timed region than in the (unsampled) warm-up steps, and the queries of all GPUs of a node go through the same
+    driver lock, so querying 8 GPUs per tick costs every rank what an 8x shorter period costs a single GPU.  The first tick is
+    immediate; a region of T seconds yields 1 + T/3 samples from as many different GPUs (`gpus_sampled`).  Falls back to one
+    `nvidia-smi` query per tick when NVML is unavailable."""
 
     _REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
@@ -48,10 +51,15 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.n_gpus, self.period = n_gpus, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.sampled_gpus = set()
+        self._tick = 0
         self._stop_ev = threading.Event()
 
     def _sample_nvml(self, nv, handles):
-        for h in handles:
+        i = self._tick % len(handles)
+        self._tick += 1
+        self.sampled_gpus.add(i)
+        for h in handles[i: i + 1]:
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
             if self.max_mhz is None:
                 self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
@@ -69,6 +77,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True,
                              timeout=10).stdout.strip().splitlines()
+        self.sampled_gpus.update(range(min(self.n_gpus, len(out))))
         for line in out[: self.n_gpus]:
             f = line.split(",")
             self.samples.append(float(f[0]))
@@ -102,7 +111,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=10)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "n_samples": len(s), "gpus_sampled": self.n_gpus}
+                "n_samples": len(s), "gpus_sampled": len(self.sampled_gpus), "gpus": self.n_gpus}
 
 
 class _NoSampler:

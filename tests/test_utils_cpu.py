@@ -175,3 +175,30 @@ def test_group_padding_drops_rows_that_belong_to_no_group():
     off = offsets.tolist()
     ref = torch.stack([dy[off[g]:off[g + 1]].t() @ x[off[g]:off[g + 1]] for g in range(3)])
     torch.testing.assert_close(got, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_bench_clock_sampler_queries_one_gpu_per_tick(monkeypatch):
+    """The bench's clock sampler must touch ONE GPU per tick (round robin): NVML queries of all GPUs share a driver lock with
+    CUDA-graph launches."""
+    import importlib.util
+    import os
+    import sys
+    import time
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    fake = types.SimpleNamespace(
+        NVML_CLOCK_SM=0, nvmlInit=lambda: None, nvmlDeviceGetHandleByIndex=lambda i: i,
+        nvmlDeviceGetClockInfo=lambda h, k: (calls.append(h), 1500 + 10 * h)[1], nvmlDeviceGetMaxClockInfo=lambda h, k: 1965,
+        nvmlDeviceGetCurrentClocksEventReasons=lambda h: 0x4 if h == 2 else 0)
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    s = bench.ClockSampler(8, period=0.05)
+    s.start()
+    time.sleep(0.33)
+    out = s.stop()
+    assert calls[:4] == [0, 1, 2, 3] and len(calls) == out["n_samples"] <= 8     # one GPU per tick, in order, first tick immediate
+    assert out["gpus_sampled"] == len(set(calls)) and out["gpus"] == 8 and out["sm_max_mhz"] == 1965
+    assert out["reasons"] == ["sw_power_cap"] and out["sm_mhz"] in [1500 + 10 * h for h in set(calls)]
