@@ -29,7 +29,7 @@ from realhf_b200.base.topology import PipeModelDataParallelTopology
 class CommonExperimentConfig(Experiment):
     experiment_name: str = "default-exp"
     trial_name: str = "default-trial"
-    mode: str = "local"  # local | slurm
+    mode: str = "local"  # local | slurm | ray
     debug: bool = True
     partition: Optional[str] = None  # Slurm partition; None: the cluster spec's, else "dev"
     wandb_mode: str = "disabled"  # disabled | online | offline (exported as WANDB_MODE to the master worker)

@@ -292,7 +292,6 @@ def make(mode: str, expr_name: str, trial_name: str, **kw) -> SchedulerClient:
     if mode == "slurm":
         return SlurmSchedulerClient(expr_name, trial_name, **kw)
     if mode == "ray":
-        # Not supported, by design: the reference's Ray mode only replaces process launching (controller.py:398-575); this
-        # framework launches one process per GPU through the local / slurm clients and its own control plane (docs/distributed.md)
-        raise NotImplementedError("mode=ray is not supported: use `local` (one node) or `slurm` (multi-node); see docs/distributed.md")
+        from realhf_b200.scheduler.ray import RaySchedulerClient
+        return RaySchedulerClient(expr_name, trial_name, **kw)
     raise NotImplementedError(mode)

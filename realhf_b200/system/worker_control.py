@@ -9,7 +9,12 @@ Differences from the reference: the server lives on its own daemon thread instea
 loop — a model worker in the middle of a 10 s generation MFC still answers `ping` / `status` at once, which is what makes
 the answers useful for liveness and progress monitoring — and handlers only flip flags / read state that the main loop owns
 (`pause`, `resume`, `exit` are picked up between steps, exactly where the name_resolve control key was read before; that
-key keeps working for shells that cannot reach the worker's port).  The Ray transport of the reference is not provided.
+key keeps working for shells that cannot reach the worker's port).
+
+Two transports, as in the reference: ZMQ REQ/REP (default; the address is published in name_resolve) and a pair of queues
+(`comm=(request_queue, reply_queue)`: anything with `put(item, timeout=)` / `get(timeout=)` — `ray.util.queue.Queue` in Ray
+mode (reference `worker_control.py:48-64`, `:118-150`), `multiprocessing` / `queue.Queue` elsewhere), for deployments where
+the workers' ports are not reachable from the controller.
 """
 
 from __future__ import annotations
@@ -50,18 +55,66 @@ class WorkerException(Exception):
         self.worker_name, self.worker_status, self.scenario = worker_name, status, scenario
 
 
+class _ZmqRepTransport:
+    def __init__(self, host: Optional[str]):
+        from realhf_b200.system.stream import host_ip
+        self._sock = zmq.Context.instance().socket(zmq.REP)
+        self._sock.setsockopt(zmq.LINGER, 0)
+        port = self._sock.bind_to_random_port("tcp://*")
+        self.address = f"tcp://{host or host_ip()}:{port}"
+        self._poller = zmq.Poller()
+        self._poller.register(self._sock, zmq.POLLIN)
+
+    def recv(self, timeout_ms: int) -> Optional[bytes]:
+        """None: nothing arrived in time.  Raises `ConnectionError` once the socket is gone."""
+        try:
+            if not dict(self._poller.poll(timeout_ms)):
+                return None
+            return self._sock.recv()
+        except zmq.ZMQError as e:
+            raise ConnectionError(str(e)) from e
+
+    def send(self, data: bytes):
+        try:
+            self._sock.send(data)
+        except zmq.ZMQError as e:
+            raise ConnectionError(str(e)) from e
+
+    def close(self):
+        self._sock.close(0)
+
+
+class _QueueTransport:
+    """Server side of the queue transport: requests arrive on `comm[0]`, replies leave on `comm[1]`."""
+
+    address = "queue://"
+
+    def __init__(self, comm):
+        self._req, self._rep = comm
+
+    def recv(self, timeout_ms: int) -> Optional[bytes]:
+        try:
+            return self._req.get(timeout=timeout_ms / 1000.0)
+        except Exception as e:  # queue.Empty / ray.util.queue.Empty (distinct classes, same meaning)
+            if type(e).__name__ == "Empty":
+                return None
+            raise ConnectionError(f"{type(e).__name__}: {e}") from e
+
+    def send(self, data: bytes):
+        self._rep.put(data)
+
+    def close(self):
+        pass
+
+
 class WorkerServer:
     """Serves `command -> handler(**kwargs)` requests for one worker.  Built-in commands: ping, status, pause, resume, exit,
     interrupt; workers add their own with `register_handler` (e.g. `progress`, `memory`)."""
 
-    def __init__(self, exp: str, trial: str, worker_name: str, host: Optional[str] = None):
-        from realhf_b200.system.stream import host_ip
+    def __init__(self, exp: str, trial: str, worker_name: str, host: Optional[str] = None, comm=None):
         self.exp, self.trial, self.worker_name = exp, trial, worker_name
-        self._ctx = zmq.Context.instance()
-        self._sock = self._ctx.socket(zmq.REP)
-        self._sock.setsockopt(zmq.LINGER, 0)
-        port = self._sock.bind_to_random_port("tcp://*")
-        self.address = f"tcp://{host or host_ip()}:{port}"
+        self._transport = _QueueTransport(comm) if comm is not None else _ZmqRepTransport(host)
+        self.address = self._transport.address
         self._handlers: Dict[str, Callable[..., Any]] = {}
         self.status = WorkerServerStatus.READY
         self.paused = threading.Event()      # set: the main loop must not start new work
@@ -116,14 +169,13 @@ class WorkerServer:
         return not self.exit_requested.is_set()
 
     def _serve(self):
-        poller = zmq.Poller()
-        poller.register(self._sock, zmq.POLLIN)
         while not self._stop.is_set():
             try:
-                if not dict(poller.poll(100)):
+                raw = self._transport.recv(100)
+                if raw is None:
                     continue
-                cmd, kwargs = pickle.loads(self._sock.recv())
-            except zmq.ZMQError:
+                cmd, kwargs = pickle.loads(raw)
+            except ConnectionError:
                 return
             try:
                 fn = self._handlers.get(cmd)
@@ -134,8 +186,8 @@ class WorkerServer:
                 reply = ("err", f"{type(e).__name__}: {e}")
             self.n_served += 1
             try:
-                self._sock.send(pickle.dumps(reply))
-            except zmq.ZMQError:
+                self._transport.send(pickle.dumps(reply))
+            except ConnectionError:
                 return
 
     def close(self):
@@ -145,7 +197,7 @@ class WorkerServer:
             name_resolve.delete(control_addr_key(self.exp, self.trial, self.worker_name))
         except Exception:
             pass
-        self._sock.close(0)
+        self._transport.close()
 
 
 def _ttl() -> float:
@@ -153,14 +205,66 @@ def _ttl() -> float:
     return float(os.environ.get("REAL_STATUS_TTL", "120"))
 
 
+class _ZmqReqChannel:
+    def __init__(self, addr: str):
+        self.addr = addr
+        self._open()
+
+    def _open(self):
+        self._s = zmq.Context.instance().socket(zmq.REQ)
+        self._s.setsockopt(zmq.LINGER, 0)
+        self._s.connect(self.addr)
+
+    def send(self, data: bytes):
+        self._s.send(data)
+
+    def recv(self, timeout_s: float) -> Optional[bytes]:
+        if not self._s.poll(max(0, int(1000 * timeout_s))):
+            # a REQ socket that missed its reply is stuck in the wrong state: replace it
+            self._s.close(0)
+            self._open()
+            return None
+        return self._s.recv()
+
+    def close(self):
+        self._s.close(0)
+
+
+class _QueueChannel:
+    """Client side of the queue transport.  A reply that arrives after its request timed out would be mistaken for the
+    answer to the next request, so the reply queue is drained before every new request."""
+
+    def __init__(self, request_q, reply_q):
+        self._req, self._rep = request_q, reply_q
+
+    def send(self, data: bytes):
+        while True:
+            try:
+                self._rep.get(block=False)
+            except Exception as e:
+                if type(e).__name__ == "Empty":
+                    break
+                raise
+        self._req.put(data)
+
+    def recv(self, timeout_s: float) -> Optional[bytes]:
+        try:
+            return self._rep.get(timeout=max(timeout_s, 1e-3))
+        except Exception as e:
+            if type(e).__name__ == "Empty":
+                return None
+            raise
+
+    def close(self):
+        pass
+
+
 class WorkerControlPanel:
     """Client side: connect to workers by name, send single or group requests, poll statuses."""
 
     def __init__(self, exp: str, trial: str, timeout: float = 10.0):
         self.exp, self.trial, self.timeout = exp, trial, timeout
-        self._ctx = zmq.Context.instance()
-        self._socks: Dict[str, zmq.Socket] = {}
-        self._addr: Dict[str, str] = {}
+        self._socks: Dict[str, Any] = {}
 
     @property
     def worker_names(self) -> List[str]:
@@ -181,20 +285,21 @@ class WorkerControlPanel:
         return names
 
     def _open(self, name: str, addr: str):
-        s = self._ctx.socket(zmq.REQ)
-        s.setsockopt(zmq.LINGER, 0)
-        s.connect(addr)
-        self._socks[name], self._addr[name] = s, addr
+        if not addr.startswith("tcp://"):
+            raise ValueError(f"worker {name} serves `{addr}`: queue-transport workers are reached with `attach_queues`")
+        self._socks[name] = _ZmqReqChannel(addr)
+
+    def attach_queues(self, worker_name: str, request_q, reply_q):
+        """Queue transport: talk to `worker_name` through the queue pair its `WorkerServer(comm=...)` was built with."""
+        self._socks[worker_name] = _QueueChannel(request_q, reply_q)
 
     def request(self, worker_name: str, command: str, timeout: Optional[float] = None, **kwargs) -> Any:
         s = self._socks[worker_name]
         s.send(pickle.dumps((command, kwargs)))
-        if not s.poll(int(1000 * (timeout if timeout is not None else self.timeout))):
-            # a REQ socket that missed its reply is stuck in the wrong state: replace it, report the worker as lost
-            s.close(0)
-            self._open(worker_name, self._addr[worker_name])
+        raw = s.recv(timeout if timeout is not None else self.timeout)
+        if raw is None:
             raise WorkerException(worker_name, WorkerServerStatus.LOST, f"waiting for the reply to `{command}`")
-        kind, payload = pickle.loads(s.recv())
+        kind, payload = pickle.loads(raw)
         if kind == "err":
             raise RuntimeError(f"worker {worker_name} failed `{command}`: {payload}")
         return payload
@@ -209,13 +314,11 @@ class WorkerControlPanel:
         out: Dict[str, Any] = {}
         deadline = time.monotonic() + (timeout if timeout is not None else self.timeout)
         for n in names:
-            s = self._socks[n]
-            if not s.poll(max(0, int(1000 * (deadline - time.monotonic())))):
-                s.close(0)
-                self._open(n, self._addr[n])
+            raw = self._socks[n].recv(max(0.0, deadline - time.monotonic()))
+            if raw is None:
                 out[n] = WorkerException(n, WorkerServerStatus.LOST, f"waiting for the reply to `{command}`")
                 continue
-            kind, payload = pickle.loads(s.recv())
+            kind, payload = pickle.loads(raw)
             out[n] = payload if kind == "ok" else RuntimeError(f"worker {n} failed `{command}`: {payload}")
         return out
 
@@ -225,5 +328,5 @@ class WorkerControlPanel:
 
     def close(self):
         for s in self._socks.values():
-            s.close(0)
+            s.close()
         self._socks.clear()
