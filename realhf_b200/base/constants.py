@@ -32,7 +32,7 @@ PARAM_REALLOC_PATH = os.path.join(FILEROOT, "param_realloc")
 NCCL_TIMEOUT_MIN = 30
 
 # environment flags forwarded to workers (same names as the reference, constants.py:77-112)
-FORWARDED_ENV = ["REAL_MODE", "REAL_RECOVER_RUN", "REAL_SAVE_RECOVER_STATES", "REAL_CUDA_TMARK", "REAL_DUMP_TRACE",
+FORWARDED_ENV = ["REAL_MODE", "REAL_RECOVER_RUN", "REAL_SAVE_RECOVER_STATES", "REAL_CUDA_TMARK", "REAL_TIME_MARK", "REAL_DUMP_TRACE",
                  "REAL_DUMP_MEMORY", "REAL_SAVE_MAX_SHARD_SIZE_BYTE", "REAL_FILEROOT", "REAL_NAME_RESOLVE",
                  "REAL_NAME_RESOLVE_ROOT", "REAL_GEMM", "REAL_PDL", "REAL_GEMM_2CTA", "REAL_FUSED_TP", "REAL_REALLOC_DIRECT", "REAL_ISOLATE_GPUS",
                  "REAL_DATASET_CACHE", "REAL_FAULT_INJECT", "REAL_STATUS_TTL", "REAL_TENSORBOARD", "WANDB_MODE", "WANDB_API_KEY", "REAL_WATCH_CONTROLLER", "REAL_ATTN", "REAL_ATTN_BWD", "REAL_LAYERNORM", "REAL_MOE_GROUPED_WGRAD", "CLUSTER_SPEC_PATH", "PYTHONPATH"]

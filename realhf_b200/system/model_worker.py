@@ -43,6 +43,7 @@ class ModelWorker:
         self.interfaces: Dict[str, model_api.ModelInterface] = {}
         self.shard_ids: Dict[ModelName, ModelShardID] = {}
         self.data_storage: Dict[Any, SequenceSample] = {}
+        self._n_calls: Dict[str, int] = {}
         self.dataloader = None
         self.data_iter = None
         self.epoch = 0
@@ -394,10 +395,13 @@ class ModelWorker:
             t0 = time.perf_counter()
             if self.device.type == "cuda":
                 torch.cuda.reset_peak_memory_stats(self.device)
+            self._n_calls[rpc.name] = call = self._n_calls.get(rpc.name, 0) + 1
+            monitor.time_mark(f"{rpc.name}_start", f"model_worker/{self.index}", step=call - 1)  # REAL_TIME_MARK=1
             with self._mfc_profile(rpc.name), monitor.cuda_tmarked(rpc.name, _TMARK_OF[h], str(name)):
                 res = getattr(self.interfaces[rpc.name], h)(model, inp, n_mbs=rpc.n_mbs)
             if self.device.type == "cuda":
                 torch.cuda.synchronize()
+            monitor.time_mark(f"{rpc.name}_end", f"model_worker/{self.index}", step=call - 1)
             dt = time.perf_counter() - t0
             ctx = self.ctxs[name]
             mem = self._memory_stats()
