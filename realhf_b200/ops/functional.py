@@ -508,18 +508,33 @@ def segment_copy_ref(src_flat_bytes, dst_flat_bytes, src_off, dst_off, lens, eta
 class SegmentPlan:
     """A reusable list of (src_byte_off, dst_byte_off, n_bytes) segments, uploaded once."""
 
-    def __init__(self, src_off: List[int], dst_off: List[int], lens: List[int], device):
-        self.n = len(lens)
-        self.src_off_h, self.dst_off_h, self.lens_h = list(src_off), list(dst_off), list(lens)
-        cum = [0]
-        for ln in lens:
-            cum.append(cum[-1] + ln)
-        self.total = cum[-1]
+    def __init__(self, src_off, dst_off, lens, device):
+        """Offsets / lengths in bytes: python lists or integer numpy arrays (reallocation plans of 7B models have millions of
+        segments; everything here is vectorised)."""
+        import numpy as np
+        so, do, ln = (np.asarray(x, dtype=np.int64).reshape(-1) for x in (src_off, dst_off, lens))
+        self.n = int(ln.shape[0])
+        self._host = (so, do, ln)
+        cum = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(ln, out=cum[1:])
+        self.total = int(cum[-1])
         self.device = torch.device(device)
         if self.device.type == "cuda":
-            self.src_off = torch.tensor(src_off, dtype=torch.int64, device=device)
-            self.dst_off = torch.tensor(dst_off, dtype=torch.int64, device=device)
-            self.cum = torch.tensor(cum, dtype=torch.int64, device=device)
+            self.src_off = torch.from_numpy(so.copy()).to(device)
+            self.dst_off = torch.from_numpy(do.copy()).to(device)
+            self.cum = torch.from_numpy(cum).to(device)
+
+    @property
+    def src_off_h(self) -> List[int]:
+        return self._host[0].tolist()
+
+    @property
+    def dst_off_h(self) -> List[int]:
+        return self._host[1].tolist()
+
+    @property
+    def lens_h(self) -> List[int]:
+        return self._host[2].tolist()
 
     def run(self, src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_ptr: int = 0, eta: float = 1.0):
         """Copy every segment from `src` into `dst` (or the raw — possibly peer — address `dst_ptr`)."""

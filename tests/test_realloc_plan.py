@@ -64,3 +64,38 @@ def test_executor_local_and_ema():
     ex.run(src.flat_param.data, dst.flat_param.data)
     for name in dst.p:
         assert torch.equal(dst.p[name].data, src.p[name].data)
+
+
+@pytest.mark.parametrize("pair", [((1, 2, 4), (2, 1, 4)), ((1, 1, 8), (1, 1, 8)), ((1, 1, 8), (1, 2, 4)), ((1, 2, 4), (1, 1, 8)),
+                                  ((1, 4, 2), (1, 1, 8)), ((2, 1, 4), (1, 8, 1))])
+def test_replicated_kv_heads_are_written_exactly_once(pair):
+    """n_kv_heads < tp: several source ranks hold the same KV head.  Every destination element must be written exactly once
+    (an EMA merge applied twice would be wrong), also when source and destination share the TP degree."""
+    cfg = hf_io.family("llama").make_test_config()
+    cfg.n_kv_heads, cfg.n_q_heads = 2, 8
+    (spp, sdp, stp), (dpp, ddp, dtp) = pair
+    s_topo, d_topo = ProcessTopology(spp, sdp, stp), ProcessTopology(dpp, ddp, dtp)
+    plan = realloc.derive_plan(cfg, s_topo, list(range(8)), d_topo, list(range(8)))
+    hits = {w: torch.zeros(n, dtype=torch.int32) for w, n in plan.dst_numel.items()}
+    for t in plan.transfers:
+        for do, ln in zip(t.dst_off, t.lens):
+            hits[t.dst_worker][do:do + ln] += 1
+    for w, h in hits.items():
+        assert int(h.min()) == 1 and int(h.max()) == 1, (w, int(h.min()), int(h.max()))
+
+
+def test_plan_derivation_of_a_7b_model_is_fast():
+    """LLaMA-7B, dp8 -> dp4*tp2: 2.1 M row segments (column-split weights give one segment per row).  Each worker derives the
+    plan at start-up; a quadratic interval routine here once cost ~10 minutes."""
+    import time
+
+    from realhf_b200.api.model import ReaLModelConfig
+    cfg = ReaLModelConfig(n_layers=32, n_kv_heads=32, n_q_heads=32, hidden_dim=4096, intermediate_dim=11008, vocab_size=32000,
+                          n_positions=4096, layer_norm_type="rms", mlp_type="llama", apply_rotary=True, use_attention_bias=False,
+                          use_attn_proj_bias=False, use_mlp_bias=False)
+    t0 = time.perf_counter()
+    plan = realloc.derive_plan(cfg, ProcessTopology(1, 8, 1), list(range(8)), ProcessTopology(1, 4, 2), list(range(8)))
+    dt = time.perf_counter() - t0
+    assert dt < 20.0, dt
+    assert len(plan.transfers) == 8 and all(t.src_worker == t.dst_worker for t in plan.transfers)   # dp-replicated source: local copies
+    assert sum(t.numel for t in plan.transfers) == 8 * plan.dst_numel[0]
