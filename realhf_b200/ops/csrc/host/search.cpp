@@ -13,6 +13,7 @@
 #include <pybind11/stl.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -61,6 +62,8 @@ struct Problem {
   double link_bw = 770e9;    // bytes/s per GPU per direction (measured NVLink 5 peer copy)
   double realloc_latency_us = 30.0;
   int n_iters = 2;
+  // optional: planned reallocation times, (role, src mesh, dp, tp, pp, dst mesh, dp, tp, pp) -> us; overrides the closed form
+  std::map<std::array<int, 9>, double> realloc_table;
 };
 
 struct SimResult {
@@ -73,6 +76,10 @@ struct SimResult {
 // Time to give `dst` layout a copy of the role's weights from `src` layout.
 double realloc_cost_us(const Problem& P, int role, const Candidate& src, const Candidate& dst) {
   if (src.mesh == dst.mesh && src.tp == dst.tp && src.pp == dst.pp && src.dp == dst.dp) return 0.0;
+  if (!P.realloc_table.empty()) {
+    auto it = P.realloc_table.find({role, src.mesh, src.dp, src.tp, src.pp, dst.mesh, dst.dp, dst.tp, dst.pp});
+    if (it != P.realloc_table.end()) return it->second;
+  }
   const double shard = P.role_bytes[role] / (double)(dst.tp * dst.pp);
   // a destination GPU that already holds the same TP/PP shard (same mesh, same tp/pp, only dp differs) copies locally
   const bool same_shards = src.mesh == dst.mesh && src.tp == dst.tp && src.pp == dst.pp;
@@ -233,6 +240,16 @@ Problem problem_from_py(const py::dict& d) {
   if (d.contains("n_iters")) P.n_iters = d["n_iters"].cast<int>();
   if (d.contains("realloc_latency_us")) P.realloc_latency_us = d["realloc_latency_us"].cast<double>();
   P.role_bytes = d["role_bytes"].cast<std::vector<double>>();
+  if (d.contains("realloc_table")) {
+    for (auto item : d["realloc_table"].cast<py::list>()) {
+      py::tuple kv = item.cast<py::tuple>();
+      auto k = kv[0].cast<std::vector<int>>();
+      if (k.size() != 9) throw std::invalid_argument("realloc_table keys have 9 integers");
+      std::array<int, 9> a;
+      std::copy(k.begin(), k.end(), a.begin());
+      P.realloc_table[a] = kv[1].cast<double>();
+    }
+  }
   for (auto m : d["meshes"].cast<std::vector<std::vector<int>>>()) {
     GpuSet s;
     for (int g : m) s.set(g);

@@ -3,8 +3,9 @@ let the native MCMC + simulator (`_C/host_ext`: `multi_mcmc_search`) pick one pe
 
 Parity: `realhf/search_engine/{search,enumerate,estimate,param_realloc}.py` + `csrc/search`.  The reference's Python
 driver is broken against its own DFG API; this one is exercised by `tests/test_search.py`.
-Costs come from an analytic roofline model fed by the measured peaks (`MEASURED_PEAKS.json`) or, when available, from
-the layer profiler's table (`search/layers.py`).
+Costs come from the layer profiler's table (`search/layers.py` -> `search/cost_model.py::estimate_mfc`) when the model has one,
+else from the analytic roofline model below fed by the measured peaks (`MEASURED_PEAKS.json`).  The MCMC's best allocations are
+re-ranked with parameter-reallocation times computed by the real planner (`refine_with_planned_realloc`).
 """
 
 from __future__ import annotations
@@ -112,12 +113,24 @@ def estimate(rpc: MFCDef, shape: Dict[str, float], par: ParallelismConfig, hw: H
     return t * 1e6, static, active
 
 
+def profile_table_for(mcfg: ModelTrainEvalConfig):
+    """The layer-profile table of a model family / size (`search/cost_model.py::ProfileTable.find`), or None."""
+    from realhf_b200.search.cost_model import ProfileTable
+    name = f"{mcfg.type._class}-{mcfg.type.size or 7}"
+    return ProfileTable.find(name)
+
+
 def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int, gen_len: int,
-                  n_ppo_minibatches: int, hw: HardwareModel, max_cands: int = 1000):
+                  n_ppo_minibatches: int, hw: HardwareModel, max_cands: int = 1000, use_profile_tables: bool = True):
+    """Candidates per MFC = every (sub-mesh, dp x tp x pp) that fits the batch, costed by the table-driven model
+    (`search/cost_model.py::estimate_mfc`) when the role's model has a layer-profile table, else by the roofline formulas above."""
+    from realhf_b200.search.cost_model import CommModel, estimate_mfc
     G = build_graph(rpcs)
     roles = sorted({r.role for r in rpcs})
     role_idx = {r: i for i, r in enumerate(roles)}
     shapes = {r: model_shape(models[r]) for r in roles}
+    tables = {r: (profile_table_for(models[r]) if use_profile_tables else None) for r in roles}
+    comm = CommModel.from_measured(min(8, mesh.n_gpus_per_node))
     trainable = {r.role for r in rpcs if r.interface_type == ModelInterfaceType.TRAIN_STEP}
     sub = [mesh] + [m for m in mesh.sub_device_meshes() if m != mesh]
     mesh_ranks = [m.global_ranks() for m in sub]
@@ -131,9 +144,15 @@ def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelT
                     continue
                 if shapes[r.role]["v"] % par.model_parallel_size or shapes[r.role]["L"] < par.pipeline_parallel_size:
                     continue
-                g = gen_len if r.interface_type == ModelInterfaceType.GENERATE else gen_len
-                t, st, ac = estimate(r, shapes[r.role], par, hw, seq_len, g, n_ppo_minibatches if r.interface_type == ModelInterfaceType.TRAIN_STEP else 1,
-                                     r.role in trainable)
+                n_mini = n_ppo_minibatches if r.interface_type == ModelInterfaceType.TRAIN_STEP else 1
+                if tables[r.role] is not None:
+                    c = estimate_mfc(r.interface_type, r.n_seqs, shapes[r.role], par.data_parallel_size, par.model_parallel_size,
+                                     par.pipeline_parallel_size, hw, tables[r.role], comm, seq_len, gen_len, n_minibatches=n_mini,
+                                     n_mbs=max(1, getattr(r, "n_mbs", 1) or 1), trainable_role=r.role in trainable,
+                                     use_sequence_parallel=par.model_parallel_size > 1, gpus_per_node=mesh.n_gpus_per_node)
+                    t, st, ac = c.time_us, c.mem_static, c.mem_active
+                else:
+                    t, st, ac = estimate(r, shapes[r.role], par, hw, seq_len, gen_len, n_mini, r.role in trainable)
                 cands.append((mi, par.data_parallel_size, par.model_parallel_size, par.pipeline_parallel_size, t, st, ac, par))
         cands.sort(key=lambda c: c[4])
         cands = cands[:max_cands]
@@ -143,18 +162,54 @@ def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelT
     edges = [(name_idx[u], name_idx[v]) for u, v in G.edges()]
     prob = dict(n_gpus=mesh.n_nodes * mesh.n_gpus_per_node, mem_cap=hw.mem_cap, link_bw=hw.link_bw, n_iters=2,
                 role_bytes=[2 * shapes[r]["n"] for r in roles], meshes=mesh_ranks, edges=edges, rpcs=prpcs)
+    prob["_shapes"] = [shapes[r] for r in roles]      # python-side only (the native parser ignores unknown keys)
     return prob, table, sub
+
+
+def refine_with_planned_realloc(prob: dict, results: List[dict], hw: HardwareModel, gpus_per_node: int = 8) -> List[dict]:
+    """Re-rank the MCMC's best allocations with the parameter-reallocation times of the REAL planner.
+
+    The search itself uses the simulator's closed form (destination shard bytes / link bandwidth).  For each of its top results the
+    (train layout -> other layout) pairs are planned with `parallel/realloc.py::derive_plan`, costed per GPU
+    (`cost_model.realloc_time_us`), handed to the simulator as an override table, and the results are re-simulated and re-sorted."""
+    from realhf_b200.search.cost_model import CommModel, config_from_shape, realloc_time_us
+    h = host()
+    comm = CommModel.from_measured(min(8, gpus_per_node))
+    rpcs = prob["rpcs"]
+    train_of = {r["role"]: i for i, r in enumerate(rpcs) if r["kind"] == 2}
+    table: Dict[Tuple[int, ...], float] = {}
+    for res in results:
+        for i, r in enumerate(rpcs):
+            t = train_of.get(r["role"])
+            if t is None or t == i:
+                continue
+            src, dst = rpcs[t]["cands"][res["choice"][t]], r["cands"][res["choice"][i]]
+            key = (r["role"],) + tuple(int(x) for x in src[:4]) + tuple(int(x) for x in dst[:4])
+            if key in table or tuple(src[:4]) == tuple(dst[:4]):
+                continue
+            cfg = config_from_shape(prob["_shapes"][r["role"]])
+            table[key] = realloc_time_us(cfg, (src[1], src[2], src[3]), prob["meshes"][src[0]], (dst[1], dst[2], dst[3]),
+                                         prob["meshes"][dst[0]], hw, comm, gpus_per_node)
+    p2 = dict(prob, realloc_table=[(list(k), v) for k, v in table.items()])
+    out = []
+    for res in results:
+        sim = h.simulate_allocation(p2, list(res["choice"]))
+        out.append(dict(res, cost=sim["cost"], time_us=sim["time_us"], max_mem=sim["max_mem"], time_us_closed_form=res["time_us"]))
+    out.sort(key=lambda d: d["cost"])
+    return out, p2
 
 
 def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int = 128,
                            num_gen_tokens: int = 256, n_ppo_minibatches: int = 4, time_limit_s: float = 5.0,
-                           hw: Optional[HardwareModel] = None, return_details: bool = False):
+                           hw: Optional[HardwareModel] = None, return_details: bool = False, refine_realloc: bool = True):
     h = host()
     if h is None:
         raise RuntimeError("allocation search needs the native host extension: run `python -m realhf_b200.ops.build`")
     hw = hw or HardwareModel.from_measured()
     prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw)
     results = h.multi_mcmc_search(prob, [0.5, 2.0, 8.0, 32.0], time_limit_s, 1, 10)
+    if refine_realloc:
+        results, prob = refine_with_planned_realloc(prob, results, hw, device_mesh.n_gpus_per_node)
     best = results[0]
     allocs = []
     for r, ci, cands in zip(rpcs, best["choice"], table):

@@ -50,3 +50,118 @@ def test_search_mode_resolves_into_experiment_config():
     cfg.allocation_mode = "search"
     sysc = cfg.initial_setup()
     assert len(sysc.model_worker) == 8 and len(sysc.model_rpcs) == 6
+
+
+# ------------------------------------------------------------------------------------------ table-driven cost model (search/cost_model.py)
+
+_SHAPE_7B = dict(h=4096, L=32, f=11008, v=32000, n=32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 2 * 32000 * 4096)
+
+
+def test_profile_table_interpolates_and_extrapolates():
+    from realhf_b200.search.cost_model import ProfileTable
+    t = ProfileTable([dict(layer="block", op="fwd", bs=1, seqlen=100, time_us=10.0), dict(layer="block", op="fwd", bs=4, seqlen=100, time_us=40.0),
+                      dict(layer="block", op="fwd", bs=8, seqlen=100, time_us=60.0), dict(layer="block", op="fwd", bs=1, seqlen=4000, time_us=999.0),
+                      dict(layer="block", op="decode", bs=16, seqlen=384, time_us=120.0)])
+    assert t.time_us("block", "fwd", 250, 128) == pytest.approx(25.0)       # between 100 and 400 tokens, nearest profiled length = 100
+    assert t.time_us("block", "fwd", 600, 128) == pytest.approx(50.0)
+    assert t.time_us("block", "fwd", 1600, 128) == pytest.approx(60.0 + (20.0 / 400) * 800)   # slope of the last two points
+    assert t.time_us("block", "fwd", 50, 128) == pytest.approx(5.0)
+    assert t.time_us("block", "fwd", 1, 128) == pytest.approx(2.5)          # floor: a quarter of the smallest measurement
+    assert t.time_us("block", "fwd", 4000, 3500) == pytest.approx(999.0)    # nearest sequence length in log space
+    assert t.time_us("block", "decode", 16, 512) == pytest.approx(120.0)
+    assert t.time_us("head", "fwd", 10, 10) is None and not t.has("head", "fwd")
+
+
+def test_shipped_7b_table_reproduces_the_measured_mfc_times():
+    """Calibration check: per-MFC device times of the headline PPO run (profiles/bench_n{1,2,8}_r2_*.json) at dp = N."""
+    from realhf_b200.api.config import ModelInterfaceType as T
+    from realhf_b200.search.cost_model import CommModel, ProfileTable, estimate_mfc
+    from realhf_b200.search.engine import HardwareModel
+    hw, cm, tb = HardwareModel(), CommModel(), ProfileTable.find("llama-7")
+    assert tb is not None and "NOT a layer-profiler run" in tb.meta["source"]
+    measured = {1: dict(inf=875.0, train=3227.5, gen=5138.9), 2: dict(inf=455.0, train=1652.3, gen=3402.2), 8: dict(inf=118.0, train=665.9, gen=2622.9)}
+    for n, ms in measured.items():
+        inf = estimate_mfc(T.INFERENCE, 128, _SHAPE_7B, n, 1, 1, hw, tb, cm, 128, 512)
+        tr = estimate_mfc(T.TRAIN_STEP, 128, _SHAPE_7B, n, 1, 1, hw, tb, cm, 128, 512, n_minibatches=4, optimizer_bytes_per_param=4.0)
+        gen = estimate_mfc(T.GENERATE, 128, _SHAPE_7B, n, 1, 1, hw, tb, cm, 128, 512, trainable_role=True)
+        assert inf.time_us / 1e3 == pytest.approx(ms["inf"], rel=0.10)
+        assert tr.time_us / 1e3 == pytest.approx(ms["train"], rel=0.12)
+        assert gen.time_us / 1e3 == pytest.approx(ms["gen"], rel=0.22)       # the N=8 run has 0.5 s no per-kernel model explains (ROADMAP)
+    # tensor-parallel decode pays two in-graph all-reduces per layer: at 128 prompts it does not beat data-parallel decode on 8 GPUs
+    dp8 = estimate_mfc(T.GENERATE, 128, _SHAPE_7B, 8, 1, 1, hw, tb, cm, 128, 512, trainable_role=True).time_us
+    tp8 = estimate_mfc(T.GENERATE, 128, _SHAPE_7B, 1, 8, 1, hw, tb, cm, 128, 512, trainable_role=True).time_us
+    assert tp8 > dp8
+    # memory: ZeRO-1 shards the optimizer state over dp, a pipeline splits the weights
+    a = estimate_mfc(T.TRAIN_STEP, 128, _SHAPE_7B, 1, 1, 1, hw, tb, cm, 128, 512, n_minibatches=4)
+    b = estimate_mfc(T.TRAIN_STEP, 128, _SHAPE_7B, 8, 1, 1, hw, tb, cm, 128, 512, n_minibatches=4)
+    c = estimate_mfc(T.TRAIN_STEP, 128, _SHAPE_7B, 2, 1, 4, hw, tb, cm, 128, 512, n_minibatches=4)
+    assert a.mem_static == pytest.approx(16 * _SHAPE_7B["n"], rel=1e-6) and b.mem_static < 0.4 * a.mem_static and c.mem_static < b.mem_static
+
+
+def test_realloc_cost_comes_from_the_planner():
+    from realhf_b200.search.cost_model import CommModel, config_from_shape, realloc_time_us
+    from realhf_b200.search.engine import HardwareModel
+    hw, cm = HardwareModel(), CommModel()
+    cfg = config_from_shape(dict(h=1024, L=4, f=2816, v=32000))
+    n_bytes = 2.0 * cfg.n_params()
+    g8, lo, hi = list(range(8)), [0, 1, 2, 3], [4, 5, 6, 7]
+    assert realloc_time_us(cfg, (8, 1, 1), g8, (8, 1, 1), g8, hw, cm) == 0.0
+    # dp8 -> dp4 x tp2 on the same GPUs: every GPU copies its own half locally (read + write at HBM speed), no link traffic
+    local = realloc_time_us(cfg, (8, 1, 1), g8, (4, 2, 1), g8, hw, cm)
+    assert local == pytest.approx(cm.coll_latency_us + 2 * (n_bytes / 2) / hw.hbm_bw * 1e6, rel=0.02)
+    # dp4 on GPUs 0-3 -> dp4 on GPUs 4-7: a full copy over NVLink per destination GPU
+    remote = realloc_time_us(cfg, (4, 1, 1), lo, (4, 1, 1), hi, hw, cm)
+    assert remote == pytest.approx(cm.coll_latency_us + n_bytes / cm.p2p_bw * 1e6, rel=0.02)
+    # tp4 on GPUs 0-3 -> dp4 on GPUs 4-7: every source GPU feeds its quarter to all four destinations
+    fan = realloc_time_us(cfg, (1, 4, 1), lo, (4, 1, 1), hi, hw, cm)
+    assert fan == pytest.approx(remote, rel=0.05)
+    # two nodes: NIC bandwidth
+    far = realloc_time_us(cfg, (4, 1, 1), lo, (4, 1, 1), [8, 9, 10, 11], hw, cm)
+    assert far > 10 * remote
+
+
+def test_simulator_honours_planned_realloc_times_and_the_search_reranks_with_them():
+    h = host()
+    prob = dict(n_gpus=2, mem_cap=100.0, link_bw=1e6, n_iters=1, role_bytes=[100.0], meshes=[[0, 1], [0]], edges=[(0, 1)], realloc_latency_us=0.0,
+                rpcs=[dict(name="gen", role=0, kind=0, cands=[(1, 1, 1, 1, 10.0, 1.0, 1.0)]),
+                      dict(name="train", role=0, kind=2, cands=[(0, 2, 1, 1, 10.0, 1.0, 1.0)])])
+    closed = h.simulate_allocation(prob, [0, 0])["time_us"]
+    assert closed == pytest.approx(10.0 + 10.0 + 100.0 / 1e6 * 1e6)                       # gen pays the closed-form realloc: bytes / link_bw
+    planned = h.simulate_allocation(dict(prob, realloc_table=[([0, 0, 2, 1, 1, 1, 1, 1, 1], 3.0)]), [0, 0])["time_us"]
+    assert planned == pytest.approx(23.0)
+    from realhf_b200.search.engine import search_rpc_allocations
+    cfg = _ppo()
+    allocs, det = search_rpc_allocations(cfg.global_device_mesh, list(cfg.rpcs.values()), cfg.models, seq_len=128, num_gen_tokens=512,
+                                         time_limit_s=1.0, return_details=True)
+    assert all("time_us_closed_form" in r for r in det["results"])
+    assert det["results"] == sorted(det["results"], key=lambda r: r["cost"])
+    for key, us in det["problem"].get("realloc_table", []):
+        assert len(key) == 9 and us > 0
+
+
+def test_layer_profiler_rows_feed_the_cost_model():
+    """CPU run of the layer profiler (wall-clock timing) on a toy model: block / embedding / head / decode / optimizer rows, and a
+    cost estimate computed from nothing but those rows."""
+    import torch
+
+    from realhf_b200.api.config import ModelInterfaceType as T
+    from realhf_b200.models import hf_io
+    from realhf_b200.search import layers
+    from realhf_b200.search.cost_model import ProfileTable, estimate_mfc
+    from realhf_b200.search.engine import HardwareModel
+    cfg = hf_io.family("llama").make_test_config()
+    kw = dict(device="cpu", dtype=torch.float32)
+    rows = layers.profile_layers(cfg, [2, 4], [16], **kw) + layers.profile_head(cfg, [2, 4], [16], **kw) \
+        + layers.profile_decode(cfg, [2], [16], n_tokens=4, **kw) + layers.profile_optimizer(cfg, **kw)
+    kinds = {(r["layer"], r["op"]) for r in rows}
+    assert {("block", "fwd"), ("block", "fwd_bwd"), ("embedding", "fwd"), ("head", "fwd"), ("head", "fwd_bwd"), ("head", "decode"),
+            ("block", "decode"), ("optimizer", "step")} <= kinds
+    assert all(r["time_us"] >= 0 for r in rows)
+    tb = ProfileTable(rows)
+    shape = dict(h=cfg.hidden_dim, L=cfg.n_layers, f=cfg.intermediate_dim, v=cfg.vocab_size, n=cfg.n_params())
+    one = estimate_mfc(T.INFERENCE, 4, shape, 1, 1, 1, HardwareModel(), tb, None, 8, 8)
+    two = estimate_mfc(T.INFERENCE, 4, shape, 2, 1, 1, HardwareModel(), tb, None, 8, 8)
+    blk = tb.time_us("block", "fwd", 64, 16)
+    assert one.time_us >= cfg.n_layers * blk and two.time_us < one.time_us
+    gen = estimate_mfc(T.GENERATE, 4, shape, 1, 1, 1, HardwareModel(), tb, None, 8, 8)
+    assert gen.breakdown["decode_step"] >= cfg.n_layers * tb.time_us("block", "decode", 4, 12) * 0.99
