@@ -67,6 +67,10 @@ class ExperimentSaveEvalControl:
     eval_freq_steps: Optional[int] = None
     eval_freq_secs: Optional[int] = None
     benchmark_steps: Optional[int] = None
+    # B200-native addition.  How many steps may be in flight in the master's dataflow walk: 2 lets MFCs of step s+1 whose inputs and
+    # weights are ready (generation after `actor_train` of step s) run while the rest of step s (`critic_train`) is still busy on
+    # other GPUs, like the reference's free-running request coroutines; 1 puts a barrier after every step.
+    max_inflight_steps: int = 2
 
 
 @dataclasses.dataclass

@@ -2,8 +2,11 @@
 
 Parity: `realhf/system/master_worker.py` (lazy init :927-1271, request/reply coroutines :455-680, data loading
 :683-781, save / eval / benchmark control :1307-1400, e2e logging :1407-1488, recover info :1541-1554).
-One asyncio coroutine per MFC; an MFC fires as soon as `n_seqs` samples carry all of its input keys, so independent
-MFCs (rew_inf / ref_inf / critic_inf of PPO) overlap when their meshes are disjoint.
+One long-lived asyncio coroutine per MFC; an MFC fires as soon as `n_seqs` samples carry all of its input keys, so independent
+MFCs (rew_inf / ref_inf / critic_inf of PPO) overlap when their meshes are disjoint -- also ACROSS steps: like the reference's
+free-running request coroutines (master_worker.py:455-680: one semaphore per MFC plus "never run ahead of the train step of your
+own role"), the generation of step s+1 starts as soon as `actor_train` of step s has replied, while `critic_train` of step s is
+still running on its own GPUs.  `exp_ctrl.max_inflight_steps` bounds the look-ahead (1 = a barrier after every step).
 """
 
 from __future__ import annotations
@@ -12,11 +15,11 @@ import asyncio
 import collections
 import os
 import time
-from typing import Dict, Hashable, List, Tuple
+from typing import Dict, Hashable, List, Optional, Tuple
 
 import numpy as np
 
-from realhf_b200.base.asyncio_utils import gather_or_raise
+from realhf_b200.base import asyncio_utils
 from realhf_b200.api import system as system_api
 from realhf_b200.api.config import ModelInterfaceType, ModelName
 from realhf_b200.api.data import DataBatchMeta, SequenceSample
@@ -46,6 +49,7 @@ class MasterWorker:
         self.sink_rpcs = [r for r in self.rpcs if r.is_dst]
         self.data_owner: Dict[Tuple[Hashable, str], int] = {}
         self._pending: Dict[str, asyncio.Future] = {}
+        self._ready_batch: List[Tuple[List[Payload], List[Payload], asyncio.Future]] = []
         self.step = self.epoch = self.epoch_step = 0
         self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
         self.rpc_mem: Dict[str, dict] = {}
@@ -53,7 +57,10 @@ class MasterWorker:
         self._t_start = time.time()
         self.stats_log: List[Dict] = []
         self._metrics = None
-        self._consumed_ids_this_epoch: List[Hashable] = []
+        self._ids_by_step: Dict[int, List[Hashable]] = {}     # ids the source MFC consumed in each (global) step
+        self._recovered_ignore: List[Hashable] = []
+        self._epoch_first_step = 0
+        self._rpc_secs_by_step: Dict[int, Dict[str, float]] = collections.defaultdict(lambda: collections.defaultdict(float))
 
     # ------------------------------------------------------------------ transport helpers
     async def _request(self, p: Payload) -> Payload:
@@ -61,6 +68,50 @@ class MasterWorker:
         self._pending[p.request_id] = fut
         self.stream.post(p)
         return await fut
+
+    async def _dispatch(self, phase1: List[Payload], phase2: List[Payload]) -> List[Payload]:
+        """Post the requests of one MFC.  MFCs that become ready within `REAL_MASTER_BATCH_MS` (2 ms) of each other -- in PPO
+        `actor_train` and `critic_train` always do: the same reply makes both runnable -- are posted together: first the phase-1
+        (data redistribution) requests of all of them, then their phase-2 (compute) requests.  Each needs tensors that live on the
+        OTHER one's workers; posted one MFC after the other, the second one's source workers would be busy computing the first
+        one before they get to send (model workers are serial), and two MFCs on disjoint GPUs would run one after the other.
+        The reference reaches the same end on the worker side by running the pre-hooks of all queued requests first
+        (model_worker.py:483-503), which needs its three-phase handshake; here the order stays a single global one."""
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        self._ready_batch.append((phase1, phase2, fut))
+        if len(self._ready_batch) == 1:
+            loop.call_later(float(os.environ.get("REAL_MASTER_BATCH_MS", "2")) / 1e3, self._flush_batch)
+        return await fut
+
+    def _flush_batch(self):
+        batch, self._ready_batch = self._ready_batch, []
+        loop = asyncio.get_running_loop()
+        futs: Dict[int, List[asyncio.Future]] = {i: [] for i in range(len(batch))}
+        for phase in (0, 1):
+            for i, entry in enumerate(batch):
+                for p in entry[phase]:
+                    f = loop.create_future()
+                    self._pending[p.request_id] = f
+                    self.stream.post(p)
+                    futs[i].append(f)
+        for i, entry in enumerate(batch):
+            asyncio.ensure_future(self._collect(futs[i], entry[2]))
+
+    @staticmethod
+    async def _collect(futs: List[asyncio.Future], out: asyncio.Future):
+        """Replies of one MFC (phase-1 requests first, then phase-2, in posting order) -> the future its coroutine awaits."""
+        try:
+            res = await asyncio.gather(*futs)
+        except asyncio.CancelledError:
+            out.cancel()
+            raise
+        except Exception as e:
+            if not out.done():
+                out.set_exception(e)
+            return
+        if not out.done():
+            out.set_result(res)
 
     async def _pump(self):
         """Routes replies to the futures waiting for them."""
@@ -126,9 +177,14 @@ class MasterWorker:
         return [self.workers_of[name][topo.get_rank(pipe=pp - 1, data=d, model=0)] for d in range(dp)]
 
     # ------------------------------------------------------------------ data loading
-    async def _load_data(self):
+    def _epoch_of(self, step: int) -> int:
+        """Epoch index of global step `step` (steps that are in flight ahead of `self.step` may belong to the next epoch)."""
+        return self.epoch + (self.epoch_step + (step - self.step)) // self.ft_spec.steps_per_epoch
+
+    async def _load_data(self, step: Optional[int] = None):
         src_workers = self._dp_heads(self.src_rpc.model_name)
-        ignore = list(self.recover_info.hash_vals_to_ignore) if (self.recover_info and self.epoch == self.recover_info.recover_start.epoch) else []
+        epoch = self.epoch if step is None else self._epoch_of(step)
+        ignore = list(self.recover_info.hash_vals_to_ignore) if (self.recover_info and epoch == self.recover_info.recover_start.epoch) else []
         replies = await self._group_request(src_workers, "fetch", data=dict(ignore_ids=ignore))
         samples = []
         for w, r in zip(src_workers, replies):
@@ -165,7 +221,17 @@ class MasterWorker:
                                      trailing=tuple(meta.trailing_shapes[key] or ()), src=src, dsts=need))
         return plan
 
-    async def _run_rpc_once(self, rpc: MFCDef):
+    async def _run_rpc_once(self, rpc: MFCDef, step: Optional[int] = None):
+        step = self.step if step is None else step
+        if rpc.is_src:
+            # usually one fetch; after a recover run whole batches may be filtered out (ids consumed before the failure)
+            attempts = 0
+            while self.buffer.n_ready_for(rpc) < rpc.n_seqs:
+                await self._load_data(step)
+                attempts += 1
+                if attempts > 2 * self.ft_spec.steps_per_epoch + 2:
+                    raise RuntimeError(f"dataset cannot supply {rpc.n_seqs} fresh sequences "
+                                       f"({self.buffer.n_ready_for(rpc)} ready after {attempts} fetches)")
         ids, meta = await self.buffer.get_batch_for_rpc(rpc)
         topo = self.topos[rpc.model_name]
         pp, dp, tp = topo.dims
@@ -182,7 +248,7 @@ class MasterWorker:
         involved = set(self.workers_of[rpc.model_name])
         for e in plan:
             involved.add(e["src"])
-        pre_hooks, pre_data, post_hooks, post_data = ["data_transfer"], [plan], [], []
+        pre_hooks, pre_data, post_hooks, post_data = [], [], [], []
         for h in rpc._pre_hooks:
             if isinstance(h, ParamReallocHook):
                 src, dst = (h.source, rpc.model_name) if h.source is not None else (rpc.model_name, h.target)
@@ -204,13 +270,20 @@ class MasterWorker:
             elif isinstance(h, OffloadHook):
                 post_hooks.append("offload")
                 post_data.append(dict(model=rpc.model_name))
-        # post every request of this MFC back-to-back: workers see MFCs in one global order
-        t0 = time.perf_counter()
-        futs = []
+        # Phase 1: the redistribution of the input data, as hook-only requests to the workers that send or receive something.
+        # Phase 2: the call itself (with the reallocation / offload hooks).  MFCs that become ready together are dispatched as
+        # "all their phase-1 requests, then all their phase-2 requests" (`_dispatch`), still ONE global order on FIFO channels.
+        movers = sorted({e["src"] for e in plan} | {d for e in plan for d in e["dsts"]})
+        phase1 = [Payload(handler=w, handle_name="empty", model_name=rpc.model_name, pre_hooks=["data_transfer"], pre_hook_data=[plan])
+                  for w in movers]
+        phase2 = []
         member = {}
         for r in range(topo.world_size()):
             member[self.workers_of[rpc.model_name][r]] = topo.get_coord(r)
-        for w in sorted(involved):
+        hook_workers = set(member)
+        for hd in pre_data + [d for h, d in zip(post_hooks, post_data) if h == "param_realloc"]:
+            hook_workers |= set(self.workers_of[hd["src"]]) | set(self.workers_of[hd["dst"]])
+        for w in sorted(hook_workers):
             if w in member:
                 c = member[w]
                 p = Payload(handler=w, handle_name=rpc.interface_type.value, model_name=rpc.model_name,
@@ -220,9 +293,12 @@ class MasterWorker:
                 p = Payload(handler=w, handle_name="empty", model_name=rpc.model_name, pre_hooks=pre_hooks, pre_hook_data=pre_data,
                             post_hooks=[h for h in post_hooks if h == "param_realloc"],
                             post_hook_data=[d for h, d in zip(post_hooks, post_data) if h == "param_realloc"])
-            futs.append(self._request(p))
-        replies = await asyncio.gather(*futs)
-        self.rpc_secs[rpc.name] += time.perf_counter() - t0
+            phase2.append(p)
+        t0 = time.perf_counter()
+        replies = (await self._dispatch(phase1, phase2))[len(phase1):]
+        self._rpc_secs_by_step[step][rpc.name] += time.perf_counter() - t0
+        if step == self.step:
+            self.rpc_secs[rpc.name] = self._rpc_secs_by_step[step][rpc.name]   # live view of the step being finished (control panel)
         heads = set(self._dp_heads(rpc.model_name))
         stats = []
         mems = [r.data["mem"] for r in replies if isinstance(r.data, dict) and r.data.get("mem")]
@@ -248,47 +324,78 @@ class MasterWorker:
                 stats.append(r.data["stats"])
         if stats and rpc.log_return_value:
             merged = {k: float(np.mean([s[k] for s in stats if k in s])) for k in stats[0] if isinstance(stats[0][k], (int, float))}
-            logger.info(f"[{rpc.name}] step {self.step}: " + ", ".join(f"{k}={v:.4g}" for k, v in merged.items()))
-            rec = {"rpc": rpc.name, "step": self.step, "epoch": self.epoch, "time": time.time(), **merged}
+            logger.info(f"[{rpc.name}] step {step}: " + ", ".join(f"{k}={v:.4g}" for k, v in merged.items()))
+            rec = {"rpc": rpc.name, "step": step, "epoch": self._epoch_of(step), "time": time.time(), **merged}
             self.stats_log.append(rec)
             self._write_stats(rec)
         if rpc.is_src:
-            self._consumed_ids_this_epoch += ids
+            self._ids_by_step.setdefault(step, []).extend(ids)
         return ids
 
     # ------------------------------------------------------------------ main loop
-    async def _run_step(self):
-        t0 = time.perf_counter()
-        # usually one fetch; after a recover run whole batches may be filtered out (ids consumed before the failure)
-        attempts = 0
-        while self.buffer.n_ready_for(self.src_rpc) < self.src_rpc.n_seqs:
-            await self._load_data()
-            attempts += 1
-            if attempts > 2 * self.ft_spec.steps_per_epoch + 2:
-                raise RuntimeError(f"dataset cannot supply {self.src_rpc.n_seqs} fresh sequences "
-                                   f"({self.buffer.n_ready_for(self.src_rpc)} ready after {attempts} fetches)")
-        # one coroutine per MFC; the first failure cancels the others (they would wait for its outputs forever)
-        results = await gather_or_raise([self._run_rpc_once(r) for r in self.rpcs])
+    async def _mfc_loop(self, rpc: MFCDef, first: int, last: int):
+        """All traversals [first, last) of one MFC.  Traversal s may start when
+          * its own traversal s-1 has replied (this loop is sequential),
+          * the train step of its own role has finished traversal s-1 (nobody computes with weights older than one update;
+            reference: master_worker.py:502-509),
+          * for a train step: step s-1 is finalised (its checkpoint / evaluation is not racing with the next update),
+          * s is inside the look-ahead window: s < finalised steps + `max_inflight_steps`,
+          * the trial is not paused,
+        and, as always, when the buffer holds `n_seqs` samples with all of its input keys."""
+        is_train = rpc.interface_type == ModelInterfaceType.TRAIN_STEP
+        train = next((r for r in self.rpcs if r.role == rpc.role and r.interface_type == ModelInterfaceType.TRAIN_STEP), None)
+        W = self._window
+
+        def may_start(s: int) -> bool:
+            if self._stop_launch:
+                return True
+            if self._hold or s >= self._finalized + W:
+                return False
+            if train is not None and train is not rpc and self._done[train.name] < s:
+                return False
+            return not is_train or self._finalized >= s
+
+        for s in range(first, last):
+            async with self._cv:
+                await self._cv.wait_for(lambda: may_start(s))
+                if self._stop_launch:
+                    return
+            await self._run_rpc_once(rpc, s)
+            async with self._cv:
+                self._done[rpc.name] = s + 1
+                self._cv.notify_all()
+
+    async def _finish_step(self, t0: float) -> float:
+        """Book-keeping after every MFC has finished traversal `self.step`."""
+        s = self.step
         done = self.buffer.pop_fully_consumed()
         if done:
-            for k in [k for k in self.data_owner if k[0] in set(done)]:
+            gone = set(done)
+            for k in [k for k in self.data_owner if k[0] in gone]:
                 del self.data_owner[k]
             await self._group_request(list(range(self.cfg.n_model_workers)), "clear_data_cache", data=done)
+        secs = self._rpc_secs_by_step.pop(s, {})
+        self.rpc_secs.clear()
+        self.rpc_secs.update(secs)
         self.step += 1
         self.epoch_step += 1
         if self.epoch_step >= self.ft_spec.steps_per_epoch:
             self.epoch += 1
             self.epoch_step = 0
-            self._consumed_ids_this_epoch = []
+            self._epoch_first_step = self.step
+            self._recovered_ignore = []
+            for k in [k for k in self._ids_by_step if k < self.step]:
+                del self._ids_by_step[k]
         dt = time.perf_counter() - t0
         logger.info(f"step {self.step} (epoch {self.epoch}, {self.epoch_step}/{self.ft_spec.steps_per_epoch}) e2e {dt:.3f}s; "
-                    + ", ".join(f"{k} {v:.2f}s" for k, v in self.rpc_secs.items()))
+                    + ", ".join(f"{k} {v:.2f}s" for k, v in secs.items()))
         self._log_throughput(dt)
         if self.rpc_mem:
             logger.info("peak memory: " + ", ".join(
                 f"{k} {m.get('peak_allocated_gb', 0):.1f}/{m.get('peak_reserved_gb', 0):.1f} GB alloc/reserved @worker{m.get('worker')}"
                 for k, m in self.rpc_mem.items()))
         self.rpc_secs.clear()
+        self.rpc_secs.update(self._rpc_secs_by_step.get(self.step, {}))
         return dt
 
     def _ckpt_tag(self) -> str:
@@ -323,20 +430,59 @@ class MasterWorker:
         ec = self.cfg.exp_ctrl
         times = []
         total = self.ft_spec.total_train_steps
+        last = total if ec.benchmark_steps is None else min(total, max(self.step, ec.benchmark_steps))
+        self._window = max(1, int(os.environ.get("REAL_MASTER_INFLIGHT_STEPS", getattr(ec, "max_inflight_steps", 2) or 1)))
+        self._cv = asyncio.Condition()
+        self._done = {r.name: self.step for r in self.rpcs}     # traversals every MFC has finished (global step numbering)
+        self._stop_launch = self._hold = False
+        self._finalized = self.step                               # steps whose MFCs AND post-step work (save / eval) are done
+        self._epoch_first_step = self.step - self.epoch_step
+        if self.recover_info is not None:   # a second failure in the same epoch must still skip what the first run consumed
+            self._recovered_ignore = list(self.recover_info.hash_vals_to_ignore)
+        loops = [asyncio.ensure_future(self._mfc_loop(r, self.step, last)) for r in self.rpcs]
+
+        async def set_flags(**kw):
+            async with self._cv:
+                for k, v in kw.items():
+                    setattr(self, k, v)
+                self._cv.notify_all()
+
         try:
-            while self.step < total:
-                if not await self._check_control():
+            while self.step < last:
+                # controller commands act between steps; while paused no new MFC is launched (MFCs of the next step that are already
+                # running finish on the workers)
+                await set_flags(_hold=True)
+                go_on = await self._check_control()
+                await set_flags(_hold=False)
+                if not go_on:
                     logger.info(f"stop requested by the controller at step {self.step}")
                     break
-                times.append(await self._run_step())
+                t0 = time.perf_counter()
+                s = self.step
+
+                async def step_done():
+                    async with self._cv:
+                        await self._cv.wait_for(lambda: all(self._done[r.name] > s for r in self.rpcs))
+
+                # the first failure of any MFC loop cancels the others (they would wait for its outputs forever)
+                waiter = asyncio.ensure_future(step_done())
+                await asyncio.wait([waiter] + [t for t in loops if not t.done()], return_when=asyncio.FIRST_COMPLETED)
+                while not waiter.done():
+                    asyncio_utils.raise_first_exception(loops)
+                    await asyncio.wait([waiter] + [t for t in loops if not t.done()], return_when=asyncio.FIRST_COMPLETED)
+                asyncio_utils.raise_first_exception(loops)
+                times.append(await self._finish_step(t0))
                 if self.save_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
                     await self._save()
                 if self.eval_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
                     await self._eval()
+                await set_flags(_finalized=self.step)   # wake the loops waiting for the window / the finalised step
                 if ec.benchmark_steps is not None and self.step >= ec.benchmark_steps:
                     logger.info(f"benchmark finished: avg #e2e# time {np.mean(times):.3f}s over {len(times)} steps")
                     break
         finally:
+            self._stop_launch = True
+            await asyncio_utils.cancel_all(loops)
             if os.environ.get("REAL_SAVE_RECOVER_STATES", "0") == "1":
                 self._dump_recover()
             try:
@@ -429,10 +575,18 @@ class MasterWorker:
             self._metrics = MetricSinks(self.exp, self.trial, constants.run_dirs(self.exp, self.trial)["log"])
         self._metrics.log(rec)
 
+    def _consumed_ids_this_epoch(self) -> List[Hashable]:
+        """Ids consumed by the FINALISED steps of the current epoch (plus what a previous, recovered run of this epoch consumed).
+        Prompts that a look-ahead generation of an unfinished step already took are not in the list: nothing was trained on them."""
+        out = list(self._recovered_ignore)
+        for st in range(self._epoch_first_step, self.step):
+            out += self._ids_by_step.get(st, [])
+        return out
+
     def _dump_recover(self):
         info = recover.RecoverInfo(recover_start=recover.StepInfo(self.epoch, self.epoch_step, self.step),
                                    last_step_info=recover.StepInfo(self.epoch, max(self.epoch_step - 1, 0), max(self.step - 1, 0)),
-                                   hash_vals_to_ignore=list(self._consumed_ids_this_epoch))
+                                   hash_vals_to_ignore=self._consumed_ids_this_epoch())
         recover.dump_recover_info(info, self.exp, self.trial)
 
     def run(self):

@@ -157,11 +157,16 @@ def test_layer_profiler_rows_feed_the_cost_model():
     assert {("block", "fwd"), ("block", "fwd_bwd"), ("embedding", "fwd"), ("head", "fwd"), ("head", "fwd_bwd"), ("head", "decode"),
             ("block", "decode"), ("optimizer", "step")} <= kinds
     assert all(r["time_us"] >= 0 for r in rows)
+    # wall-clock rows of a loaded CI machine are noisy: the composition checks below run on the same rows with deterministic times
+    for r in rows:
+        n = r["bs"] if r["op"] in ("decode", "step") else r["bs"] * r["seqlen"]
+        r["time_us"] = 50.0 + 3.0 * n
     tb = ProfileTable(rows)
     shape = dict(h=cfg.hidden_dim, L=cfg.n_layers, f=cfg.intermediate_dim, v=cfg.vocab_size, n=cfg.n_params())
     one = estimate_mfc(T.INFERENCE, 4, shape, 1, 1, 1, HardwareModel(), tb, None, 8, 8)
     two = estimate_mfc(T.INFERENCE, 4, shape, 2, 1, 1, HardwareModel(), tb, None, 8, 8)
     blk = tb.time_us("block", "fwd", 64, 16)
+    assert blk == pytest.approx(50.0 + 3.0 * 64)
     assert one.time_us >= cfg.n_layers * blk and two.time_us < one.time_us
     gen = estimate_mfc(T.GENERATE, 4, shape, 1, 1, 1, HardwareModel(), tb, None, 8, 8)
     assert gen.breakdown["decode_step"] >= cfg.n_layers * tb.time_us("block", "decode", 4, 12) * 0.99
