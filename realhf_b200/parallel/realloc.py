@@ -35,13 +35,13 @@ from realhf_b200.ops.functional import SegmentPlan
 class Transfer:
     src_worker: int
     dst_worker: int
-    src_off: List[int]   # element offsets in the source flat buffer
-    dst_off: List[int]   # element offsets in the destination flat buffer
-    lens: List[int]      # elements
+    src_off: Sequence[int]   # element offsets in the source flat buffer   } int64 numpy arrays when produced by `derive_plan`
+    dst_off: Sequence[int]   # element offsets in the destination flat buffer } (a 70B reshard has tens of millions of row
+    lens: Sequence[int]      # elements                                        } segments: python lists of them cost minutes)
 
     @property
     def numel(self) -> int:
-        return sum(self.lens)
+        return int(np.asarray(self.lens, dtype=np.int64).sum())
 
 
 @dataclasses.dataclass
@@ -175,8 +175,12 @@ def _spec_sources(spec, cfg: ReaLModelConfig, s_tp: int, d_tp: int, dtp: int, ca
 
 
 def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Sequence[int], dst_topo: ProcessTopology,
-                dst_workers: Sequence[int]) -> ReallocPlan:
+                dst_workers: Sequence[int], volumes_only: bool = False, for_worker: Optional[int] = None):
     """`*_workers[r]` = worker (GPU) index of layout-local rank r.  Critic / actor pairs must share the architecture.
+    `volumes_only`: return {(source worker, destination worker): elements} without materialising the segments (what the
+    allocation search's cost model needs; a 70B plan over 64 GPUs has tens of millions of segments).
+    `for_worker`: materialise only the transfers this worker sends or receives (what its `ReallocExecutor` runs); `dst_numel`
+    still covers every destination.
 
     Cost: the interval intersection runs once per distinct parameter geometry and (source tp, destination tp rank) pair; the
     per-layer work is numpy offset arithmetic.  LLaMA-7B, dp8 -> dp4*tp2 (2.1 M row segments before coalescing): ~1 s."""
@@ -187,6 +191,8 @@ def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Se
     layer_to_src_pp = {l: p for p, (a, b) in src_stage.items() for l in range(a, b)}
     src_layouts = {p: build_layout(cfg, range(*src_stage[p]), s_tp)[0] for p in range(s_pp)}
     chunks: Dict[Tuple[int, int], List[Tuple[np.ndarray, np.ndarray, np.ndarray]]] = {}
+    volumes: Dict[Tuple[int, int], int] = {}
+    ln_sum: Dict[int, int] = {}      # id(len array of a cached geometry entry) -> its sum
     dst_numel: Dict[int, int] = {}
     cache: dict = {}
     for dpp in range(d_pp):
@@ -208,12 +214,22 @@ def derive_plan(cfg: ReaLModelConfig, src_topo: ProcessTopology, src_workers: Se
                         # pick the source DP replica: same GPU if possible, else spread by destination dp rank
                         cands = [src_workers[src_topo.get_rank(pipe=spp, data=k, model=stp)] for k in range(s_dp)]
                         sw = dw if dw in cands else cands[(ddp * d_tp + dtp) % s_dp]
-                        chunks.setdefault((sw, dw), []).append((so + sslot.offset, do + dslot.offset, ln))
+                        if for_worker is not None and sw != for_worker and dw != for_worker:
+                            continue
+                        if volumes_only:
+                            n = ln_sum.get(id(ln))
+                            if n is None:
+                                n = ln_sum[id(ln)] = int(ln.sum())
+                            volumes[(sw, dw)] = volumes.get((sw, dw), 0) + n
+                        else:
+                            chunks.setdefault((sw, dw), []).append((so + sslot.offset, do + dslot.offset, ln))
+    if volumes_only:
+        return volumes
     transfers = []
     for (sw, dw), parts in sorted(chunks.items()):
         so, do, ln = (np.concatenate([p[i] for p in parts]) for i in range(3))
         so, do, ln = _coalesce_arrays(so, do, ln)
-        transfers.append(Transfer(sw, dw, so.tolist(), do.tolist(), ln.tolist()))
+        transfers.append(Transfer(sw, dw, so, do, ln))
     return ReallocPlan(transfers, dst_numel)
 
 

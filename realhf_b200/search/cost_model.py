@@ -312,15 +312,16 @@ def _plan_bytes(cfg: ReaLModelConfig, src: Tuple[int, int, int], src_ranks: Sequ
     if hit is not None:
         return hit
     (s_dp, s_tp, s_pp), (d_dp, d_tp, d_pp) = src, dst
-    plan = derive_plan(cfg, ProcessTopology(s_pp, s_dp, s_tp), list(src_ranks), ProcessTopology(d_pp, d_dp, d_tp), list(dst_ranks))
+    vols = derive_plan(cfg, ProcessTopology(s_pp, s_dp, s_tp), list(src_ranks), ProcessTopology(d_pp, d_dp, d_tp), list(dst_ranks),
+                       volumes_only=True)
     out = {"local": {}, "send": {}, "recv": {}}
-    for t in plan.transfers:
-        b = 2.0 * t.numel
-        if t.src_worker == t.dst_worker:
-            out["local"][t.src_worker] = out["local"].get(t.src_worker, 0.0) + b
+    for (sw, dw), numel in vols.items():
+        b = 2.0 * numel
+        if sw == dw:
+            out["local"][sw] = out["local"].get(sw, 0.0) + b
         else:
-            out["send"][t.src_worker] = out["send"].get(t.src_worker, 0.0) + b
-            out["recv"][t.dst_worker] = out["recv"].get(t.dst_worker, 0.0) + b
+            out["send"][sw] = out["send"].get(sw, 0.0) + b
+            out["recv"][dw] = out["recv"].get(dw, 0.0) + b
     _PLAN_BYTES_CACHE[key] = out
     return out
 

@@ -197,7 +197,7 @@ class ModelWorker:
         mcfg = (src_model or dst_model).module_config
         if key not in self._realloc_cache:
             plan = realloc.derive_plan(mcfg, self.cfg.model_topos[src_name], self.worker_of[src_name],
-                                       self.cfg.model_topos[dst_name], self.worker_of[dst_name])
+                                       self.cfg.model_topos[dst_name], self.worker_of[dst_name], for_worker=self.index)
             es = torch.tensor([], dtype=(src_model or dst_model).dtype).element_size()
             self._realloc_cache[key] = realloc.ReallocExecutor(plan, self.index, es, self.device)
         ex = self._realloc_cache[key]

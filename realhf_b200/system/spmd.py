@@ -113,7 +113,7 @@ class SPMDExecutor:
             from realhf_b200.parallel.fused_tp import FusedTP
             dst_ctx.symm = FusedTP(dst_ctx, max_tokens=256, max_features=real.config.hidden_dim, device=self.device)
         replica = InferenceBackend().initialize(Model(ModelName(src.name.role, src.name.replica_id + 1), m, src.tokenizer, self.device), None)
-        plan = realloc.derive_plan(real.config, src_topo, workers, dst_topo, workers)
+        plan = realloc.derive_plan(real.config, src_topo, workers, dst_topo, workers, for_worker=my_worker)
         exe = realloc.ReallocExecutor(plan, my_worker, torch.tensor([], dtype=real.dtype).element_size(), self.device)
         self.models[rpc_name] = replica
         self.hooks.setdefault(rpc_name, []).append(lambda: exe.run(real.flat_param.data, m.flat_param.data))

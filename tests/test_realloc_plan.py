@@ -99,3 +99,20 @@ def test_plan_derivation_of_a_7b_model_is_fast():
     assert dt < 20.0, dt
     assert len(plan.transfers) == 8 and all(t.src_worker == t.dst_worker for t in plan.transfers)   # dp-replicated source: local copies
     assert sum(t.numel for t in plan.transfers) == 8 * plan.dst_numel[0]
+
+
+def test_per_worker_and_volume_only_plans_agree_with_the_full_plan():
+    cfg = hf_io.family("llama").make_test_config()
+    cfg.n_layers = 8
+    s_topo, d_topo = ProcessTopology(2, 1, 2), ProcessTopology(1, 2, 4)
+    sw, dw = [0, 1, 2, 3], list(range(8))
+    full = realloc.derive_plan(cfg, s_topo, sw, d_topo, dw)
+    vols = realloc.derive_plan(cfg, s_topo, sw, d_topo, dw, volumes_only=True)
+    assert vols == {(t.src_worker, t.dst_worker): t.numel for t in full.transfers}
+    for w in range(8):
+        mine = realloc.derive_plan(cfg, s_topo, sw, d_topo, dw, for_worker=w)
+        assert mine.dst_numel == full.dst_numel
+        want = [t for t in full.transfers if w in (t.src_worker, t.dst_worker)]
+        assert [(t.src_worker, t.dst_worker) for t in mine.transfers] == [(t.src_worker, t.dst_worker) for t in want]
+        for a, b in zip(mine.transfers, want):
+            assert list(a.src_off) == list(b.src_off) and list(a.dst_off) == list(b.dst_off) and list(a.lens) == list(b.lens)
