@@ -193,7 +193,7 @@ def run_master_runtime(args):
     dev = "cpu" if args.tiny and not torch.cuda.is_available() else "cuda"
     exp_name = f"bench-{uuid.uuid4().hex[:6]}"
     qs = ["ppo", f"experiment_name={exp_name}", "trial_name=t0", f"device={dev}", f"dtype={'fp32' if dev == 'cpu' else 'bf16'}",
-          f"n_gpus_per_node={n}", "allocation_mode=manual", f"dataset.path={data}", f"dataset.train_bs_n_seqs={args.prompts}",
+          f"n_gpus_per_node={n}", f"allocation_mode={'manual' if args.allocation == 'dp' else args.allocation}", f"dataset.path={data}", f"dataset.train_bs_n_seqs={args.prompts}",
           f"dataset.max_prompt_len={args.prompt_len}", "dataset.pad_to_max_length=true",
           f"ppo.gen.max_new_tokens={args.new_tokens}", f"ppo.gen.min_new_tokens={args.new_tokens}", "ppo.gen.top_p=0.9", "ppo.gen.top_k=1000",
           "ppo.gen.use_cuda_graph=true", "ppo.gen.force_cudagraph_recapture=true", "ppo.ppo_n_minibatches=4",
@@ -207,11 +207,20 @@ def run_master_runtime(args):
                f"{role}.optimizer.share_grad_buffer=true", f"{role}.optimizer.lr_scheduler_type=constant", f"{role}.optimizer.warmup_steps_proportion=0.0"]
         if dev == "cpu":
             qs += [f"{role}.optimizer.state_dtype=fp32", f"{role}.optimizer.grad_dtype=fp32"]
-    for mfc in ("actor_gen", "actor_train", "critic_train", "critic_inf", "ref_inf", "rew_inf"):
-        qs += [f"{mfc}.parallel.data_parallel_size={n}"]
+    if args.allocation == "dp":
+        for mfc in ("actor_gen", "actor_train", "critic_train", "critic_inf", "ref_inf", "rew_inf"):
+            qs += [f"{mfc}.parallel.data_parallel_size={n}"]
     for mfc in ("critic_inf", "ref_inf", "rew_inf"):
         qs += [f"{mfc}.n_mbs={inf_mbs}"]
     exp = build_experiment(qs)
+    layouts = None
+    if args.allocation != "dp":   # resolve once here to report what the mode chose (the launcher resolves the same thing again)
+        try:
+            layouts = {a.rpc.name if hasattr(a.rpc, "name") else str(a.rpc):
+                       f"gpus{a.device_mesh.global_ranks()} d{a.parallel.data_parallel_size}"
+                       f"m{a.parallel.model_parallel_size}p{a.parallel.pipeline_parallel_size}" for a in exp._get_rpc_allocations()}
+        except Exception as e:  # reporting only
+            layouts = {"unresolved": repr(e)}
     t0 = time.perf_counter()
     main_start(exp, timeout=3600)
     wall_total = time.perf_counter() - t0
@@ -236,7 +245,8 @@ def run_master_runtime(args):
         "runtime": "master/worker (quickstart -> launcher -> master worker + one model worker process per GPU, ZMQ control plane)",
         "timer": "master worker host clock around each DFG traversal (includes dataset fetch, data transfer, all six MFCs, replies)",
         "config": {"model": "LLaMA-7B actor + 7B critic + 7B ref + 7B reward" + ("" if headline else " [DEBUG shapes]"),
-                   "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens, "parallelism": f"dp{n} (all 6 MFCs), ZeRO-1 flat AdamW",
+                   "global_batch": args.prompts, "seq_len": args.prompt_len + args.new_tokens,
+                   "parallelism": f"dp{n} (all 6 MFCs), ZeRO-1 flat AdamW" if layouts is None else f"allocation_mode={args.allocation}: {layouts}",
                    "mfc_ms": {k: round(v, 1) for k, v in mfc.items()}, "launch_to_exit_s": round(wall_total, 1)},
         "impl": "ours"}), flush=True)
     return 0
@@ -284,6 +294,10 @@ def main():
     ap.add_argument("--runtime", default="spmd", choices=["spmd", "master"],
                     help="spmd (default): every rank walks the DFG in-process (launched by torchrun for N > 1); master: the production "
                          "master/worker runtime launched through the quickstart + local scheduler (run WITHOUT torchrun: it spawns its own workers)")
+    ap.add_argument("--allocation", default="dp", choices=["dp", "search", "heuristic"],
+                    help="--runtime master only: `dp` = every MFC data-parallel over all GPUs (the SPMD arm's allocation); `search` / `heuristic` "
+                         "= the quickstart allocation modes (per-MFC device meshes and layouts, parameter reallocation, MFCs of different "
+                         "steps overlapping on disjoint GPUs)")
     ap.add_argument("--profile-mfc", default="", help="debug only: comma-separated MFC names to wrap in torch.profiler during the LAST timed step; "
                                                      "prints kernel-time totals and the top kernels per MFC to stderr (the run's numbers are then not a bench value)")
     ap.add_argument("--tiny", action="store_true", help="debug only: toy model shapes for --runtime master (CPU smoke test of the arm)")

@@ -86,6 +86,10 @@ class MasterWorker:
 
     def _flush_batch(self):
         batch, self._ready_batch = self._ready_batch, []
+        if getattr(self, "_stop_launch", False):   # the walk is being torn down: nothing new goes to the workers
+            for entry in batch:
+                entry[2].cancel()
+            return
         loop = asyncio.get_running_loop()
         futs: Dict[int, List[asyncio.Future]] = {i: [] for i in range(len(batch))}
         for phase in (0, 1):
