@@ -54,6 +54,7 @@ class MasterWorker:
         self.rpc_secs: Dict[str, float] = collections.defaultdict(float)
         self.rpc_mem: Dict[str, dict] = {}
         self._rpc_batch_lens: Dict[str, List[int]] = {}
+        self._rpc_batch_lens_by_step: Dict[int, Dict[str, List[int]]] = {}
         self._t_start = time.time()
         self.stats_log: List[Dict] = []
         self._metrics = None
@@ -247,7 +248,7 @@ class MasterWorker:
         else:
             parts = meta.get_split_spec(dp, min_size=max(1, (rpc.n_mbs or 1) * (2 * pp if pp > 1 else 1))).partitions
         part = {d: ids[a:b] for d, (a, b) in enumerate(parts)}
-        self._rpc_batch_lens[rpc.name] = self._batch_lens(meta)
+        self._rpc_batch_lens_by_step.setdefault(step, {})[rpc.name] = self._batch_lens(meta)
         plan = self._transfer_plan(rpc, part, meta)
         involved = set(self.workers_of[rpc.model_name])
         for e in plan:
@@ -379,6 +380,7 @@ class MasterWorker:
                 del self.data_owner[k]
             await self._group_request(list(range(self.cfg.n_model_workers)), "clear_data_cache", data=done)
         secs = self._rpc_secs_by_step.pop(s, {})
+        self._rpc_batch_lens = self._rpc_batch_lens_by_step.pop(s, {})
         self.rpc_secs.clear()
         self.rpc_secs.update(secs)
         self.step += 1
@@ -470,11 +472,13 @@ class MasterWorker:
 
                 # the first failure of any MFC loop cancels the others (they would wait for its outputs forever)
                 waiter = asyncio.ensure_future(step_done())
-                await asyncio.wait([waiter] + [t for t in loops if not t.done()], return_when=asyncio.FIRST_COMPLETED)
-                while not waiter.done():
-                    asyncio_utils.raise_first_exception(loops)
-                    await asyncio.wait([waiter] + [t for t in loops if not t.done()], return_when=asyncio.FIRST_COMPLETED)
-                asyncio_utils.raise_first_exception(loops)
+                try:
+                    while not waiter.done():
+                        await asyncio.wait([waiter] + [t for t in loops if not t.done()], return_when=asyncio.FIRST_COMPLETED)
+                        asyncio_utils.raise_first_exception(loops)
+                finally:
+                    if not waiter.done():
+                        waiter.cancel()
                 times.append(await self._finish_step(t0))
                 if self.save_ctl.check(epochs=int(self.epoch_step == 0), steps=1):
                     await self._save()

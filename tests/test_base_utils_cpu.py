@@ -542,3 +542,28 @@ def test_padding_roundtrips():
     ids2, cu4, mx4, n_pad = padding.pad_sequence_parallel_input(ids, cu, 7, tp=4, pad_id=0)
     assert ids2.numel() == 16 and n_pad == 1 and cu4.tolist() == [0, 7, 9, 14, 15, 16] and mx4 == 7
     assert padding.pad_sequence_parallel_input(ids2, cu4, 7, tp=4)[3] == 0
+
+
+def test_numpy_ray_and_slurm_helpers():
+    import numpy as np
+
+    from realhf_b200.base import numpy_utils, ray_utils, slurm_utils
+    assert numpy_utils.shape_leq((2, 3), (2, 4)) and not numpy_utils.shape_leq((2, 5), (2, 4)) and not numpy_utils.shape_leq((2,), (2, 4))
+    assert numpy_utils.shape_union((2, 3), (1, 7), (4, 1)) == (4, 7)
+    a, b = np.arange(2 * 3).reshape(2, 3), np.arange(2 * 2 * 2).reshape(2, 2, 2) + 100
+    packed = np.concatenate([a, b.reshape(2, 4)], axis=-1)
+    back = numpy_utils.split_to_shapes(packed, {"a": (2, 3), "b": (2, 2, 2)}, axis=1)
+    assert np.array_equal(back["a"], a) and np.array_equal(back["b"], b)
+    with pytest.raises(ValueError):
+        numpy_utils.split_to_shapes(packed, {"a": (2, 3)}, axis=1)
+    assert isinstance(ray_utils.check_ray_availability(), bool) and isinstance(slurm_utils.check_slurm_availability(), bool)
+    nodes = slurm_utils.parse_nodelist("NODE[01-03,07],NODE10", "NODE")
+    assert nodes == ["NODE01", "NODE02", "NODE03", "NODE07", "NODE10"]
+    assert slurm_utils.nodelist_from_nodes(nodes, "NODE") == "NODE[01-03,07,10]"
+    assert slurm_utils.nodelist_from_nodes(["NODE05"], "NODE") == "NODE05"
+    assert slurm_utils.parse_nodelist(slurm_utils.nodelist_from_nodes(nodes, "NODE"), "NODE") == nodes
+    with pytest.raises(ValueError):
+        slurm_utils.parse_nodelist("gpu[1-2]", "NODE")
+    assert slurm_utils.are_ones_contiguous(np.array([0, 1, 1, 0])) and not slurm_utils.are_ones_contiguous(np.array([1, 0, 1]))
+    assert sorted(["node10", "node2", "node1"], key=slurm_utils.slurm_hostname_key) == ["node1", "node2", "node10"]
+    assert slurm_utils.parse_node_id("NODE07", "NODE") == 7
