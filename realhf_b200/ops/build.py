@@ -143,7 +143,8 @@ def build_host(force: bool = False) -> Path:
 def sass_summary() -> dict:
     """Count the Blackwell-native SASS mnemonics in the built library (evidence for profiles/)."""
     out = _run([str(CUDA_HOME / "bin" / "cuobjdump"), "-sass", str(OPS_LIB)])
-    keys = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS", "MULTIMEM", "UTCBAR"]
+    keys = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS", "LDGMC", "UTCBAR"]  # LDGMC = multimem.ld_reduce
+    # (multimem.st lowers to an ordinary STG on the multicast address and has no mnemonic of its own)
     import re
     pats = {k: re.compile(r"(?<![A-Z0-9_.])" + k + r"(?![A-Z0-9])") for k in keys}  # whole mnemonic: `HMMA` must not count `UTCHMMA`
     return {k: sum(1 for line in out.splitlines() if pats[k].search(line)) for k in keys}
