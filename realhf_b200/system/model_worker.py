@@ -350,6 +350,7 @@ class ModelWorker:
                 self.data_storage.pop(i, None)
             if self.device.type == "cuda" and self.cfg.cuda_cache_cleanliness:
                 torch.cuda.empty_cache()
+                self._dirty_cache = False
             if monitor.TIME_MARK_DB:
                 monitor.dump_tmark_db(os.path.join(constants.run_dirs(self.exp, self.trial)["log"], f"time_marks{self.index}.pkl"))
             return None
@@ -394,6 +395,12 @@ class ModelWorker:
                 inp.remap_keys_(rpc.input_key_remap)
             t0 = time.perf_counter()
             if self.device.type == "cuda":
+                if h == "generate" and self.cfg.cuda_cache_cleanliness and getattr(self, "_dirty_cache", False):
+                    # With the master's look-ahead the generation of step s+1 can be queued before `clear_data_cache` of step s:
+                    # give the KV cache (tens of GB in one piece) the blocks the training step left in the caching allocator
+                    torch.cuda.empty_cache()
+                    self._dirty_cache = False
+                self._dirty_cache = getattr(self, "_dirty_cache", False) or h == "train_step"
                 torch.cuda.reset_peak_memory_stats(self.device)
             self._n_calls[rpc.name] = call = self._n_calls.get(rpc.name, 0) + 1
             monitor.time_mark(f"{rpc.name}_start", f"model_worker/{self.index}", step=call - 1)  # REAL_TIME_MARK=1
