@@ -202,3 +202,31 @@ def test_bench_clock_sampler_queries_one_gpu_per_tick(monkeypatch):
     assert calls[:4] == [0, 1, 2, 3] and len(calls) == out["n_samples"] <= 8     # one GPU per tick, in order, first tick immediate
     assert out["gpus_sampled"] == len(set(calls)) and out["gpus"] == 8 and out["sm_max_mhz"] == 1965
     assert out["reasons"] == ["sw_power_cap"] and out["sm_mhz"] in [1500 + 10 * h for h in set(calls)]
+
+
+def test_bench_clock_sampler_round_robin_with_a_fake_nvml(monkeypatch):
+    """bench.py's sampler queries ONE GPU per tick (round robin) and folds clocks / throttle reasons into the JSON `clocks` entry."""
+    import importlib.util
+    import os
+    import sys
+    import time
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    fake = types.SimpleNamespace(
+        NVML_CLOCK_SM=0, nvmlInit=lambda: None, nvmlDeviceGetHandleByIndex=lambda i: i,
+        nvmlDeviceGetClockInfo=lambda h, k: calls.append(h) or 1900.0 - 10 * h, nvmlDeviceGetMaxClockInfo=lambda h, k: 1965.0,
+        nvmlDeviceGetCurrentClocksEventReasons=lambda h: 0x4 if h == 2 else 0)
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    s = bench.ClockSampler(4, period=0.02)
+    s.start()
+    time.sleep(0.25)
+    out = s.stop()
+    assert calls[:8] == [0, 1, 2, 3, 0, 1, 2, 3]                      # one GPU per tick, in turn
+    assert out["gpus"] == 4 and out["gpus_sampled"] == 4 and out["n_samples"] == len(calls) >= 8
+    assert out["sm_max_mhz"] == 1965.0 and 1870.0 <= out["sm_mhz"] <= 1900.0 and out["reasons"] == ["sw_power_cap"]
+    assert bench._NoSampler().stop() is None
