@@ -62,8 +62,13 @@ def stop_experiment(exp: str, trial: str):
 class Controller:
     """Polls worker status keys; raises on ERROR (reference: Controller.start polling loop, controller.py:275-318)."""
 
-    def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int):
+    def __init__(self, exp: str, trial: str, sched: sched_client.SchedulerClient, n_model_workers: int,
+                 ignore_worker_error: bool = False):
         self.exp, self.trial, self.sched, self.n = exp, trial, sched, n_model_workers
+        # debugging aid of the reference launcher (`--ignore_worker_error`, apps/main.py:375): a failing MODEL worker is reported but
+        # does not end the trial, so that the surviving processes can be inspected; a failing master always ends it
+        self.ignore_worker_error = ignore_worker_error
+        self._reported = set()
         self._seen = set()
         self._lost_since = {}
         # liveness lease of the launcher itself: workers exit when it expires (apps/remote.py::_watch_controller)
@@ -91,6 +96,15 @@ class Controller:
                     out[k] = "LOST" if k in self._seen else "UNKNOWN"
         return out
 
+    def _filter_ignored(self, bad: dict) -> dict:
+        if not self.ignore_worker_error:
+            return bad
+        for k, v in bad.items():
+            if not k.startswith("master_worker") and k not in self._reported:
+                self._reported.add(k)
+                logger.error(f"{k} is {v}; continuing because the trial was started with ignore_worker_error")
+        return {k: v for k, v in bad.items() if k.startswith("master_worker")}
+
     def wait(self, timeout: Optional[float] = None, poll: float = 0.5, status_poll: float = 5.0):
         t0 = time.monotonic()
         last_status = t0
@@ -106,11 +120,13 @@ class Controller:
                     else:
                         self._lost_since.pop(k, None)
                 bad = {k: v for k, v in st.items() if v == "ERROR" or (v == "LOST" and now - self._lost_since[k] >= status_ttl())}
+                bad = self._filter_ignored(bad)
                 if bad:
                     raise sched_client.JobException(self.sched.run_name, sorted(bad)[0], "localhost", sched_client.JobState.FAILED)
             infos = self.sched.find_all()
             master = next((i for i in infos if i.name.startswith("master_worker")), None)
             failed = [i for i in infos if i.state == sched_client.JobState.FAILED]
+            failed = [i for i in failed if i.name in self._filter_ignored({i.name: "FAILED"})]
             if failed:
                 raise sched_client.JobException(self.sched.run_name, failed[0].name, "localhost", failed[0].state)
             if master is not None and master.state == sched_client.JobState.COMPLETED:
@@ -172,7 +188,7 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
     mw = sched_cfg.model_worker
     sched.submit_array("model_worker", sched_client.remote_worker_cmd(exp, trial, debug, "model_worker"), count=mw.count,
                        **res(mw.scheduling))
-    ctl = Controller(exp, trial, sched, mw.count)
+    ctl = Controller(exp, trial, sched, mw.count, ignore_worker_error=bool(getattr(exp_cfg, "ignore_worker_error", False)))
     try:
         ctl.wait(timeout=timeout)
         sched.wait(timeout=60)
@@ -198,10 +214,48 @@ def main_start(exp_cfg: Experiment, recover_count: int = 0, timeout: Optional[fl
 
 
 # ------------------------------------------------------------------------------------------- command line
+def start_registered(args):
+    """`start`: build the experiment registered under `--experiment_name` and launch it (parity: apps/main.py:76-231, where the
+    name selects `config_package.make_experiment(name)` and the flags configure the launcher, not the experiment)."""
+    import realhf_b200.experiments.algos  # noqa: F401  (registers the quickstart experiments)
+    from realhf_b200.api.quickstart import QUICKSTART_EXPERIMENTS
+    from realhf_b200.api.system import ALL_EXPERIMENT_CLASSES
+    env_vars = {}
+    if args.user_code:
+        from realhf_b200.base.importing import import_usercode
+        import_usercode(args.user_code, "real_user_code")
+        env_vars["REAL_USER_CODE"] = os.path.abspath(args.user_code)
+        os.environ["REAL_USER_CODE"] = env_vars["REAL_USER_CODE"]
+    name = args.experiment_name
+    if name in ALL_EXPERIMENT_CLASSES:
+        exp = ALL_EXPERIMENT_CLASSES[name]()
+    elif name in QUICKSTART_EXPERIMENTS:
+        exp = QUICKSTART_EXPERIMENTS[name]()
+    else:
+        raise SystemExit(f"no experiment registered as `{name}` (registered: "
+                         f"{sorted(set(ALL_EXPERIMENT_CLASSES) | set(QUICKSTART_EXPERIMENTS))}); --user_code FILE imports the module that registers it")
+    for n in (name, args.trial_name):
+        if "_" in n:
+            raise SystemExit(f"experiment_name / trial_name must not contain `_` (got `{n}`)")
+    exp.experiment_name, exp.trial_name = name, args.trial_name
+    for k in ("mode", "partition", "wandb_mode", "recover_mode", "recover_retries", "debug", "ignore_worker_error"):
+        setattr(exp, k, getattr(args, k))
+    if args.image_name is not None:
+        exp.image_name = args.image_name
+    if args.allocation_mode is not None:
+        exp.allocation_mode = args.allocation_mode
+    return main_start(exp, timeout=args.timeout, env_vars=env_vars)
+
+
 def main(argv=None):
     """`python -m realhf_b200.apps.main <cmd>`: operate on a trial from another shell (parity: apps/main.py:233-257,330-450;
     experiments are STARTED with `python -m realhf_b200.apps.quickstart <experiment> key=value ...`).
 
+      start -e NAME -f TRIAL [...]      launch a REGISTERED experiment (`api.system.register_experiment`, or a quickstart experiment with
+                                        its default options; `--user_code FILE` imports the module that registers it, here and in
+                                        every worker) with the reference's launcher flags: --mode, --partition, --wandb_mode,
+                                        --image_name, --ignore_worker_error, --debug, --recover_mode, --recover_retries,
+                                        --allocation_mode
       status -e EXP -f TRIAL            worker statuses (RUNNING / PAUSED / COMPLETED / ERROR / LOST)
       pause | resume -e EXP -f TRIAL    the master stops issuing model function calls after its current step / continues
       stop -e EXP -f TRIAL [--mode M]   graceful stop through the master; with --mode slurm also `scancel` the trial's jobs
@@ -221,6 +275,20 @@ def main(argv=None):
         if name == "status":
             sp.add_argument("--n_model_workers", "-n", type=int, default=None)
             sp.add_argument("--rpc", action="store_true", help="also query every worker's control endpoint (live progress, memory)")
+    sp = sub.add_parser("start")
+    sp.add_argument("--experiment_name", "-e", required=True, help="name the experiment was registered under")
+    sp.add_argument("--trial_name", "-f", required=True)
+    sp.add_argument("--mode", default="local", choices=["local", "slurm", "ray"])
+    sp.add_argument("--partition", default=None, help="slurm partition")
+    sp.add_argument("--wandb_mode", default="disabled", choices=["online", "offline", "disabled"])
+    sp.add_argument("--image_name", default=None, help="container image of the workers (slurm)")
+    sp.add_argument("--ignore_worker_error", action="store_true", help="keep the other workers running when one fails (debugging)")
+    sp.add_argument("--debug", action="store_true", help="run workers without -O (assertions on)")
+    sp.add_argument("--recover_mode", default="disabled", choices=["disabled", "auto", "save", "resume"])
+    sp.add_argument("--recover_retries", type=int, default=1)
+    sp.add_argument("--allocation_mode", default=None, help="override the experiment's allocation mode (manual / heuristic / search / d2m2p1 ...)")
+    sp.add_argument("--user_code", default=None, help="python file that registers the experiment (imported here and by every worker)")
+    sp.add_argument("--timeout", type=float, default=None)
     sp = sub.add_parser("find_config")
     sp.add_argument("--regex", "-r", required=True)
     sub.add_parser("profile_layers", add_help=False)
@@ -230,11 +298,14 @@ def main(argv=None):
         return profile_layers.main(rest)
     if rest:
         ap.error(f"unrecognized arguments: {rest}")
+    if args.cmd == "start":
+        return start_registered(args)
     if args.cmd == "find_config":
         import realhf_b200.experiments.algos  # noqa: F401
         import realhf_b200.experiments.profile  # noqa: F401
         from realhf_b200.api.quickstart import QUICKSTART_EXPERIMENTS
-        names = sorted(n for n in QUICKSTART_EXPERIMENTS if re.match(args.regex, n))
+        from realhf_b200.api.system import ALL_EXPERIMENT_CLASSES
+        names = sorted(n for n in set(QUICKSTART_EXPERIMENTS) | set(ALL_EXPERIMENT_CLASSES) if re.match(args.regex, n))
         print("\n".join(names) if names else "No matched experiment names.")
         return names
     exp, trial = args.experiment_name, args.trial_name

@@ -273,3 +273,40 @@ def test_sft_evaluation_under_pipeline_parallelism_reports_the_last_stage(tmp_pa
     train = [r for r in stats if r["rpc"] == "trainDefault"]
     assert len(evals) == 2 and all(3.0 < r["loss"] < 7.0 and r["ppl"] > 20 for r in evals), evals   # ~ln(vocab), not 0.0
     assert abs(evals[0]["loss"] - train[0]["loss"]) < 0.5
+
+
+def test_start_subcommand_launches_a_registered_experiment_from_user_code(tmp_path):
+    """`python -m realhf_b200.apps.main start -e NAME -f TRIAL --user_code FILE ...` (parity: apps/main.py `start`): the experiment is
+    built from the registry, the launcher flags configure the run, the workers import the same user code."""
+    _env(tmp_path)
+    from realhf_b200.apps import main as M
+    ckpt = str(tmp_path / "llama")
+    cfg, tok, words = fixtures.make_checkpoint(ckpt, "llama")
+    data = str(tmp_path / "sft.jsonl")
+    fixtures.write_sft_dataset(data, words, n=32)
+    code = tmp_path / "my_exp.py"
+    code.write_text(f'''
+from realhf_b200.api.system import register_experiment
+from realhf_b200.experiments.algos import SFTConfig
+
+
+def make():
+    c = SFTConfig(device="cpu", dtype="fp32", n_nodes=1, n_gpus_per_node=2, allocation_mode="manual")
+    c.allocation.parallel.data_parallel_size = 2
+    c.model.type._class, c.model.path = "llama", {ckpt!r}
+    c.model.optimizer.grad_dtype, c.model.gradient_checkpointing = "fp32", False
+    c.dataset.train_path, c.dataset.train_bs_n_seqs, c.dataset.max_seqlen = {data!r}, 8, 64
+    c.exp_ctrl.total_train_epochs, c.exp_ctrl.benchmark_steps = 1, 2
+    return c
+
+
+register_experiment("mysft", make)
+''')
+    name = "mysft"
+    M.main(["start", "-e", name, "-f", "t0", "--mode", "local", "--user_code", str(code), "--recover_mode", "disabled", "--timeout", "600",
+            "--allocation_mode", "d2m1p1"])
+    log = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", name, "t0", "master_worker-0")).read()
+    assert "benchmark finished" in log and log.count("[trainDefault]") == 2
+    assert name in M.main(["find_config", "-r", "mys.*"])
+    with pytest.raises(SystemExit):
+        M.main(["start", "-e", "doesnotexist", "-f", "t0"])
