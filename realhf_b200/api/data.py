@@ -367,10 +367,10 @@ def make_dataset(cfg: Union[str, config_api.DatasetAbstraction], seed: int, dp_r
     return ds
 
 
-def make_dataloader(cfg: Union[str, config_api.DataLoaderAbstraction], dataset) -> torch.utils.data.DataLoader:
+def make_dataloader(cfg: Union[str, config_api.DataLoaderAbstraction], dataset, **overrides) -> torch.utils.data.DataLoader:
     if isinstance(cfg, str):
         cfg = config_api.DataLoaderAbstraction(type_=cfg)
-    return ALL_DATALOADER_CLASSES[cfg.type_](dataset, **cfg.args)
+    return ALL_DATALOADER_CLASSES[cfg.type_](dataset, **{**cfg.args, **overrides})
 
 
 def load_hf_tokenizer(path: str, fast: bool = True, padding_side: Optional[str] = None):

@@ -51,7 +51,8 @@ class ReaLMoEConfig:
     routing_type: str = "aux_loss"  # aux_loss | sinkhorn | none
     aux_loss_coeff: float = 1e-3
     capacity_factor: Optional[float] = None
-    pad_to_capacity: bool = False
+    pad_to_capacity: bool = False   # accepted for compatibility: dropped assignments get a zero routing weight and the grouped GEMM
+                                    # takes device-side row offsets, so no expert batch needs padding to a static capacity
     token_drop_policy: str = "probs"  # probs | position
     z_loss_coeff: float = 0.0
     input_jitter_eps: float = 0.0

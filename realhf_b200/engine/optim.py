@@ -523,13 +523,19 @@ class FlatAdamW:
         skipped = bool(self._skip.item())  # fp16 only: the one host sync dynamic loss scaling needs
         c = self.cfg
         if skipped:
-            self.loss_scale = max(c.min_loss_scale, self.loss_scale / 2)
+            # `hysteresis` overflowing steps are tolerated (each one is skipped) before the scale is halved; the credit refills
+            # when the scale grows again (DeepSpeed / Megatron dynamic loss scaler semantics)
+            self._hysteresis_left = getattr(self, "_hysteresis_left", c.hysteresis) - 1
+            if self._hysteresis_left <= 0:
+                self.loss_scale = max(c.min_loss_scale, self.loss_scale / 2)
+                self._hysteresis_left = c.hysteresis
             self._good_steps = 0
         else:
             self._good_steps += 1
             if self._good_steps >= c.loss_scale_window:
                 self.loss_scale *= 2
                 self._good_steps = 0
+                self._hysteresis_left = c.hysteresis
 
     # ------------------------------------------------------------------ ZeRO-3: parameters sharded between calls
     # Between model function calls only this rank's 1/dp slice of the flat parameter buffer stays resident (on the GPU,

@@ -10,6 +10,7 @@ data-parallel on every GPU instead of being cut by TP/PP.
 from __future__ import annotations
 
 import dataclasses
+import os
 import re
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -107,9 +108,31 @@ class CommonExperimentConfig(Experiment):
         return heuristic_allocation(self)
 
     def _search(self) -> List[RPCAllocation]:
+        """`allocation_mode=search`.  With `allocation_use_cache` the result is stored under the profiler cache, keyed by everything
+        the search depends on (cluster shape, MFCs and batch sizes, model families / sizes / paths, sequence lengths), and reused
+        by later launches of the same problem (reference: `allocation_use_cache`, experiments/common/common.py:330-350)."""
         from realhf_b200.search.engine import search_rpc_allocations
-        return search_rpc_allocations(self.global_device_mesh, list(self.rpcs.values()), self.models, seq_len=self.max_prompt_len or 1024,
-                                      **self.search_kwargs)
+        kw = dict(seq_len=self.max_prompt_len or 1024, **self.search_kwargs)
+        cache = None
+        if self.allocation_use_cache:
+            import hashlib
+            import pickle
+            from realhf_b200.base import constants
+            key = repr((self.n_nodes, self.n_gpus_per_node, sorted((n, r.n_seqs, r.interface_type.value, r.role) for n, r in self.rpcs.items()),
+                        sorted((role, m.type._class, m.type.size, m.type.is_critic, m.path) for role, m in self.models.items()),
+                        sorted((k, repr(v)) for k, v in kw.items())))
+            cache = os.path.join(constants.PROFILER_CACHE_PATH, "allocations", hashlib.sha1(key.encode()).hexdigest()[:16] + ".pkl")
+            if os.path.exists(cache):
+                with open(cache, "rb") as f:
+                    saved = pickle.load(f)
+                by_name = self.rpcs
+                return [RPCAllocation(by_name[name], mesh, par) for name, mesh, par in saved]
+        allocs = search_rpc_allocations(self.global_device_mesh, list(self.rpcs.values()), self.models, **kw)
+        if cache is not None:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            with open(cache, "wb") as f:
+                pickle.dump([(a.rpc.name, a.device_mesh, a.parallel) for a in allocs], f)
+        return allocs
 
     def _get_rpc_allocations(self) -> List[RPCAllocation]:
         rpcs, mesh = self.rpcs, self.global_device_mesh
@@ -226,7 +249,8 @@ class CommonExperimentConfig(Experiment):
                 sid = ModelShardID.from_parallelism_rank(a.rpc.model_name, topo, r)
                 shards_of[ranks[r]].append(StandaloneModelShardAbstraction(
                     id=sid, model=model, backend=backend,
-                    eval_dataset=(self.eval_datasets[0] if self.eval_datasets else None), eval_bs=128))
+                    eval_dataset=(self.eval_datasets[0] if self.eval_datasets else None),
+                    eval_bs=int(getattr(getattr(self, "dataset", None), "valid_bs_n_seqs", 128) or 128)))
                 if a is src_rpc and sid.tp_rank == 0 and sid.pp_rank == topo.get_dim("pipe") - 1:
                     data_owner_workers.add(ranks[r])
         for i in range(self.n_workers):

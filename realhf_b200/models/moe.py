@@ -191,7 +191,7 @@ def moe_forward(model, i: int, h: torch.Tensor) -> torch.Tensor:
             0, tok[sel], (y_sorted * w_sorted[sel].to(y_sorted.dtype).unsqueeze(-1)).to(h.dtype))
         return TP.reduce_from_tp(out, ctx)
     x_sorted = h.index_select(0, tok)
-    if _use_grouped_kernel(x_sorted, w_gu, w_dn):
+    if mcfg.use_grouped_gemm and _use_grouped_kernel(x_sorted, w_gu, w_dn):   # use_grouped_gemm=False: one GEMM pair per expert
         y_sorted = grouped_mlp_device(x_sorted, _count_experts(flat_e, E), w_gu, w_dn, c.activation_function)
     else:
         counts = torch.bincount(flat_e, minlength=E).tolist()

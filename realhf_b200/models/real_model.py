@@ -108,6 +108,10 @@ class ReaLModel(nn.Module):
     def __init__(self, config: ReaLModelConfig, ctx: Optional[ParallelContext] = None, dtype=torch.bfloat16,
                  device="cpu", layer_range: Optional[Tuple[int, int]] = None):
         super().__init__()
+        if not config.do_layernorm_before:
+            # the option exists in the reference's config for OPT-350m-style post-LN blocks; none of the registered model families
+            # uses it, and silently running pre-LN instead would load such a checkpoint into the wrong network
+            raise NotImplementedError("do_layernorm_before=False (post-LN blocks) is not supported")
         self.config = config
         self.ctx = ctx if ctx is not None else ParallelContext.single()
         self.dtype = dtype

@@ -126,6 +126,7 @@ class ModelWorker:
             self.models[name] = model
             self.backends[name] = model_api.make_backend(shard.backend)
             self._eval_dataset_cfg = shard.eval_dataset
+            self._eval_bs = int(getattr(shard, "eval_bs", 128) or 128)
         for rpc in cfg.model_rpcs:
             if rpc.model_name in self.models:
                 self.interfaces[rpc.name] = model_api.make_interface(rpc.interface_impl)
@@ -135,7 +136,8 @@ class ModelWorker:
         if cfg.datasets:
             src = next(r for r in cfg.model_rpcs if r.is_src)
             ctx = self.ctxs[src.model_name]
-            cache_root = os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "..", "..", "cache") if os.environ.get("REAL_DATASET_CACHE", "0") == "1" else None
+            use_cache = cfg.use_dataset_cache or os.environ.get("REAL_DATASET_CACHE", "0") == "1"   # tokenised samples cached on disk
+            cache_root = os.path.join(constants.run_dirs(self.exp, self.trial)["log"], "..", "..", "cache") if use_cache else None
             ds = [data_api.make_dataset(d, cfg.seed, ctx.dp_rank, ctx.dp_size, cfg.tokenizer_name_or_path, self.exp, self.trial, cache_root)
                   for d in cfg.datasets]
             dataset = ds[0] if len(ds) == 1 else torch.utils.data.ConcatDataset(ds)
@@ -348,7 +350,10 @@ class ModelWorker:
         if h == "clear_data_cache":
             for i in req.data:
                 self.data_storage.pop(i, None)
-            if self.device.type == "cuda" and self.cfg.cuda_cache_cleanliness:
+            self._n_cache_clears = getattr(self, "_n_cache_clears", 0) + 1
+            freq = self.cfg.cuda_cache_clear_freq
+            if self.device.type == "cuda" and (self.cfg.cuda_cache_cleanliness or (freq and self._n_cache_clears % freq == 0)):
+                # `cuda_cache_cleanliness`: after every step; otherwise every `cuda_cache_clear_freq` steps (reference: cache_clear_freq)
                 torch.cuda.empty_cache()
                 self._dirty_cache = False
             if monitor.TIME_MARK_DB:
@@ -384,7 +389,8 @@ class ModelWorker:
                 return {}
             ctx = self.ctxs[name]
             ds = data_api.make_dataset(self._eval_dataset_cfg, self.cfg.seed, ctx.dp_rank, ctx.dp_size, self.cfg.tokenizer_name_or_path)
-            dl = data_api.make_dataloader("packed_eval", ds)
+            # `dataset.valid_bs_n_seqs` sequences per evaluation batch over the whole DP group (reference: eval_bs of the shard)
+            dl = data_api.make_dataloader("packed_eval", ds, batch_size=max(1, self._eval_bs // ctx.dp_size))
             return self.interfaces[rpc.name].evaluate(model, dl)
         if h in ("generate", "inference", "train_step"):
             self._maybe_inject_fault(h)

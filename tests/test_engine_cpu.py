@@ -249,3 +249,28 @@ def test_w8a8_decode_wiring_under_cpu_emulation(fam, monkeypatch):
     d = torch.stack(diffs)
     assert d[:, 0].max().item() < 1e-4            # the first token comes from the unquantised prefill
     assert 1e-6 < d[:, 1:].mean().item() < 0.3, d  # the rest from the quantised decode: close, and not identical
+
+
+def test_loss_scale_hysteresis_and_unsupported_post_ln():
+    """fp16-style dynamic loss scaling: `hysteresis` overflowing steps are tolerated before the scale halves; the credit refills when the
+    scale grows.  `do_layernorm_before=False` is rejected instead of being ignored."""
+    import dataclasses as dc
+
+    from realhf_b200.engine.optim import FlatAdamW, OptimizerConfig
+    cfg = hf_io.family("llama").make_test_config()
+    m = ReaLModel(cfg, dtype=torch.float32).instantiate(seed=1)
+    opt = FlatAdamW(m, OptimizerConfig(grad_dtype="fp32", hysteresis=2, loss_scale_window=3, initial_loss_scale=1024.0, min_loss_scale=1.0))
+    opt.loss_scale = 1024.0
+
+    def step(overflow):
+        opt._skip.fill_(bool(overflow))
+        opt._update_loss_scale()
+        return opt.loss_scale
+
+    assert step(True) == 1024.0          # first overflow: tolerated
+    assert step(True) == 512.0           # second: halve, credit back to 2
+    assert step(True) == 512.0
+    assert step(False) == 512.0 and step(False) == 512.0 and step(False) == 1024.0   # window of 3 good steps doubles it
+    assert step(True) == 1024.0          # the credit was refilled by the growth
+    with pytest.raises(NotImplementedError):
+        ReaLModel(dc.replace(cfg, do_layernorm_before=False), dtype=torch.float32)

@@ -170,3 +170,22 @@ def test_layer_profiler_rows_feed_the_cost_model():
     assert one.time_us >= cfg.n_layers * blk and two.time_us < one.time_us
     gen = estimate_mfc(T.GENERATE, 4, shape, 1, 1, 1, HardwareModel(), tb, None, 8, 8)
     assert gen.breakdown["decode_step"] >= cfg.n_layers * tb.time_us("block", "decode", 4, 12) * 0.99
+
+
+def test_allocation_use_cache_reuses_the_stored_search_result(tmp_path, monkeypatch):
+    from realhf_b200.base import constants
+    from realhf_b200.search import engine
+    monkeypatch.setattr(constants, "PROFILER_CACHE_PATH", str(tmp_path / "profiler"))
+    cfg = _ppo()
+    cfg.allocation_mode, cfg.allocation_use_cache = "search", True
+    calls = []
+    real = engine.search_rpc_allocations
+    monkeypatch.setattr(engine, "search_rpc_allocations", lambda *a, **k: calls.append(1) or real(*a, **dict(k, time_limit_s=0.5)))
+    first = cfg._get_rpc_allocations()
+    second = cfg._get_rpc_allocations()
+    assert len(calls) == 1                                   # the second resolution came from the cache file
+    assert [(a.rpc.name, a.device_mesh.global_ranks(), a.parallel) for a in first] == [(a.rpc.name, a.device_mesh.global_ranks(), a.parallel) for a in second]
+    other = _ppo(n_seqs=64)                                   # a different problem does not hit the same entry
+    other.allocation_mode, other.allocation_use_cache = "search", True
+    other._get_rpc_allocations()
+    assert len(calls) == 2
