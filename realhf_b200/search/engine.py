@@ -205,7 +205,9 @@ def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: 
     h = host()
     if h is None:
         raise RuntimeError("allocation search needs the native host extension: run `python -m realhf_b200.ops.build`")
-    hw = hw or HardwareModel.from_measured()
+    if hw is None:
+        hw = HardwareModel.from_measured()
+        hw.mem_cap = min(hw.mem_cap, float(device_mesh.gpu_memory_capacity))   # a mesh may declare less than the cluster spec
     prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw)
     results = h.multi_mcmc_search(prob, [0.5, 2.0, 8.0, 32.0], time_limit_s, 1, 10)
     if refine_realloc:
