@@ -93,13 +93,19 @@ class MasterWorker:
             return
         loop = asyncio.get_running_loop()
         futs: Dict[int, List[asyncio.Future]] = {i: [] for i in range(len(batch))}
-        for phase in (0, 1):
-            for i, entry in enumerate(batch):
-                for p in entry[phase]:
-                    f = loop.create_future()
-                    self._pending[p.request_id] = f
-                    self.stream.post(p)
-                    futs[i].append(f)
+        try:
+            for phase in (0, 1):
+                for i, entry in enumerate(batch):
+                    for p in entry[phase]:
+                        f = loop.create_future()
+                        self._pending[p.request_id] = f
+                        self.stream.post(p)
+                        futs[i].append(f)
+        except Exception as e:   # a timer callback has no caller to raise to: hand the failure to the MFC coroutines, which end the walk
+            for entry in batch:
+                if not entry[2].done():
+                    entry[2].set_exception(RuntimeError(f"could not post the requests of an MFC: {e!r}"))
+            return
         for i, entry in enumerate(batch):
             asyncio.ensure_future(self._collect(futs[i], entry[2]))
 
