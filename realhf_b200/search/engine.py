@@ -120,8 +120,44 @@ def profile_table_for(mcfg: ModelTrainEvalConfig):
     return ProfileTable.find(name)
 
 
+class MFCProfile:
+    """Measured whole-MFC times from `quickstart profile` (`experiments/profile.py`: rows {handle, interface, layout "d2m2p1", bs,
+    seqlen, n_mbs, secs}).  An exact hit -- same handle, layout, global batch and sequence length -- replaces the cost model's
+    time for that candidate (the reference's search consumes its profile statistics the same way, by exact key:
+    search_engine/estimate.py:263-360); everything else stays estimated."""
+
+    _HANDLE = {ModelInterfaceType.GENERATE: "generate", ModelInterfaceType.INFERENCE: "inference", ModelInterfaceType.TRAIN_STEP: "train_step"}
+
+    def __init__(self, rows: List[dict]):
+        self.rows = [r for r in rows if "secs" in r and "layout" in r]
+        self._idx = {}
+        for r in self.rows:
+            key = (r["handle"], r["layout"], int(r["bs"]), int(r["seqlen"]))
+            best = self._idx.get(key)
+            if best is None or r["secs"] < best["secs"]:      # several n_mbs for one point: the launcher can pick the fastest
+                self._idx[key] = r
+
+    @classmethod
+    def find(cls) -> Optional["MFCProfile"]:
+        p = os.environ.get("REAL_MFC_PROFILE", "")
+        if p and os.path.exists(p):
+            with open(p) as f:
+                return cls(json.load(f))
+        return None
+
+    def time_us(self, rpc: MFCDef, par: ParallelismConfig, seq_len: int, gen_len: int) -> Optional[float]:
+        handle = self._HANDLE[rpc.interface_type]
+        sl = seq_len if rpc.interface_type == ModelInterfaceType.GENERATE else seq_len + gen_len
+        lay = f"d{par.data_parallel_size}m{par.model_parallel_size}p{par.pipeline_parallel_size}"
+        r = self._idx.get((handle, lay, int(rpc.n_seqs), int(sl)))
+        if r is None or (r.get("interface") and rpc.interface_impl is not None and r["interface"] != rpc.interface_impl.type_):
+            return None
+        return float(r["secs"]) * 1e6
+
+
 def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int, gen_len: int,
-                  n_ppo_minibatches: int, hw: HardwareModel, max_cands: int = 1000, use_profile_tables: bool = True):
+                  n_ppo_minibatches: int, hw: HardwareModel, max_cands: int = 1000, use_profile_tables: bool = True,
+                  mfc_profile: Optional[MFCProfile] = None):
     """Candidates per MFC = every (sub-mesh, dp x tp x pp) that fits the batch, costed by the table-driven model
     (`search/cost_model.py::estimate_mfc`) when the role's model has a layer-profile table, else by the roofline formulas above."""
     from realhf_b200.search.cost_model import CommModel, estimate_mfc
@@ -153,6 +189,10 @@ def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelT
                     t, st, ac = c.time_us, c.mem_static, c.mem_active
                 else:
                     t, st, ac = estimate(r, shapes[r.role], par, hw, seq_len, gen_len, n_mini, r.role in trainable)
+                if mfc_profile is not None:
+                    measured = mfc_profile.time_us(r, par, seq_len, gen_len)
+                    if measured is not None:
+                        t = measured
                 cands.append((mi, par.data_parallel_size, par.model_parallel_size, par.pipeline_parallel_size, t, st, ac, par))
         cands.sort(key=lambda c: c[4])
         cands = cands[:max_cands]
@@ -201,14 +241,16 @@ def refine_with_planned_realloc(prob: dict, results: List[dict], hw: HardwareMod
 
 def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int = 128,
                            num_gen_tokens: int = 256, n_ppo_minibatches: int = 4, time_limit_s: float = 5.0,
-                           hw: Optional[HardwareModel] = None, return_details: bool = False, refine_realloc: bool = True):
+                           hw: Optional[HardwareModel] = None, return_details: bool = False, refine_realloc: bool = True,
+                           mfc_profile: Optional["MFCProfile"] = None):
     h = host()
     if h is None:
         raise RuntimeError("allocation search needs the native host extension: run `python -m realhf_b200.ops.build`")
     if hw is None:
         hw = HardwareModel.from_measured()
         hw.mem_cap = min(hw.mem_cap, float(device_mesh.gpu_memory_capacity))   # a mesh may declare less than the cluster spec
-    prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw)
+    prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw,
+                                     mfc_profile=mfc_profile if mfc_profile is not None else MFCProfile.find())
     results = h.multi_mcmc_search(prob, [0.5, 2.0, 8.0, 32.0], time_limit_s, 1, 10)
     if refine_realloc:
         results, prob = refine_with_planned_realloc(prob, results, hw, device_mesh.n_gpus_per_node)

@@ -189,3 +189,27 @@ def test_allocation_use_cache_reuses_the_stored_search_result(tmp_path, monkeypa
     other.allocation_mode, other.allocation_use_cache = "search", True
     other._get_rpc_allocations()
     assert len(calls) == 2
+
+
+def test_measured_mfc_times_from_the_profile_experiment_override_the_estimate():
+    """Rows of `quickstart profile` (handle, layout, global batch, sequence length -> seconds) replace the modelled time of exactly
+    those candidates; the search then follows the measurement."""
+    from realhf_b200.search.engine import HardwareModel, MFCProfile, build_problem, search_rpc_allocations
+    cfg = _ppo()
+    rpcs = list(cfg.rpcs.values())
+    hw = HardwareModel()
+    base, table, _ = build_problem(cfg.global_device_mesh, rpcs, cfg.models, 128, 512, 4, hw)
+    # claim that tensor-parallel generation over all 8 GPUs takes 1 ms, measured
+    rows = [dict(handle="generate", interface="ppo_actor", layout="d1m8p1", bs=128, seqlen=128, n_mbs=1, secs=0.001),
+            dict(handle="generate", interface="ppo_actor", layout="d1m8p1", bs=128, seqlen=128, n_mbs=2, secs=0.5),     # slower n_mbs: ignored
+            dict(handle="train_step", interface="sft", layout="d8m1p1", bs=128, seqlen=640, n_mbs=1, secs=0.001)]     # other interface: ignored
+    prof = MFCProfile(rows)
+    prob, table2, _ = build_problem(cfg.global_device_mesh, rpcs, cfg.models, 128, 512, 4, hw, mfc_profile=prof)
+    gi = next(i for i, r in enumerate(rpcs) if r.name == "actor_gen")
+    hit = [c for c in table2[gi] if (c[1], c[2], c[3]) == (1, 8, 1) and c[0] == 0]
+    assert hit and hit[0][4] == pytest.approx(1000.0)
+    ti = next(i for i, r in enumerate(rpcs) if r.name == "actor_train")
+    assert sorted(c[4] for c in table2[ti]) == sorted(c[4] for c in table[ti])          # the sft row did not touch a ppo_actor MFC
+    allocs = search_rpc_allocations(cfg.global_device_mesh, rpcs, cfg.models, seq_len=128, num_gen_tokens=512, time_limit_s=1.0, mfc_profile=prof)
+    gen = next(a for a in allocs if a.rpc.name == "actor_gen")
+    assert (gen.parallel.data_parallel_size, gen.parallel.model_parallel_size, gen.parallel.pipeline_parallel_size) == (1, 8, 1)
