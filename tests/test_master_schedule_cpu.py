@@ -161,5 +161,11 @@ def test_look_ahead_never_exceeds_the_window():
 
 
 def test_a_failing_mfc_stops_the_walk_instead_of_hanging_it():
+    m = SimMaster(_master_cfg(2), 4, fail_at=("critic_train", 1))
     with pytest.raises(RuntimeError, match="injected failure"):
-        _run(window=2, n_steps=4, fail_at=("critic_train", 1))
+        m.run()
+    # recover bookkeeping: step 0 is finalised, step 1 failed; the generation of step 2 may already have taken its prompts
+    # (look-ahead), but nothing was trained on them: only the prompts of finalised steps count as consumed
+    assert m.step == 1
+    assert sorted(m._consumed_ids_this_epoch()) == sorted(m._ids_by_step[0]) and len(m._ids_by_step[0]) == BS
+    assert 1 in m._ids_by_step and set(m._ids_by_step[1]).isdisjoint(m._ids_by_step[0])
