@@ -60,7 +60,7 @@ setup(
     long_description_content_type="text/markdown",
     python_requires=">=3.10",
     packages=find_packages(include=["realhf_b200", "realhf_b200.*"]),
-    package_data={"realhf_b200": ["_C/*.so", "ops/csrc/*.cu", "ops/csrc/*.cuh", "ops/csrc/*.cpp", "ops/csrc/host/*"]},
+    package_data={"realhf_b200": ["_C/*.so", "ops/csrc/*.cu", "ops/csrc/*.cuh", "ops/csrc/*.cpp", "ops/csrc/host/*", "search/tables/*.json"]},
     install_requires=["torch>=2.5", "numpy", "networkx", "pyzmq", "psutil", "transformers", "pybind11"],
     extras_require={"attention-lib": ["flash-attn"], "logging": ["tensorboard", "wandb"]},
     entry_points={"console_scripts": ["realhf-b200=realhf_b200.apps.quickstart:main", "realhf-b200-ctl=realhf_b200.apps.main:main"]},
