@@ -116,3 +116,29 @@ def test_per_worker_and_volume_only_plans_agree_with_the_full_plan():
         assert [(t.src_worker, t.dst_worker) for t in mine.transfers] == [(t.src_worker, t.dst_worker) for t in want]
         for a, b in zip(mine.transfers, want):
             assert list(a.src_off) == list(b.src_off) and list(a.dst_off) == list(b.dst_off) and list(a.lens) == list(b.lens)
+
+
+@pytest.mark.parametrize("fam", ["mixtral", "qwen2", "gemma"])
+@pytest.mark.parametrize("pair", [((1, 1, 1), (1, 1, 2)), ((1, 2, 2), (2, 1, 1)), ((2, 1, 2), (1, 2, 4)), ((1, 1, 4), (1, 2, 2)), ((1, 1, 2), (4, 1, 1))])
+def test_plans_of_moe_gqa_and_tied_embedding_families(fam, pair):
+    """Expert tensors ([E, 2F, H] / [E, H, F], F-sharded over TP), grouped-query attention with biases (qwen2) and tied embeddings
+    (gemma): the planned segments reproduce the directly sharded destination and write every element exactly once."""
+    cfg = hf_io.family(fam).make_test_config()
+    src_layout, dst_layout = pair
+    s_topo, src = build_shards(cfg, src_layout, seed=5)
+    d_topo, dst_ref = build_shards(cfg, dst_layout, seed=5)
+    ns, nd = s_topo.world_size(), d_topo.world_size()
+    src_workers, dst_workers = list(range(ns)), list(range(8 - nd, 8))
+    plan = realloc.derive_plan(cfg, s_topo, src_workers, d_topo, dst_workers)
+    dst_flat = {w: torch.full((plan.dst_numel[w],), float("nan")) for w in dst_workers}
+    hits = {w: torch.zeros(plan.dst_numel[w], dtype=torch.int32) for w in dst_workers}
+    for t in plan.transfers:
+        s = src[src_workers.index(t.src_worker)].flat_param.data
+        for so, do, ln in zip(t.src_off, t.dst_off, t.lens):
+            dst_flat[t.dst_worker][do:do + ln] = s[so:so + ln]
+            hits[t.dst_worker][do:do + ln] += 1
+    for r in range(nd):
+        ref, got = dst_ref[r], dst_flat[dst_workers[r]]
+        for name, slot in ref.slots.items():
+            torch.testing.assert_close(got[slot.offset:slot.offset + slot.numel].view(slot.shape), ref.p[name].data, rtol=0, atol=0)
+            assert int(hits[dst_workers[r]][slot.offset:slot.offset + slot.numel].max()) == 1, name
