@@ -169,3 +169,27 @@ def test_a_failing_mfc_stops_the_walk_instead_of_hanging_it():
     assert m.step == 1
     assert sorted(m._consumed_ids_this_epoch()) == sorted(m._ids_by_step[0]) and len(m._ids_by_step[0]) == BS
     assert 1 in m._ids_by_step and set(m._ids_by_step[1]).isdisjoint(m._ids_by_step[0])
+
+
+def test_the_allocation_search_simulator_predicts_the_masters_step_time():
+    """The native list-scheduling simulator behind `allocation_mode=search` (mesh exclusivity, DFG edges, "users of a role wait for
+    its train step" across iterations) and the real master walking the same allocation over simulated workers must agree on the
+    steady-state step time -- otherwise the search optimises a runtime that does not exist."""
+    from realhf_b200.ops import host
+    h = host()
+    if h is None:
+        pytest.skip("host extension not built")
+    names = list(DUR)
+    role = dict(actor_gen=0, actor_train=0, ref_inf=1, rew_inf=2, critic_inf=3, critic_train=3)
+    kind = dict(actor_gen=0, rew_inf=1, ref_inf=1, critic_inf=1, actor_train=2, critic_train=2)
+    mesh = dict(actor_gen=0, actor_train=0, ref_inf=0, rew_inf=1, critic_inf=1, critic_train=1)
+    idx = {n: i for i, n in enumerate(names)}
+    edges = [(idx["actor_gen"], idx[n]) for n in names if n != "actor_gen"]
+    edges += [(idx[a], idx[b]) for a in ("rew_inf", "ref_inf", "critic_inf") for b in ("actor_train", "critic_train")]
+    prob = dict(n_gpus=4, mem_cap=1e18, link_bw=1e18, n_iters=3, role_bytes=[0.0] * 4, meshes=[[0, 1], [2, 3]], edges=edges,
+                realloc_latency_us=0.0,
+                rpcs=[dict(name=n, role=role[n], kind=kind[n], cands=[(mesh[n], 2, 1, 1, DUR[n] * 1e6, 0.0, 0.0)]) for n in names])
+    predicted = h.simulate_allocation(prob, [0] * len(names))["time_us"] / 1e6
+    m, times, _ = _run(window=2, n_steps=5)
+    steady = sorted(times[1:])[len(times[1:]) // 2]
+    assert steady == pytest.approx(predicted, rel=0.12), (predicted, times)
