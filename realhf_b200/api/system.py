@@ -48,9 +48,10 @@ class WorkerInformation:
     worker_type: str = ""
     worker_index: int = -1
     worker_count: int = 0
-    worker_tag: Optional[str] = None
-    host_key: Optional[str] = None
-    watch_keys: Union[str, List[str], None] = None
+    worker_tag: Optional[str] = None      # free-form label (reference schema; shows up in the pickled config only)
+    host_key: Optional[str] = None        # reference schema: name-resolve key of the worker's host (workers publish their addresses
+                                          # through the stream / process-group keys instead)
+    watch_keys: Union[str, List[str], None] = None   # more keys whose disappearance ends the worker (besides the controller's lease)
 
     def system_setup(self, experiment_name, trial_name, worker_type, worker_index, worker_count):
         self.experiment_name, self.trial_name = experiment_name, trial_name
@@ -91,7 +92,7 @@ class ModelWorker:
     msid2mwid: Optional[Dict[ModelShardID, int]] = None
     data_transfer_pairs: Optional[List[Tuple[ModelName, ModelName]]] = None
     sync_param_pairs: Optional[List[Tuple[ModelName, ModelName]]] = None
-    profile_mode: bool = False
+    profile_mode: bool = False   # reference schema: its `profile` experiment runs inside the workers; here it runs in-process (experiments/profile.py)
     worker_info: Optional[WorkerInformation] = None
 
     def __post_init__(self):
@@ -122,7 +123,7 @@ class TasksGroup:
 class ExperimentScheduling:
     model_worker: TasksGroup
     master_worker: TasksGroup
-    controller_image: Optional[str] = None
+    controller_image: Optional[str] = None   # reference schema (container of the controller job; the launcher runs where it is started)
 
 
 @dataclasses.dataclass

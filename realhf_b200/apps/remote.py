@@ -31,15 +31,19 @@ def status_ttl() -> float:
     return float(os.environ.get("REAL_STATUS_TTL", "120"))
 
 
-def _watch_controller(exp: str, trial: str):
+def _watch_controller(exp: str, trial: str, extra_keys=None):
     """Exit when the launcher's liveness key disappears (controller killed / its node lost): orphaned workers would otherwise
-    hold their GPUs forever (reference: `watch_names`, system/worker_base.py:660-666)."""
+    hold their GPUs forever (reference: `watch_names`, system/worker_base.py:660-666).  `extra_keys`: the worker's
+    `WorkerInformation.watch_keys` -- more name-resolve keys whose disappearance ends this worker."""
     ttl = status_ttl()
+    keys = [status_key(exp, trial, "controller", 0)]
+    if extra_keys:
+        keys += [extra_keys] if isinstance(extra_keys, str) else list(extra_keys)
 
     def _die():
-        logger.error("the controller's liveness key expired: exiting")
+        logger.error(f"a watched liveness key expired ({keys}): exiting")
         os._exit(3)
-    name_resolve.watch_names([status_key(exp, trial, "controller", 0)], _die, poll_frequency=max(0.5, ttl / 3), wait_timeout=300)
+    name_resolve.watch_names(keys, _die, poll_frequency=max(0.5, ttl / 3), wait_timeout=300)
 
 
 def main_worker(args):
@@ -58,7 +62,9 @@ def main_worker(args):
     key = status_key(args.experiment_name, args.trial_name, args.worker_type, args.jobstep_id)
     name_resolve.add(key, "RUNNING", replace=True, keepalive_ttl=status_ttl())
     if os.environ.get("REAL_WATCH_CONTROLLER", "1") == "1":
-        _watch_controller(args.experiment_name, args.trial_name)
+        wcfg = cfg.model_worker[args.jobstep_id] if args.worker_type == "model_worker" else cfg.master_worker[0]
+        info = getattr(wcfg, "worker_info", None)
+        _watch_controller(args.experiment_name, args.trial_name, getattr(info, "watch_keys", None))
     try:
         if args.worker_type == "model_worker":
             from realhf_b200.system.model_worker import ModelWorker
