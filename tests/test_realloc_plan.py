@@ -142,3 +142,45 @@ def test_plans_of_moe_gqa_and_tied_embedding_families(fam, pair):
         for name, slot in ref.slots.items():
             torch.testing.assert_close(got[slot.offset:slot.offset + slot.numel].view(slot.shape), ref.p[name].data, rtol=0, atol=0)
             assert int(hits[dst_workers[r]][slot.offset:slot.offset + slot.numel].max()) == 1, name
+
+
+def test_interval_sweep_and_coalescing_against_brute_force():
+    """`_uncovered` (linear sweep of sorted segments against a sorted cover) and `_coalesce_arrays` on random inputs, compared
+    element by element with a set-based reference."""
+    import random
+
+    import numpy as np
+    rng = random.Random(0)
+    for _ in range(1500):
+        cov, cov_set = [], set()
+        for _round in range(3):
+            segs, pos = [], 0
+            for _k in range(rng.randint(0, 6)):
+                pos += rng.randint(0, 5)
+                ln = rng.randint(1, 6)
+                segs.append((rng.randint(0, 100), pos, ln))
+                pos += ln
+            got = realloc._uncovered(list(segs), cov)
+            want = []
+            for so, do, ln in sorted(segs, key=lambda t: t[1]):
+                for x in range(do, do + ln):
+                    if x not in cov_set:
+                        cov_set.add(x)
+                        want.append((x, so + x - do))
+            assert sorted((d + i, s + i) for s, d, l in got for i in range(l)) == sorted(want)
+            assert all(cov[i][1] < cov[i + 1][0] for i in range(len(cov) - 1))           # sorted, disjoint, maximal
+            assert {x for a, b in cov for x in range(a, b)} == cov_set
+    for _ in range(300):
+        n = rng.randint(1, 12)
+        so, do, ln, s, d = [], [], [], 0, 0
+        for _k in range(n):
+            if rng.random() < 0.5:        # a gap on one side breaks adjacency
+                s += rng.randint(1, 3)
+            if rng.random() < 0.3:
+                d += rng.randint(1, 3)
+            l = rng.randint(1, 4)
+            so.append(s); do.append(d); ln.append(l)
+            s += l; d += l
+        a, b, c = realloc._coalesce_arrays(np.array(so), np.array(do), np.array(ln))
+        assert sorted((x + i, y + i) for x, y, l in zip(a, b, c) for i in range(l)) == sorted((x + i, y + i) for x, y, l in zip(so, do, ln) for i in range(l))
+        assert all(not (a[i] + c[i] == a[i + 1] and b[i] + c[i] == b[i + 1]) for i in range(len(c) - 1))   # nothing left to merge
