@@ -251,3 +251,35 @@ def test_bench_clock_sampler_round_robin_with_a_fake_nvml(monkeypatch):
     assert out["gpus"] == 4 and out["gpus_sampled"] == 4 and out["n_samples"] == len(calls) >= 8
     assert out["sm_max_mhz"] == 1965.0 and 1870.0 <= out["sm_mhz"] <= 1900.0 and out["reasons"] == ["sw_power_cap"]
     assert bench._NoSampler().stop() is None
+
+
+def test_bench_driver_contract_without_a_gpu():
+    """What the round driver relies on and what can be checked on CPU: `--impl reference` prints ONE JSON line with
+    `"impl": "reference"` and exits 0 (from rank 0 only when launched through torchrun), the default flags are the documented ones,
+    and the generation-layout choice is made by the allocation search's cost model for every node size the driver runs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bench = os.path.join(root, "bench.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    p = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "8", "--steps", "2", "--warmup", "3"], capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and ("unavailable" in out or "value" in out)
+    p1 = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "8"], capture_output=True, text=True, timeout=300,
+                        env=dict(env, RANK="3", LOCAL_RANK="3", WORLD_SIZE="8"))
+    assert p1.returncode == 0 and not [l for l in p1.stdout.splitlines() if l.startswith("{")]
+    h = subprocess.run([sys.executable, bench, "--help"], capture_output=True, text=True, timeout=300, env=env)
+    assert h.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--runtime", "--allocation", "--optimizer"):
+        assert flag in h.stdout
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_contract", bench)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for world in (1, 2, 4, 8):
+        c = mod.choose_gen_tp(world, 128, 128, 512, 32)
+        assert c["best"] in c["pred_s"] and all(world % tp == 0 for tp in c["pred_s"])
