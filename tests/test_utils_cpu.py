@@ -283,3 +283,23 @@ def test_bench_driver_contract_without_a_gpu():
     for world in (1, 2, 4, 8):
         c = mod.choose_gen_tp(world, 128, 128, 512, 32)
         assert c["best"] in c["pred_s"] and all(world % tp == 0 for tp in c["pred_s"])
+
+
+def test_graft_entry_points_exist_and_the_native_libraries_load_without_a_gpu():
+    """`__graft_entry__.build()` is the driver's "does it build" check (nvcc cross-compiles sm_100a without a GPU) and `smoke()` its
+    first GPU step: both must exist; the built libraries must load on a CPU-only machine and carry tcgen05 / TMA code."""
+    import importlib.util
+    import inspect
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("graft_entry_for_test", os.path.join(root, "__graft_entry__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert callable(mod.build) and callable(mod.smoke)
+    assert not inspect.signature(mod.build).parameters and not inspect.signature(mod.smoke).parameters
+    from realhf_b200 import ops
+    from realhf_b200.ops import build as B
+    if not B.OPS_LIB.exists():
+        pytest.skip("kernels not built in this checkout (run python -m realhf_b200.ops.build)")
+    assert ops.lib() is not None and ops.host() is not None
+    sass = B.sass_summary()
+    assert sass["UTCHMMA"] > 0 and sass["UTMALDG"] > 0 and sass["LDTM"] > 0 and sass["HMMA"] == 0     # tcgen05 + TMA + TMEM loads, no legacy mma
