@@ -112,7 +112,8 @@ class CommonExperimentConfig(Experiment):
         the search depends on (cluster shape, MFCs and batch sizes, model families / sizes / paths, sequence lengths), and reused
         by later launches of the same problem (reference: `allocation_use_cache`, experiments/common/common.py:330-350)."""
         from realhf_b200.search.engine import search_rpc_allocations
-        kw = dict(seq_len=self.max_prompt_len or 1024, **self.search_kwargs)
+        kw = dict(seq_len=self.max_prompt_len or 1024, cross_step_overlap=int(getattr(self.exp_ctrl, "max_inflight_steps", 2) or 1) > 1,
+                  **self.search_kwargs)
         cache = None
         if self.allocation_use_cache:
             import hashlib

@@ -242,7 +242,7 @@ def refine_with_planned_realloc(prob: dict, results: List[dict], hw: HardwareMod
 def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelTrainEvalConfig], seq_len: int = 128,
                            num_gen_tokens: int = 256, n_ppo_minibatches: int = 4, time_limit_s: float = 5.0,
                            hw: Optional[HardwareModel] = None, return_details: bool = False, refine_realloc: bool = True,
-                           mfc_profile: Optional["MFCProfile"] = None):
+                           mfc_profile: Optional["MFCProfile"] = None, cross_step_overlap: bool = True):
     h = host()
     if h is None:
         raise RuntimeError("allocation search needs the native host extension: run `python -m realhf_b200.ops.build`")
@@ -251,6 +251,9 @@ def search_rpc_allocations(device_mesh: DeviceMesh, rpcs: List[MFCDef], models: 
         hw.mem_cap = min(hw.mem_cap, float(device_mesh.gpu_memory_capacity))   # a mesh may declare less than the cluster spec
     prob, table, sub = build_problem(device_mesh, rpcs, models, seq_len, num_gen_tokens, n_ppo_minibatches, hw,
                                      mfc_profile=mfc_profile if mfc_profile is not None else MFCProfile.find())
+    # the master walks the graph with a look-ahead of one step (`exp_ctrl.max_inflight_steps=2`): the simulator then scores the
+    # steady state of two overlapping iterations; with a barrier after every step (`=1`) one traversal is the whole story
+    prob["n_iters"] = 2 if cross_step_overlap else 1
     results = h.multi_mcmc_search(prob, [0.5, 2.0, 8.0, 32.0], time_limit_s, 1, 10)
     if refine_realloc:
         results, prob = refine_with_planned_realloc(prob, results, hw, device_mesh.n_gpus_per_node)
