@@ -303,3 +303,21 @@ def test_graft_entry_points_exist_and_the_native_libraries_load_without_a_gpu():
     assert ops.lib() is not None and ops.host() is not None
     sass = B.sass_summary()
     assert sass["UTCHMMA"] > 0 and sass["UTMALDG"] > 0 and sass["LDTM"] > 0 and sass["HMMA"] == 0     # tcgen05 + TMA + TMEM loads, no legacy mma
+
+
+def test_bench_json_line_carries_every_key_of_the_driver_contract():
+    """Static check of the JSON line the SPMD arm prints (it needs a GPU to run): all keys the round driver reads are there."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    main = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "main")
+    dicts = [n for n in ast.walk(main) if isinstance(n, ast.Dict)]
+    keysets = [{k.value for k in d.keys if isinstance(k, ast.Constant)} for d in dicts]
+    top = next(ks for ks in keysets if {"metric", "value", "unit"} <= ks)
+    assert {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "clocks", "e2e", "gpu_launches", "impl"} <= top
+    assert any({"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= ks for ks in keysets)             # e2e
+    assert any({"model", "global_batch", "seq_len", "parallelism"} <= ks for ks in keysets)                        # config
+    src = open(os.path.join(root, "bench.py")).read()
+    assert "pin_memory()" in src and "non_blocking=True" in src          # inputs come from pinned host memory inside the timed region
+    assert 'ap.add_argument("--warmup", type=int, default=3)' in src     # W >= 3 by default
