@@ -92,7 +92,8 @@ class ModelWorker:
     msid2mwid: Optional[Dict[ModelShardID, int]] = None
     data_transfer_pairs: Optional[List[Tuple[ModelName, ModelName]]] = None
     sync_param_pairs: Optional[List[Tuple[ModelName, ModelName]]] = None
-    profile_mode: bool = False   # reference schema: its `profile` experiment runs inside the workers; here it runs in-process (experiments/profile.py)
+    profile_mode: bool = False   # inputs of every MFC are fabricated by `ModelInterface.mock` (profiling through the full runtime; the
+                                 # `profile` quickstart experiment itself runs in-process, experiments/profile.py)
     worker_info: Optional[WorkerInformation] = None
 
     def __post_init__(self):

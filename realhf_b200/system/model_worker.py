@@ -399,6 +399,8 @@ class ModelWorker:
             inp = SequenceSample.gather([self.data_storage[i] for i in ids], keys=rpc.input_keys)
             if rpc.input_key_remap:
                 inp.remap_keys_(rpc.input_key_remap)
+            if self.cfg.profile_mode:   # profiling experiments: the interface fabricates the keys this handle needs from the ids alone
+                inp = self.interfaces[rpc.name].mock(h, model, inp)   # (reference: model_worker.py:740-741)
             t0 = time.perf_counter()
             if self.device.type == "cuda":
                 if h == "generate" and self.cfg.cuda_cache_cleanliness and getattr(self, "_dirty_cache", False):
