@@ -125,7 +125,8 @@ def _grad_pool_get(numel: int, dtype, device, symm_group=None):
     key = (dtype, str(device), id(symm_group) if symm_group is not None else None)
     ent = _GRAD_POOL.get(key)
     if ent is None or ent[0].numel() < numel:
-        assert ent is None, "grad pool must be sized by its largest user first (create the largest model's optimizer first)"
+        # A later, larger user (a bigger model, or the same model under a data-parallel degree with a coarser padding) gets a new
+        # buffer that also serves everybody after it; earlier users keep the smaller one they were given (correct, just not shared)
         ent = _alloc_flat(numel, dtype, device, symm_group)
         _GRAD_POOL[key] = ent
     return ent[0][:numel], ent[1]
