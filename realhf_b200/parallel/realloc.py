@@ -264,12 +264,24 @@ class ReallocExecutor:
     def dst_numel(self) -> Optional[int]:
         return self.plan.dst_numel.get(self.me)
 
+    def whole_local_copy(self) -> bool:
+        """This worker's part of the plan is ONE local copy of its entire source buffer onto its entire destination buffer, and
+        nothing arrives from peers: the destination shard IS the source shard (same tp / pp position, e.g. a dp4 generation
+        replica on half of the GPUs of a dp8 training layout).  The caller may then alias the buffers instead of copying."""
+        if self.recvs or len(self.local) != 1:
+            return False
+        t = self.local[0]
+        n = self.plan.dst_numel.get(self.me)
+        return len(t.lens) == 1 and int(t.src_off[0]) == 0 and int(t.dst_off[0]) == 0 and n is not None and int(t.lens[0]) == n
+
     def run(self, src_flat: Optional[torch.Tensor], dst_flat: Optional[torch.Tensor], eta: float = 1.0,
-            peer_dst_ptrs: Optional[Dict[int, int]] = None, group=None, notify: bool = False):
+            peer_dst_ptrs: Optional[Dict[int, int]] = None, group=None, notify: bool = False, skip_local: bool = False):
         """peer_dst_ptrs: dst worker -> device address of its destination flat buffer mapped into this process.
-        When given for every send, transfers are direct peer stores; else pack + isend/irecv + unpack."""
-        for pl in self.local_plans:
-            pl.run(src_flat, dst_flat, eta=eta)
+        When given for every send, transfers are direct peer stores; else pack + isend/irecv + unpack.
+        `skip_local`: the destination aliases the source on this worker (see `whole_local_copy`)."""
+        if not skip_local:
+            for pl in self.local_plans:
+                pl.run(src_flat, dst_flat, eta=eta)
         direct = peer_dst_ptrs is not None and all(t.dst_worker in peer_dst_ptrs for t in self.sends)
         if direct:
             for t, pl in zip(self.sends, self.direct_plans):

@@ -310,3 +310,32 @@ register_experiment("mysft", make)
     assert name in M.main(["find_config", "-r", "mys.*"])
     with pytest.raises(SystemExit):
         M.main(["start", "-e", "doesnotexist", "-f", "t0"])
+
+
+def test_generation_replica_on_a_sub_mesh_aliases_the_training_weights(tmp_path):
+    """actor_train dp2 on both workers, actor_gen dp1 on worker 1 only: the generation replica's shard on worker 1 IS the training
+    shard (tp = pp = 1), so the reallocation aliases the flat buffer instead of copying it; training still changes what is generated
+    from (the run completes, losses are finite, the alias is logged once)."""
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    actor, critic = str(tmp_path / "actor"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(actor, "llama")
+    fixtures.make_checkpoint(critic, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=32)
+    args = ["ppo", f"experiment_name=alias-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=2",
+            "allocation_mode=manual", f"dataset.path={data}", "dataset.train_bs_n_seqs=8", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=6", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=2",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=3"]
+    for role, path in (("actor", actor), ("ref", actor), ("critic", critic), ("rew", critic)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    args += ["actor_gen.parallel.data_parallel_size=1", "actor_gen.device_mesh=NODE01:1", "actor_train.parallel.data_parallel_size=2",
+             "critic_train.parallel.data_parallel_size=2", "critic_inf.parallel.data_parallel_size=2",
+             "ref_inf.parallel.data_parallel_size=2", "rew_inf.parallel.data_parallel_size=2"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=900)
+    log = _master_log(exp)
+    assert log.count("[actor_train]") == 3 and "benchmark finished" in log, log[-3000:]
+    w1 = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "model_worker-1")).read()
+    assert w1.count("aliased, no copy") == 1, w1[-3000:]
