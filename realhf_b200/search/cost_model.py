@@ -335,6 +335,12 @@ def realloc_time_us(cfg: ReaLModelConfig, src: Tuple[int, int, int], src_ranks: 
     if tuple(src) == tuple(dst) and list(src_ranks) == list(dst_ranks):
         return 0.0
     b = _plan_bytes(cfg, tuple(src), src_ranks, tuple(dst), dst_ranks)
+    if not b["send"] and not b["recv"]:
+        d_dp, d_tp, d_pp = dst
+        if d_tp == src[1] and d_pp == src[2]:
+            # every destination GPU already holds exactly its shard (same tp / pp position, only the dp degree or the set of GPUs
+            # differs): the runtime aliases the source's flat buffer, nothing is copied (system/model_worker.py::_param_realloc)
+            return comm.coll_latency_us
     gpus = set(b["local"]) | set(b["send"]) | set(b["recv"])
     cross_node = len({g // gpus_per_node for g in list(src_ranks) + list(dst_ranks)}) > 1
     link = comm.inter_node_bw if cross_node else comm.p2p_bw

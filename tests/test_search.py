@@ -109,6 +109,8 @@ def test_realloc_cost_comes_from_the_planner():
     # dp8 -> dp4 x tp2 on the same GPUs: every GPU copies its own half locally (read + write at HBM speed), no link traffic
     local = realloc_time_us(cfg, (8, 1, 1), g8, (4, 2, 1), g8, hw, cm)
     assert local == pytest.approx(cm.coll_latency_us + 2 * (n_bytes / 2) / hw.hbm_bw * 1e6, rel=0.02)
+    # dp8 -> dp4 on half of the same GPUs: the destination shard IS the source shard on every GPU, the runtime aliases it
+    assert realloc_time_us(cfg, (8, 1, 1), g8, (4, 1, 1), hi, hw, cm) == cm.coll_latency_us
     # dp4 on GPUs 0-3 -> dp4 on GPUs 4-7: a full copy over NVLink per destination GPU
     remote = realloc_time_us(cfg, (4, 1, 1), lo, (4, 1, 1), hi, hw, cm)
     assert remote == pytest.approx(cm.coll_latency_us + n_bytes / cm.p2p_bw * 1e6, rel=0.02)
