@@ -32,6 +32,7 @@ struct GpuSet {
   uint64_t w[2] = {0, 0};
   bool overlaps(const GpuSet& o) const { return (w[0] & o.w[0]) || (w[1] & o.w[1]); }
   bool equals(const GpuSet& o) const { return w[0] == o.w[0] && w[1] == o.w[1]; }
+  bool subset_of(const GpuSet& o) const { return !(w[0] & ~o.w[0]) && !(w[1] & ~o.w[1]); }
   void set(int i) { w[i >> 6] |= (1ull << (i & 63)); }
   bool test(int i) const { return (w[i >> 6] >> (i & 63)) & 1; }
   int count() const { return __builtin_popcountll(w[0]) + __builtin_popcountll(w[1]); }
@@ -103,7 +104,11 @@ SimResult simulate(const Problem& P, const std::vector<int>& choice) {
     const int t = train_of[P.rpcs[i].role];
     if (t >= 0 && t != i) {
       extra[i] = realloc_cost_us(P, P.rpcs[i].role, *c[t], *c[i]);
-      if (extra[i] > 0) extra_mem[i] = P.role_bytes[P.rpcs[i].role] / (double)(c[i]->tp * c[i]->pp);
+      // a replica with unsharded layers (tp = pp = 1 on both sides) on GPUs that all belong to the training mesh holds exactly the
+      // training shard: the runtime aliases the training buffer, the replica costs no memory (model_worker.py::_param_realloc)
+      const bool aliased = c[t]->tp == 1 && c[t]->pp == 1 && c[i]->tp == 1 && c[i]->pp == 1 &&
+                           P.meshes[c[i]->mesh].subset_of(P.meshes[c[t]->mesh]);
+      if (extra[i] > 0 && !aliased) extra_mem[i] = P.role_bytes[P.rpcs[i].role] / (double)(c[i]->tp * c[i]->pp);
     }
   }
   // ---- list scheduling over n_iters iterations

@@ -215,3 +215,17 @@ def test_measured_mfc_times_from_the_profile_experiment_override_the_estimate():
     allocs = search_rpc_allocations(cfg.global_device_mesh, rpcs, cfg.models, seq_len=128, num_gen_tokens=512, time_limit_s=1.0, mfc_profile=prof)
     gen = next(a for a in allocs if a.rpc.name == "actor_gen")
     assert (gen.parallel.data_parallel_size, gen.parallel.model_parallel_size, gen.parallel.pipeline_parallel_size) == (1, 8, 1)
+
+
+def test_simulator_does_not_charge_memory_for_an_aliased_replica():
+    """A tp = pp = 1 replica on GPUs of the training mesh aliases the training weights (system/model_worker.py::_param_realloc): the
+    memory model must not count a second copy, or the search would reject allocations that fit."""
+    h = host()
+    base = dict(n_gpus=4, mem_cap=100.0, link_bw=1e9, n_iters=1, role_bytes=[60.0], meshes=[[0, 1, 2, 3], [2, 3], [0, 1]], edges=[(0, 1)])
+    train = dict(name="train", role=0, kind=2, cands=[(0, 4, 1, 1, 10.0, 60.0, 10.0)])
+    sub = dict(name="gen", role=0, kind=0, cands=[(1, 2, 1, 1, 10.0, 0.0, 10.0), (1, 1, 2, 1, 10.0, 0.0, 10.0)])
+    prob = dict(base, rpcs=[sub, train])
+    aliased = h.simulate_allocation(prob, [0, 0])      # dp2 on GPUs 2-3 of a dp4 training mesh: same shard, no second copy
+    resharded = h.simulate_allocation(prob, [1, 0])    # tp2: a real replica of half the weights
+    assert aliased["max_mem"] == pytest.approx(60.0 + 10.0)
+    assert resharded["max_mem"] == pytest.approx(60.0 + 10.0 + 30.0)
