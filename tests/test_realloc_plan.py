@@ -184,3 +184,18 @@ def test_interval_sweep_and_coalescing_against_brute_force():
         a, b, c = realloc._coalesce_arrays(np.array(so), np.array(do), np.array(ln))
         assert sorted((x + i, y + i) for x, y, l in zip(a, b, c) for i in range(l)) == sorted((x + i, y + i) for x, y, l in zip(so, do, ln) for i in range(l))
         assert all(not (a[i] + c[i] == a[i + 1] and b[i] + c[i] == b[i + 1]) for i in range(len(c) - 1))   # nothing left to merge
+
+
+def test_whole_local_copy_is_detected_exactly_when_the_shards_coincide():
+    cfg = hf_io.family("llama").make_test_config()
+
+    def ex(src, sw, dst, dw, me):
+        plan = realloc.derive_plan(cfg, ProcessTopology(*src), sw, ProcessTopology(*dst), dw, for_worker=me)
+        return realloc.ReallocExecutor(plan, me, 4, "cpu")
+
+    assert ex((1, 2, 1), [0, 1], (1, 1, 1), [1], 1).whole_local_copy()            # dp2 -> dp1 on one of its GPUs: same shard
+    assert not ex((1, 2, 1), [0, 1], (1, 1, 1), [1], 0).whole_local_copy()        # worker 0 is not a destination at all
+    assert not ex((1, 1, 1), [0], (1, 1, 1), [1], 1).whole_local_copy()           # the weights come from another GPU
+    assert not ex((1, 2, 1), [0, 1], (1, 1, 2), [0, 1], 0).whole_local_copy()     # tp2 destination: half of every split tensor
+    assert ex((1, 2, 2), [0, 1, 2, 3], (1, 1, 2), [2, 3], 2).whole_local_copy()   # tp2 on both sides, same tp position
+    assert not ex((2, 1, 1), [0, 1], (1, 1, 1), [0], 0).whole_local_copy()        # pipeline stages merge: stage 1 arrives from a peer
