@@ -118,7 +118,8 @@ class GRPOInterface(ModelInterface):
             packed_input_ids=input_.data["packed_input_ids"]))
         loss_fn = functools.partial(_grpo_loss, eps_clip=self.eps_clip, kl_coef=self.kl_coef, temperature=self.gconfig.temperature)
         stats: Dict[str, float] = {}
-        mbs = batch.split(min(self.n_minibatches, batch.bs))
+        from realhf_b200.interfaces.ppo import _dp_group, _n_minibatches
+        mbs = batch.split(_n_minibatches(self.n_minibatches, batch.bs, _dp_group(model)))   # same number of steps on every DP rank
         for mb in mbs:
             st = eng.train_batch(mb, loss_fn, version_steps=model.version.global_step, num_micro_batches=n_mbs)
             for k, v in st.items():

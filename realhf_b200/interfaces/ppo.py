@@ -68,6 +68,21 @@ def _actor_loss_from_output(out: ModelOutput, mb: SequenceSample, *, kl_adapter,
     return loss, stat
 
 
+def _n_minibatches(wanted: int, local_bs: int, dp_group) -> int:
+    """Every rank of a data-parallel group must take the same number of optimizer steps (each one contains the gradient
+    collectives of the group).  A rank that received fewer sequences than `n_minibatches` cannot: fail with the reason instead of
+    running fewer steps than its peers and leaving them inside a collective.  (The master gives every DP rank of a train MFC at
+    least `n_minibatches` sequences whenever the batch has that many per rank.)"""
+    if local_bs >= wanted:
+        return wanted
+    import torch.distributed as dist
+    if dp_group is not None and dist.is_initialized() and dist.get_world_size(dp_group) > 1:
+        raise ValueError(f"this data-parallel rank received {local_bs} sequences but ppo_n_minibatches={wanted}: every rank needs at least one "
+                         f"sequence per minibatch -- raise dataset.train_bs_n_seqs, lower ppo.ppo_n_minibatches or use a smaller "
+                         f"data-parallel degree for the training MFCs")
+    return max(1, local_bs)
+
+
 @dataclasses.dataclass
 class PPOActorInterface(ModelInterface):
     n_minibatches: int = 4
@@ -191,7 +206,7 @@ class PPOActorInterface(ModelInterface):
         ctx = _engine_ctx(model)
         pp = ctx.pp_size if ctx is not None else 1
         n_mbs = n_mbs or 1
-        minibatches = batch.split(min(self.n_minibatches, batch.bs), min_size=(pp * 2 * n_mbs if pp > 1 else n_mbs))
+        minibatches = batch.split(_n_minibatches(self.n_minibatches, batch.bs, group), min_size=(pp * 2 * n_mbs if pp > 1 else n_mbs))
 
         sums = dict(n_seqs=float(len(seqlens)), task_reward=scores.sum(), n_tokens=loss_mask.count_nonzero(),
                     kl_reward=(kl_rewards * loss_mask).sum(), advantage=adv.sum(),
@@ -331,7 +346,7 @@ class PPOCriticInterface(ModelInterface):
         ctx = _engine_ctx(model)
         pp = ctx.pp_size if ctx is not None else 1
         n_mbs = n_mbs or 1
-        minibatches = batch.split(min(self.n_minibatches, batch.bs), min_size=(pp * 2 * n_mbs if pp > 1 else n_mbs))
+        minibatches = batch.split(_n_minibatches(self.n_minibatches, batch.bs, group), min_size=(pp * 2 * n_mbs if pp > 1 else n_mbs))
         loss_fn = functools.partial(_critic_loss_from_output, value_eps_clip=self.value_eps_clip,
                                     loss_fn_type=self.value_loss_type, rms=self.rms)
         train_stats: Dict[str, torch.Tensor] = collections.defaultdict(float)

@@ -252,7 +252,12 @@ class MasterWorker:
             assert per * dp == len(ids), f"balanced_dp needs n_seqs % dp == 0 ({len(ids)} % {dp})"
             parts = [(k * per, (k + 1) * per) for k in range(dp)]
         else:
-            parts = meta.get_split_spec(dp, min_size=max(1, (rpc.n_mbs or 1) * (2 * pp if pp > 1 else 1))).partitions
+            need = max(1, (rpc.n_mbs or 1) * (2 * pp if pp > 1 else 1))
+            if rpc.interface_type == ModelInterfaceType.TRAIN_STEP:
+                # every DP rank runs the interface's minibatch loop (one optimizer step with the group's gradient collectives per
+                # minibatch): it needs at least that many sequences, or the ranks would take different numbers of steps
+                need = max(need, int((getattr(rpc.interface_impl, "args", None) or {}).get("n_minibatches", 1) or 1))
+            parts = meta.get_split_spec(dp, min_size=need).partitions
         part = {d: ids[a:b] for d, (a, b) in enumerate(parts)}
         self._rpc_batch_lens_by_step.setdefault(step, {})[rpc.name] = self._batch_lens(meta)
         plan = self._transfer_plan(rpc, part, meta)

@@ -339,3 +339,33 @@ def test_generation_replica_on_a_sub_mesh_aliases_the_training_weights(tmp_path)
     assert log.count("[actor_train]") == 3 and "benchmark finished" in log, log[-3000:]
     w1 = open(os.path.join(os.environ["REAL_FILEROOT"], "logs", exp.experiment_name, "t0", "model_worker-1")).read()
     assert w1.count("aliased, no copy") == 1, w1[-3000:]
+
+
+def test_every_dp_rank_of_a_train_mfc_gets_enough_sequences_for_its_minibatches(tmp_path):
+    """16 prompts, critic_train on dp4 with 4 PPO minibatches: a purely token-balanced split hands some rank 3 sequences and another 5,
+    the 3-sequence rank would take 3 optimizer steps while its peers take 4 and wait in the gradient collective of the 4th.  The master
+    asks the partitioner for at least `n_minibatches` sequences per rank; when the batch is too small for that the interface fails
+    with the reason (12 prompts) instead of desynchronising the group."""
+    from realhf_b200.interfaces.ppo import _n_minibatches
+    assert _n_minibatches(4, 7, None) == 4 and _n_minibatches(4, 3, None) == 3      # no DP group: fewer steps are harmless
+    _env(tmp_path)
+    from realhf_b200.apps.main import main_start
+    from realhf_b200.apps.quickstart import build_experiment
+    actor, critic = str(tmp_path / "actor"), str(tmp_path / "critic")
+    cfg, tok, words = fixtures.make_checkpoint(actor, "llama")
+    fixtures.make_checkpoint(critic, "llama", is_critic=True, seed=5)
+    data = str(tmp_path / "prompts.jsonl")
+    fixtures.write_prompt_dataset(data, words, n=48)
+    args = ["ppo", f"experiment_name=mb-{uuid.uuid4().hex[:6]}", "trial_name=t0", "device=cpu", "dtype=fp32", "n_gpus_per_node=4",
+            "allocation_mode=manual", f"dataset.path={data}", "dataset.train_bs_n_seqs=16", "dataset.max_prompt_len=16",
+            "ppo.gen.max_new_tokens=4", "ppo.gen.min_new_tokens=2", "ppo.gen.top_k=20", "ppo.ppo_n_minibatches=4",
+            "exp_ctrl.total_train_epochs=1", "exp_ctrl.benchmark_steps=3"]
+    for role, path in (("actor", actor), ("ref", actor), ("critic", critic), ("rew", critic)):
+        args += [f"{role}.type._class=llama", f"{role}.path={path}", f"{role}.optimizer.grad_dtype=fp32", f"{role}.gradient_checkpointing=false"]
+    args += ["actor_gen.parallel.data_parallel_size=4", "actor_train.parallel.data_parallel_size=2", "actor_train.parallel.model_parallel_size=2",
+             "critic_train.parallel.data_parallel_size=4", "critic_inf.parallel.data_parallel_size=4",
+             "ref_inf.parallel.data_parallel_size=4", "rew_inf.parallel.data_parallel_size=4"]
+    exp = build_experiment(args)
+    main_start(exp, timeout=900)
+    log = _master_log(exp)
+    assert log.count("[critic_train]") == 3 and "benchmark finished" in log, log[-3000:]
