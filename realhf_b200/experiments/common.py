@@ -216,6 +216,11 @@ class CommonExperimentConfig(Experiment):
             if a.rpc.n_seqs < a.parallel.data_parallel_size * a.parallel.pipeline_parallel_size:
                 raise ValueError(f"MFC {a.rpc.name}: batch of {a.rpc.n_seqs} sequences is too small for dp x pp = "
                                  f"{a.parallel.data_parallel_size * a.parallel.pipeline_parallel_size}")
+            if a.rpc.balanced_dp and a.rpc.n_seqs % a.parallel.data_parallel_size:
+                # found at launch, not by the master in the middle of the first step
+                raise ValueError(f"MFC {a.rpc.name} splits its batch into equal shares per data-parallel rank (balanced_dp): "
+                                 f"{a.rpc.n_seqs} sequences are not divisible by dp = {a.parallel.data_parallel_size}; "
+                                 f"change the batch size (dataset.train_bs_n_seqs) or the data-parallel degree of this MFC")
 
     def _get_model_worker_configs(self, rpc_allocs: List[RPCAllocation]) -> List[ModelWorker]:
         src_rpc = next(a for a in rpc_allocs if a.rpc.is_src)

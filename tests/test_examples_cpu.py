@@ -144,3 +144,11 @@ def test_load_and_eval_rw_example_scores_sequences(tmp_path):
     # packing must not leak between sequences: scoring one sequence alone gives the same values
     alone, _ = rw.score(model, [seqs[1]])
     torch.testing.assert_close(alone[0], per_token[1], atol=1e-5, rtol=1e-5)
+
+
+def test_batch_not_divisible_by_the_dp_degree_of_a_balanced_mfc_is_rejected_at_launch():
+    from realhf_b200.apps.quickstart import build_experiment
+    exp = build_experiment(["gen", "experiment_name=g", "trial_name=t", "device=cpu", "n_gpus_per_node=4", "allocation_mode=d4m1p1",
+                            "dataset.train_bs_n_seqs=6", "model.type._class=llama"])
+    with pytest.raises(ValueError, match="not divisible by dp = 4"):
+        exp.initial_setup()
