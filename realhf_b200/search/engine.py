@@ -178,6 +178,8 @@ def build_problem(mesh: DeviceMesh, rpcs: List[MFCDef], models: Dict[str, ModelT
             for par in find_parallel_strategies(m):
                 if r.n_seqs < par.data_parallel_size * par.pipeline_parallel_size:
                     continue
+                if getattr(r, "balanced_dp", False) and r.n_seqs % par.data_parallel_size:
+                    continue   # equal shares per DP rank are impossible under this layout
                 if shapes[r.role]["v"] % par.model_parallel_size or shapes[r.role]["L"] < par.pipeline_parallel_size:
                     continue
                 n_mini = n_ppo_minibatches if r.interface_type == ModelInterfaceType.TRAIN_STEP else 1
